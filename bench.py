@@ -1,0 +1,376 @@
+#!/usr/bin/env python
+"""bench.py -- image-pair matches/sec of the all-pairs 2-NN matching path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload cfg2|cfg3|cfg4|cfg5|...]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's CPU BFMatcher path on the host cores
+
+A "step" is one pass of the hot path over the whole workload: every image pair q<t of the
+synthetic descriptor set (findBestPair's loop, /root/reference/src/Sfm.cpp:511-515) goes through
+2-NN + ratio test (getMatching, src/Sfm.cpp:590-608).  One "pair-match" = one such pair.
+
+  value  : pair-matches/s with descriptors already resident in HBM, results left in HBM
+           (sfmm_match_pairs_device), device-timed with CUDA events, max over ranks.
+  e2e    : the same metric through the public API with HOST buffers: H2D of the descriptors,
+           (NCCL broadcast), matching, (NCCL gather to rank 0), D2H of the match table.
+  roofline: the 2-NN kernel against the POPC-pipe (binary) or FP32/tensor (float) peak.
+  cpu_baseline: the reference's own CPU path (OpenCV BFMatcher via cv2, else the C oracle) on a
+           bounded sample of the same pairs, timed on this box's host cores (N=1, rank 0).
+
+Default workload at N GPUs: AKAZE-shape 486-bit descriptors, 5000 per image (BASELINE.json
+configs[1]); the image count grows with N so that every GPU keeps ~1225 pairs (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (kind, images at N=1, descriptors per image, weak-scale images with N?)
+    "cfg2": ("binary", 50, 5000, True),     # configs[1]: 50 x 5k x 486 bit, 1 GPU
+    "cfg3": ("binary", 200, 10000, False),  # configs[2]: 200 x 10k, sharded over 2/4/8
+    "cfg4": ("float", 300, 8000, False),    # configs[3]: 300 x 8k x 128 f32
+    "cfg5": ("binary", 1000, 20000, False), # configs[4]: headline, ~500k pairs
+    "cfg5s": ("binary", 40, 20000, True),   # cfg5's pair shape (20k x 20k) on a 40-image subset
+    "orb": ("orb", 100, 2000, True),        # ORB shape: 256 bit
+    "float2": ("float", 40, 4000, True),
+}
+
+
+def images_for(n1: int, gpus: int, weak: bool) -> int:
+    if not weak or gpus == 1:
+        return n1
+    target = gpus * n1 * (n1 - 1) // 2
+    n = int(math.ceil((1 + math.sqrt(1 + 8 * target)) / 2))
+    while n * (n - 1) // 2 < target:
+        n += 1
+    return n
+
+
+def make_descriptors(kind: str, n_images: int, n_desc: int, seed: int = 0):
+    from sfm_danpipeline_b200 import synth
+    if kind == "binary":
+        return synth.binary_images(n_images, n_desc, synth.AKAZE_BITS, seed), 0
+    if kind == "orb":
+        return synth.binary_images(n_images, n_desc, synth.ORB_BITS, seed), 0
+    return synth.float_images(n_images, n_desc, 128, seed, integer=True), 1
+
+
+# ------------------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock and throttle reasons of one GPU while the timed region runs (pynvml)."""
+
+    def __init__(self, index: int, period: float = 0.1):
+        self.index, self.period = index, period
+        self.samples, self.reasons = [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                 "hw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                 "sw_thermal_slowdown": getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                 "sw_power_cap": getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4),
+                 "hw_power_brake": getattr(nv, "nvmlClocksEventReasonHwPowerBrakeSlowdown", 0x80)}
+        get = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                mask = get(self.h)
+                for k, bit in names.items():
+                    if mask & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self.nv:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._t:
+            self._t.join()
+
+    def summary(self):
+        if not self.samples:
+            return None
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": float(self.max_mhz or 0),
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------ CPU arm
+def cpu_pair_fn(norm: int):
+    """(callable(Q,T)->n_matches, kind, cores, description).  cv2 is the very OpenCV code the
+    reference links (cv::BFMatcher::knnMatch -> cv::batchDistance); the C oracle is the port."""
+    import oracle
+    cores = os.cpu_count() or 1
+    if oracle.have_cv2():
+        import cv2
+        cv2.setNumThreads(cores)
+        ratio = np.float32(0.8)
+
+        def run(Q, T):
+            d, _i = oracle.knn2_cv2(Q, T, norm)
+            d = d.astype(np.float32)
+            return int((d[:, 0] <= ratio * d[:, 1]).sum())
+
+        return run, "reference", cv2.getNumThreads(), f"cv2 {cv2.__version__} batchDistance(K=2)+ratio (OpenCV BFMatcher code path)"
+    oracle.build()
+
+    def run(Q, T):
+        return len(oracle.match_pair(Q, T, norm, 0.8, False, threads=cores))
+
+    return run, "port", cores, "oracle/bf_oracle.c knn2 + ratio, python thread pool over query rows"
+
+
+def time_cpu_sample(descs, norm, budget_s: float, max_pairs: int, seed: int = 0):
+    from sfm_danpipeline_b200 import synth
+    run, kind, cores, how = cpu_pair_fn(norm)
+    pairs = synth.all_pairs(len(descs))
+    rng = np.random.default_rng(seed)
+    order = rng.permutation(len(pairs))
+    q, t = pairs[order[0]]
+    run(descs[q], descs[t])  # warm-up pair
+    done, t0 = 0, time.perf_counter()
+    for k in order[1:1 + max_pairs]:
+        q, t = pairs[k]
+        run(descs[q], descs[t])
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    dt = time.perf_counter() - t0
+    return done / dt, kind, cores, f"{done} of {len(pairs)} pairs ({how}), {dt:.1f} s"
+
+
+def run_reference_arm(args, kind, n_images, n_desc):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    descs, norm = make_descriptors(kind, min(n_images, 24), n_desc, args.seed)
+    per_step = []
+    how = cores = kind_s = None
+    for s in range(args.warmup + args.steps):
+        v, kind_s, cores, how = time_cpu_sample(descs, norm, args.cpu_seconds / max(args.steps, 1), 64, seed=s)
+        if s >= args.warmup:
+            per_step.append(v)
+    value = float(np.mean(per_step))
+    line = {"impl": "reference", "metric": "image-pair matches/sec (all-pairs 2-NN + ratio test)", "value": value,
+            "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "u8" if norm == 0 else "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {kind} {n_desc} descriptors/image; each step = a bounded random sample of the pairs"},
+            "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind_s, "sample": how},
+            "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--images", type=int, default=0)
+    ap.add_argument("--desc", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cross-check", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    kind, n1, n_desc, weak = WORKLOADS[args.workload]
+    n_desc = args.desc or n_desc
+    n_images = args.images or images_for(n1, args.gpus, weak)
+    if args.impl == "reference":
+        return run_reference_arm(args, kind, n_images, n_desc)
+
+    import torch
+    import torch.distributed as dist
+    from sfm_danpipeline_b200 import FLOAT_AUTO, Matcher
+    from sfm_danpipeline_b200 import distributed as D
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    descs, norm = make_descriptors(kind, n_images, n_desc, args.seed) if rank == 0 or True else (None, None)
+    rows = [d.shape[0] for d in descs]
+    pairs = D.all_pairs(n_images)
+    shards = D.shard_pairs(pairs, rows, world)
+    mine = pairs[shards[rank]]
+    dev = torch.device("cuda", local)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    m = Matcher(norm, 0.8, args.cross_check, device=local, float_mode=FLOAT_AUTO)
+    # ---- resident arm: descriptors in HBM before the timed region -------------------------
+    if world > 1:
+        D.broadcast_descriptors(m, descs if rank == 0 else None, 0)
+    else:
+        m.set_descriptors(descs)
+    cap = int(np.asarray(rows, np.int64)[mine[:, 0]].sum())
+    d_counts = torch.empty(max(len(mine), 1), dtype=torch.int32, device=dev)
+    d_matches = torch.empty((max(cap, 1), 4), dtype=torch.int32, device=dev)
+    torch.cuda.synchronize()
+
+    def resident_step():
+        flush.zero_()
+        torch.cuda.synchronize()
+        n = m.match_pairs_device(mine, d_counts.data_ptr(), d_matches.data_ptr(), cap)
+        return n, m.stats()
+
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    launches0 = m.stats()["kernel_launches"]
+    dev_ms = knn_ms = knn_work = 0.0
+    knn_launches = 0
+    n_matches = 0
+    with ClockSampler(local) as clk:
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            n_matches, st = resident_step()
+            dev_ms += st["last_match_ms"]
+            knn_ms += st["last_knn_ms"]
+            knn_work += st["last_knn_work"]
+            knn_launches += st["last_knn_launches"]
+        barrier()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+    launches = m.stats()["kernel_launches"] - launches0
+    stat = torch.tensor([dev_ms, float(launches), knn_ms, knn_work, float(knn_launches), float(n_matches)],
+                        dtype=torch.float64, device=dev)
+    if world > 1:
+        mx = stat.clone()
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        sm = stat.clone()
+        dist.all_reduce(sm, op=dist.ReduceOp.SUM)
+        dev_ms_max, launches_sum, total_matches = mx[0].item(), int(sm[1].item()), int(sm[5].item())
+    else:
+        dev_ms_max, launches_sum, total_matches = dev_ms, int(launches), int(n_matches)
+    ms_per_step = dev_ms_max / args.steps
+    value = len(pairs) / (ms_per_step * 1e-3)
+
+    # ---- end-to-end arm: host buffers in, host table out ----------------------------------
+    def e2e_step():
+        s0 = m.stats()
+        if world > 1:
+            table, _ = D.match_all_pairs_distributed(m, descs if rank == 0 else None, 0)
+        else:
+            m.set_descriptors(descs)
+            m.match_all_pairs()
+            table = m.result_table()
+        s1 = m.stats()
+        return table, s1["h2d_bytes"] - s0["h2d_bytes"], s1["d2h_bytes"] - s0["d2h_bytes"]
+
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e2e_steps = max(2, min(args.steps, 3))
+    for _ in range(e2e_steps):
+        flush.zero_()
+        table, h2d, d2h = e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+    if world > 1:
+        tmax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_ms = tmax.item()
+        if rank == 0:
+            d2h = int(table.matches.nbytes + table.counts.nbytes)
+    e2e_value = len(pairs) / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        knn_s = knn_ms * 1e-3
+        if norm == 0:
+            peak = n_sm * 16 * sm_max_mhz * 1e6 / 1e9  # GPOPC32/s: 16 POPC/clk/SM x SMs x max SM clock
+            roof = {"bound": "popc", "achieved": knn_work / knn_s / 1e9, "peak": peak, "unit": "GPOPC32/s",
+                    "peak_source": f"nominal 16 POPC/clk/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
+                                   "measured issue rates in profiles/pipe_bench_r01.txt",
+                    "traffic": None}
+        else:
+            peak = n_sm * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # fp32 FMA lanes: exact mode runs on CUDA cores
+            roof = {"bound": "fp32", "achieved": knn_work / knn_s / 1e12, "peak": peak, "unit": "TFLOP/s",
+                    "peak_source": f"128 FFMA lanes/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz; algorithmic FLOPs = 2*Nq*Nt*128",
+                    "traffic": None}
+        roof["frac"] = roof["achieved"] / roof["peak"]
+        roof["kernel_ms_per_launch"] = knn_ms / max(knn_launches, 1)
+        roof["kernel_share_of_step"] = knn_ms / max(dev_ms, 1e-9)
+        row_bytes = descs[0].shape[1] * descs[0].itemsize
+        alg_bytes = float(sum((rows[q] + rows[t]) * row_bytes for q, t in mine)) * args.steps + 16.0 * n_matches * args.steps
+        roof["hbm"] = {"algorithmic_GBps": alg_bytes / knn_s / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
+                       "note": "compute-bound path: HBM is reported, not the binding roof"}
+        line = {
+            "metric": "image-pair matches/sec (all-pairs 2-NN + ratio test)", "value": value, "unit": "pairs/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
+            "dtype": "u8" if norm == 0 else "f32", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {n_images} images x {n_desc} x "
+                                   f"{'486-bit AKAZE-shape' if kind == 'binary' else ('256-bit ORB-shape' if kind == 'orb' else '128-d f32 SIFT-shape')}"
+                                   f" descriptors, all {len(pairs)} pairs q<t, ratio 0.8, cross_check={bool(args.cross_check)}",
+                       "pairs": int(len(pairs)), "pairs_per_gpu": int(len(mine)), "matches_per_step": total_matches,
+                       "l2": "flushed between steps (256 MiB memset outside the timed events)",
+                       "parallelism": f"pairs sharded over {world} rank(s); NCCL broadcast + gather only in e2e"},
+            "wall_ms_per_step": wall_ms / args.steps,
+            "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
+                    "d2h_bytes_per_step": int(d2h)},
+            "gpu_launches": launches_sum,
+            "roofline": roof,
+            "clocks": clk.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            v, kind_s, cores, how = time_cpu_sample(descs, norm, args.cpu_seconds, 64)
+            line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind_s, "sample": how}
+        print(json.dumps(line), flush=True)
+    m.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,167 @@
+"""Host-side mirror of the reference's matching interface on top of the C ABI.
+
+Reference interface (C++): ``void StructFromMotion::getMatching(const int& idx_query,
+const int& idx_train, Matching* goodMatches)`` (/root/reference/include/Sfm.h:89,
+src/Sfm.cpp:590-608) over ``std::vector<cv::Mat> imagesDescriptors`` (include/Sfm.h:29), driven
+for all q<t by ``findBestPair`` (src/Sfm.cpp:511-515).  This class keeps the names and argument
+meaning; match lists come back as numpy records with cv::DMatch's fields.  All arithmetic runs
+in the CUDA library -- there is no CPU path here.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import _lib
+from ._lib import DMATCH_DTYPE, NORM_HAMMING, NORM_L2, SfmmError
+
+
+class Matcher:
+    """One ``cv::BFMatcher(norm, false)`` + ratio loop, for every image pair, on one B200.
+
+    norm         ``NORM_L2`` (the reference's hard-wired choice, src/Sfm.cpp:593) for float32
+                 descriptors or ``NORM_HAMMING`` for uint8 (AKAZE / ORB) descriptors
+    ratio        ``NN_MATCH_RATIO`` (include/Sfm.h:60)
+    cross_check  north-star extra stage, off by default like the reference
+    """
+
+    def __init__(self, norm: int = NORM_L2, ratio: float = 0.8, cross_check: bool = False, device: int = 0,
+                 float_mode: int = _lib.FLOAT_AUTO, pair_batch: int = 0):
+        self._L = _lib.load()
+        cfg = _lib.SfmmConfig()
+        self._L.sfmm_default_config(C.byref(cfg))
+        cfg.device, cfg.norm, cfg.ratio = int(device), int(norm), float(ratio)
+        cfg.cross_check, cfg.float_mode, cfg.pair_batch = int(bool(cross_check)), int(float_mode), int(pair_batch)
+        self._ctx = C.c_void_p()
+        rc = self._L.sfmm_create(C.byref(cfg), C.byref(self._ctx))
+        if rc != 0:
+            raise SfmmError(rc, self._L.sfmm_last_error(None).decode())
+        self.norm, self.device = int(norm), int(device)
+        self.rows: list[int] = []
+        self.cols = 0
+
+    # -- lifetime -------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "_ctx", None) and self._ctx.value:
+            self._L.sfmm_destroy(self._ctx)
+            self._ctx = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SfmmError(rc, self._L.sfmm_last_error(self._ctx).decode())
+
+    # -- descriptors ----------------------------------------------------------------------
+    def set_descriptors(self, descriptors: Sequence[np.ndarray]):
+        """imagesDescriptors: one (rows_i, cols) uint8 / float32 array per image (rows may be strided)."""
+        n = len(descriptors)
+        want = np.uint8 if self.norm == NORM_HAMMING else np.float32
+        cols = descriptors[0].shape[1] if n else 1
+        keep = []
+        for d in descriptors:
+            if d.ndim != 2 or d.dtype != want or d.shape[1] != cols:
+                raise SfmmError(_lib.SFMM_EINVAL, f"every descriptor set must be (rows, {cols}) {want.__name__}")
+            if d.shape[0] and d.strides[1] != d.itemsize:
+                d = np.ascontiguousarray(d)
+            keep.append(d)
+        ptrs = (C.c_void_p * max(n, 1))(*[d.ctypes.data if d.shape[0] else None for d in keep])
+        rows = (C.c_int32 * max(n, 1))(*[d.shape[0] for d in keep])
+        steps = (C.c_size_t * max(n, 1))(*[d.strides[0] if d.shape[0] > 1 else d.shape[1] * d.itemsize for d in keep])
+        self._check(self._L.sfmm_set_descriptors(self._ctx, n, ptrs, rows, cols, steps,
+                                                 _lib.U8 if want is np.uint8 else _lib.F32))
+        self.rows, self.cols = [d.shape[0] for d in keep], cols
+
+    def reserve_descriptors(self, rows: Sequence[int], cols: int):
+        """Allocate the device layout only (non-root ranks, before the blob broadcast)."""
+        n = len(rows)
+        r = (C.c_int32 * max(n, 1))(*[int(x) for x in rows])
+        self._check(self._L.sfmm_set_descriptors(self._ctx, n, None, r, int(cols), None,
+                                                 _lib.U8 if self.norm == NORM_HAMMING else _lib.F32))
+        self.rows, self.cols = [int(x) for x in rows], int(cols)
+
+    def descriptor_blob(self) -> tuple[int, int]:
+        """(device pointer, bytes) of the packed descriptor blob."""
+        p, b = C.c_void_p(), C.c_size_t()
+        self._check(self._L.sfmm_descriptor_blob(self._ctx, C.byref(p), C.byref(b)))
+        return int(p.value or 0), int(b.value)
+
+    # -- matching -------------------------------------------------------------------------
+    def match_all_pairs(self):
+        """findBestPair's q<t loop, once; afterwards getMatching is a look-up."""
+        self._check(self._L.sfmm_match_all_pairs(self._ctx))
+
+    def match_pairs(self, pairs):
+        qt = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+        self._check(self._L.sfmm_match_pairs(self._ctx, qt.ctypes.data, len(qt)))
+
+    def match_pairs_device(self, pairs, d_counts_ptr: int, d_matches_ptr: int, capacity: int) -> int:
+        """Match into caller-owned DEVICE buffers (see sfmm_match_pairs_device); returns #records."""
+        qt = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+        n = C.c_int64()
+        self._check(self._L.sfmm_match_pairs_device(self._ctx, qt.ctypes.data, len(qt), d_counts_ptr, d_matches_ptr,
+                                                    int(capacity), C.byref(n)))
+        return int(n.value)
+
+    def getMatching(self, idx_query: int, idx_train: int) -> np.ndarray:
+        """The reference's entry point: the ratio-filtered 1-NN list of (idx_query, idx_train)."""
+        p, n = C.c_void_p(), C.c_int32()
+        self._check(self._L.sfmm_get_pair(self._ctx, int(idx_query), int(idx_train), C.byref(p), C.byref(n)))
+        if n.value == 0:
+            return np.zeros(0, DMATCH_DTYPE)
+        buf = (C.c_char * (n.value * DMATCH_DTYPE.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, DMATCH_DTYPE).copy()
+
+    get_matching = getMatching
+
+    def match_pair(self, idx_query: int, idx_train: int) -> np.ndarray:
+        """getMatching computed on demand (no table)."""
+        cap = max(self.rows[idx_query], 1)
+        out = np.zeros(cap, DMATCH_DTYPE)
+        n = C.c_int32()
+        self._check(self._L.sfmm_match_pair(self._ctx, int(idx_query), int(idx_train), out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value].copy()
+
+    def knn_pair(self, idx_query: int, idx_train: int):
+        """knnMatch(k=2) as arrays: (train_idx[nq,2] int32, distance[nq,2] float32)."""
+        nq = self.rows[idx_query]
+        idx = np.empty((nq, 2), np.int32)
+        dist = np.empty((nq, 2), np.float32)
+        self._check(self._L.sfmm_knn_pair(self._ctx, int(idx_query), int(idx_train), idx.ctypes.data, dist.ctypes.data))
+        return idx, dist
+
+    def result_table(self):
+        """(pairs[n,2], counts[n], offsets[n], matches[total]) of everything matched so far (copies)."""
+        n, m = C.c_int64(), C.c_int64()
+        qt, cnt, off, mat = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+        self._check(self._L.sfmm_result_table(self._ctx, C.byref(n), C.byref(qt), C.byref(cnt), C.byref(off),
+                                              C.byref(mat), C.byref(m)))
+
+        def arr(ptr, count, dt):
+            if count == 0:
+                return np.zeros(0, dt)
+            buf = (C.c_char * (count * np.dtype(dt).itemsize)).from_address(ptr.value)
+            return np.frombuffer(buf, dt).copy()
+
+        return (arr(qt, 2 * n.value, np.int32).reshape(-1, 2), arr(cnt, n.value, np.int32),
+                arr(off, n.value, np.int64), arr(mat, m.value, DMATCH_DTYPE))
+
+    def clear_results(self):
+        self._check(self._L.sfmm_clear_results(self._ctx))
+
+    def stats(self) -> dict:
+        s = _lib.SfmmStats()
+        self._check(self._L.sfmm_get_stats(self._ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}

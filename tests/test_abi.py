@@ -1,0 +1,86 @@
+"""CPU tests of the drop-in boundary: the C-ABI library loads, exports exactly what
+include/sfm_match.h declares, and refuses to run without a GPU (no fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from sfm_danpipeline_b200 import _lib, Matcher, SfmmError
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _has_gpu():
+    import torch
+    return torch.cuda.is_available()
+
+
+def test_library_is_built_and_loads():
+    L = _lib.load()
+    assert b"sm_100a" in L.sfmm_version()
+
+
+def test_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "sfm_match.h")).read()
+    declared = set(re.findall(r"SFMM_API\s+[\w\s\*]+?\b(sfmm_\w+)\s*\(", hdr))
+    assert declared == set(_lib.EXPORTS), declared ^ set(_lib.EXPORTS)
+    L = _lib.load()
+    for name in declared:
+        assert getattr(L, name) is not None
+
+
+def test_header_cites_the_reference_interface():
+    hdr = open(os.path.join(ROOT, "include", "sfm_match.h")).read()
+    for cite in ("src/Sfm.cpp:590-608", "src/Sfm.cpp:511-515", "include/Sfm.h:60", "include/Utilities.h:27"):
+        assert cite in hdr
+
+
+def test_dmatch_layout_is_cv_dmatch():
+    assert _lib.DMATCH_DTYPE.itemsize == 16
+    assert [_lib.DMATCH_DTYPE.fields[k][1] for k in ("queryIdx", "trainIdx", "imgIdx", "distance")] == [0, 4, 8, 12]
+
+
+def test_default_config_is_the_reference_constants():
+    cfg = _lib.SfmmConfig()
+    _lib.load().sfmm_default_config(C.byref(cfg))
+    assert cfg.struct_size == C.sizeof(_lib.SfmmConfig)
+    assert cfg.norm == _lib.NORM_L2 and cfg.cross_check == 0
+    assert np.float32(cfg.ratio) == np.float32(0.8)
+
+
+def test_row_pitch():
+    L = _lib.load()
+    assert L.sfmm_row_pitch(61, _lib.U8) == 64 and L.sfmm_row_pitch(32, _lib.U8) == 32
+    assert L.sfmm_row_pitch(64, _lib.U8) == 64 and L.sfmm_row_pitch(65, _lib.U8) == 128
+    assert L.sfmm_row_pitch(128, _lib.F32) == 512 and L.sfmm_row_pitch(129, _lib.U8) == 0
+
+
+def test_bad_config_is_rejected_before_touching_cuda():
+    L = _lib.load()
+    cfg = _lib.SfmmConfig()
+    L.sfmm_default_config(C.byref(cfg))
+    cfg.norm = 7
+    ctx = C.c_void_p()
+    assert L.sfmm_create(C.byref(cfg), C.byref(ctx)) == _lib.SFMM_EINVAL
+    assert b"norm" in L.sfmm_last_error(None)
+    assert L.sfmm_create(None, C.byref(ctx)) == _lib.SFMM_EINVAL
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful without a CUDA device")
+def test_no_gpu_means_error_not_fallback():
+    with pytest.raises(SfmmError) as e:
+        Matcher(_lib.NORM_HAMMING)
+    assert e.value.code == _lib.SFMM_ENODEVICE
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_product_package_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "sfm_danpipeline_b200")
+    for dirpath, _d, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h", ".hpp", ".cpp")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
+                assert "liboracle" not in src and "bf_oracle" not in src, f

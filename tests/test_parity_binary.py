@@ -1,0 +1,165 @@
+"""GPU parity, binary descriptors: the CUDA path through the C ABI vs the oracle / cv2 goldens.
+
+Bar: bit-exact match indices and Hamming distances (north_star)."""
+import numpy as np
+import pytest
+
+import oracle
+from sfm_danpipeline_b200 import Matcher, NORM_HAMMING, SfmmError, synth
+from _golden import GoldenSet
+
+pytestmark = pytest.mark.gpu
+
+
+def _expect_equal(got, exp):
+    assert got.dtype == exp.dtype
+    assert got.tobytes() == exp.tobytes(), (len(got), len(exp))
+
+
+@pytest.mark.parametrize("name", ["temple_akaze", "temple_orb", "synth_binary"])
+@pytest.mark.parametrize("cross", [False, True])
+def test_all_pairs_equal_cv2_golden(name, cross):
+    g = GoldenSet(name)
+    with Matcher(NORM_HAMMING, 0.8, cross) as m:
+        m.set_descriptors(g.descs)
+        m.match_all_pairs()
+        for p, (q, t, *_r) in enumerate(g.pairs):
+            got = m.getMatching(q, t)
+            eq, et, ed = g.expected(p, cross)
+            assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all(), (name, q, t)
+            assert (got["distance"] == ed).all() and (got["imgIdx"] == 0).all()
+
+
+@pytest.mark.parametrize("name", ["temple_akaze", "temple_orb"])
+def test_raw_knn_equals_cv2_golden(name):
+    g = GoldenSet(name)
+    with Matcher(NORM_HAMMING) as m:
+        m.set_descriptors(g.descs)
+        for q, t, kd, ki, *_r in g.pairs[::5]:
+            idx, dist = m.knn_pair(q, t)
+            assert (idx == ki).all() and (dist == kd).all()
+
+
+@pytest.mark.parametrize("cols", [16, 32, 61, 64, 100, 128])
+def test_widths_and_ties_vs_oracle(cols):
+    rng = np.random.default_rng(cols)
+    # few distinct byte values => many exact distance ties, exercising lowest-index tie-breaking
+    descs = [rng.integers(0, 2, (n, cols), dtype=np.uint8) * 255 for n in (700, 513, 1024, 3)]
+    for cross in (False, True):
+        with Matcher(NORM_HAMMING, 0.8, cross) as m:
+            m.set_descriptors(descs)
+            m.match_all_pairs()
+            for (q, t) in synth.all_pairs(len(descs)):
+                _expect_equal(m.getMatching(q, t), oracle.match_pair(descs[q], descs[t], 0, 0.8, cross, threads=4))
+
+
+def test_cfg2_shape_sample_vs_oracle():
+    # configs[1]: 486-bit AKAZE-shape, 5k rows per image; a few pairs at full size
+    descs = synth.binary_images(4, 5000, seed=0)
+    with Matcher(NORM_HAMMING) as m:
+        m.set_descriptors(descs)
+        m.match_all_pairs()
+        for (q, t) in [(0, 1), (1, 3), (2, 3)]:
+            exp = oracle.match_pair(descs[q], descs[t], 0, 0.8, False, threads=8)
+            _expect_equal(m.getMatching(q, t), exp)
+            assert 400 < len(exp) < 900  # the generator's ~n/8 ratio-passing matches
+        idx, dist = m.knn_pair(0, 1)
+        d, i = oracle.knn2_c(descs[0], descs[1], 0, threads=8)
+        assert (idx == i).all() and (dist == d.astype(np.float32)).all()
+        ties = (d[:, 0] == d[:, 1]).mean()
+        assert ties > 0.02  # the data really exercises tie-breaking
+
+
+def test_ragged_and_degenerate_images():
+    rng = np.random.default_rng(1)
+    descs = [rng.integers(0, 256, (n, 61), dtype=np.uint8) for n in (0, 1, 2, 130, 1500, 0, 37)]
+    for cross in (False, True):
+        with Matcher(NORM_HAMMING, 0.9, cross) as m:
+            m.set_descriptors(descs)
+            m.match_all_pairs()
+            for (q, t) in synth.all_pairs(len(descs)):
+                _expect_equal(m.getMatching(q, t), oracle.match_pair(descs[q], descs[t], 0, 0.9, cross))
+                _expect_equal(m.match_pair(q, t), oracle.match_pair(descs[q], descs[t], 0, 0.9, cross))
+            # reverse direction and self pairs on demand
+            _expect_equal(m.match_pair(4, 3), oracle.match_pair(descs[4], descs[3], 0, 0.9, cross))
+            _expect_equal(m.match_pair(4, 4), oracle.match_pair(descs[4], descs[4], 0, 0.9, cross))
+            idx, dist = m.knn_pair(3, 1)  # one train row: second neighbour missing
+            assert (idx[:, 1] == -1).all() and (dist[:, 1] == np.finfo(np.float32).max).all()
+            assert (idx[:, 0] == 0).all()
+
+
+def test_strided_rows_and_padding_are_neutral():
+    rng = np.random.default_rng(2)
+    wide = rng.integers(0, 256, (400, 80), dtype=np.uint8)
+    a, b = wide[:200, :61], wide[200:, :61]  # row step 80, 61 used bytes
+    with Matcher(NORM_HAMMING) as m:
+        m.set_descriptors([a, b])
+        got = m.match_pair(0, 1)
+    _expect_equal(got, oracle.match_pair(np.ascontiguousarray(a), np.ascontiguousarray(b), 0))
+
+
+def test_duplicate_rows_lowest_index_in_both_slots():
+    T = np.zeros((300, 61), np.uint8)
+    T[7, 0] = 1
+    Q = np.zeros((2, 61), np.uint8)
+    Q[1, 0] = 1
+    with Matcher(NORM_HAMMING) as m:
+        m.set_descriptors([Q, T])
+        idx, dist = m.knn_pair(0, 1)
+        assert idx.tolist() == [[0, 1], [7, 0]] and dist.tolist() == [[0.0, 0.0], [0.0, 1.0]]
+        got = m.match_pair(0, 1)  # 0 <= 0.8*0 passes; 0 <= 0.8*1 passes
+        assert got["trainIdx"].tolist() == [0, 7]
+
+
+def test_batched_launches_give_the_same_table():
+    descs = synth.binary_images(7, [300, 650, 1, 512, 513, 90, 1200], seed=3)
+    with Matcher(NORM_HAMMING) as a, Matcher(NORM_HAMMING, pair_batch=4) as b:
+        a.set_descriptors(descs)
+        b.set_descriptors(descs)
+        a.match_all_pairs()
+        b.match_all_pairs()
+        ta, tb = a.result_table(), b.result_table()
+        for x, y in zip(ta, tb):
+            assert x.tobytes() == y.tobytes()
+        pairs, counts, offs, mat = ta
+        assert pairs.tolist() == [list(p) for p in synth.all_pairs(7)]
+        for i, (q, t) in enumerate(pairs):
+            _expect_equal(mat[offs[i]:offs[i] + counts[i]], a.getMatching(q, t))
+
+
+def test_error_codes():
+    with Matcher(NORM_HAMMING) as m:
+        with pytest.raises(SfmmError) as e:
+            m.match_all_pairs()
+        assert e.value.code == -4  # no descriptors yet
+        with pytest.raises(SfmmError) as e:
+            m.set_descriptors([np.zeros((4, 128), np.float32)])
+        assert e.value.code == -1  # Hamming needs uint8
+        m.set_descriptors([np.zeros((4, 61), np.uint8), np.zeros((5, 61), np.uint8)])
+        with pytest.raises(SfmmError) as e:
+            m.getMatching(0, 1)
+        assert e.value.code == -4  # not computed yet
+        with pytest.raises(SfmmError) as e:
+            m.match_pair(0, 2)
+        assert e.value.code == -5
+        with pytest.raises(SfmmError) as e:
+            m.set_descriptors([np.zeros((1 << 18, 32), np.uint8)])
+        assert e.value.code == -5  # OpenCV's 2^18 row limit
+
+
+def test_full_size_properties_cfg2():
+    # size-independent checks at configs[1] scale: ascending queryIdx, one entry per query,
+    # self-match of an image finds itself at distance 0, permutation equivariance of the train set
+    descs = synth.binary_images(3, 5000, seed=9)
+    perm = np.random.default_rng(0).permutation(5000)
+    with Matcher(NORM_HAMMING) as m:
+        m.set_descriptors([descs[0], descs[1], descs[1][perm]])
+        m.match_all_pairs()
+        a, b = m.getMatching(0, 1), m.getMatching(0, 2)
+        assert (np.diff(a["queryIdx"]) > 0).all()
+        assert len(a) == len(b) and (a["queryIdx"] == b["queryIdx"]).all() and (a["distance"] == b["distance"]).all()
+        # same train rows up to ties broken by position
+        same = perm[b["trainIdx"]] == a["trainIdx"]
+        assert same.mean() > 0.95
+        idx, dist = m.knn_pair(1, 1)
+        assert (dist[:, 0] == 0).all()
