@@ -656,6 +656,7 @@ SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) 
         if (!hc.data) return fail(ctx, SFMM_ENOMEM, "match_pairs: out of host memory for the match table");
         if (total) std::memcpy(hc.data.get(), h_m, static_cast<size_t>(total) * sizeof(SfmDMatch));
         const SfmDMatch* base = hc.data.get();
+        int64_t running = 0;
         ctx->chunks.push_back(std::move(hc));
         for (int64_t i = 0; i < n; ++i) {
             const int32_t q = qt[2 * (done + i)], t = qt[2 * (done + i) + 1];
@@ -663,8 +664,12 @@ SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) 
             ctx->res_qt.push_back(q);
             ctx->res_qt.push_back(t);
             ctx->res_counts.push_back(h_cnt[i]);
-            ctx->res_offsets.push_back(ctx->n_matches + static_cast<int64_t>(h_off[i]));
-            ctx->res_slots.push_back(PairSlot{base + h_off[i], h_cnt[i]});
+            // records are laid out in pair order, so the offset is the running total (h_off[i] for
+            // non-empty pairs; empty pairs have no filter tile and get the position they would occupy)
+            const int64_t local = h_cnt[i] ? static_cast<int64_t>(h_off[i]) : running;
+            running = local + h_cnt[i];
+            ctx->res_offsets.push_back(ctx->n_matches + local);
+            ctx->res_slots.push_back(PairSlot{base + local, h_cnt[i]});
         }
         ctx->n_matches += static_cast<int64_t>(total);
         ctx->flat_valid = false;
