@@ -66,10 +66,16 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
 }
 
 // ------------------------------------------------------------------ bit counting
-// 3:2 compressor on 32 bit lanes: s = a^b^c (LOP3 0x96), c = majority(a,b,c) (LOP3 0xE8).
+// 3:2 compressor on 32 bit lanes: sum = a^b^c (LOP3 0x96), carry = majority(a,b,c) (LOP3 0xE8).
+// Written as PTX so that neither NVVM nor ptxas re-associates the XOR of query and train word
+// into the compressor (that costs 6 instead of 5 LOP3 per three words, and the ALU pipe is the
+// binding one: ncu profiles/ncu_binary_r01.txt shows alu 94 %, xu 79 %, fma 3 %).
 __device__ __forceinline__ void csa(uint32_t a, uint32_t b, uint32_t c, uint32_t& sum, uint32_t& carry) {
-    sum = a ^ b ^ c;
-    carry = (a & b) | (c & (a ^ b));
+    uint32_t s, m;
+    asm("lop3.b32 %0, %1, %2, %3, 0x96;" : "=r"(s) : "r"(a), "r"(b), "r"(c));
+    asm("lop3.b32 %0, %1, %2, %3, 0xe8;" : "=r"(m) : "r"(a), "r"(b), "r"(c));
+    sum = s;
+    carry = m;
 }
 
 // One compression pass: N words of equal weight -> N - 2*(N/3) words of that weight (in place
@@ -83,26 +89,36 @@ __device__ __forceinline__ void csa_pass(uint32_t (&same)[N], uint32_t* carry) {
     for (int r = 0; r < N - 3 * G; ++r) same[G + r] = same[3 * G + r];
 }
 
+// acc + sum_i popc(x[i]) * weight.  `weight` comes from kernel parameters (constant bank), so
+// the multiply-add stays an IMAD on the otherwise idle FMA pipe instead of being strength-
+// reduced to shift/add instructions on the ALU pipe.
 template <int N>
-__device__ __forceinline__ uint32_t popc_sum(const uint32_t* x) {
-    uint32_t s = 0;
+__device__ __forceinline__ uint32_t popc_mad(const uint32_t* x, uint32_t weight, uint32_t acc) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) s += __popc(x[i]);
-    return s;
+    for (int i = 0; i < N; ++i) asm("mad.lo.u32 %0, %1, %2, %0;" : "+r"(acc) : "r"(__popc(x[i])), "r"(weight));
+    return acc;
 }
 
-// Hamming distance of two W-word rows.
+// Weights of the bit-count planes already shifted into key position: w[k] = 2^k << IDX_BITS.
+struct KeyWeights {
+    uint32_t w[3];
+};
+
+// Packed key  (hamming(q,b) << IDX_BITS) + t  of two W-word rows.
 //   CSA_LEVEL 0: W POPC.
 //   CSA_LEVEL 1: one pass on the XOR words                          (W=16: 6 ones + 5 twos = 11 POPC)
 //   CSA_LEVEL 2: + a second pass on the surviving "ones"            (W=16: 2 ones + 7 twos =  9 POPC)
 //   CSA_LEVEL 3: + a pass on the "twos"                             (W=16: 2 + 3 twos + 2 fours = 7 POPC)
+// Pipe budget per 32 evaluations at level 2, W=16: 30 LOP3 + 3 VIMNMX on ALU (66 cycles/SMSP),
+// 9 POPC on XU (72 cycles), 9 IMAD on FMA (18 cycles)  ->  16/9 of the plain-POPC rate.
 template <int W, int CSA_LEVEL>
-__device__ __forceinline__ uint32_t hamming(const uint32_t (&q)[W], const uint32_t (&b)[W]) {
+__device__ __forceinline__ uint32_t hamming_key(const uint32_t (&q)[W], const uint32_t (&b)[W], uint32_t t,
+                                                const KeyWeights& kw) {
     uint32_t x[W];
 #pragma unroll
     for (int j = 0; j < W; ++j) x[j] = q[j] ^ b[j];
     if constexpr (CSA_LEVEL == 0 || W < 3) {
-        return popc_sum<W>(x);
+        return popc_mad<W>(x, kw.w[0], t);
     } else {
         constexpr int G1 = W / 3;         // carries of pass 1
         constexpr int N1 = W - 2 * G1;    // ones left after pass 1
@@ -119,6 +135,7 @@ __device__ __forceinline__ uint32_t hamming(const uint32_t (&q)[W], const uint32
 #pragma unroll
             for (int i = 0; i < N2; ++i) x[i] = ones1[i];
         }
+        uint32_t key = popc_mad<N2>(x, kw.w[0], t);
         if constexpr (CSA_LEVEL >= 3 && NT >= 3) {
             constexpr int G3 = NT / 3;
             constexpr int NT2 = NT - 2 * G3;
@@ -127,9 +144,10 @@ __device__ __forceinline__ uint32_t hamming(const uint32_t (&q)[W], const uint32
 #pragma unroll
             for (int i = 0; i < NT; ++i) t2[i] = twos[i];
             csa_pass<NT>(t2, fours);
-            return popc_sum<N2>(x) + 2u * popc_sum<NT2>(t2) + 4u * popc_sum<G3>(fours);
+            key = popc_mad<NT2>(t2, kw.w[1], key);
+            return popc_mad<G3>(fours, kw.w[2], key);
         } else {
-            return popc_sum<N2>(x) + 2u * popc_sum<NT>(twos);
+            return popc_mad<NT>(twos, kw.w[1], key);
         }
     }
 }
@@ -146,7 +164,7 @@ template <int W, int TQ, int THREADS, int TT, int CSA_LEVEL, bool CROSS>
 __global__ void __launch_bounds__(THREADS)
 binary_knn2_kernel(const uint32_t* __restrict__ blob, const KnnTile* __restrict__ tiles,
                    const PairDesc* __restrict__ pairs, KnnEntry* __restrict__ knn,
-                   unsigned long long* __restrict__ colmin) {
+                   unsigned long long* __restrict__ colmin, const KeyWeights kw) {
     static_assert(W % 4 == 0, "rows are 16-byte multiples");
     extern __shared__ __align__(128) unsigned char smem_raw[];
     auto& sm = *reinterpret_cast<BinaryKnnSmem<W, TQ, THREADS, TT>*>(smem_raw);
@@ -219,13 +237,13 @@ binary_knn2_kernel(const uint32_t* __restrict__ blob, const KnnTile* __restrict_
             [[maybe_unused]] uint32_t cmin = 0xFFFFFFFFu;
 #pragma unroll
             for (int k = 0; k < TQ; ++k) {
-                const uint32_t d = hamming<W, CSA_LEVEL>(q[k], b);
-                const uint32_t key = (d << IDX_BITS) + t;
+                const uint32_t key = hamming_key<W, CSA_LEVEL>(q[k], b, t, kw);
                 const uint32_t hi = max(m1[k], key);
                 m1[k] = min(m1[k], key);
                 m2[k] = min(m2[k], hi);
                 if constexpr (CROSS) {
-                    const uint32_t ck = qrow[k] < pd.nq ? (d << IDX_BITS) + qrow[k] : 0xFFFFFFFFu;
+                    // same distance, query index in the low bits instead of the train index
+                    const uint32_t ck = qrow[k] < pd.nq ? key - t + qrow[k] : 0xFFFFFFFFu;
                     cmin = min(cmin, ck);
                 }
             }

@@ -249,7 +249,8 @@ cudaError_t launch_binary_t(SfmmCtx* ctx, uint32_t n_tiles) {
     static_assert(sizeof(Smem) <= 48 * 1024, "fits the default dynamic shared memory limit");
     kern<<<n_tiles, BK_THREADS, sizeof(Smem), ctx->stream>>>(ctx->blob.as<uint32_t>(), ctx->d_tiles.as<KnnTile>(),
                                                              ctx->d_pairs.as<PairDesc>(), ctx->d_knn.as<KnnEntry>(),
-                                                             ctx->d_colmin.as<unsigned long long>());
+                                                             ctx->d_colmin.as<unsigned long long>(),
+                                                             KeyWeights{{1u << IDX_BITS, 2u << IDX_BITS, 4u << IDX_BITS}});
     return cudaGetLastError();
 }
 
