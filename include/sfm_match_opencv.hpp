@@ -1,0 +1,109 @@
+// sfm_match_opencv.hpp -- header-only C++11 adapter between the reference's OpenCV types and the
+// C ABI of libsfmmatch.so (sfm_match.h).  Compile it inside iTree3DMap (it only needs
+// <opencv2/core.hpp>); nothing here touches CUDA.
+//
+// Reference types kept at the boundary (file:line in the reference tree):
+//     std::vector<cv::Mat>  imagesDescriptors                 include/Sfm.h:29
+//     using Matching = std::vector<cv::DMatch>                include/Utilities.h:27
+//     void getMatching(const int&, const int&, Matching*)     include/Sfm.h:89, src/Sfm.cpp:590-608
+#ifndef SFM_MATCH_OPENCV_HPP_
+#define SFM_MATCH_OPENCV_HPP_
+
+#include <cstring>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include <opencv2/core.hpp>
+
+#include "sfm_match.h"
+
+namespace sfmm {
+
+static_assert(sizeof(cv::DMatch) == sizeof(SfmDMatch), "cv::DMatch and SfmDMatch must have the same layout");
+
+// The reference has no error channel on this path (void functions; cv::Exception propagates):
+// ABI error codes become exceptions of the same spirit.
+struct Error : std::runtime_error {
+    int code;
+    Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
+};
+
+class AllPairsMatcher {
+  public:
+    // normType: cv::NORM_L2 (what src/Sfm.cpp:593 passes) or cv::NORM_HAMMING / NORM_HAMMING2-free
+    // binary matching for the AKAZE / ORB detectors (src/Sfm.cpp:331-384).
+    explicit AllPairsMatcher(int normType = cv::NORM_L2, float ratio = 0.8f, bool crossCheck = false, int device = 0)
+        : ctx_(nullptr) {
+        SfmmConfig cfg;
+        sfmm_default_config(&cfg);
+        cfg.device = device;
+        cfg.norm = (normType == cv::NORM_HAMMING) ? SFMM_NORM_HAMMING : SFMM_NORM_L2;
+        cfg.ratio = ratio;
+        cfg.cross_check = crossCheck ? 1 : 0;
+        const int rc = sfmm_create(&cfg, &ctx_);
+        if (rc != SFMM_OK) throw Error(rc, sfmm_last_error(nullptr));
+    }
+    ~AllPairsMatcher() { sfmm_destroy(ctx_); }
+    AllPairsMatcher(const AllPairsMatcher&) = delete;
+    AllPairsMatcher& operator=(const AllPairsMatcher&) = delete;
+
+    // Call once after extractFeature() (src/Sfm.cpp:21): uploads every image's descriptors and
+    // runs findBestPair's whole q<t loop (src/Sfm.cpp:511-515) on the GPU.
+    void compute(const std::vector<cv::Mat>& imagesDescriptors) {
+        const int n = static_cast<int>(imagesDescriptors.size());
+        std::vector<const void*> data(n);
+        std::vector<int32_t> rows(n);
+        std::vector<size_t> steps(n);
+        int cols = 1, type = SFMM_F32;
+        for (int i = 0; i < n; ++i) {
+            const cv::Mat& m = imagesDescriptors[i];
+            if (m.empty()) {  // an image without keypoints: cv::Mat() -- zero rows
+                data[i] = nullptr; rows[i] = 0; steps[i] = 0;
+                continue;
+            }
+            if (m.depth() != CV_8U && m.depth() != CV_32F) throw Error(SFMM_EINVAL, "descriptors must be CV_8U or CV_32F");
+            cols = m.cols;
+            type = (m.depth() == CV_8U) ? SFMM_U8 : SFMM_F32;
+            data[i] = m.data; rows[i] = m.rows; steps[i] = m.step;
+        }
+        check(sfmm_set_descriptors(ctx_, n, data.data(), rows.data(), cols, steps.data(), type));
+        check(sfmm_match_all_pairs(ctx_));
+    }
+
+    // Drop-in body of StructFromMotion::getMatching: APPENDS to *goodMatches like the
+    // reference's push_back loop (src/Sfm.cpp:603-607); no clear().
+    void getMatching(const int& idx_query, const int& idx_train, std::vector<cv::DMatch>* goodMatches) {
+        const SfmDMatch* m = nullptr;
+        int32_t n = 0;
+        int rc = sfmm_get_pair(ctx_, idx_query, idx_train, &m, &n);
+        if (rc == SFMM_ESTATE) {  // a pair outside the q<t table (never requested by the reference): on demand
+            std::vector<SfmDMatch> tmp(1);
+            rc = sfmm_match_pair(ctx_, idx_query, idx_train, tmp.data(), 0, &n);
+            if (rc != SFMM_ERANGE && rc != SFMM_OK) check(rc);
+            tmp.resize(n > 0 ? n : 1);
+            check(sfmm_match_pair(ctx_, idx_query, idx_train, tmp.data(), static_cast<int32_t>(tmp.size()), &n));
+            append(tmp.data(), n, goodMatches);
+            return;
+        }
+        check(rc);
+        append(m, n, goodMatches);
+    }
+
+    SfmmCtx* handle() { return ctx_; }
+
+  private:
+    static void append(const SfmDMatch* m, int32_t n, std::vector<cv::DMatch>* out) {
+        if (n <= 0) return;
+        const size_t old = out->size();
+        out->resize(old + static_cast<size_t>(n));
+        std::memcpy(static_cast<void*>(out->data() + old), m, static_cast<size_t>(n) * sizeof(SfmDMatch));
+    }
+    void check(int rc) {
+        if (rc != SFMM_OK) throw Error(rc, sfmm_last_error(ctx_));
+    }
+    SfmmCtx* ctx_;
+};
+
+}  // namespace sfmm
+#endif  // SFM_MATCH_OPENCV_HPP_

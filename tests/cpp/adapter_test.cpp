@@ -1,0 +1,49 @@
+// Drives include/sfm_match_opencv.hpp the way a patched StructFromMotion would: imagesDescriptors in,
+// getMatching(q,t,&vector<cv::DMatch>) out (append semantics).  Reads descriptor sets and the
+// expected lists from a flat binary file written by tests/test_cpp_adapter.py (oracle output).
+// exit 0 = identical, 1 = mismatch, 2 = usage/io, 77 = no GPU.
+#include <cstdio>
+#include <vector>
+#include "sfm_match_opencv.hpp"
+
+static bool rd(FILE* f, void* p, size_t n) { return fread(p, 1, n, f) == n; }
+
+int main(int argc, char** argv) {
+    if (argc < 2) return 2;
+    FILE* f = fopen(argv[1], "rb");
+    if (!f) return 2;
+    int32_t hdr[4];  // n_images, cols, depth(0=u8,1=f32), cross
+    if (!rd(f, hdr, sizeof hdr)) return 2;
+    const int n = hdr[0], cols = hdr[1], depth = hdr[2] ? CV_32F : CV_8U, esz = hdr[2] ? 4 : 1;
+    std::vector<int32_t> rows(n);
+    if (!rd(f, rows.data(), sizeof(int32_t) * n)) return 2;
+    std::vector<std::vector<unsigned char>> store(n);
+    std::vector<cv::Mat> imagesDescriptors(n);
+    for (int i = 0; i < n; ++i) {
+        store[i].resize(static_cast<size_t>(rows[i]) * cols * esz);
+        if (rows[i] && !rd(f, store[i].data(), store[i].size())) return 2;
+        if (rows[i]) imagesDescriptors[i] = cv::Mat(rows[i], cols, depth, store[i].data());
+    }
+    try {
+        sfmm::AllPairsMatcher matcher(hdr[2] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
+        matcher.compute(imagesDescriptors);
+        for (int q = 0; q < n - 1; ++q)
+            for (int t = q + 1; t < n; ++t) {
+                int32_t cnt;
+                if (!rd(f, &cnt, 4)) return 2;
+                std::vector<cv::DMatch> expect(cnt);
+                if (cnt && !rd(f, expect.data(), sizeof(cv::DMatch) * cnt)) return 2;
+                std::vector<cv::DMatch> good(1);  // pre-existing element: getMatching must append
+                matcher.getMatching(q, t, &good);
+                if (static_cast<int>(good.size()) != cnt + 1 || good[0].queryIdx != -1) { printf("size mismatch %d,%d\n", q, t); return 1; }
+                if (cnt && memcmp(static_cast<const void*>(good.data() + 1), expect.data(), sizeof(cv::DMatch) * cnt)) { printf("content mismatch %d,%d\n", q, t); return 1; }
+            }
+        std::vector<cv::DMatch> rev;  // q>t is never asked by the reference; the adapter computes it on demand
+        matcher.getMatching(1, 0, &rev);
+        printf("adapter ok: %d images, reverse pair gave %zu matches\n", n, rev.size());
+    } catch (const sfmm::Error& e) {
+        printf("sfmm::Error %d: %s\n", e.code, e.what());
+        return e.code == SFMM_ENODEVICE ? 77 : 1;
+    }
+    return 0;
+}

@@ -1,0 +1,29 @@
+// Minimal stand-in for <opencv2/core.hpp> -- TEST ONLY.  OpenCV's C++ headers are not installed
+// in this image; this mock declares just the members include/sfm_match_opencv.hpp uses, with
+// OpenCV's documented layout for cv::DMatch, so that the adapter can be compiled and driven.
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#define CV_8U 0
+#define CV_32F 5
+namespace cv {
+enum { NORM_L2 = 4, NORM_HAMMING = 6 };
+struct DMatch {
+    DMatch() : queryIdx(-1), trainIdx(-1), imgIdx(-1), distance(3.402823466e+38f) {}
+    int queryIdx, trainIdx, imgIdx;
+    float distance;
+};
+struct Mat {  // continuous row-major matrix header over caller memory
+    Mat() : rows(0), cols(0), data(nullptr), step(0), depth_(CV_8U) {}
+    Mat(int r, int c, int depth, void* d, size_t s = 0)
+        : rows(r), cols(c), data(static_cast<unsigned char*>(d)), step(s ? s : static_cast<size_t>(c) * (depth == CV_32F ? 4 : 1)), depth_(depth) {}
+    bool empty() const { return rows == 0 || cols == 0 || data == nullptr; }
+    int depth() const { return depth_; }
+    int rows, cols;
+    unsigned char* data;
+    size_t step;
+    int depth_;
+};
+}  // namespace cv

@@ -1,0 +1,57 @@
+"""The C++ side of the drop-in: include/sfm_match_opencv.hpp compiled against a mock <opencv2/core.hpp>
+(OpenCV's C++ headers are not in this image) and linked to libsfmmatch.so."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle
+from sfm_danpipeline_b200 import _lib, synth
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "tests", "cpp", "adapter_test.cpp")
+EXE = os.path.join(ROOT, "tests", "cpp", "adapter_test")
+
+
+def _build():
+    lib_dir = os.path.dirname(_lib.LIB_PATH)
+    if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(SRC), os.path.getmtime(
+            os.path.join(ROOT, "include", "sfm_match_opencv.hpp"))):
+        subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+                               "-I", os.path.join(ROOT, "tests", "cpp", "mock_opencv"), SRC, "-o", EXE,
+                               "-L", lib_dir, "-lsfmmatch", "-Wl,-rpath," + lib_dir])
+    return EXE
+
+
+def test_adapter_compiles_as_cxx11_against_the_abi():
+    _lib.load()
+    _build()
+
+
+def _write_case(path, descs, norm, cross):
+    with open(path, "wb") as f:
+        f.write(np.array([len(descs), descs[0].shape[1], norm, int(cross)], np.int32).tobytes())
+        f.write(np.array([d.shape[0] for d in descs], np.int32).tobytes())
+        for d in descs:
+            f.write(np.ascontiguousarray(d).tobytes())
+        for q, t in synth.all_pairs(len(descs)):
+            m = oracle.match_pair(descs[q], descs[t], norm, 0.8, cross)
+            f.write(np.int32(len(m)).tobytes())
+            f.write(m.tobytes())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,cross", [("binary", False), ("binary", True), ("float", False)])
+def test_patched_getmatching_equals_oracle(tmp_path, kind, cross):
+    exe = _build()
+    if kind == "binary":
+        descs, norm = synth.binary_images(4, [600, 0, 333, 1030], seed=21), 0
+        descs[1] = np.zeros((0, 61), np.uint8)
+    else:
+        descs, norm = synth.float_images(3, [300, 200, 150], seed=22), 1
+    case = str(tmp_path / "case.bin")
+    _write_case(case, descs, norm, cross)
+    r = subprocess.run([exe, case], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "adapter ok" in r.stdout
