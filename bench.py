@@ -44,6 +44,7 @@ WORKLOADS = {
     "cfg5s": ("binary", 40, 20000, True),   # cfg5's pair shape (20k x 20k) on a 40-image subset
     "orb": ("orb", 100, 2000, True),        # ORB shape: 256 bit
     "float2": ("float", 40, 4000, True),
+    "cfg4s": ("float", 60, 8000, True),     # cfg4's pair shape (8k x 8k x 128 f32) on a 60-image subset
 }
 
 
@@ -201,6 +202,7 @@ def main():
     ap.add_argument("--desc", type=int, default=0)
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cross-check", action="store_true")
+    ap.add_argument("--float-mode", default="auto", choices=["auto", "exact", "tensor"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -240,7 +242,7 @@ def main():
     dev = torch.device("cuda", local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    m = Matcher(norm, 0.8, args.cross_check, device=local, float_mode=FLOAT_AUTO)
+    m = Matcher(norm, 0.8, args.cross_check, device=local, float_mode={"auto": 0, "exact": 1, "tensor": 2}[args.float_mode])
     # ---- resident arm: descriptors in HBM before the timed region -------------------------
     if world > 1:
         D.broadcast_descriptors(m, descs if rank == 0 else None, 0)
@@ -331,6 +333,12 @@ def main():
             roof = {"bound": "popc", "achieved": knn_work / knn_s / 1e9, "peak": peak, "unit": "GPOPC32/s",
                     "peak_source": f"nominal 16 POPC/clk/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                    "measured issue rates in profiles/pipe_bench_r01.txt",
+                    "traffic": None}
+        elif m.stats()["float_path"] == 2:
+            tf32 = 0.5 * float(peaks.get("bf16_tflops", 1590.0))  # TF32 dense = half the measured bf16 cuBLAS rate
+            roof = {"bound": "tensor", "achieved": knn_work / knn_s / 1e12, "peak": tf32, "unit": "TFLOP/s",
+                    "peak_source": "0.5 x MEASURED_PEAKS.json bf16_tflops (TF32 dense is half the bf16 rate); "
+                                   "algorithmic FLOPs = 2*Nq*Nt*128 per pair, tcgen05 kind::tf32",
                     "traffic": None}
         else:
             peak = n_sm * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # fp32 FMA lanes: exact mode runs on CUDA cores

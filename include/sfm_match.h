@@ -98,6 +98,7 @@ typedef struct SfmmStats {
     double last_knn_ms;        /* of which: the 2-NN distance kernel(s) */
     double last_knn_work;      /* algorithmic work of those launches: POPC32 ops (Hamming) or FLOPs (L2) */
     int64_t last_knn_launches; /* number of 2-NN kernel launches behind last_knn_ms */
+    int64_t float_path;        /* L2 only: 0 = not decided yet, SFMM_FLOAT_EXACT or SFMM_FLOAT_TENSOR = the kernel in use */
 } SfmmStats;
 
 typedef struct SfmmCtx SfmmCtx;

@@ -1,0 +1,376 @@
+// Tensor-core L2 2-NN kernel for float descriptors (SIFT 128-d / SURF 64-d) on sm_100a -- SFMM_FLOAT_TENSOR.
+//
+// Replaces, for CV_32F descriptor sets, matcher->knnMatch(q, t, knn, 2) with
+// cv::BFMatcher(cv::NORM_L2,false) at /root/reference/src/Sfm.cpp:593,599.
+//
+// d^2(q,t) = |q|^2 + |t|^2 - 2 q.t : the q.t contraction runs on the 5th-generation tensor cores
+// (tcgen05.mma kind::tf32, operands staged in shared memory by TMA with the 128-byte swizzle,
+// fp32 accumulators in TMEM), the rest is a fused epilogue that never writes the distance matrix:
+//
+//   warp 0      TMA producer : query tile once, then train tiles through a 2-stage smem ring
+//   warp 1      MMA issuer   : one elected lane, 4*KB tcgen05.mma (M=128,N=128,K=8) per train tile
+//                              into a 4-stage TMEM ring (4 x 128 columns = all 512 columns)
+//   warp 2      TMEM allocator
+//   warps 4-11  epilogue     : tcgen05.ld 32x32b.x32 -> d^2 (one FADD + one FFMA) -> packed integer key
+//                              (one IMAD) -> branch-free top-2 (2.5 VIMNMX per column); see Top2
+//
+// Exactness contract.  This mode is selected only for descriptor sets the prepare kernel proved
+// "TF32-exact": every value an integer with |v| <= 2047 (11 significant bits: exactly
+// representable in TF32) and every row norm^2 <= 2^20, so every product, every partial sum of the
+// contraction, |t|^2 - 2 q.t and d^2 = |q|^2 + s are integers below 2^22 -- exact in fp32 whatever
+// the summation order, and small enough for sqrtf to keep distinct d^2 distinct.  Real SIFT output is of this kind (OpenCV quantises to 0..255, norm ~512;
+// verified on data/temple).  Then d = sqrtf(d^2) is bit-identical to OpenCV's
+// sqrtf(sum (a-b)^2), and candidates are inserted in ascending train index with a strict '<'
+// -- OpenCV's own insertion rule -- so indices, distances and ties are bit-exact.  Anything else
+// (arbitrary floats) is routed to float_exact.cuh by SFMM_FLOAT_AUTO.
+#pragma once
+#include <cuda.h>
+
+#include "binary_knn.cuh"  // mbarrier / PTX helpers
+#include "common.cuh"
+
+namespace sfmm {
+
+static constexpr int FT_M = 128;         // query rows per CTA (UMMA M)
+static constexpr int FT_N = 128;         // train rows per MMA tile (UMMA N)
+static constexpr int FT_KB_ELEMS = 32;   // floats per 128-byte swizzle row
+static constexpr int FT_B_STAGES = 2;
+static constexpr int FT_ACC_STAGES = 4;  // 4 x 128 fp32 columns = 512 TMEM columns
+static constexpr int FT_THREADS = 384;   // 4 control warps + 8 epilogue warps
+static constexpr int FT_EPI_WARPS = 8;
+static constexpr uint32_t FT_KBLOCK_BYTES = FT_M * 128;  // one K-block of a 128-row tile: 16 KB
+
+// ------------------------------------------------------------------ tcgen05 / TMA PTX
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate; M=128, N=128, K=8 per instruction.
+__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
+// start address >> 4 in bits [0,14), LBO bits [16,30) (unused for swizzled K-major), SBO >> 4 in
+// bits [32,46) = 1024 B (8 rows x 128 B), version 1 in bits [46,48), layout SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+    d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (bits 4-5 = 1), A=B=TF32 (bits 7-9,
+// 10-12 = 2), both K-major, N>>3 in bits [17,23), M>>4 in bits [24,29).
+static constexpr uint32_t FT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((FT_N >> 3) << 17) | ((FT_M >> 4) << 24);
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) {
+    float r;
+    asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c));
+    return r;
+}
+
+// ------------------------------------------------------------------ prepare: norms + TF32-exactness proof
+// One warp per row.  flags[0] |= 1 when a value is not an integer in [-2047, 2047];
+// flags[1] = max over rows of the float bits of |x|^2 (non-negative floats order as unsigned).
+__global__ void float_prepare_kernel(const float* __restrict__ blob, int kq, uint32_t total_rows, int cols,
+                                     float* __restrict__ norms, unsigned int* __restrict__ flags) {
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const float* p = blob + (size_t)row * kq * 4;
+    float acc = 0.f;
+    bool bad = false;
+    for (int c = lane; c < cols; c += 32) {
+        const float v = p[c];
+        bad |= !(fabsf(v) <= 2047.f) || (v != truncf(v));
+        acc = fmaf(v, v, acc);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) acc += __shfl_xor_sync(0xFFFFFFFFu, acc, d);
+    bad = __any_sync(0xFFFFFFFFu, bad);
+    if (lane == 0) {
+        norms[row] = acc;
+        if (bad) atomicOr(&flags[0], 1u);
+        atomicMax(&flags[1], __float_as_uint(acc));
+    }
+}
+
+// ------------------------------------------------------------------ the kernel
+struct FtSmem {  // after the 1024-byte aligned operand area
+    uint64_t a_full;
+    uint64_t b_full[FT_B_STAGES];
+    uint64_t b_empty[FT_B_STAGES];
+    uint64_t acc_full[FT_ACC_STAGES];
+    uint64_t acc_empty[FT_ACC_STAGES];
+    uint64_t nb_full[FT_ACC_STAGES];
+    uint64_t nb_empty[FT_ACC_STAGES];
+    uint32_t tmem_base;
+    uint32_t pad;
+    alignas(16) float nb[FT_ACC_STAGES][FT_N];  // |t|^2 of the train tile, bulk-copied next to the operands
+    uint4 merge[FT_M];                          // (d2_1, i1, d2_2, i2) of the upper column half
+};
+
+static inline size_t float_tensor_smem_bytes(int kblocks) {
+    return 1024 /*alignment slack*/ + (size_t)(1 + FT_B_STAGES) * kblocks * FT_KBLOCK_BYTES + sizeof(FtSmem);
+}
+
+// Top-2 bookkeeping of the epilogue.
+//
+// For TF32-exact data with row norm^2 <= 2^20 every d^2 = |q|^2 + |t|^2 - 2 q.t is an integer below
+// 2^22.  Adding 2^23 in fp32 (exact) leaves that integer in the low mantissa bits, so
+//     key = float_bits(d^2 + 2^23) * 512 + column      (one IMAD; the exponent bits shift out)
+// is the 31-bit integer  d^2 << 9 | column-in-tile : unsigned min/max on it orders by
+// (distance, lowest column) -- no branches, no divergence, data-independent cost.  Inside a tile
+// the two smallest keys are kept with 5 VIMNMX per two columns; once per tile they are merged
+// into the running (d^2, train index) pair with a strict '<' in arrival order, which is
+// cv::batchDistance's insertion rule.  sqrtf is injective on integers below 2^22 (consecutive
+// roots are more than an ulp apart), so ties and order on d^2 are ties and order on d.
+struct Top2 {
+    uint32_t d1, d2;  // squared distances (integers), 0xFFFFFFFF = none
+    int i1, i2;
+    __device__ __forceinline__ void init() {
+        d1 = d2 = 0xFFFFFFFFu;
+        i1 = i2 = -1;
+    }
+    __device__ __forceinline__ void offer(uint32_t d, int t) {  // strict '<', arrival order
+        const bool lt1 = d < d1, lt2 = d < d2;
+        d2 = lt1 ? d1 : (lt2 ? d : d2);
+        i2 = lt1 ? i1 : (lt2 ? t : i2);
+        d1 = lt1 ? d : d1;
+        i1 = lt1 ? t : i1;
+    }
+};
+
+// (m1 <= m2) <- two smallest of {m1, m2, a, b}
+__device__ __forceinline__ void top2_pair(uint32_t& m1, uint32_t& m2, uint32_t a, uint32_t b) {
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    const uint32_t loser = max(m1, lo);
+    m1 = min(m1, lo);
+    m2 = __vimin3_u32(m2, loser, hi);
+}
+
+// Keys of this thread's 64 columns of one accumulator tile and their two smallest.
+//   d^2 + 2^23 = (|t|^2 + |q|^2 + 2^23) - 2 q.t   FADD + FFMA, exact
+//   key        = bits * 512 + column               one IMAD (key_mul = 512 comes from the kernel
+//                                                  parameters so that it is not strength-reduced
+//                                                  into a shift + add on the ALU pipe)
+// PARTIAL: columns past the train set (another image's rows / padding) get the "none" key.
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+    return v;
+}
+
+template <bool PARTIAL>
+__device__ __forceinline__ void tile_top2(const uint32_t (&acc)[2][32], uint32_t nb_saddr, float cq, uint32_t key_mul,
+                                          uint32_t col0, uint32_t n_rows, uint32_t& m1, uint32_t& m2) {
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+#pragma unroll
+        for (int e = 0; e < 32; e += 4) {
+            const float4 nb = lds128(nb_saddr + (c * 32 + e) * 4);  // same address in every lane: broadcast
+            const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+            uint32_t k[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint32_t bits = __float_as_uint(fmaf(__uint_as_float(acc[c][e + i]), -2.f, nbv[i] + cq));
+                const uint32_t lc = c * 32 + e + i;  // column inside this thread's 64-wide half of the tile
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(bits), "r"(key_mul), "r"(lc));
+                if (PARTIAL) k[i] = col0 + c * 32 + e + i < n_rows ? k[i] : 0xFFFFFFFFu;
+            }
+            top2_pair(m1, m2, k[0], k[1]);
+            top2_pair(m1, m2, k[2], k[3]);
+        }
+    }
+}
+
+template <int KB /* K-blocks of 32 floats: 4 for 128-d, 2 for 64-d */>
+__global__ void __launch_bounds__(FT_THREADS, 1)
+float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ norms,
+                         const KnnTile* __restrict__ tiles, const PairDesc* __restrict__ pairs,
+                         KnnEntry* __restrict__ knn, const uint32_t key_mul /* = 512 */) {
+    extern __shared__ unsigned char ft_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sA = base;                                   // KB x 16 KB
+    unsigned char* sB = base + (size_t)KB * FT_KBLOCK_BYTES;    // FT_B_STAGES x KB x 16 KB
+    FtSmem& sm = *reinterpret_cast<FtSmem*>(base + (size_t)(1 + FT_B_STAGES) * KB * FT_KBLOCK_BYTES);
+
+    const KnnTile tile = tiles[blockIdx.x];
+    const PairDesc pd = pairs[tile.pair];
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t n_rows = tile.t1 - tile.t0;
+    const uint32_t n_tiles = (n_rows + FT_N - 1) / FT_N;
+
+    if (threadIdx.x == 0) {
+        mbar_init(&sm.a_full, 1);
+        for (int s = 0; s < FT_B_STAGES; ++s) {
+            mbar_init(&sm.b_full[s], 1);
+            mbar_init(&sm.b_empty[s], 1);
+        }
+        for (int s = 0; s < FT_ACC_STAGES; ++s) {
+            mbar_init(&sm.acc_full[s], 1);
+            mbar_init(&sm.acc_empty[s], FT_EPI_WARPS);
+            mbar_init(&sm.nb_full[s], 1);
+            mbar_init(&sm.nb_empty[s], FT_EPI_WARPS);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {  // whole warp: allocate all 512 TMEM columns (1 CTA per SM: smem-limited)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            mbar_expect_tx(&sm.a_full, KB * FT_KBLOCK_BYTES);
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d(sA + kb * FT_KBLOCK_BYTES, &tmap, kb * FT_KB_ELEMS, (int)(pd.q_row0 + tile.q0), &sm.a_full);
+            for (uint32_t j = 0; j < n_tiles; ++j) {
+                const uint32_t s = j % FT_B_STAGES;
+                const uint32_t a = j % FT_ACC_STAGES;
+                mbar_wait(&sm.nb_empty[a], ((j / FT_ACC_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&sm.nb_full[a], FT_N * sizeof(float));
+                // image rows start at multiples of 4 and t0 at multiples of 128: 16-byte aligned source;
+                // the norms array is padded so that the copy may run past the image's last row
+                tma_load_1d(sm.nb[a], norms + pd.t_row0 + tile.t0 + j * FT_N, FT_N * sizeof(float), &sm.nb_full[a]);
+                mbar_wait(&sm.b_empty[s], ((j / FT_B_STAGES) & 1) ^ 1);
+                mbar_expect_tx(&sm.b_full[s], KB * FT_KBLOCK_BYTES);
+                unsigned char* dst = sB + (size_t)s * KB * FT_KBLOCK_BYTES;
+                const int row = (int)(pd.t_row0 + tile.t0 + j * FT_N);
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb) tma_load_2d(dst + kb * FT_KBLOCK_BYTES, &tmap, kb * FT_KB_ELEMS, row, &sm.b_full[s]);
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            mbar_wait(&sm.a_full, 0);
+            for (uint32_t j = 0; j < n_tiles; ++j) {
+                const uint32_t s = j % FT_B_STAGES, a = j % FT_ACC_STAGES;
+                mbar_wait(&sm.b_full[s], (j / FT_B_STAGES) & 1);
+                mbar_wait(&sm.acc_empty[a], ((j / FT_ACC_STAGES) & 1) ^ 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB + (size_t)s * KB * FT_KBLOCK_BYTES);
+                const uint32_t d_tmem = tmem_base + a * FT_N;
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {  // 4 x (K=8 tf32 = 32 bytes) inside the 128-byte swizzle row
+                        const uint64_t da = umma_desc_sw128(a_addr + kb * FT_KBLOCK_BYTES + k * 32);
+                        const uint64_t db = umma_desc_sw128(b_addr + kb * FT_KBLOCK_BYTES + k * 32);
+                        tc_mma_tf32(d_tmem, da, db, FT_IDESC, (kb | k) ? 1u : 0u);
+                    }
+                tc_commit(&sm.b_empty[s]);   // smem stage reusable once these MMAs have read it
+                tc_commit(&sm.acc_full[a]);  // accumulator ready for the epilogue
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: fused top-2 =====================
+        const uint32_t ew = warp - 4;
+        const uint32_t quarter = ew & 3, half = ew >> 2;   // TMEM lanes 32*quarter.., columns 64*half..
+        const uint32_t row = quarter * 32 + lane;          // row of the query tile == TMEM lane
+        const uint32_t qrow = tile.q0 + row;
+        const float nq2 = qrow < pd.nq ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
+        const float cq = nq2 + 8388608.f;  // |q|^2 + 2^23 (exact): see Top2
+        Top2 best;
+        best.init();
+        for (uint32_t j = 0; j < n_tiles; ++j) {
+            const uint32_t a = j % FT_ACC_STAGES;
+            mbar_wait(&sm.acc_full[a], (j / FT_ACC_STAGES) & 1);
+            tc_fence_after();
+            uint32_t acc[2][32];
+            const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + a * FT_N + half * 64;
+            tc_ld_32x32(taddr, acc[0]);
+            tc_ld_32x32(taddr + 32, acc[1]);
+            tc_wait_ld();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.acc_empty[a]);  // TMEM stage free: the MMA of tile j+4 may start
+            mbar_wait(&sm.nb_full[a], (j / FT_ACC_STAGES) & 1);
+
+            const uint32_t col0 = j * FT_N + half * 64;   // first column of this thread, relative to tile.t0
+            const uint32_t nb_saddr = smem_u32(&sm.nb[a][half * 64]);
+            uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;   // two smallest keys of this tile
+            if (col0 + 64 <= n_rows) tile_top2<false>(acc, nb_saddr, cq, key_mul, col0, n_rows, m1, m2);
+            else tile_top2<true>(acc, nb_saddr, cq, key_mul, col0, n_rows, m1, m2);  // last tile only (warp-uniform)
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.nb_empty[a]);
+            // merge the tile's two best into the running pair (ascending tiles = arrival order)
+            const int tbase = (int)(tile.t0 + col0);
+            if (m1 != 0xFFFFFFFFu) best.offer(m1 >> 9, tbase + (int)(m1 & 511u));
+            if (m2 != 0xFFFFFFFFu) best.offer(m2 >> 9, tbase + (int)(m2 & 511u));
+        }
+        // merge the two column halves of each row: lexicographic (d^2, index), then d = sqrtf(d^2)
+        // (an exact integer under the root: bit-identical to OpenCV's sqrtf(sum (a-b)^2))
+        if (half == 1) sm.merge[row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
+        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+        if (half == 0 && qrow < pd.nq) {
+            const uint4 o = sm.merge[row];
+            unsigned long long k1 = best.i1 < 0 ? KEY_NONE : make_key(best.d1, (uint32_t)best.i1);
+            unsigned long long k2 = best.i2 < 0 ? KEY_NONE : make_key(best.d2, (uint32_t)best.i2);
+            const unsigned long long o1 = (int)o.y < 0 ? KEY_NONE : make_key(o.x, o.y);
+            const unsigned long long o2 = (int)o.w < 0 ? KEY_NONE : make_key(o.z, o.w);
+            unsigned long long hi = max(k1, o1);
+            k1 = min(k1, o1);
+            k2 = min(min(k2, hi), o2);
+            KnnEntry e;  // integer d^2 -> float bits of d
+            e.x = k1 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32))), (uint32_t)k1);
+            e.y = k2 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k2 >> 32))), (uint32_t)k2);
+            knn[pd.knn_off + (size_t)tile.split * pd.nq + qrow] = e;
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+}  // namespace sfmm

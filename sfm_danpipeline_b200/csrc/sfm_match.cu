@@ -25,6 +25,7 @@
 #include "common.cuh"
 #include "filter.cuh"
 #include "float_exact.cuh"
+#include "float_tensor.cuh"
 
 using namespace sfmm;
 
@@ -96,6 +97,13 @@ struct SfmmCtx {
     mutable std::string err;
     int csa_level = 2;
     size_t fx_attr_smem = 0;
+    size_t ft_attr_smem = 0;
+
+    // float path state (norms + TF32-exactness proof, see float_tensor.cuh)
+    bool float_prepared = false;
+    bool tensor_eligible = false;
+    bool use_tensor = false;
+    CUtensorMap tmap{};
 
     // descriptors (imagesDescriptors, include/Sfm.h:29)
     int32_t n_images = 0;
@@ -110,7 +118,7 @@ struct SfmmCtx {
 
     // per-launch scratch
     DevBuf d_pairs, d_tiles, d_ftiles, d_knn, d_colmin, d_tile_count, d_tile_off, d_pair_count, d_pair_off,
-        d_matches, d_idx, d_dist;
+        d_matches, d_idx, d_dist, d_norms, d_flags;
     void* pinned = nullptr;
     size_t pinned_cap = 0;
 
@@ -184,8 +192,8 @@ inline uint64_t pair_key(int32_t q, int32_t t) { return (static_cast<uint64_t>(s
 int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
     const bool is_float = ctx->elem_type == SFMM_F32;
     const int W = is_float ? 0 : binary_words(ctx->cols);
-    const int q_tile = is_float ? FX_BQ : BK_THREADS * (W >= 32 ? 2 : 4);
-    const int t_gran = is_float ? FX_BT : BK_TT;
+    const int q_tile = is_float ? (ctx->use_tensor ? FT_M : FX_BQ) : BK_THREADS * (W >= 32 ? 2 : 4);
+    const int t_gran = is_float ? (ctx->use_tensor ? FT_N : FX_BT) : BK_TT;
     plan.pairs.resize(n);
     uint64_t base_tiles = 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -289,6 +297,79 @@ cudaError_t launch_float_exact(SfmmCtx* ctx, uint32_t n_tiles) {
     return cudaGetLastError();
 }
 
+template <int KB>
+cudaError_t launch_float_tensor_t(SfmmCtx* ctx, uint32_t n_tiles) {
+    const size_t smem = float_tensor_smem_bytes(KB);
+    if (smem > ctx->ft_attr_smem) {
+        cudaError_t e = cudaFuncSetAttribute(float_tensor_knn2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        ctx->ft_attr_smem = smem;
+    }
+    float_tensor_knn2_kernel<KB><<<n_tiles, FT_THREADS, smem, ctx->stream>>>(
+        ctx->tmap, ctx->d_norms.as<float>(), ctx->d_tiles.as<KnnTile>(), ctx->d_pairs.as<PairDesc>(), ctx->d_knn.as<KnnEntry>(), 512u);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_float_tensor(SfmmCtx* ctx, uint32_t n_tiles) {
+    switch (ctx->cols / FT_KB_ELEMS) {
+        case 1: return launch_float_tensor_t<1>(ctx, n_tiles);
+        case 2: return launch_float_tensor_t<2>(ctx, n_tiles);
+        case 3: return launch_float_tensor_t<3>(ctx, n_tiles);
+        case 4: return launch_float_tensor_t<4>(ctx, n_tiles);
+    }
+    return cudaErrorInvalidValue;
+}
+
+// Float descriptors only, once per descriptor set (lazily, so that a blob filled by an NCCL
+// broadcast is seen): row norms, the TF32-exactness proof and the TMA tensor map; picks the path.
+int prepare_float(SfmmCtx* ctx) {
+    if (ctx->elem_type != SFMM_F32 || ctx->float_prepared) return SFMM_OK;
+    ctx->tensor_eligible = false;
+    ctx->use_tensor = false;
+    const bool shape_ok = ctx->cols % FT_KB_ELEMS == 0 && ctx->cols <= 4 * FT_KB_ELEMS && ctx->total_rows > 0;
+    if (ctx->cfg.float_mode != SFMM_FLOAT_EXACT && shape_ok && !ctx->cfg.cross_check) {
+        CU_TRY(ctx, ctx->d_norms.ensure((static_cast<size_t>(ctx->total_rows) + 2 * FT_N) * sizeof(float)));  // + tail for the bulk copies
+        CU_TRY(ctx, ctx->d_flags.ensure(2 * sizeof(unsigned int)));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(unsigned int), ctx->stream));
+        const uint32_t rows = static_cast<uint32_t>(ctx->total_rows);
+        float_prepare_kernel<<<(rows + 7) / 8, 256, 0, ctx->stream>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), rows,
+                                                                     ctx->cols, ctx->d_norms.as<float>(), ctx->d_flags.as<unsigned int>());
+        CU_TRY(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches += 1;
+        unsigned int flags[2] = {1, 0};
+        CU_TRY(ctx, cudaMemcpyAsync(flags, ctx->d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        float max_norm2;
+        std::memcpy(&max_norm2, &flags[1], sizeof(float));
+        ctx->tensor_eligible = flags[0] == 0 && max_norm2 <= 1048576.f;  // integers, |v|<=2047, |x|^2 <= 2^20
+        if (ctx->tensor_eligible) {
+            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+            void* fn = nullptr;
+            cudaDriverEntryPointQueryResult qres;
+            CU_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+            if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, SFMM_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
+            const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ctx->pitch / 4), static_cast<cuuint64_t>(ctx->total_rows)};
+            const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ctx->pitch)};
+            const cuuint32_t box[2] = {FT_KB_ELEMS, FT_M};
+            const cuuint32_t estr[2] = {1, 1};
+            const CUresult r = reinterpret_cast<EncodeFn>(fn)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ctx->blob.p, gdim, gstride, box, estr,
+                                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+            if (r != CUDA_SUCCESS) return fail(ctx, SFMM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+            ctx->use_tensor = true;
+        }
+    }
+    if (ctx->cfg.float_mode == SFMM_FLOAT_TENSOR && !ctx->use_tensor)
+        return fail(ctx, SFMM_EINVAL,
+                    "SFMM_FLOAT_TENSOR needs TF32-exact descriptors (integer values |v|<=2047, row norm^2 <= 2^20), a width that is a "
+                    "multiple of 32 up to 128 and cross_check off; use SFMM_FLOAT_AUTO or SFMM_FLOAT_EXACT");
+    ctx->float_prepared = true;
+    ctx->stats.float_path = ctx->use_tensor ? SFMM_FLOAT_TENSOR : SFMM_FLOAT_EXACT;
+    return SFMM_OK;
+}
+
 // Uploads the plan and runs the 2-NN kernel; leaves merged-able partial lists in d_knn (+ d_colmin).
 int run_knn(SfmmCtx* ctx, const ChunkPlan& plan, bool timed) {
     const bool cross = ctx->cfg.cross_check != 0;
@@ -313,7 +394,8 @@ int run_knn(SfmmCtx* ctx, const ChunkPlan& plan, bool timed) {
     if (plan.tiles.empty()) return SFMM_OK;
     if (timed) CU_TRY(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
     cudaError_t e;
-    if (ctx->elem_type == SFMM_F32) e = launch_float_exact(ctx, static_cast<uint32_t>(plan.tiles.size()));
+    if (ctx->elem_type == SFMM_F32) e = ctx->use_tensor ? launch_float_tensor(ctx, static_cast<uint32_t>(plan.tiles.size()))
+                                                    : launch_float_exact(ctx, static_cast<uint32_t>(plan.tiles.size()));
     else e = cross ? launch_binary<true>(ctx, static_cast<uint32_t>(plan.tiles.size()))
                    : launch_binary<false>(ctx, static_cast<uint32_t>(plan.tiles.size()));
     CU_TRY(ctx, e);
@@ -478,7 +560,7 @@ SFMM_API void sfmm_destroy(SfmmCtx* ctx) {
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
     for (DevBuf* b : {&ctx->blob, &ctx->d_pairs, &ctx->d_tiles, &ctx->d_ftiles, &ctx->d_knn, &ctx->d_colmin, &ctx->d_tile_count,
-                      &ctx->d_tile_off, &ctx->d_pair_count, &ctx->d_pair_off, &ctx->d_matches, &ctx->d_idx, &ctx->d_dist})
+                      &ctx->d_tile_off, &ctx->d_pair_count, &ctx->d_pair_off, &ctx->d_matches, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags})
         b->release();
     if (ctx->pinned) cudaFreeHost(ctx->pinned);
     for (auto& ev : ctx->ev)
@@ -506,6 +588,8 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
     if (pitch == 0) return fail(ctx, SFMM_EINVAL, "set_descriptors: unsupported descriptor width (binary <= 128 bytes)");
     if (elem_type == SFMM_F32 && cols > 256) return fail(ctx, SFMM_EINVAL, "set_descriptors: float descriptors wider than 256 are not supported");
     const size_t elem = elem_type == SFMM_U8 ? 1 : 4;
+    // every image starts at a blob row that is a multiple of 4 (16-byte aligned slices of the
+    // per-row norm array for the TMA bulk copies of the tensor path); pad rows are zero
     uint64_t total = 0;
     for (int32_t i = 0; i < n_images; ++i) {
         if (rows[i] < 0) return fail(ctx, SFMM_EINVAL, "set_descriptors: negative row count");
@@ -513,7 +597,7 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
         if (data && rows[i] > 0 && !data[i]) return fail(ctx, SFMM_EINVAL, "set_descriptors: NULL image data");
         if (step_bytes && rows[i] > 1 && step_bytes[i] < static_cast<size_t>(cols) * elem)
             return fail(ctx, SFMM_EINVAL, "set_descriptors: row step smaller than a row");
-        total += static_cast<uint64_t>(rows[i]);
+        total += (static_cast<uint64_t>(rows[i]) + 3) & ~3ull;
     }
     if (total >= (1ull << 32)) return fail(ctx, SFMM_ERANGE, "set_descriptors: more than 2^32 rows in total");
     int rc = bind_device(ctx);
@@ -521,6 +605,9 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
     CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
     clear_results(ctx);
     ctx->elem_type = -1;
+    ctx->float_prepared = false;
+    ctx->use_tensor = false;
+    ctx->stats.float_path = 0;
     const size_t bytes = static_cast<size_t>(total) * pitch;
     CU_TRY(ctx, ctx->blob.ensure(std::max<size_t>(bytes, 16)));
     ctx->rows.assign(rows, rows + n_images);
@@ -528,7 +615,7 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
     uint64_t r0 = 0;
     for (int32_t i = 0; i < n_images; ++i) {
         ctx->row0[i] = static_cast<uint32_t>(r0);
-        r0 += static_cast<uint64_t>(rows[i]);
+        r0 += (static_cast<uint64_t>(rows[i]) + 3) & ~3ull;
     }
     if (data && bytes) {
         // re-pitch on the host into pinned memory (zeroed padding: zeros are Hamming/L2 neutral), one H2D per slab
@@ -554,6 +641,11 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
                 if (fill + pitch > slab && (rc = flush())) return rc;
                 std::memcpy(stage + fill, src + static_cast<size_t>(r) * step, row_bytes);
                 if (pitch > row_bytes) std::memset(stage + fill + row_bytes, 0, pitch - row_bytes);
+                fill += pitch;
+            }
+            for (int32_t r = rows[i]; r & 3; ++r) {  // zero rows up to the next multiple of 4
+                if (fill + pitch > slab && (rc = flush())) return rc;
+                std::memset(stage + fill, 0, pitch);
                 fill += pitch;
             }
         }
@@ -590,6 +682,7 @@ SFMM_API int sfmm_match_pairs_device(SfmmCtx* ctx, const int32_t* qt, int64_t n_
     if (n_pairs < 0 || (n_pairs > 0 && (!qt || !d_counts)) || match_capacity < 0 || !n_matches)
         return fail(ctx, SFMM_EINVAL, "match_pairs_device: bad argument");
     if ((rc = bind_device(ctx))) return rc;
+    if ((rc = prepare_float(ctx))) return rc;
     *n_matches = 0;
     ctx->stats.last_knn_ms = ctx->stats.last_knn_work = 0;
     ctx->stats.last_knn_launches = 0;
@@ -624,6 +717,7 @@ SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) 
     if (rc) return rc;
     if (n_pairs < 0 || (n_pairs > 0 && !qt)) return fail(ctx, SFMM_EINVAL, "match_pairs: bad argument");
     if ((rc = bind_device(ctx))) return rc;
+    if ((rc = prepare_float(ctx))) return rc;
     ctx->stats.last_knn_ms = ctx->stats.last_knn_work = 0;
     ctx->stats.last_knn_launches = 0;
     CU_TRY(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
@@ -744,6 +838,7 @@ SFMM_API int sfmm_match_pair(SfmmCtx* ctx, int32_t q, int32_t t, SfmDMatch* out,
     if (!count || cap < 0 || (cap > 0 && !out)) return fail(ctx, SFMM_EINVAL, "match_pair: bad argument");
     if (q < 0 || q >= ctx->n_images || t < 0 || t >= ctx->n_images) return fail(ctx, SFMM_ERANGE, "match_pair: image index out of range");
     if ((rc = bind_device(ctx))) return rc;
+    if ((rc = prepare_float(ctx))) return rc;
     *count = 0;
     const int32_t qt[2] = {q, t};
     ChunkPlan plan;
@@ -782,6 +877,7 @@ SFMM_API int sfmm_knn_pair(SfmmCtx* ctx, int32_t q, int32_t t, int32_t* train_id
         return SFMM_OK;
     }
     if ((rc = bind_device(ctx))) return rc;
+    if ((rc = prepare_float(ctx))) return rc;
     // plan as a normal pair but force the knn launch even when nt == 1
     const int32_t qt[2] = {q, t};
     ChunkPlan plan;
@@ -791,7 +887,7 @@ SFMM_API int sfmm_knn_pair(SfmmCtx* ctx, int32_t q, int32_t t, int32_t* train_id
         pd.n_splits = 1;
         const bool is_float = ctx->elem_type == SFMM_F32;
         const int W = is_float ? 0 : binary_words(ctx->cols);
-        const uint32_t q_tile = is_float ? FX_BQ : BK_THREADS * (W >= 32 ? 2 : 4);
+        const uint32_t q_tile = is_float ? (ctx->use_tensor ? FT_M : FX_BQ) : BK_THREADS * (W >= 32 ? 2 : 4);
         for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile) plan.tiles.push_back(KnnTile{0, q0, 0, pd.nt, 0});
         plan.knn_entries = pd.nq;
         plan.col_entries = pd.nt;

@@ -6,7 +6,7 @@ import numpy as np
 import pytest
 
 import oracle
-from sfm_danpipeline_b200 import FLOAT_EXACT, Matcher, NORM_L2, synth
+from sfm_danpipeline_b200 import FLOAT_AUTO, FLOAT_EXACT, FLOAT_TENSOR, Matcher, NORM_L2, SfmmError, synth
 from _golden import GoldenSet
 
 pytestmark = pytest.mark.gpu
@@ -85,3 +85,80 @@ def test_ragged_float_and_widths():
                 for (q, t) in synth.all_pairs(len(descs)):
                     exp = oracle.match_pair(descs[q], descs[t], 1, 0.85, cross)
                     assert m.getMatching(q, t).tobytes() == exp.tobytes(), (cols, q, t, cross)
+
+
+# ----------------------------------------------------------------- tensor-core (tcgen05 TF32) mode
+@pytest.mark.parametrize("mode", [FLOAT_TENSOR, FLOAT_AUTO])
+def test_tensor_mode_temple_sift_bit_exact(mode):
+    g = GoldenSet("temple_sift")
+    with Matcher(NORM_L2, 0.8, False, float_mode=mode) as m:
+        m.set_descriptors(g.descs)
+        m.match_all_pairs()
+        assert m.stats()["float_path"] == FLOAT_TENSOR  # real SIFT output is TF32-exact: AUTO must pick the tensor path
+        for p, (q, t, kd, ki, *_r) in enumerate(g.pairs):
+            got = m.getMatching(q, t)
+            eq, et, ed = g.expected(p)
+            assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all(), (q, t)
+            assert (got["distance"] == ed).all()
+        for q, t, kd, ki, *_r in g.pairs[::7]:
+            idx, dist = m.knn_pair(q, t)
+            assert (idx == ki).all() and (dist == kd).all()
+
+
+def test_tensor_mode_cfg4_shape_vs_oracle_and_exact_kernel():
+    descs = synth.float_images(3, [8000, 8000, 777], seed=0)  # configs[3] shape
+    with Matcher(NORM_L2, float_mode=FLOAT_TENSOR) as mt, Matcher(NORM_L2, float_mode=FLOAT_EXACT) as mx:
+        mt.set_descriptors(descs)
+        mx.set_descriptors(descs)
+        mt.match_all_pairs()
+        mx.match_all_pairs()
+        for a, b in zip(mt.result_table(), mx.result_table()):
+            assert a.tobytes() == b.tobytes()  # the two kernels agree bit for bit on every pair
+        exp = oracle.match_pair(descs[0], descs[1], 1, 0.8, False, threads=8)
+        assert mt.getMatching(0, 1).tobytes() == exp.tobytes()
+        for (q, t) in [(0, 1), (2, 0), (1, 2)]:  # raw 2-NN lists incl. the partial last tile and a short train set
+            ia, da = mt.knn_pair(q, t)
+            ib, db = mx.knn_pair(q, t)
+            assert (ia == ib).all() and (da == db).all()
+
+
+def test_tensor_mode_ties_duplicates_and_ragged():
+    rng = np.random.default_rng(8)
+    base = np.floor(rng.random((300, 128), dtype=np.float32) * 60).astype(np.float32)
+    T = np.concatenate([base, base[:50], base[100:130]])  # duplicated train rows => exact distance ties
+    Q = np.concatenate([base[:200] + (rng.random((200, 128)) < 0.02), base[:3]]).astype(np.float32)
+    sets = [Q, T, base[:1], base[:2], np.zeros((0, 128), np.float32), base[:129]]
+    with Matcher(NORM_L2, 0.9, False, float_mode=FLOAT_TENSOR) as m:
+        m.set_descriptors(sets)
+        m.match_all_pairs()
+        for (q, t) in synth.all_pairs(len(sets)):
+            exp = oracle.match_pair(sets[q], sets[t], 1, 0.9, False)
+            assert m.getMatching(q, t).tobytes() == exp.tobytes(), (q, t)
+        idx, dist = m.knn_pair(0, 1)
+        d, i = oracle.knn2_c(Q, T, 1)
+        assert (idx == i).all() and (dist == d).all()
+        assert (d[:, 0] == d[:, 1]).sum() > 20  # ties really occur, lowest index must win in both slots
+
+
+@pytest.mark.parametrize("cols", [32, 64, 96])
+def test_tensor_mode_other_widths(cols):
+    rng = np.random.default_rng(cols)
+    descs = [np.floor(rng.random((n, cols), dtype=np.float32) * 100).astype(np.float32) for n in (400, 333, 130)]
+    with Matcher(NORM_L2, float_mode=FLOAT_TENSOR) as m:
+        m.set_descriptors(descs)
+        m.match_all_pairs()
+        for (q, t) in synth.all_pairs(3):
+            assert m.getMatching(q, t).tobytes() == oracle.match_pair(descs[q], descs[t], 1).tobytes()
+
+
+def test_auto_falls_back_to_exact_kernel_for_arbitrary_floats():
+    g = GoldenSet("synth_float")  # non-integer values: not TF32-exact
+    with Matcher(NORM_L2, float_mode=FLOAT_AUTO) as m:
+        m.set_descriptors(g.descs)
+        m.match_all_pairs()
+        assert m.stats()["float_path"] == FLOAT_EXACT
+    with Matcher(NORM_L2, float_mode=FLOAT_TENSOR) as m:
+        m.set_descriptors(g.descs)
+        with pytest.raises(SfmmError) as e:
+            m.match_all_pairs()
+        assert e.value.code == -1 and "TF32-exact" in str(e.value)
