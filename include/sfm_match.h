@@ -142,7 +142,8 @@ SFMM_API int sfmm_match_all_pairs(SfmmCtx* ctx);
 SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs);
 
 /* Body of the patched getMatching (src/Sfm.cpp:590-608): borrow the match list of pair (q,t).
- * *matches stays valid until sfmm_set_descriptors / sfmm_clear_results / sfmm_destroy.
+ * *matches stays valid until the next sfmm_match_pairs / sfmm_match_all_pairs (the table may grow),
+ * sfmm_set_descriptors, sfmm_clear_results or sfmm_destroy.
  * SFMM_ESTATE if the pair has not been computed. */
 SFMM_API int sfmm_get_pair(const SfmmCtx* ctx, int32_t q, int32_t t, const SfmDMatch** matches,
                            int32_t* count);

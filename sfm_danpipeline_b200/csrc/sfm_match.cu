@@ -4,9 +4,11 @@
 //
 // Reference path being replaced: StructFromMotion::getMatching (/root/reference/src/Sfm.cpp:590-608)
 // driven by findBestPair's q<t loop (:511-515).  The scheduler turns a list of image pairs into
-//   1. "knn tiles"   (query-row tile x train-row range)  -> binary_knn2_kernel / float kernels
+// "chunks" (one kernel launch each):
+//   1. "knn tiles"    (query-row tile x train-row range) -> binary_knn2_kernel / float kernels
 //   2. "filter tiles" (1024 query rows)                  -> ratio test + cross-check + compaction
-// and moves the compacted cv::DMatch-layout records to host memory.
+// Two chunk slots (own stream, own scratch, own pinned staging) are kept in flight so that the
+// device->host copy and host-side bookkeeping of chunk k overlap the kernels of chunk k+1.
 #include <algorithm>
 #include <cfloat>
 #include <cstdio>
@@ -15,6 +17,7 @@
 #include <memory>
 #include <new>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -62,13 +65,28 @@ struct DevBuf {
     T* as() const { return static_cast<T*>(p); }
 };
 
-struct HostChunk {  // one block of match records on the host (stable address)
-    std::unique_ptr<SfmDMatch[]> data;
-    int64_t n = 0;
+struct PinBuf {  // page-locked host staging
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const size_t want = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMallocHost(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
 };
 
-struct PairSlot {  // where a computed pair lives
-    const SfmDMatch* ptr;
+struct PairSlot {  // where a computed pair lives in the host table
+    int64_t offset;
     int32_t count;
 };
 
@@ -85,6 +103,35 @@ struct ChunkPlan {
     uint64_t col_entries = 0;
     uint64_t max_matches = 0;
     double work = 0;  // algorithmic POPC32 ops / FLOPs of the knn launch
+    void clear() {
+        pairs.clear(); tiles.clear(); ftiles.clear();
+        knn_entries = col_entries = max_matches = 0;
+        work = 0;
+    }
+};
+
+// One chunk in flight: its stream, device scratch, pinned staging and events.
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_knn0 = nullptr, ev_knn1 = nullptr, ev_done = nullptr;
+    DevBuf d_pairs, d_tiles, d_ftiles, d_knn, d_colmin, d_tile_count, d_tile_off, d_pair_count, d_pair_off, d_matches;
+    PinBuf meta;     // [total u64][pair_off u64 x n][pair_count i32 x n]
+    PinBuf records;  // SfmDMatch staging
+    ChunkPlan plan;
+    int64_t first = 0, n = 0;  // pair range [first, first+n) of the caller's list
+    bool busy = false;
+    void release() {
+        for (DevBuf* b : {&d_pairs, &d_tiles, &d_ftiles, &d_knn, &d_colmin, &d_tile_count, &d_tile_off, &d_pair_count, &d_pair_off, &d_matches})
+            b->release();
+        meta.release();
+        records.release();
+        if (ev_knn0) cudaEventDestroy(ev_knn0);
+        if (ev_knn1) cudaEventDestroy(ev_knn1);
+        if (ev_done) cudaEventDestroy(ev_done);
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+        ev_knn0 = ev_knn1 = ev_done = nullptr;
+    }
 };
 
 }  // namespace
@@ -92,8 +139,9 @@ struct ChunkPlan {
 struct SfmmCtx {
     SfmmConfig cfg{};
     int sm_count = 0;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    Slot slot[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_pack[2] = {nullptr, nullptr};
     mutable std::string err;
     int csa_level = 2;
     size_t fx_attr_smem = 0;
@@ -104,6 +152,7 @@ struct SfmmCtx {
     bool tensor_eligible = false;
     bool use_tensor = false;
     CUtensorMap tmap{};
+    DevBuf d_norms, d_flags;
 
     // descriptors (imagesDescriptors, include/Sfm.h:29)
     int32_t n_images = 0;
@@ -112,26 +161,23 @@ struct SfmmCtx {
     int32_t cols = 0;
     int32_t elem_type = -1;
     size_t pitch = 0;
-    uint64_t total_rows = 0;
+    uint64_t total_rows = 0;  // blob rows, including the zero rows that align every image to 4 rows
     DevBuf blob;
     size_t blob_bytes = 0;
+    PinBuf pack[2];  // double-buffered re-pitch staging for set_descriptors
 
-    // per-launch scratch
-    DevBuf d_pairs, d_tiles, d_ftiles, d_knn, d_colmin, d_tile_count, d_tile_off, d_pair_count, d_pair_off,
-        d_matches, d_idx, d_dist, d_norms, d_flags;
-    void* pinned = nullptr;
-    size_t pinned_cap = 0;
+    DevBuf d_idx, d_dist;  // sfmm_knn_pair
 
     // result table
     std::vector<int32_t> res_qt;
     std::vector<int32_t> res_counts;
     std::vector<int64_t> res_offsets;  // offsets into the consolidated view
     std::vector<PairSlot> res_slots;
-    std::vector<HostChunk> chunks;
+    std::vector<SfmDMatch> table;  // every record, in the order the pairs were given
     std::unordered_map<uint64_t, int64_t> index;
-    mutable std::vector<SfmDMatch> flat;  // consolidated copy (built lazily when >1 chunk)
-    mutable bool flat_valid = false;
     int64_t n_matches = 0;
+    int64_t call_pairs = 0;  // pairs of the sfmm_match_pairs call in progress
+    size_t call_base = 0;    // table size when it started
 
     SfmmStats stats{};
 };
@@ -162,38 +208,30 @@ int binary_words(int cols) {  // 32-bit words per packed row
     return 0;
 }
 
-int ensure_pinned(SfmmCtx* ctx, size_t bytes) {
-    if (bytes <= ctx->pinned_cap) return SFMM_OK;
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    ctx->pinned = nullptr;
-    ctx->pinned_cap = 0;
-    const size_t want = bytes + bytes / 4 + 4096;
-    CU_TRY(ctx, cudaMallocHost(&ctx->pinned, want));
-    ctx->pinned_cap = want;
-    return SFMM_OK;
-}
-
 void clear_results(SfmmCtx* ctx) {
     ctx->res_qt.clear();
     ctx->res_counts.clear();
     ctx->res_offsets.clear();
     ctx->res_slots.clear();
-    ctx->chunks.clear();
+    ctx->table.clear();
     ctx->index.clear();
-    ctx->flat.clear();
-    ctx->flat_valid = false;
     ctx->n_matches = 0;
 }
 
 inline uint64_t pair_key(int32_t q, int32_t t) { return (static_cast<uint64_t>(static_cast<uint32_t>(q)) << 32) | static_cast<uint32_t>(t); }
 
+uint32_t query_tile_rows(const SfmmCtx* ctx) {
+    if (ctx->elem_type == SFMM_F32) return ctx->use_tensor ? FT_M : FX_BQ;
+    return BK_THREADS * (binary_words(ctx->cols) >= 32 ? 2 : 4);
+}
+
 // ---------------------------------------------------------------------------- planning
-// Turn pairs [begin,end) of qt into device work descriptors.
+// Turn n pairs of qt into device work descriptors.
 int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
+    plan.clear();
     const bool is_float = ctx->elem_type == SFMM_F32;
-    const int W = is_float ? 0 : binary_words(ctx->cols);
-    const int q_tile = is_float ? (ctx->use_tensor ? FT_M : FX_BQ) : BK_THREADS * (W >= 32 ? 2 : 4);
-    const int t_gran = is_float ? (ctx->use_tensor ? FT_N : FX_BT) : BK_TT;
+    const uint32_t q_tile = query_tile_rows(ctx);
+    const uint32_t t_gran = is_float ? (ctx->use_tensor ? FT_N : FX_BT) : BK_TT;
     plan.pairs.resize(n);
     uint64_t base_tiles = 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -204,7 +242,7 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
     }
     // Small jobs (a single getMatching call, the temple set) do not fill 148 SMs with one tile
     // per query-row tile: split the train range so that at least ~2 waves of CTAs exist.
-    const uint64_t want_tiles = static_cast<uint64_t>(ctx->sm_count) * 8;
+    const uint64_t want_tiles = static_cast<uint64_t>(ctx->sm_count) * (ctx->use_tensor ? 2 : 8);
     uint32_t splits_wanted = 1;
     if (base_tiles > 0 && base_tiles < want_tiles)
         splits_wanted = static_cast<uint32_t>(std::min<uint64_t>(32, (want_tiles + base_tiles - 1) / base_tiles));
@@ -250,40 +288,38 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
 
 // ---------------------------------------------------------------------------- launches
 template <int W, int CSA, bool CROSS>
-cudaError_t launch_binary_t(SfmmCtx* ctx, uint32_t n_tiles) {
+cudaError_t launch_binary_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     constexpr int TQ = BkTq<W>::v;
     using Smem = BinaryKnnSmem<W, TQ, BK_THREADS, BK_TT>;
-    auto kern = binary_knn2_kernel<W, TQ, BK_THREADS, BK_TT, CSA, CROSS>;
     static_assert(sizeof(Smem) <= 48 * 1024, "fits the default dynamic shared memory limit");
-    kern<<<n_tiles, BK_THREADS, sizeof(Smem), ctx->stream>>>(ctx->blob.as<uint32_t>(), ctx->d_tiles.as<KnnTile>(),
-                                                             ctx->d_pairs.as<PairDesc>(), ctx->d_knn.as<KnnEntry>(),
-                                                             ctx->d_colmin.as<unsigned long long>(),
-                                                             KeyWeights{{1u << IDX_BITS, 2u << IDX_BITS, 4u << IDX_BITS}});
+    binary_knn2_kernel<W, TQ, BK_THREADS, BK_TT, CSA, CROSS><<<n_tiles, BK_THREADS, sizeof(Smem), sl.stream>>>(
+        ctx->blob.as<uint32_t>(), sl.d_tiles.as<KnnTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
+        sl.d_colmin.as<unsigned long long>(), KeyWeights{{1u << IDX_BITS, 2u << IDX_BITS, 4u << IDX_BITS}});
     return cudaGetLastError();
 }
 
 template <int W, bool CROSS>
-cudaError_t launch_binary_w(SfmmCtx* ctx, uint32_t n_tiles) {
+cudaError_t launch_binary_w(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     switch (ctx->csa_level) {
-        case 0: return launch_binary_t<W, 0, CROSS>(ctx, n_tiles);
-        case 1: return launch_binary_t<W, 1, CROSS>(ctx, n_tiles);
-        case 3: return launch_binary_t<W, 3, CROSS>(ctx, n_tiles);
-        default: return launch_binary_t<W, 2, CROSS>(ctx, n_tiles);
+        case 0: return launch_binary_t<W, 0, CROSS>(ctx, sl, n_tiles);
+        case 1: return launch_binary_t<W, 1, CROSS>(ctx, sl, n_tiles);
+        case 3: return launch_binary_t<W, 3, CROSS>(ctx, sl, n_tiles);
+        default: return launch_binary_t<W, 2, CROSS>(ctx, sl, n_tiles);
     }
 }
 
 template <bool CROSS>
-cudaError_t launch_binary(SfmmCtx* ctx, uint32_t n_tiles) {
+cudaError_t launch_binary(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     switch (binary_words(ctx->cols)) {
-        case 4: return launch_binary_w<4, CROSS>(ctx, n_tiles);
-        case 8: return launch_binary_w<8, CROSS>(ctx, n_tiles);
-        case 16: return launch_binary_w<16, CROSS>(ctx, n_tiles);
-        case 32: return launch_binary_w<32, CROSS>(ctx, n_tiles);
+        case 4: return launch_binary_w<4, CROSS>(ctx, sl, n_tiles);
+        case 8: return launch_binary_w<8, CROSS>(ctx, sl, n_tiles);
+        case 16: return launch_binary_w<16, CROSS>(ctx, sl, n_tiles);
+        case 32: return launch_binary_w<32, CROSS>(ctx, sl, n_tiles);
     }
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_float_exact(SfmmCtx* ctx, uint32_t n_tiles) {
+cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     const int kq = static_cast<int>(ctx->pitch / 16);
     const size_t smem = float_exact_smem_bytes(kq);
     if (smem > ctx->fx_attr_smem) {  // per context == per device
@@ -291,31 +327,31 @@ cudaError_t launch_float_exact(SfmmCtx* ctx, uint32_t n_tiles) {
         if (e != cudaSuccess) return e;
         ctx->fx_attr_smem = smem;
     }
-    float_exact_knn2_kernel<<<n_tiles, FX_THREADS, smem, ctx->stream>>>(
-        ctx->blob.as<float>(), kq, ctx->d_tiles.as<KnnTile>(), ctx->d_pairs.as<PairDesc>(), ctx->d_knn.as<KnnEntry>(),
-        ctx->d_colmin.as<unsigned long long>(), ctx->cfg.cross_check ? 1 : 0);
+    float_exact_knn2_kernel<<<n_tiles, FX_THREADS, smem, sl.stream>>>(
+        ctx->blob.as<float>(), kq, sl.d_tiles.as<KnnTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
+        sl.d_colmin.as<unsigned long long>(), ctx->cfg.cross_check ? 1 : 0);
     return cudaGetLastError();
 }
 
 template <int KB>
-cudaError_t launch_float_tensor_t(SfmmCtx* ctx, uint32_t n_tiles) {
+cudaError_t launch_float_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     const size_t smem = float_tensor_smem_bytes(KB);
     if (smem > ctx->ft_attr_smem) {
         cudaError_t e = cudaFuncSetAttribute(float_tensor_knn2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         ctx->ft_attr_smem = smem;
     }
-    float_tensor_knn2_kernel<KB><<<n_tiles, FT_THREADS, smem, ctx->stream>>>(
-        ctx->tmap, ctx->d_norms.as<float>(), ctx->d_tiles.as<KnnTile>(), ctx->d_pairs.as<PairDesc>(), ctx->d_knn.as<KnnEntry>(), 512u);
+    float_tensor_knn2_kernel<KB><<<n_tiles, FT_THREADS, smem, sl.stream>>>(
+        ctx->tmap, ctx->d_norms.as<float>(), sl.d_tiles.as<KnnTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), 512u);
     return cudaGetLastError();
 }
 
-cudaError_t launch_float_tensor(SfmmCtx* ctx, uint32_t n_tiles) {
+cudaError_t launch_float_tensor(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     switch (ctx->cols / FT_KB_ELEMS) {
-        case 1: return launch_float_tensor_t<1>(ctx, n_tiles);
-        case 2: return launch_float_tensor_t<2>(ctx, n_tiles);
-        case 3: return launch_float_tensor_t<3>(ctx, n_tiles);
-        case 4: return launch_float_tensor_t<4>(ctx, n_tiles);
+        case 1: return launch_float_tensor_t<1>(ctx, sl, n_tiles);
+        case 2: return launch_float_tensor_t<2>(ctx, sl, n_tiles);
+        case 3: return launch_float_tensor_t<3>(ctx, sl, n_tiles);
+        case 4: return launch_float_tensor_t<4>(ctx, sl, n_tiles);
     }
     return cudaErrorInvalidValue;
 }
@@ -324,21 +360,22 @@ cudaError_t launch_float_tensor(SfmmCtx* ctx, uint32_t n_tiles) {
 // broadcast is seen): row norms, the TF32-exactness proof and the TMA tensor map; picks the path.
 int prepare_float(SfmmCtx* ctx) {
     if (ctx->elem_type != SFMM_F32 || ctx->float_prepared) return SFMM_OK;
+    cudaStream_t st = ctx->slot[0].stream;
     ctx->tensor_eligible = false;
     ctx->use_tensor = false;
     const bool shape_ok = ctx->cols % FT_KB_ELEMS == 0 && ctx->cols <= 4 * FT_KB_ELEMS && ctx->total_rows > 0;
     if (ctx->cfg.float_mode != SFMM_FLOAT_EXACT && shape_ok && !ctx->cfg.cross_check) {
         CU_TRY(ctx, ctx->d_norms.ensure((static_cast<size_t>(ctx->total_rows) + 2 * FT_N) * sizeof(float)));  // + tail for the bulk copies
         CU_TRY(ctx, ctx->d_flags.ensure(2 * sizeof(unsigned int)));
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(unsigned int), ctx->stream));
+        CU_TRY(ctx, cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(unsigned int), st));
         const uint32_t rows = static_cast<uint32_t>(ctx->total_rows);
-        float_prepare_kernel<<<(rows + 7) / 8, 256, 0, ctx->stream>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), rows,
-                                                                     ctx->cols, ctx->d_norms.as<float>(), ctx->d_flags.as<unsigned int>());
+        float_prepare_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), rows, ctx->cols,
+                                                             ctx->d_norms.as<float>(), ctx->d_flags.as<unsigned int>());
         CU_TRY(ctx, cudaGetLastError());
         ctx->stats.kernel_launches += 1;
         unsigned int flags[2] = {1, 0};
-        CU_TRY(ctx, cudaMemcpyAsync(flags, ctx->d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(flags, ctx->d_flags.p, sizeof(flags), cudaMemcpyDeviceToHost, st));
+        CU_TRY(ctx, cudaStreamSynchronize(st));
         float max_norm2;
         std::memcpy(&max_norm2, &flags[1], sizeof(float));
         ctx->tensor_eligible = flags[0] == 0 && max_norm2 <= 1048576.f;  // integers, |v|<=2047, |x|^2 <= 2^20
@@ -370,105 +407,182 @@ int prepare_float(SfmmCtx* ctx) {
     return SFMM_OK;
 }
 
-// Uploads the plan and runs the 2-NN kernel; leaves merged-able partial lists in d_knn (+ d_colmin).
-int run_knn(SfmmCtx* ctx, const ChunkPlan& plan, bool timed) {
-    const bool cross = ctx->cfg.cross_check != 0;
-    CU_TRY(ctx, ctx->d_pairs.ensure(std::max<size_t>(1, plan.pairs.size()) * sizeof(PairDesc)));
-    CU_TRY(ctx, ctx->d_tiles.ensure(std::max<size_t>(1, plan.tiles.size()) * sizeof(KnnTile)));
-    CU_TRY(ctx, ctx->d_ftiles.ensure(std::max<size_t>(1, plan.ftiles.size()) * sizeof(FilterTile)));
-    CU_TRY(ctx, ctx->d_knn.ensure(std::max<uint64_t>(1, plan.knn_entries) * sizeof(KnnEntry)));
-    CU_TRY(ctx, ctx->d_colmin.ensure(std::max<uint64_t>(1, cross ? plan.col_entries : 1) * sizeof(unsigned long long)));
-    if (!plan.pairs.empty())
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->d_pairs.p, plan.pairs.data(), plan.pairs.size() * sizeof(PairDesc),
-                                    cudaMemcpyHostToDevice, ctx->stream));
-    if (!plan.tiles.empty())
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->d_tiles.p, plan.tiles.data(), plan.tiles.size() * sizeof(KnnTile),
-                                    cudaMemcpyHostToDevice, ctx->stream));
-    if (!plan.ftiles.empty())
-        CU_TRY(ctx, cudaMemcpyAsync(ctx->d_ftiles.p, plan.ftiles.data(), plan.ftiles.size() * sizeof(FilterTile),
-                                    cudaMemcpyHostToDevice, ctx->stream));
-    ctx->stats.h2d_bytes += plan.pairs.size() * sizeof(PairDesc) + plan.tiles.size() * sizeof(KnnTile) +
-                            plan.ftiles.size() * sizeof(FilterTile);
-    if (cross && plan.col_entries)
-        CU_TRY(ctx, cudaMemsetAsync(ctx->d_colmin.p, 0xFF, plan.col_entries * sizeof(unsigned long long), ctx->stream));
-    if (plan.tiles.empty()) return SFMM_OK;
-    if (timed) CU_TRY(ctx, cudaEventRecord(ctx->ev[2], ctx->stream));
-    cudaError_t e;
-    if (ctx->elem_type == SFMM_F32) e = ctx->use_tensor ? launch_float_tensor(ctx, static_cast<uint32_t>(plan.tiles.size()))
-                                                    : launch_float_exact(ctx, static_cast<uint32_t>(plan.tiles.size()));
-    else e = cross ? launch_binary<true>(ctx, static_cast<uint32_t>(plan.tiles.size()))
-                   : launch_binary<false>(ctx, static_cast<uint32_t>(plan.tiles.size()));
-    CU_TRY(ctx, e);
-    if (timed) CU_TRY(ctx, cudaEventRecord(ctx->ev[3], ctx->stream));
-    ctx->stats.kernel_launches += 1;
-    return SFMM_OK;
-}
-
 template <bool IS_FLOAT, bool CROSS>
-cudaError_t launch_filter(SfmmCtx* ctx, const ChunkPlan& plan, int32_t* d_counts, SfmDMatch* d_matches, uint64_t capacity) {
-    const uint32_t nft = static_cast<uint32_t>(plan.ftiles.size());
+cudaError_t launch_filter(SfmmCtx* ctx, Slot& sl, int32_t* d_counts, SfmDMatch* d_matches, uint64_t capacity) {
+    const uint32_t nft = static_cast<uint32_t>(sl.plan.ftiles.size());
     const float ratio = ctx->cfg.ratio;
-    filter_count_kernel<IS_FLOAT, CROSS><<<nft, FILTER_THREADS, 0, ctx->stream>>>(
-        ctx->d_ftiles.as<FilterTile>(), ctx->d_pairs.as<PairDesc>(), ctx->d_knn.as<KnnEntry>(),
-        ctx->d_colmin.as<unsigned long long>(), ratio, ctx->d_tile_count.as<uint32_t>());
-    tile_scan_kernel<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->d_tile_count.as<uint32_t>(),
-                                                          ctx->d_tile_off.as<unsigned long long>(), nft);
-    filter_write_kernel<IS_FLOAT, CROSS><<<nft, FILTER_THREADS, 0, ctx->stream>>>(
-        ctx->d_ftiles.as<FilterTile>(), ctx->d_pairs.as<PairDesc>(), ctx->d_knn.as<KnnEntry>(),
-        ctx->d_colmin.as<unsigned long long>(), ratio, ctx->d_tile_off.as<unsigned long long>(), d_matches, capacity,
-        d_counts, ctx->d_pair_off.as<unsigned long long>());
+    filter_count_kernel<IS_FLOAT, CROSS><<<nft, FILTER_THREADS, 0, sl.stream>>>(
+        sl.d_ftiles.as<FilterTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), ratio,
+        sl.d_tile_count.as<uint32_t>());
+    tile_scan_kernel<<<1, SCAN_THREADS, 0, sl.stream>>>(sl.d_tile_count.as<uint32_t>(), sl.d_tile_off.as<unsigned long long>(), nft);
+    filter_write_kernel<IS_FLOAT, CROSS><<<nft, FILTER_THREADS, 0, sl.stream>>>(
+        sl.d_ftiles.as<FilterTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), ratio,
+        sl.d_tile_off.as<unsigned long long>(), d_matches, capacity, d_counts, sl.d_pair_off.as<unsigned long long>());
     return cudaGetLastError();
 }
 
-// Ratio test + cross-check + compaction of the lists left by run_knn into caller-chosen DEVICE
-// buffers.  On return (stream synchronised) *total = records produced (may exceed capacity:
-// nothing past capacity is written).
-int run_filter(SfmmCtx* ctx, const ChunkPlan& plan, int32_t* d_counts, SfmDMatch* d_matches, uint64_t capacity,
-               uint64_t* total) {
-    const size_t np = plan.pairs.size();
-    const size_t nft = plan.ftiles.size();
-    *total = 0;
-    if (np) CU_TRY(ctx, cudaMemsetAsync(d_counts, 0, np * sizeof(int32_t), ctx->stream));
-    CU_TRY(ctx, ctx->d_pair_off.ensure(std::max<size_t>(1, np) * sizeof(unsigned long long)));
-    if (np) CU_TRY(ctx, cudaMemsetAsync(ctx->d_pair_off.p, 0, np * sizeof(unsigned long long), ctx->stream));
-    if (nft == 0) {
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+// Plans `n` pairs and enqueues everything for them on the slot's stream, without waiting:
+// plan upload, 2-NN kernel, ratio/cross-check/compaction into (d_counts, d_matches) -- the
+// slot's own buffers when NULL --, and the device->host copy of the chunk's metadata.
+//   knn_only: stop after the 2-NN kernel (sfmm_knn_pair);  force_single_split: plan nt==1 pairs too.
+int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64_t n, int32_t* d_counts, SfmDMatch* d_matches,
+                 uint64_t capacity, bool knn_only = false, bool force_single_split = false) {
+    int rc = plan_chunk(ctx, qt + 2 * first, n, sl.plan);
+    if (rc) return rc;
+    ChunkPlan& plan = sl.plan;
+    if (force_single_split && plan.tiles.empty() && n == 1 && plan.pairs[0].nq > 0 && plan.pairs[0].nt > 0) {
+        PairDesc& pd = plan.pairs[0];  // nt == 1: planned as "no matches"; the raw list still has one neighbour
+        pd.n_splits = 1;
+        const uint32_t q_tile = query_tile_rows(ctx);
+        for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile) plan.tiles.push_back(KnnTile{0, q0, 0, pd.nt, 0});
+        plan.knn_entries = pd.nq;
+        plan.col_entries = pd.nt;
+    }
+    sl.first = first;
+    sl.n = n;
+    sl.busy = true;
+    const bool cross = ctx->cfg.cross_check != 0;
+    const size_t np = plan.pairs.size(), nft = plan.ftiles.size();
+    CU_TRY(ctx, sl.d_pairs.ensure(std::max<size_t>(1, np) * sizeof(PairDesc)));
+    CU_TRY(ctx, sl.d_tiles.ensure(std::max<size_t>(1, plan.tiles.size()) * sizeof(KnnTile)));
+    CU_TRY(ctx, sl.d_ftiles.ensure(std::max<size_t>(1, nft) * sizeof(FilterTile)));
+    CU_TRY(ctx, sl.d_knn.ensure(std::max<uint64_t>(1, plan.knn_entries) * sizeof(KnnEntry)));
+    CU_TRY(ctx, sl.d_colmin.ensure(std::max<uint64_t>(1, cross ? plan.col_entries : 1) * sizeof(unsigned long long)));
+    if (np) CU_TRY(ctx, cudaMemcpyAsync(sl.d_pairs.p, plan.pairs.data(), np * sizeof(PairDesc), cudaMemcpyHostToDevice, sl.stream));
+    if (!plan.tiles.empty())
+        CU_TRY(ctx, cudaMemcpyAsync(sl.d_tiles.p, plan.tiles.data(), plan.tiles.size() * sizeof(KnnTile), cudaMemcpyHostToDevice, sl.stream));
+    if (nft) CU_TRY(ctx, cudaMemcpyAsync(sl.d_ftiles.p, plan.ftiles.data(), nft * sizeof(FilterTile), cudaMemcpyHostToDevice, sl.stream));
+    ctx->stats.h2d_bytes += np * sizeof(PairDesc) + plan.tiles.size() * sizeof(KnnTile) + nft * sizeof(FilterTile);
+    if (cross && plan.col_entries)
+        CU_TRY(ctx, cudaMemsetAsync(sl.d_colmin.p, 0xFF, plan.col_entries * sizeof(unsigned long long), sl.stream));
+    CU_TRY(ctx, cudaEventRecord(sl.ev_knn0, sl.stream));
+    if (!plan.tiles.empty()) {
+        const uint32_t nt = static_cast<uint32_t>(plan.tiles.size());
+        cudaError_t e;
+        if (ctx->elem_type == SFMM_F32) e = ctx->use_tensor ? launch_float_tensor(ctx, sl, nt) : launch_float_exact(ctx, sl, nt);
+        else e = cross ? launch_binary<true>(ctx, sl, nt) : launch_binary<false>(ctx, sl, nt);
+        CU_TRY(ctx, e);
+        ctx->stats.kernel_launches += 1;
+    }
+    CU_TRY(ctx, cudaEventRecord(sl.ev_knn1, sl.stream));
+    if (knn_only) {
+        CU_TRY(ctx, cudaEventRecord(sl.ev_done, sl.stream));
         return SFMM_OK;
     }
-    CU_TRY(ctx, ctx->d_tile_count.ensure(nft * sizeof(uint32_t)));
-    CU_TRY(ctx, ctx->d_tile_off.ensure((nft + 1) * sizeof(unsigned long long)));
-    const bool is_float = ctx->elem_type == SFMM_F32, cross = ctx->cfg.cross_check != 0;
-    cudaError_t e;
-    if (is_float) e = cross ? launch_filter<true, true>(ctx, plan, d_counts, d_matches, capacity)
-                            : launch_filter<true, false>(ctx, plan, d_counts, d_matches, capacity);
-    else e = cross ? launch_filter<false, true>(ctx, plan, d_counts, d_matches, capacity)
-                   : launch_filter<false, false>(ctx, plan, d_counts, d_matches, capacity);
-    CU_TRY(ctx, e);
-    ctx->stats.kernel_launches += 3;
-    CU_TRY(ctx, ensure_pinned(ctx, 64) == SFMM_OK ? cudaSuccess : cudaErrorMemoryAllocation);
-    CU_TRY(ctx, cudaMemcpyAsync(ctx->pinned, ctx->d_tile_off.as<unsigned long long>() + nft, sizeof(unsigned long long),
-                                cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-    *total = *static_cast<unsigned long long*>(ctx->pinned);
-    ctx->stats.d2h_bytes += sizeof(unsigned long long);
+    // ---- ratio test + cross-check + compaction
+    const bool own = d_counts == nullptr;
+    if (own) {
+        CU_TRY(ctx, sl.d_pair_count.ensure(std::max<size_t>(1, np) * sizeof(int32_t)));
+        CU_TRY(ctx, sl.d_matches.ensure(std::max<uint64_t>(1, plan.max_matches) * sizeof(SfmDMatch)));
+        d_counts = sl.d_pair_count.as<int32_t>();
+        d_matches = sl.d_matches.as<SfmDMatch>();
+        capacity = plan.max_matches;
+    }
+    CU_TRY(ctx, sl.d_pair_off.ensure(std::max<size_t>(1, np) * sizeof(unsigned long long)));
+    CU_TRY(ctx, sl.meta.ensure(sizeof(unsigned long long) + np * (sizeof(unsigned long long) + sizeof(int32_t)) + 64));
+    if (np) {
+        CU_TRY(ctx, cudaMemsetAsync(d_counts, 0, np * sizeof(int32_t), sl.stream));
+        CU_TRY(ctx, cudaMemsetAsync(sl.d_pair_off.p, 0, np * sizeof(unsigned long long), sl.stream));
+    }
+    unsigned long long* h_total = static_cast<unsigned long long*>(sl.meta.p);
+    *h_total = 0;
+    if (nft) {
+        CU_TRY(ctx, sl.d_tile_count.ensure(nft * sizeof(uint32_t)));
+        CU_TRY(ctx, sl.d_tile_off.ensure((nft + 1) * sizeof(unsigned long long)));
+        const bool is_float = ctx->elem_type == SFMM_F32;
+        cudaError_t e;
+        if (is_float) e = cross ? launch_filter<true, true>(ctx, sl, d_counts, d_matches, capacity)
+                                : launch_filter<true, false>(ctx, sl, d_counts, d_matches, capacity);
+        else e = cross ? launch_filter<false, true>(ctx, sl, d_counts, d_matches, capacity)
+                       : launch_filter<false, false>(ctx, sl, d_counts, d_matches, capacity);
+        CU_TRY(ctx, e);
+        ctx->stats.kernel_launches += 3;
+        CU_TRY(ctx, cudaMemcpyAsync(h_total, sl.d_tile_off.as<unsigned long long>() + nft, sizeof(unsigned long long),
+                                    cudaMemcpyDeviceToHost, sl.stream));
+        ctx->stats.d2h_bytes += sizeof(unsigned long long);
+    }
+    if (own && np) {  // host table wanted: per-pair offsets and counts ride along
+        unsigned long long* h_off = h_total + 1;
+        int32_t* h_cnt = reinterpret_cast<int32_t*>(h_off + np);
+        CU_TRY(ctx, cudaMemcpyAsync(h_off, sl.d_pair_off.p, np * sizeof(unsigned long long), cudaMemcpyDeviceToHost, sl.stream));
+        CU_TRY(ctx, cudaMemcpyAsync(h_cnt, d_counts, np * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+        ctx->stats.d2h_bytes += static_cast<int64_t>(np * (sizeof(unsigned long long) + sizeof(int32_t)));
+    }
+    CU_TRY(ctx, cudaEventRecord(sl.ev_done, sl.stream));
     return SFMM_OK;
 }
 
-void account_knn_time(SfmmCtx* ctx, const ChunkPlan& plan) {
-    if (plan.tiles.empty()) return;
-    float ms = 0.f;
-    if (cudaEventElapsedTime(&ms, ctx->ev[2], ctx->ev[3]) == cudaSuccess) {
-        ctx->stats.last_knn_ms += ms;
-        ctx->stats.last_knn_work += plan.work;
-        ctx->stats.last_knn_launches += 1;
-    } else {
-        (void)cudaGetLastError();
+// Waits for the chunk's kernels; *total = records produced (may exceed the capacity given: nothing
+// past it was written).  Accounts the 2-NN kernel time.
+int wait_chunk(SfmmCtx* ctx, Slot& sl, uint64_t* total) {
+    CU_TRY(ctx, cudaEventSynchronize(sl.ev_done));
+    if (total) *total = sl.meta.p ? *static_cast<unsigned long long*>(sl.meta.p) : 0;
+    if (!sl.plan.tiles.empty()) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, sl.ev_knn0, sl.ev_knn1) == cudaSuccess) {
+            ctx->stats.last_knn_ms += ms;
+            ctx->stats.last_knn_work += sl.plan.work;
+            ctx->stats.last_knn_launches += 1;
+        } else {
+            (void)cudaGetLastError();
+        }
     }
+    sl.busy = false;
+    return SFMM_OK;
 }
 
-// How many pairs of qt[from..n) fit the per-launch budget.
-int64_t chunk_extent(const SfmmCtx* ctx, const int32_t* qt, int64_t from, int64_t n) {
-    const uint64_t row_budget = 8u << 20;  // query rows per launch: 128 MB of 2-NN scratch, 128 MB of records
+// Host-table path: bring the finished chunk's records to the host and index them.
+int collect_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt) {
+    uint64_t total = 0;
+    int rc = wait_chunk(ctx, sl, &total);
+    if (rc) return rc;
+    const size_t np = static_cast<size_t>(sl.n);
+    const unsigned long long* h_off = static_cast<unsigned long long*>(sl.meta.p) + 1;
+    const int32_t* h_cnt = reinterpret_cast<const int32_t*>(h_off + np);
+    const size_t old_size = ctx->table.size();
+    if (total) {
+        // grow the table once per call where possible: extrapolate from the chunks seen so far
+        if (ctx->table.capacity() < old_size + total) {
+            const double seen = static_cast<double>(sl.first + sl.n), all = static_cast<double>(std::max<int64_t>(ctx->call_pairs, sl.first + sl.n));
+            const size_t guess = static_cast<size_t>((static_cast<double>(old_size - ctx->call_base + total) * all / seen) * 1.05) + 1024;
+            try {
+                ctx->table.reserve(std::max(old_size + static_cast<size_t>(total), ctx->call_base + guess));
+            } catch (const std::bad_alloc&) {
+                return fail(ctx, SFMM_ENOMEM, "match_pairs: out of host memory for the match table");
+            }
+        }
+        CU_TRY(ctx, sl.records.ensure(static_cast<size_t>(total) * sizeof(SfmDMatch)));
+        CU_TRY(ctx, cudaMemcpyAsync(sl.records.p, sl.d_matches.p, static_cast<size_t>(total) * sizeof(SfmDMatch), cudaMemcpyDeviceToHost,
+                                    ctx->copy_stream));
+        CU_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+        const SfmDMatch* rec = static_cast<const SfmDMatch*>(sl.records.p);
+        try {
+            ctx->table.insert(ctx->table.end(), rec, rec + total);
+        } catch (const std::bad_alloc&) {
+            return fail(ctx, SFMM_ENOMEM, "match_pairs: out of host memory for the match table");
+        }
+        ctx->stats.d2h_bytes += static_cast<int64_t>(total * sizeof(SfmDMatch));
+    }
+    int64_t running = 0;
+    for (size_t i = 0; i < np; ++i) {
+        const int32_t q = qt[2 * (sl.first + i)], t = qt[2 * (sl.first + i) + 1];
+        ctx->index[pair_key(q, t)] = static_cast<int64_t>(ctx->res_slots.size());
+        ctx->res_qt.push_back(q);
+        ctx->res_qt.push_back(t);
+        ctx->res_counts.push_back(h_cnt[i]);
+        // records are laid out in pair order, so the offset is the running total (h_off[i] for
+        // non-empty pairs; empty pairs have no filter tile and get the position they would occupy)
+        const int64_t local = h_cnt[i] ? static_cast<int64_t>(h_off[i]) : running;
+        running = local + h_cnt[i];
+        ctx->res_offsets.push_back(ctx->n_matches + local);
+        ctx->res_slots.push_back(PairSlot{ctx->n_matches + local, h_cnt[i]});
+    }
+    ctx->n_matches += static_cast<int64_t>(total);
+    return SFMM_OK;
+}
+
+// How many pairs of qt[from..n) fit a launch of at most `row_budget` query rows.
+int64_t chunk_extent(const SfmmCtx* ctx, const int32_t* qt, int64_t from, int64_t n, uint64_t row_budget) {
     const int64_t pair_cap = ctx->cfg.pair_batch > 0 ? ctx->cfg.pair_batch : (1 << 20);
     uint64_t rows = 0;
     int64_t i = from;
@@ -480,6 +594,7 @@ int64_t chunk_extent(const SfmmCtx* ctx, const int32_t* qt, int64_t from, int64_
     }
     return i - from;
 }
+constexpr uint64_t MAX_CHUNK_ROWS = 8u << 20;  // query rows per launch: 128 MB of 2-NN scratch, 128 MB of records
 
 int require_descriptors(const SfmmCtx* ctx) {
     if (!ctx) return SFMM_EINVAL;
@@ -492,12 +607,42 @@ int bind_device(const SfmmCtx* ctx) {
     return SFMM_OK;
 }
 
+int sync_all(SfmmCtx* ctx) {
+    for (Slot& sl : ctx->slot) CU_TRY(ctx, cudaStreamSynchronize(sl.stream));
+    CU_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    return SFMM_OK;
+}
+
+void begin_stats(SfmmCtx* ctx) {
+    ctx->stats.last_knn_ms = ctx->stats.last_knn_work = 0;
+    ctx->stats.last_knn_launches = 0;
+}
+
+// Re-pitch blob rows [r0, r1) of the caller's images into `dst` (pitch bytes per row, zeroed padding).
+void pack_rows(const SfmmCtx* ctx, const void* const* data, const size_t* step_bytes, size_t row_bytes, uint64_t r0, uint64_t r1,
+               unsigned char* dst) {
+    const size_t pitch = ctx->pitch;
+    // image holding blob row r0
+    int32_t img = static_cast<int32_t>(std::upper_bound(ctx->row0.begin(), ctx->row0.end(), static_cast<uint32_t>(r0)) - ctx->row0.begin()) - 1;
+    for (uint64_t r = r0; r < r1; ++r, dst += pitch) {
+        while (img + 1 < ctx->n_images && ctx->row0[img + 1] <= r) ++img;
+        const uint64_t local = r - ctx->row0[img];
+        if (local < static_cast<uint64_t>(ctx->rows[img])) {
+            const size_t step = step_bytes ? step_bytes[img] : row_bytes;
+            std::memcpy(dst, static_cast<const unsigned char*>(data[img]) + local * step, row_bytes);
+            if (pitch > row_bytes) std::memset(dst + row_bytes, 0, pitch - row_bytes);
+        } else {
+            std::memset(dst, 0, pitch);  // alignment rows between images
+        }
+    }
+}
+
 }  // namespace
 
 // =============================================================================== C ABI
 extern "C" {
 
-SFMM_API const char* sfmm_version(void) { return "0.1.0 (sm_100a)"; }
+SFMM_API const char* sfmm_version(void) { return "0.2.0 (sm_100a)"; }
 
 SFMM_API void sfmm_default_config(SfmmConfig* cfg) {
     if (!cfg) return;
@@ -542,15 +687,19 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     ctx->cfg = *cfg;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* s = std::getenv("SFMM_CSA_LEVEL")) ctx->csa_level = std::max(0, std::min(3, std::atoi(s)));
-    if ((e = cudaSetDevice(cfg->device)) != cudaSuccess || (e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
-        delete ctx;
-        return fail(nullptr, SFMM_ECUDA, std::string("stream setup: ") + cudaGetErrorString(e));
+    bool ok = (e = cudaSetDevice(cfg->device)) == cudaSuccess;
+    for (Slot& sl : ctx->slot) {
+        ok = ok && (e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) == cudaSuccess;
+        ok = ok && (e = cudaEventCreate(&sl.ev_knn0)) == cudaSuccess && (e = cudaEventCreate(&sl.ev_knn1)) == cudaSuccess &&
+             (e = cudaEventCreate(&sl.ev_done)) == cudaSuccess;
     }
-    for (auto& ev : ctx->ev)
-        if ((e = cudaEventCreate(&ev)) != cudaSuccess) {
-            sfmm_destroy(ctx);
-            return fail(nullptr, SFMM_ECUDA, std::string("cudaEventCreate: ") + cudaGetErrorString(e));
-        }
+    ok = ok && (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) == cudaSuccess;
+    ok = ok && (e = cudaEventCreate(&ctx->ev_begin)) == cudaSuccess && (e = cudaEventCreate(&ctx->ev_end)) == cudaSuccess;
+    for (auto& ev : ctx->ev_pack) ok = ok && (e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) == cudaSuccess;
+    if (!ok) {
+        sfmm_destroy(ctx);
+        return fail(nullptr, SFMM_ECUDA, std::string("stream/event setup: ") + cudaGetErrorString(e));
+    }
     *out = ctx;
     return SFMM_OK;
 }
@@ -558,14 +707,18 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
 SFMM_API void sfmm_destroy(SfmmCtx* ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
-    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-    for (DevBuf* b : {&ctx->blob, &ctx->d_pairs, &ctx->d_tiles, &ctx->d_ftiles, &ctx->d_knn, &ctx->d_colmin, &ctx->d_tile_count,
-                      &ctx->d_tile_off, &ctx->d_pair_count, &ctx->d_pair_off, &ctx->d_matches, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags})
-        b->release();
-    if (ctx->pinned) cudaFreeHost(ctx->pinned);
-    for (auto& ev : ctx->ev)
+    for (Slot& sl : ctx->slot) {
+        if (sl.stream) cudaStreamSynchronize(sl.stream);
+        sl.release();
+    }
+    if (ctx->copy_stream) {
+        cudaStreamSynchronize(ctx->copy_stream);
+        cudaStreamDestroy(ctx->copy_stream);
+    }
+    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags}) b->release();
+    for (PinBuf& p : ctx->pack) p.release();
+    for (cudaEvent_t ev : {ctx->ev_begin, ctx->ev_end, ctx->ev_pack[0], ctx->ev_pack[1]})
         if (ev) cudaEventDestroy(ev);
-    if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
 
@@ -589,7 +742,7 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
     if (elem_type == SFMM_F32 && cols > 256) return fail(ctx, SFMM_EINVAL, "set_descriptors: float descriptors wider than 256 are not supported");
     const size_t elem = elem_type == SFMM_U8 ? 1 : 4;
     // every image starts at a blob row that is a multiple of 4 (16-byte aligned slices of the
-    // per-row norm array for the TMA bulk copies of the tensor path); pad rows are zero
+    // per-row norm array for the TMA bulk copies of the tensor path); the rows in between are zero
     uint64_t total = 0;
     for (int32_t i = 0; i < n_images; ++i) {
         if (rows[i] < 0) return fail(ctx, SFMM_EINVAL, "set_descriptors: negative row count");
@@ -602,7 +755,7 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
     if (total >= (1ull << 32)) return fail(ctx, SFMM_ERANGE, "set_descriptors: more than 2^32 rows in total");
     int rc = bind_device(ctx);
     if (rc) return rc;
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    if ((rc = sync_all(ctx))) return rc;
     clear_results(ctx);
     ctx->elem_type = -1;
     ctx->float_prepared = false;
@@ -617,45 +770,46 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
         ctx->row0[i] = static_cast<uint32_t>(r0);
         r0 += (static_cast<uint64_t>(rows[i]) + 3) & ~3ull;
     }
-    if (data && bytes) {
-        // re-pitch on the host into pinned memory (zeroed padding: zeros are Hamming/L2 neutral), one H2D per slab
-        const size_t slab = std::min<size_t>(bytes, 256u << 20);
-        rc = ensure_pinned(ctx, slab);
-        if (rc) return rc;
-        const size_t row_bytes = static_cast<size_t>(cols) * elem;
-        unsigned char* stage = static_cast<unsigned char*>(ctx->pinned);
-        size_t fill = 0, dev_off = 0;
-        auto flush = [&]() -> int {
-            if (!fill) return SFMM_OK;
-            CU_TRY(ctx, cudaMemcpyAsync(static_cast<unsigned char*>(ctx->blob.p) + dev_off, stage, fill, cudaMemcpyHostToDevice, ctx->stream));
-            CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-            ctx->stats.h2d_bytes += static_cast<int64_t>(fill);
-            dev_off += fill;
-            fill = 0;
-            return SFMM_OK;
-        };
-        for (int32_t i = 0; i < n_images; ++i) {
-            const unsigned char* src = static_cast<const unsigned char*>(data[i]);
-            const size_t step = step_bytes ? step_bytes[i] : row_bytes;
-            for (int32_t r = 0; r < rows[i]; ++r) {
-                if (fill + pitch > slab && (rc = flush())) return rc;
-                std::memcpy(stage + fill, src + static_cast<size_t>(r) * step, row_bytes);
-                if (pitch > row_bytes) std::memset(stage + fill + row_bytes, 0, pitch - row_bytes);
-                fill += pitch;
-            }
-            for (int32_t r = rows[i]; r & 3; ++r) {  // zero rows up to the next multiple of 4
-                if (fill + pitch > slab && (rc = flush())) return rc;
-                std::memset(stage + fill, 0, pitch);
-                fill += pitch;
-            }
-        }
-        if ((rc = flush())) return rc;
-    }
     ctx->n_images = n_images;
     ctx->cols = cols;
     ctx->pitch = pitch;
     ctx->total_rows = total;
     ctx->blob_bytes = bytes;
+    if (data && bytes) {
+        // Re-pitch on the host into two pinned slabs (a few threads), each followed by its own
+        // async H2D: packing slab k+1 overlaps the copy of slab k.
+        cudaStream_t st = ctx->slot[0].stream;
+        const size_t row_bytes = static_cast<size_t>(cols) * elem;
+        const uint64_t slab_rows = std::max<uint64_t>(4, (16u << 20) / pitch);
+        const size_t slab_bytes = static_cast<size_t>(std::min<uint64_t>(slab_rows, total)) * pitch;
+        for (PinBuf& p : ctx->pack) CU_TRY(ctx, p.ensure(slab_bytes));
+        const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        int k = 0;
+        for (uint64_t b = 0; b < total; b += slab_rows, ++k) {
+            const uint64_t e = std::min(total, b + slab_rows);
+            PinBuf& pin = ctx->pack[k & 1];
+            if (k >= 2) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_pack[k & 1]));  // its previous copy has left the slab
+            unsigned char* dst = static_cast<unsigned char*>(pin.p);
+            const uint64_t n_rows = e - b;
+            const unsigned workers = static_cast<unsigned>(std::min<uint64_t>(std::min(8u, hw), std::max<uint64_t>(1, (n_rows * pitch) >> 20)));
+            if (workers <= 1) {
+                pack_rows(ctx, data, step_bytes, row_bytes, b, e, dst);
+            } else {
+                std::vector<std::thread> pool;
+                const uint64_t per = (n_rows + workers - 1) / workers;
+                for (unsigned w = 0; w < workers; ++w) {
+                    const uint64_t wb = b + w * per, we = std::min(e, wb + per);
+                    if (wb >= we) break;
+                    pool.emplace_back(pack_rows, ctx, data, step_bytes, row_bytes, wb, we, dst + (wb - b) * pitch);
+                }
+                for (auto& t : pool) t.join();
+            }
+            CU_TRY(ctx, cudaMemcpyAsync(static_cast<unsigned char*>(ctx->blob.p) + b * pitch, dst, n_rows * pitch, cudaMemcpyHostToDevice, st));
+            CU_TRY(ctx, cudaEventRecord(ctx->ev_pack[k & 1], st));
+            ctx->stats.h2d_bytes += static_cast<int64_t>(n_rows * pitch);
+        }
+        CU_TRY(ctx, cudaStreamSynchronize(st));
+    }
     ctx->elem_type = elem_type;
     return SFMM_OK;
 }
@@ -666,6 +820,7 @@ SFMM_API int sfmm_descriptor_blob(SfmmCtx* ctx, void** device_ptr, size_t* bytes
     if (!device_ptr || !bytes) return fail(ctx, SFMM_EINVAL, "descriptor_blob: NULL argument");
     *device_ptr = ctx->blob.p;
     *bytes = ctx->blob_bytes;
+    ctx->float_prepared = false;  // the caller may overwrite the blob (broadcast): re-derive norms/eligibility
     return SFMM_OK;
 }
 
@@ -684,28 +839,25 @@ SFMM_API int sfmm_match_pairs_device(SfmmCtx* ctx, const int32_t* qt, int64_t n_
     if ((rc = bind_device(ctx))) return rc;
     if ((rc = prepare_float(ctx))) return rc;
     *n_matches = 0;
-    ctx->stats.last_knn_ms = ctx->stats.last_knn_work = 0;
-    ctx->stats.last_knn_launches = 0;
-    CU_TRY(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
+    begin_stats(ctx);
+    Slot& sl = ctx->slot[0];  // results chain through `written`: chunks run back to back on one stream
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_begin, sl.stream));
     int64_t done = 0;
     uint64_t written = 0;
     while (done < n_pairs) {
-        const int64_t n = chunk_extent(ctx, qt, done, n_pairs);
-        ChunkPlan plan;
-        if ((rc = plan_chunk(ctx, qt + 2 * done, n, plan))) return rc;
-        if ((rc = run_knn(ctx, plan, true))) return rc;
-        uint64_t total = 0;
+        const int64_t n = chunk_extent(ctx, qt, done, n_pairs, MAX_CHUNK_ROWS);
         const uint64_t room = static_cast<uint64_t>(match_capacity) - std::min<uint64_t>(written, match_capacity);
-        if ((rc = run_filter(ctx, plan, d_counts + done, d_matches ? d_matches + written : nullptr, d_matches ? room : 0, &total))) return rc;
-        account_knn_time(ctx, plan);
+        if ((rc = launch_chunk(ctx, sl, qt, done, n, d_counts + done, d_matches ? d_matches + written : nullptr, d_matches ? room : 0))) return rc;
+        uint64_t total = 0;
+        if ((rc = wait_chunk(ctx, sl, &total))) return rc;
         if (total > room) return fail(ctx, SFMM_ERANGE, "match_pairs_device: match_capacity too small");
         written += total;
         done += n;
     }
-    CU_TRY(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_end, sl.stream));
+    CU_TRY(ctx, cudaStreamSynchronize(sl.stream));
     float ms = 0.f;
-    CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
     ctx->stats.last_match_ms = ms;
     ctx->stats.pairs_matched += n_pairs;
     *n_matches = static_cast<int64_t>(written);
@@ -718,62 +870,44 @@ SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) 
     if (n_pairs < 0 || (n_pairs > 0 && !qt)) return fail(ctx, SFMM_EINVAL, "match_pairs: bad argument");
     if ((rc = bind_device(ctx))) return rc;
     if ((rc = prepare_float(ctx))) return rc;
-    ctx->stats.last_knn_ms = ctx->stats.last_knn_work = 0;
-    ctx->stats.last_knn_launches = 0;
-    CU_TRY(ctx, cudaEventRecord(ctx->ev[0], ctx->stream));
-    int64_t done = 0;
-    while (done < n_pairs) {
-        const int64_t n = chunk_extent(ctx, qt, done, n_pairs);
-        ChunkPlan plan;
-        if ((rc = plan_chunk(ctx, qt + 2 * done, n, plan))) return rc;
-        if ((rc = run_knn(ctx, plan, true))) return rc;
-        CU_TRY(ctx, ctx->d_pair_count.ensure(static_cast<size_t>(n) * sizeof(int32_t)));
-        CU_TRY(ctx, ctx->d_matches.ensure(std::max<uint64_t>(1, plan.max_matches) * sizeof(SfmDMatch)));
-        uint64_t total = 0;
-        if ((rc = run_filter(ctx, plan, ctx->d_pair_count.as<int32_t>(), ctx->d_matches.as<SfmDMatch>(), plan.max_matches, &total))) return rc;
-        account_knn_time(ctx, plan);
-        // device -> pinned -> the chunk's host block
-        const size_t meta = (static_cast<size_t>(n) * (sizeof(int32_t) + sizeof(unsigned long long)) + 15) / 16 * 16;
-        if ((rc = ensure_pinned(ctx, meta + static_cast<size_t>(total) * sizeof(SfmDMatch)))) return rc;
-        unsigned char* pin = static_cast<unsigned char*>(ctx->pinned);
-        unsigned long long* h_off = reinterpret_cast<unsigned long long*>(pin);
-        int32_t* h_cnt = reinterpret_cast<int32_t*>(pin + static_cast<size_t>(n) * sizeof(unsigned long long));
-        SfmDMatch* h_m = reinterpret_cast<SfmDMatch*>(pin + meta);
-        CU_TRY(ctx, cudaMemcpyAsync(h_off, ctx->d_pair_off.p, static_cast<size_t>(n) * sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaMemcpyAsync(h_cnt, ctx->d_pair_count.p, static_cast<size_t>(n) * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-        if (total)
-            CU_TRY(ctx, cudaMemcpyAsync(h_m, ctx->d_matches.p, static_cast<size_t>(total) * sizeof(SfmDMatch), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
-        ctx->stats.d2h_bytes += static_cast<int64_t>(meta + total * sizeof(SfmDMatch));
-        HostChunk hc;
-        hc.n = static_cast<int64_t>(total);
-        hc.data.reset(new (std::nothrow) SfmDMatch[std::max<uint64_t>(1, total)]);
-        if (!hc.data) return fail(ctx, SFMM_ENOMEM, "match_pairs: out of host memory for the match table");
-        if (total) std::memcpy(hc.data.get(), h_m, static_cast<size_t>(total) * sizeof(SfmDMatch));
-        const SfmDMatch* base = hc.data.get();
-        int64_t running = 0;
-        ctx->chunks.push_back(std::move(hc));
-        for (int64_t i = 0; i < n; ++i) {
-            const int32_t q = qt[2 * (done + i)], t = qt[2 * (done + i) + 1];
-            ctx->index[pair_key(q, t)] = static_cast<int64_t>(ctx->res_slots.size());
-            ctx->res_qt.push_back(q);
-            ctx->res_qt.push_back(t);
-            ctx->res_counts.push_back(h_cnt[i]);
-            // records are laid out in pair order, so the offset is the running total (h_off[i] for
-            // non-empty pairs; empty pairs have no filter tile and get the position they would occupy)
-            const int64_t local = h_cnt[i] ? static_cast<int64_t>(h_off[i]) : running;
-            running = local + h_cnt[i];
-            ctx->res_offsets.push_back(ctx->n_matches + local);
-            ctx->res_slots.push_back(PairSlot{base + local, h_cnt[i]});
-        }
-        ctx->n_matches += static_cast<int64_t>(total);
-        ctx->flat_valid = false;
-        done += n;
+    begin_stats(ctx);
+    ctx->call_pairs = n_pairs;
+    ctx->call_base = ctx->table.size();
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_begin, ctx->slot[0].stream));
+    // Chunk size: about an eighth of the job (so that copies and bookkeeping overlap kernels),
+    // never more than the scratch budget, never so small that a launch cannot fill the GPU.
+    uint64_t q_rows = 0;
+    for (int64_t i = 0; i < n_pairs; ++i) {
+        const int32_t q = qt[2 * i];
+        if (q >= 0 && q < ctx->n_images) q_rows += static_cast<uint64_t>(ctx->rows[q]);
     }
-    CU_TRY(ctx, cudaEventRecord(ctx->ev[1], ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    const uint64_t min_rows = static_cast<uint64_t>(query_tile_rows(ctx)) * ctx->sm_count * 8;
+    const uint64_t budget = std::min<uint64_t>(MAX_CHUNK_ROWS, std::max<uint64_t>(min_rows, q_rows / 8 + 1));
+    int64_t next = 0;
+    int k = 0;
+    int pending[2] = {-1, -1};  // slot indices in launch order
+    auto collect_oldest = [&]() -> int {
+        const int s = pending[0];
+        pending[0] = pending[1];
+        pending[1] = -1;
+        return collect_chunk(ctx, ctx->slot[s], qt);
+    };
+    while (next < n_pairs) {
+        if (pending[1] >= 0 && (rc = collect_oldest())) return rc;  // both slots busy: free the older one
+        const int s = k & 1;
+        const int64_t n = chunk_extent(ctx, qt, next, n_pairs, budget);
+        if ((rc = launch_chunk(ctx, ctx->slot[s], qt, next, n, nullptr, nullptr, 0))) return rc;
+        (pending[0] < 0 ? pending[0] : pending[1]) = s;
+        next += n;
+        ++k;
+    }
+    while (pending[0] >= 0)
+        if ((rc = collect_oldest())) return rc;
+    // device time of the whole call: from the first launch to the later of the two streams
+    CU_TRY(ctx, cudaEventRecord(ctx->ev_end, ctx->slot[0].stream));
+    if ((rc = sync_all(ctx))) return rc;
     float ms = 0.f;
-    CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev[0], ctx->ev[1]));
+    CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
     ctx->stats.last_match_ms = ms;
     ctx->stats.pairs_matched += n_pairs;
     return SFMM_OK;
@@ -803,7 +937,7 @@ SFMM_API int sfmm_get_pair(const SfmmCtx* ctx, int32_t q, int32_t t, const SfmDM
     auto it = ctx->index.find(pair_key(q, t));
     if (it == ctx->index.end()) return fail(ctx, SFMM_ESTATE, "get_pair: pair has not been matched (call sfmm_match_all_pairs / sfmm_match_pairs)");
     const PairSlot& s = ctx->res_slots[static_cast<size_t>(it->second)];
-    *matches = s.ptr;
+    *matches = ctx->table.data() + s.offset;
     *count = s.count;
     return SFMM_OK;
 }
@@ -818,17 +952,7 @@ SFMM_API int sfmm_result_table(const SfmmCtx* ctx, int64_t* n_pairs, const int32
     *counts = ctx->res_counts.data();
     *offsets = ctx->res_offsets.data();
     *n_matches = ctx->n_matches;
-    if (ctx->chunks.size() == 1) {
-        *matches = ctx->chunks[0].data.get();
-    } else {
-        if (!ctx->flat_valid) {
-            ctx->flat.clear();
-            ctx->flat.reserve(static_cast<size_t>(ctx->n_matches));
-            for (const HostChunk& c : ctx->chunks) ctx->flat.insert(ctx->flat.end(), c.data.get(), c.data.get() + c.n);
-            ctx->flat_valid = true;
-        }
-        *matches = ctx->flat.data();
-    }
+    *matches = ctx->table.data();
     return SFMM_OK;
 }
 
@@ -841,21 +965,18 @@ SFMM_API int sfmm_match_pair(SfmmCtx* ctx, int32_t q, int32_t t, SfmDMatch* out,
     if ((rc = prepare_float(ctx))) return rc;
     *count = 0;
     const int32_t qt[2] = {q, t};
-    ChunkPlan plan;
-    if ((rc = plan_chunk(ctx, qt, 1, plan))) return rc;
-    if ((rc = run_knn(ctx, plan, false))) return rc;
-    CU_TRY(ctx, ctx->d_pair_count.ensure(sizeof(int32_t)));
-    CU_TRY(ctx, ctx->d_matches.ensure(std::max<uint64_t>(1, plan.max_matches) * sizeof(SfmDMatch)));
+    Slot& sl = ctx->slot[0];
+    if ((rc = launch_chunk(ctx, sl, qt, 0, 1, nullptr, nullptr, 0))) return rc;
     uint64_t total = 0;
-    if ((rc = run_filter(ctx, plan, ctx->d_pair_count.as<int32_t>(), ctx->d_matches.as<SfmDMatch>(), plan.max_matches, &total))) return rc;
+    if ((rc = wait_chunk(ctx, sl, &total))) return rc;
     ctx->stats.pairs_matched += 1;
     if (total > static_cast<uint64_t>(cap)) {
         *count = static_cast<int32_t>(total);
         return fail(ctx, SFMM_ERANGE, "match_pair: output capacity too small (count holds the size needed)");
     }
     if (total) {
-        CU_TRY(ctx, cudaMemcpyAsync(out, ctx->d_matches.p, static_cast<size_t>(total) * sizeof(SfmDMatch), cudaMemcpyDeviceToHost, ctx->stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+        CU_TRY(ctx, cudaMemcpyAsync(out, sl.d_matches.p, static_cast<size_t>(total) * sizeof(SfmDMatch), cudaMemcpyDeviceToHost, sl.stream));
+        CU_TRY(ctx, cudaStreamSynchronize(sl.stream));
         ctx->stats.d2h_bytes += static_cast<int64_t>(total * sizeof(SfmDMatch));
     }
     *count = static_cast<int32_t>(total);
@@ -878,33 +999,22 @@ SFMM_API int sfmm_knn_pair(SfmmCtx* ctx, int32_t q, int32_t t, int32_t* train_id
     }
     if ((rc = bind_device(ctx))) return rc;
     if ((rc = prepare_float(ctx))) return rc;
-    // plan as a normal pair but force the knn launch even when nt == 1
     const int32_t qt[2] = {q, t};
-    ChunkPlan plan;
-    if ((rc = plan_chunk(ctx, qt, 1, plan))) return rc;
-    if (plan.tiles.empty()) {  // nt == 1: planned as "no matches"; build the single split by hand
-        PairDesc& pd = plan.pairs[0];
-        pd.n_splits = 1;
-        const bool is_float = ctx->elem_type == SFMM_F32;
-        const int W = is_float ? 0 : binary_words(ctx->cols);
-        const uint32_t q_tile = is_float ? (ctx->use_tensor ? FT_M : FX_BQ) : BK_THREADS * (W >= 32 ? 2 : 4);
-        for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile) plan.tiles.push_back(KnnTile{0, q0, 0, pd.nt, 0});
-        plan.knn_entries = pd.nq;
-        plan.col_entries = pd.nt;
-    }
-    if ((rc = run_knn(ctx, plan, false))) return rc;
+    Slot& sl = ctx->slot[0];
+    if ((rc = launch_chunk(ctx, sl, qt, 0, 1, nullptr, nullptr, 0, /*knn_only=*/true, /*force_single_split=*/true))) return rc;
     CU_TRY(ctx, ctx->d_idx.ensure(static_cast<size_t>(nq) * 2 * sizeof(int32_t)));
     CU_TRY(ctx, ctx->d_dist.ensure(static_cast<size_t>(nq) * 2 * sizeof(float)));
     const int threads = 256, blocks = (nq + threads - 1) / threads;
     if (ctx->elem_type == SFMM_F32)
-        knn_decode_kernel<true><<<blocks, threads, 0, ctx->stream>>>(ctx->d_pairs.as<PairDesc>(), ctx->d_knn.as<KnnEntry>(), ctx->d_idx.as<int32_t>(), ctx->d_dist.as<float>());
+        knn_decode_kernel<true><<<blocks, threads, 0, sl.stream>>>(sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), ctx->d_idx.as<int32_t>(), ctx->d_dist.as<float>());
     else
-        knn_decode_kernel<false><<<blocks, threads, 0, ctx->stream>>>(ctx->d_pairs.as<PairDesc>(), ctx->d_knn.as<KnnEntry>(), ctx->d_idx.as<int32_t>(), ctx->d_dist.as<float>());
+        knn_decode_kernel<false><<<blocks, threads, 0, sl.stream>>>(sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), ctx->d_idx.as<int32_t>(), ctx->d_dist.as<float>());
     CU_TRY(ctx, cudaGetLastError());
     ctx->stats.kernel_launches += 1;
-    CU_TRY(ctx, cudaMemcpyAsync(train_idx, ctx->d_idx.p, static_cast<size_t>(nq) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaMemcpyAsync(distance, ctx->d_dist.p, static_cast<size_t>(nq) * 2 * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
-    CU_TRY(ctx, cudaStreamSynchronize(ctx->stream));
+    CU_TRY(ctx, cudaMemcpyAsync(train_idx, ctx->d_idx.p, static_cast<size_t>(nq) * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost, sl.stream));
+    CU_TRY(ctx, cudaMemcpyAsync(distance, ctx->d_dist.p, static_cast<size_t>(nq) * 2 * sizeof(float), cudaMemcpyDeviceToHost, sl.stream));
+    CU_TRY(ctx, cudaStreamSynchronize(sl.stream));
+    sl.busy = false;
     ctx->stats.d2h_bytes += static_cast<int64_t>(nq) * 16;
     return SFMM_OK;
 }

@@ -80,6 +80,25 @@ def broadcast_descriptors(matcher, descriptors, src: int = 0, group=None):
 
 
 # --------------------------------------------------------------------------- gather
+_PINNED: dict = {}
+
+
+def _to_host(t: torch.Tensor) -> np.ndarray:
+    """Device -> host through a cached page-locked buffer (a fresh pinned allocation per call
+    would cost more than the copy)."""
+    if t.device.type != "cuda":
+        return t.numpy()
+    n = t.numel()
+    buf = _PINNED.get(t.dtype)
+    if buf is None or buf.numel() < n:
+        buf = torch.empty(max(n + n // 4, 1 << 16), dtype=t.dtype, pin_memory=True)
+        _PINNED[t.dtype] = buf
+    view = buf[:n].view(t.shape)
+    view.copy_(t, non_blocking=True)
+    torch.cuda.current_stream(t.device).synchronize()
+    return view.numpy()
+
+
 @dataclass
 class PairTable:
     """All-pairs result on the destination rank: pair i owns matches[offsets[i]:offsets[i]+counts[i]]."""
@@ -133,7 +152,7 @@ def gather_results(pairs: np.ndarray, shards: list[np.ndarray], local_counts: to
         c_h = c_r.cpu().numpy()
         counts[shards[r]] = c_h
         offsets[shards[r]] = base[r] + np.concatenate([[0], np.cumsum(c_h[:-1], dtype=np.int64)]) if n_r else []
-    host = all_matches.cpu().numpy().view(DMATCH_DTYPE).reshape(-1)  # the one device->host read
+    host = _to_host(all_matches).view(DMATCH_DTYPE).reshape(-1)  # the one device->host read (view of a reused pinned buffer)
     return PairTable(pairs, counts, offsets, host)
 
 

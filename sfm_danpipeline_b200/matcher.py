@@ -142,8 +142,11 @@ class Matcher:
         self._check(self._L.sfmm_knn_pair(self._ctx, int(idx_query), int(idx_train), idx.ctypes.data, dist.ctypes.data))
         return idx, dist
 
-    def result_table(self):
-        """(pairs[n,2], counts[n], offsets[n], matches[total]) of everything matched so far (copies)."""
+    def result_table(self, copy: bool = True):
+        """(pairs[n,2], counts[n], offsets[n], matches[total]) of everything matched so far.
+
+        copy=False returns read-only views of the library's host table (valid until the next
+        match / set_descriptors / clear_results / close)."""
         n, m = C.c_int64(), C.c_int64()
         qt, cnt, off, mat = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
         self._check(self._L.sfmm_result_table(self._ctx, C.byref(n), C.byref(qt), C.byref(cnt), C.byref(off),
@@ -153,7 +156,11 @@ class Matcher:
             if count == 0:
                 return np.zeros(0, dt)
             buf = (C.c_char * (count * np.dtype(dt).itemsize)).from_address(ptr.value)
-            return np.frombuffer(buf, dt).copy()
+            a = np.frombuffer(buf, dt)
+            if copy:
+                return a.copy()
+            a.flags.writeable = False
+            return a
 
         return (arr(qt, 2 * n.value, np.int32).reshape(-1, 2), arr(cnt, n.value, np.int32),
                 arr(off, n.value, np.int64), arr(mat, m.value, DMATCH_DTYPE))
