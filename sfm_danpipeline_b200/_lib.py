@@ -7,7 +7,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "csrc", "libsfmmatch.so")
+LIB_PATH = os.environ.get("SFMM_LIB_PATH") or os.path.join(HERE, "csrc", "libsfmmatch.so")  # env override: kernel-variant experiments only
 
 SFMM_OK, SFMM_EINVAL, SFMM_ENOMEM, SFMM_ECUDA, SFMM_ESTATE, SFMM_ERANGE, SFMM_ENODEVICE = 0, -1, -2, -3, -4, -5, -6
 NORM_HAMMING, NORM_L2 = 0, 1

@@ -8,7 +8,7 @@
 //
 // Shape of the computation (compute bound, not HBM bound: a 20k x 20k pair reads 2.6 MB and
 // does 6.4e9 32-bit popcounts):
-//   * one thread owns TQ query rows, held in registers for the whole tile (TQ*W words);
+//   * one thread owns TQ query rows (2 for 512-bit rows), held in registers for the whole tile;
 //   * the CTA streams the train rows through shared memory in TT-row stages filled by the
 //     TMA bulk-copy engine (cp.async.bulk + mbarrier, 2 stages) -- train rows are contiguous
 //     in the blob, so a stage is one linear copy;
@@ -160,8 +160,12 @@ struct BinaryKnnSmem {
     uint32_t colmin[2][TT];  // CROSS only: per-stage column minima (distance << 18 | query index)
 };
 
+#ifndef BK_UNROLL
+#define BK_UNROLL 2
+#endif
+static constexpr int BK_UNROLL_N = BK_UNROLL;  // train rows per unrolled step of the inner loop
 template <int W, int TQ, int THREADS, int TT, int CSA_LEVEL, bool CROSS>
-__global__ void __launch_bounds__(THREADS)
+__global__ void __launch_bounds__(THREADS, (W >= 32) ? 4 : 7)  // <= 72 registers: 28 warps/SM
 binary_knn2_kernel(const uint32_t* __restrict__ blob, const KnnTile* __restrict__ tiles,
                    const PairDesc* __restrict__ pairs, KnnEntry* __restrict__ knn,
                    unsigned long long* __restrict__ colmin, const KeyWeights kw) {
@@ -225,7 +229,7 @@ binary_knn2_kernel(const uint32_t* __restrict__ blob, const KnnTile* __restrict_
         const uint32_t rows = min((uint32_t)TT, n_rows - i * TT);
         const uint32_t tbase = tile.t0 + i * TT;
         const uint4* st = reinterpret_cast<const uint4*>(sm.stage[s]);
-#pragma unroll 2
+#pragma unroll BK_UNROLL_N
         for (uint32_t r = 0; r < rows; ++r) {
             uint32_t b[W];
 #pragma unroll

@@ -224,15 +224,25 @@ template <int KB /* K-blocks of 32 floats: 4 for 128-d, 2 for 64-d */>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ norms,
                          const KnnTile* __restrict__ tiles, const PairDesc* __restrict__ pairs,
-                         KnnEntry* __restrict__ knn, const uint32_t key_mul /* = 512 */) {
+                         KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */) {
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                   // KB x 16 KB
     unsigned char* sB = base + (size_t)KB * FT_KBLOCK_BYTES;    // FT_B_STAGES x KB x 16 KB
     FtSmem& sm = *reinterpret_cast<FtSmem*>(base + (size_t)(1 + FT_B_STAGES) * KB * FT_KBLOCK_BYTES);
 
-    const KnnTile tile = tiles[blockIdx.x];
-    const PairDesc pd = pairs[tile.pair];
+    KnnTile tile = tiles[blockIdx.x];
+    PairDesc pd = pairs[tile.pair];
+    // Symmetric cross-check = the same problem with the roles swapped: a "reverse" tile (bit 31 of
+    // split) takes its rows from the train image and streams the query image; its row-wise 1-NN is
+    // the column minimum the filter needs (lowest query index on ties, by the same insertion rule).
+    const bool reverse = (tile.split >> 31) != 0;
+    tile.split &= 0x7FFFFFFFu;
+    if (reverse) {
+        const uint32_t r0 = pd.q_row0, n = pd.nq;
+        pd.q_row0 = pd.t_row0; pd.nq = pd.nt;
+        pd.t_row0 = r0; pd.nt = n;
+    }
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t n_rows = tile.t1 - tile.t0;
     const uint32_t n_tiles = (n_rows + FT_N - 1) / FT_N;
@@ -349,6 +359,7 @@ float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* 
         if (half == 1) sm.merge[row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
         if (half == 0 && qrow < pd.nq) {
+            bool return_early = false;
             const uint4 o = sm.merge[row];
             unsigned long long k1 = best.i1 < 0 ? KEY_NONE : make_key(best.d1, (uint32_t)best.i1);
             unsigned long long k2 = best.i2 < 0 ? KEY_NONE : make_key(best.d2, (uint32_t)best.i2);
@@ -357,10 +368,14 @@ float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* 
             unsigned long long hi = max(k1, o1);
             k1 = min(k1, o1);
             k2 = min(min(k2, hi), o2);
+            if (reverse) {  // column minimum of the forward problem: (d^2, lowest query index); splits merge by atomicMin
+                if (k1 != KEY_NONE) atomicMin(colmin + pd.col_off + qrow, k1);
+                return_early = true;
+            }
             KnnEntry e;  // integer d^2 -> float bits of d
             e.x = k1 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32))), (uint32_t)k1);
             e.y = k2 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k2 >> 32))), (uint32_t)k2);
-            knn[pd.knn_off + (size_t)tile.split * pd.nq + qrow] = e;
+            if (!return_early) knn[pd.knn_off + (size_t)tile.split * pd.nq + qrow] = e;
         }
     }
 

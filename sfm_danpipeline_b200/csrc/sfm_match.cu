@@ -93,7 +93,9 @@ struct PairSlot {  // where a computed pair lives in the host table
 // Binary kernel geometry (see binary_knn.cuh)
 constexpr int BK_THREADS = 128;
 constexpr int BK_TT = 128;
-template <int W> struct BkTq { static constexpr int v = (W >= 32) ? 2 : 4; };
+// query rows per thread: 32 registers of query words whatever the width (measured best: more
+// resident warps beat more reuse of the broadcast train words, profiles/binary_variants_r01.txt)
+template <int W> struct BkTq { static constexpr int v = (W >= 16) ? 2 : 4; };
 
 struct ChunkPlan {
     std::vector<PairDesc> pairs;
@@ -145,7 +147,6 @@ struct SfmmCtx {
     mutable std::string err;
     int csa_level = 2;
     size_t fx_attr_smem = 0;
-    size_t ft_attr_smem = 0;
 
     // float path state (norms + TF32-exactness proof, see float_tensor.cuh)
     bool float_prepared = false;
@@ -222,7 +223,7 @@ inline uint64_t pair_key(int32_t q, int32_t t) { return (static_cast<uint64_t>(s
 
 uint32_t query_tile_rows(const SfmmCtx* ctx) {
     if (ctx->elem_type == SFMM_F32) return ctx->use_tensor ? FT_M : FX_BQ;
-    return BK_THREADS * (binary_words(ctx->cols) >= 32 ? 2 : 4);
+    return BK_THREADS * (binary_words(ctx->cols) >= 16 ? 2 : 4);
 }
 
 // ---------------------------------------------------------------------------- planning
@@ -276,6 +277,16 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
                 kt.split = s;
                 plan.tiles.push_back(kt);
             }
+        if (ctx->use_tensor && ctx->cfg.cross_check) {
+            // tensor path: the cross-check's column minima come from "reverse" tiles (roles swapped,
+            // bit 31 of split), see float_tensor.cuh; rows = train rows, streamed = query rows
+            uint32_t rsplits = std::min<uint32_t>(splits_wanted, std::max<uint32_t>(1, pd.nq / (2 * t_gran)));
+            const uint32_t rper = ((pd.nq + rsplits - 1) / rsplits + t_gran - 1) / t_gran * t_gran;
+            rsplits = (pd.nq + rper - 1) / rper;
+            for (uint32_t r0 = 0; r0 < pd.nt; r0 += q_tile)
+                for (uint32_t s2 = 0; s2 < rsplits; ++s2)
+                    plan.tiles.push_back(KnnTile{static_cast<uint32_t>(i), r0, s2 * rper, std::min(pd.nq, (s2 + 1) * rper), s2 | 0x80000000u});
+        }
         pd.n_ftiles = (pd.nq + FILTER_TILE - 1) / FILTER_TILE;
         for (uint32_t f = 0; f < pd.n_ftiles; ++f) plan.ftiles.push_back(FilterTile{static_cast<uint32_t>(i), f * FILTER_TILE});
         plan.knn_entries += static_cast<uint64_t>(splits) * pd.nq;
@@ -336,13 +347,11 @@ cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
 template <int KB>
 cudaError_t launch_float_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     const size_t smem = float_tensor_smem_bytes(KB);
-    if (smem > ctx->ft_attr_smem) {
-        cudaError_t e = cudaFuncSetAttribute(float_tensor_knn2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        ctx->ft_attr_smem = smem;
-    }
+    cudaError_t e = cudaFuncSetAttribute(float_tensor_knn2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
     float_tensor_knn2_kernel<KB><<<n_tiles, FT_THREADS, smem, sl.stream>>>(
-        ctx->tmap, ctx->d_norms.as<float>(), sl.d_tiles.as<KnnTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), 512u);
+        ctx->tmap, ctx->d_norms.as<float>(), sl.d_tiles.as<KnnTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
+        sl.d_colmin.as<unsigned long long>(), 512u);
     return cudaGetLastError();
 }
 
@@ -364,7 +373,7 @@ int prepare_float(SfmmCtx* ctx) {
     ctx->tensor_eligible = false;
     ctx->use_tensor = false;
     const bool shape_ok = ctx->cols % FT_KB_ELEMS == 0 && ctx->cols <= 4 * FT_KB_ELEMS && ctx->total_rows > 0;
-    if (ctx->cfg.float_mode != SFMM_FLOAT_EXACT && shape_ok && !ctx->cfg.cross_check) {
+    if (ctx->cfg.float_mode != SFMM_FLOAT_EXACT && shape_ok) {
         CU_TRY(ctx, ctx->d_norms.ensure((static_cast<size_t>(ctx->total_rows) + 2 * FT_N) * sizeof(float)));  // + tail for the bulk copies
         CU_TRY(ctx, ctx->d_flags.ensure(2 * sizeof(unsigned int)));
         CU_TRY(ctx, cudaMemsetAsync(ctx->d_flags.p, 0, 2 * sizeof(unsigned int), st));
@@ -401,7 +410,7 @@ int prepare_float(SfmmCtx* ctx) {
     if (ctx->cfg.float_mode == SFMM_FLOAT_TENSOR && !ctx->use_tensor)
         return fail(ctx, SFMM_EINVAL,
                     "SFMM_FLOAT_TENSOR needs TF32-exact descriptors (integer values |v|<=2047, row norm^2 <= 2^20), a width that is a "
-                    "multiple of 32 up to 128 and cross_check off; use SFMM_FLOAT_AUTO or SFMM_FLOAT_EXACT");
+                    "multiple of 32 up to 128; use SFMM_FLOAT_AUTO or SFMM_FLOAT_EXACT");
     ctx->float_prepared = true;
     ctx->stats.float_path = ctx->use_tensor ? SFMM_FLOAT_TENSOR : SFMM_FLOAT_EXACT;
     return SFMM_OK;

@@ -162,3 +162,37 @@ def test_auto_falls_back_to_exact_kernel_for_arbitrary_floats():
         with pytest.raises(SfmmError) as e:
             m.match_all_pairs()
         assert e.value.code == -1 and "TF32-exact" in str(e.value)
+
+
+def test_tensor_mode_cross_check_temple_and_ragged():
+    g = GoldenSet("temple_sift")
+    with Matcher(NORM_L2, 0.8, True, float_mode=FLOAT_TENSOR) as m:
+        m.set_descriptors(g.descs)
+        m.match_all_pairs()
+        assert m.stats()["float_path"] == FLOAT_TENSOR
+        for p, (q, t, *_r) in enumerate(g.pairs):
+            got = m.getMatching(q, t)
+            eq, et, ed = g.expected(p, True)
+            assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all(), (q, t)
+            assert (got["distance"] == ed).all()
+    rng = np.random.default_rng(12)
+    base = np.floor(rng.random((700, 128), dtype=np.float32) * 50).astype(np.float32)
+    sets = [base[:300], np.concatenate([base[100:400], base[:40]]), base[650:], base[:1], base[5:135]]
+    with Matcher(NORM_L2, 0.95, True, float_mode=FLOAT_TENSOR) as m:
+        m.set_descriptors(sets)
+        m.match_all_pairs()
+        for (q, t) in synth.all_pairs(len(sets)):
+            exp = oracle.match_pair(sets[q], sets[t], 1, 0.95, True)
+            assert m.getMatching(q, t).tobytes() == exp.tobytes(), (q, t)
+        assert m.match_pair(1, 0).tobytes() == oracle.match_pair(sets[1], sets[0], 1, 0.95, True).tobytes()
+
+
+def test_tensor_mode_cross_check_cfg4_shape_equals_exact_kernel():
+    descs = synth.float_images(3, [8000, 4100, 130], seed=5)
+    with Matcher(NORM_L2, 0.8, True, float_mode=FLOAT_TENSOR) as mt, Matcher(NORM_L2, 0.8, True, float_mode=FLOAT_EXACT) as mx:
+        mt.set_descriptors(descs)
+        mx.set_descriptors(descs)
+        mt.match_all_pairs()
+        mx.match_all_pairs()
+        for a, b in zip(mt.result_table(), mx.result_table()):
+            assert a.tobytes() == b.tobytes()
