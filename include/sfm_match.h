@@ -173,6 +173,28 @@ SFMM_API int sfmm_match_pairs_device(SfmmCtx* ctx, const int32_t* qt, int64_t n_
                                      int32_t* d_counts, SfmDMatch* d_matches,
                                      int64_t match_capacity, int64_t* n_matches);
 
+/* ---- next rows of the path --------------------------------------------------- */
+
+/* Optional: the std::vector<std::vector<cv::Point2d>> imagesPts2D (include/Sfm.h:30, filled by
+ * keypointstoPoints at src/Sfm.cpp:323,350,378): image i has rows[i] points, xy[i] points at
+ * rows[i] x {double x, double y}.  Call after sfmm_set_descriptors and before matching; from then
+ * on sfmm_match_all_pairs / sfmm_match_pairs also gather, on the GPU, the aligned point lists that
+ * AlignedPointsFromMatch (src/Sfm.cpp:694-711) builds on the CPU for every pair. */
+SFMM_API int sfmm_set_points(SfmmCtx* ctx, int32_t n_images, const double* const* xy);
+
+/* alignedL / alignedR of pair (q,t): count x {x,y} doubles each, in match order (left[i] belongs to
+ * matches[i].queryIdx, right[i] to matches[i].trainIdx).  Same lifetime as sfmm_get_pair. */
+SFMM_API int sfmm_get_pair_points(const SfmmCtx* ctx, int32_t q, int32_t t, const double** left_xy,
+                                  const double** right_xy, int32_t* count);
+
+/* Persisted all-pairs match table (the reference has no checkpointing): a flat
+ * little-endian file -- 64-byte header, rows[n_images], qt[2*n_pairs], counts[n_pairs],
+ * offsets[n_pairs], SfmDMatch[n_matches] -- so that later runs / downstream stages skip matching.
+ * sfmm_load_table needs the same image count and row counts as the current descriptor set and
+ * replaces the table; afterwards sfmm_get_pair serves the stored lists. */
+SFMM_API int sfmm_save_table(const SfmmCtx* ctx, const char* path);
+SFMM_API int sfmm_load_table(SfmmCtx* ctx, const char* path);
+
 SFMM_API int sfmm_clear_results(SfmmCtx* ctx);
 SFMM_API int sfmm_get_stats(const SfmmCtx* ctx, SfmmStats* out);
 /* "major.minor.patch (sm_100a)" */

@@ -51,6 +51,12 @@ class AllPairsMatcher {
     // Call once after extractFeature() (src/Sfm.cpp:21): uploads every image's descriptors and
     // runs findBestPair's whole q<t loop (src/Sfm.cpp:511-515) on the GPU.
     void compute(const std::vector<cv::Mat>& imagesDescriptors) {
+        upload(imagesDescriptors);
+        check(sfmm_match_all_pairs(ctx_));
+    }
+
+  private:
+    void upload(const std::vector<cv::Mat>& imagesDescriptors) {
         const int n = static_cast<int>(imagesDescriptors.size());
         std::vector<const void*> data(n);
         std::vector<int32_t> rows(n);
@@ -68,8 +74,9 @@ class AllPairsMatcher {
             data[i] = m.data; rows[i] = m.rows; steps[i] = m.step;
         }
         check(sfmm_set_descriptors(ctx_, n, data.data(), rows.data(), cols, steps.data(), type));
-        check(sfmm_match_all_pairs(ctx_));
     }
+
+  public:
 
     // Drop-in body of StructFromMotion::getMatching: APPENDS to *goodMatches like the
     // reference's push_back loop (src/Sfm.cpp:603-607); no clear().
@@ -88,6 +95,42 @@ class AllPairsMatcher {
         }
         check(rc);
         append(m, n, goodMatches);
+    }
+
+    // ---- next rows --------------------------------------------------------------
+    // imagesPts2D (include/Sfm.h:30): after this, compute() also gathers on the GPU what
+    // AlignedPointsFromMatch (src/Sfm.cpp:694-711) builds per pair on the CPU.  Call between the
+    // descriptor upload and the matching: compute(desc, &imagesPts2D) does both in order.
+    void compute(const std::vector<cv::Mat>& imagesDescriptors, const std::vector<std::vector<cv::Point2d> >& imagesPts2D) {
+        upload(imagesDescriptors);
+        static_assert(sizeof(cv::Point2d) == 2 * sizeof(double), "cv::Point2d is two doubles");
+        std::vector<const double*> xy(imagesPts2D.size());
+        for (size_t i = 0; i < imagesPts2D.size(); ++i)
+            xy[i] = imagesPts2D[i].empty() ? nullptr : reinterpret_cast<const double*>(imagesPts2D[i].data());
+        check(sfmm_set_points(ctx_, static_cast<int32_t>(xy.size()), xy.data()));
+        check(sfmm_match_all_pairs(ctx_));
+    }
+
+    // Drop-in for AlignedPointsFromMatch(imagesPts2D[q], imagesPts2D[t], matches, alignedL, alignedR):
+    // appends, like the reference's push_back loop.
+    void getAlignedPoints(int idx_query, int idx_train, std::vector<cv::Point2d>& alignedL, std::vector<cv::Point2d>& alignedR) {
+        const double *l = nullptr, *r = nullptr;
+        int32_t n = 0;
+        check(sfmm_get_pair_points(ctx_, idx_query, idx_train, &l, &r, &n));
+        const size_t ol = alignedL.size(), orr = alignedR.size();
+        alignedL.resize(ol + n);
+        alignedR.resize(orr + n);
+        if (n > 0) {
+            std::memcpy(static_cast<void*>(alignedL.data() + ol), l, static_cast<size_t>(n) * 2 * sizeof(double));
+            std::memcpy(static_cast<void*>(alignedR.data() + orr), r, static_cast<size_t>(n) * 2 * sizeof(double));
+        }
+    }
+
+    // Persisted match table: later runs skip matching (the reference has no checkpointing).
+    void saveTable(const std::string& path) { check(sfmm_save_table(ctx_, path.c_str())); }
+    void loadTable(const std::vector<cv::Mat>& imagesDescriptors, const std::string& path) {
+        upload(imagesDescriptors);
+        check(sfmm_load_table(ctx_, path.c_str()));
     }
 
     SfmmCtx* handle() { return ctx_; }

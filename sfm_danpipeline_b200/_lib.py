@@ -23,6 +23,7 @@ EXPORTS = (
     "sfmm_set_descriptors", "sfmm_descriptor_blob", "sfmm_row_pitch", "sfmm_match_all_pairs",
     "sfmm_match_pairs", "sfmm_get_pair", "sfmm_match_pair", "sfmm_knn_pair", "sfmm_result_table",
     "sfmm_match_pairs_device", "sfmm_clear_results", "sfmm_get_stats",
+    "sfmm_set_points", "sfmm_get_pair_points", "sfmm_save_table", "sfmm_load_table",
 )
 
 
@@ -80,6 +81,10 @@ def load() -> C.CDLL:
     L.sfmm_result_table.argtypes = [vp, P(i64), P(vp), P(vp), P(vp), P(vp), P(i64)]
     L.sfmm_match_pairs_device.argtypes = [vp, vp, i64, vp, vp, i64, P(i64)]
     L.sfmm_clear_results.argtypes = [vp]
+    L.sfmm_set_points.argtypes = [vp, i32, P(vp)]
+    L.sfmm_get_pair_points.argtypes = [vp, i32, i32, P(vp), P(vp), P(i32)]
+    L.sfmm_save_table.argtypes = [vp, C.c_char_p]
+    L.sfmm_load_table.argtypes = [vp, C.c_char_p]
     L.sfmm_get_stats.argtypes = [vp, P(SfmmStats)]
     for name in EXPORTS:
         fn = getattr(L, name)

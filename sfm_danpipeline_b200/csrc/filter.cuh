@@ -127,7 +127,8 @@ filter_write_kernel(const FilterTile* __restrict__ ftiles, const PairDesc* __res
                     const KnnEntry* __restrict__ knn, const unsigned long long* __restrict__ colmin, float ratio,
                     const unsigned long long* __restrict__ tile_off, SfmDMatch* __restrict__ out,
                     unsigned long long out_capacity, int32_t* __restrict__ pair_count,
-                    unsigned long long* __restrict__ pair_off) {
+                    unsigned long long* __restrict__ pair_off, const double2* __restrict__ points,
+                    double2* __restrict__ out_left, double2* __restrict__ out_right) {
     const FilterTile ft = ftiles[blockIdx.x];
     const PairDesc pd = pairs[ft.pair];
     SfmDMatch m[FILTER_PER_THREAD];
@@ -155,7 +156,15 @@ filter_write_kernel(const FilterTile* __restrict__ ftiles, const PairDesc* __res
 #pragma unroll
     for (int k = 0; k < FILTER_PER_THREAD; ++k)
         if (keep[k]) {
-            if (pos < out_capacity) out[pos] = m[k];
+            if (pos < out_capacity) {
+                out[pos] = m[k];
+                if (points) {
+                    // AlignedPointsFromMatch (/root/reference/src/Sfm.cpp:694-711) fused into the compaction:
+                    // alignedL[i] = imagesPts2D[q][queryIdx], alignedR[i] = imagesPts2D[t][trainIdx]
+                    out_left[pos] = points[pd.q_row0 + m[k].queryIdx];
+                    out_right[pos] = points[pd.t_row0 + m[k].trainIdx];
+                }
+            }
             ++pos;
         }
     // the first tile of a pair publishes the pair's segment

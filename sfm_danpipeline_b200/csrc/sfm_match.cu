@@ -116,17 +116,19 @@ struct ChunkPlan {
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_knn0 = nullptr, ev_knn1 = nullptr, ev_done = nullptr;
-    DevBuf d_pairs, d_tiles, d_ftiles, d_knn, d_colmin, d_tile_count, d_tile_off, d_pair_count, d_pair_off, d_matches;
+    DevBuf d_pairs, d_tiles, d_ftiles, d_knn, d_colmin, d_tile_count, d_tile_off, d_pair_count, d_pair_off, d_matches, d_left, d_right;
     PinBuf meta;     // [total u64][pair_off u64 x n][pair_count i32 x n]
     PinBuf records;  // SfmDMatch staging
+    PinBuf points;   // aligned-point staging (left then right)
     ChunkPlan plan;
     int64_t first = 0, n = 0;  // pair range [first, first+n) of the caller's list
     bool busy = false;
     void release() {
-        for (DevBuf* b : {&d_pairs, &d_tiles, &d_ftiles, &d_knn, &d_colmin, &d_tile_count, &d_tile_off, &d_pair_count, &d_pair_off, &d_matches})
+        for (DevBuf* b : {&d_pairs, &d_tiles, &d_ftiles, &d_knn, &d_colmin, &d_tile_count, &d_tile_off, &d_pair_count, &d_pair_off, &d_matches, &d_left, &d_right})
             b->release();
         meta.release();
         records.release();
+        points.release();
         if (ev_knn0) cudaEventDestroy(ev_knn0);
         if (ev_knn1) cudaEventDestroy(ev_knn1);
         if (ev_done) cudaEventDestroy(ev_done);
@@ -168,6 +170,8 @@ struct SfmmCtx {
     PinBuf pack[2];  // double-buffered re-pitch staging for set_descriptors
 
     DevBuf d_idx, d_dist;  // sfmm_knn_pair
+    DevBuf d_points;       // imagesPts2D (double2 per blob row), optional
+    bool have_points = false;
 
     // result table
     std::vector<int32_t> res_qt;
@@ -175,6 +179,7 @@ struct SfmmCtx {
     std::vector<int64_t> res_offsets;  // offsets into the consolidated view
     std::vector<PairSlot> res_slots;
     std::vector<SfmDMatch> table;  // every record, in the order the pairs were given
+    std::vector<double2> pts_left, pts_right;  // aligned points of every record (when points are set)
     std::unordered_map<uint64_t, int64_t> index;
     int64_t n_matches = 0;
     int64_t call_pairs = 0;  // pairs of the sfmm_match_pairs call in progress
@@ -215,6 +220,8 @@ void clear_results(SfmmCtx* ctx) {
     ctx->res_offsets.clear();
     ctx->res_slots.clear();
     ctx->table.clear();
+    ctx->pts_left.clear();
+    ctx->pts_right.clear();
     ctx->index.clear();
     ctx->n_matches = 0;
 }
@@ -417,7 +424,7 @@ int prepare_float(SfmmCtx* ctx) {
 }
 
 template <bool IS_FLOAT, bool CROSS>
-cudaError_t launch_filter(SfmmCtx* ctx, Slot& sl, int32_t* d_counts, SfmDMatch* d_matches, uint64_t capacity) {
+cudaError_t launch_filter(SfmmCtx* ctx, Slot& sl, int32_t* d_counts, SfmDMatch* d_matches, uint64_t capacity, bool with_points) {
     const uint32_t nft = static_cast<uint32_t>(sl.plan.ftiles.size());
     const float ratio = ctx->cfg.ratio;
     filter_count_kernel<IS_FLOAT, CROSS><<<nft, FILTER_THREADS, 0, sl.stream>>>(
@@ -426,7 +433,8 @@ cudaError_t launch_filter(SfmmCtx* ctx, Slot& sl, int32_t* d_counts, SfmDMatch* 
     tile_scan_kernel<<<1, SCAN_THREADS, 0, sl.stream>>>(sl.d_tile_count.as<uint32_t>(), sl.d_tile_off.as<unsigned long long>(), nft);
     filter_write_kernel<IS_FLOAT, CROSS><<<nft, FILTER_THREADS, 0, sl.stream>>>(
         sl.d_ftiles.as<FilterTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), ratio,
-        sl.d_tile_off.as<unsigned long long>(), d_matches, capacity, d_counts, sl.d_pair_off.as<unsigned long long>());
+        sl.d_tile_off.as<unsigned long long>(), d_matches, capacity, d_counts, sl.d_pair_off.as<unsigned long long>(),
+        with_points ? ctx->d_points.as<double2>() : nullptr, sl.d_left.as<double2>(), sl.d_right.as<double2>());
     return cudaGetLastError();
 }
 
@@ -486,7 +494,12 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
         d_counts = sl.d_pair_count.as<int32_t>();
         d_matches = sl.d_matches.as<SfmDMatch>();
         capacity = plan.max_matches;
+        if (ctx->have_points) {
+            CU_TRY(ctx, sl.d_left.ensure(std::max<uint64_t>(1, plan.max_matches) * sizeof(double2)));
+            CU_TRY(ctx, sl.d_right.ensure(std::max<uint64_t>(1, plan.max_matches) * sizeof(double2)));
+        }
     }
+    const bool with_points = own && ctx->have_points;
     CU_TRY(ctx, sl.d_pair_off.ensure(std::max<size_t>(1, np) * sizeof(unsigned long long)));
     CU_TRY(ctx, sl.meta.ensure(sizeof(unsigned long long) + np * (sizeof(unsigned long long) + sizeof(int32_t)) + 64));
     if (np) {
@@ -500,10 +513,10 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
         CU_TRY(ctx, sl.d_tile_off.ensure((nft + 1) * sizeof(unsigned long long)));
         const bool is_float = ctx->elem_type == SFMM_F32;
         cudaError_t e;
-        if (is_float) e = cross ? launch_filter<true, true>(ctx, sl, d_counts, d_matches, capacity)
-                                : launch_filter<true, false>(ctx, sl, d_counts, d_matches, capacity);
-        else e = cross ? launch_filter<false, true>(ctx, sl, d_counts, d_matches, capacity)
-                       : launch_filter<false, false>(ctx, sl, d_counts, d_matches, capacity);
+        if (is_float) e = cross ? launch_filter<true, true>(ctx, sl, d_counts, d_matches, capacity, with_points)
+                                : launch_filter<true, false>(ctx, sl, d_counts, d_matches, capacity, with_points);
+        else e = cross ? launch_filter<false, true>(ctx, sl, d_counts, d_matches, capacity, with_points)
+                       : launch_filter<false, false>(ctx, sl, d_counts, d_matches, capacity, with_points);
         CU_TRY(ctx, e);
         ctx->stats.kernel_launches += 3;
         CU_TRY(ctx, cudaMemcpyAsync(h_total, sl.d_tile_off.as<unsigned long long>() + nft, sizeof(unsigned long long),
@@ -571,6 +584,21 @@ int collect_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt) {
             return fail(ctx, SFMM_ENOMEM, "match_pairs: out of host memory for the match table");
         }
         ctx->stats.d2h_bytes += static_cast<int64_t>(total * sizeof(SfmDMatch));
+        if (ctx->have_points) {
+            const size_t pb = static_cast<size_t>(total) * sizeof(double2);
+            CU_TRY(ctx, sl.points.ensure(2 * pb));
+            double2* stage = static_cast<double2*>(sl.points.p);
+            CU_TRY(ctx, cudaMemcpyAsync(stage, sl.d_left.p, pb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CU_TRY(ctx, cudaMemcpyAsync(stage + total, sl.d_right.p, pb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            CU_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
+            try {
+                ctx->pts_left.insert(ctx->pts_left.end(), stage, stage + total);
+                ctx->pts_right.insert(ctx->pts_right.end(), stage + total, stage + 2 * total);
+            } catch (const std::bad_alloc&) {
+                return fail(ctx, SFMM_ENOMEM, "match_pairs: out of host memory for the aligned points");
+            }
+            ctx->stats.d2h_bytes += static_cast<int64_t>(2 * pb);
+        }
     }
     int64_t running = 0;
     for (size_t i = 0; i < np; ++i) {
@@ -724,7 +752,7 @@ SFMM_API void sfmm_destroy(SfmmCtx* ctx) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
-    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags}) b->release();
+    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points}) b->release();
     for (PinBuf& p : ctx->pack) p.release();
     for (cudaEvent_t ev : {ctx->ev_begin, ctx->ev_end, ctx->ev_pack[0], ctx->ev_pack[1]})
         if (ev) cudaEventDestroy(ev);
@@ -769,6 +797,7 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
     ctx->elem_type = -1;
     ctx->float_prepared = false;
     ctx->use_tensor = false;
+    ctx->have_points = false;
     ctx->stats.float_path = 0;
     const size_t bytes = static_cast<size_t>(total) * pitch;
     CU_TRY(ctx, ctx->blob.ensure(std::max<size_t>(bytes, 16)));
@@ -830,6 +859,130 @@ SFMM_API int sfmm_descriptor_blob(SfmmCtx* ctx, void** device_ptr, size_t* bytes
     *device_ptr = ctx->blob.p;
     *bytes = ctx->blob_bytes;
     ctx->float_prepared = false;  // the caller may overwrite the blob (broadcast): re-derive norms/eligibility
+    return SFMM_OK;
+}
+
+SFMM_API int sfmm_set_points(SfmmCtx* ctx, int32_t n_images, const double* const* xy) {
+    int rc = require_descriptors(ctx);
+    if (rc) return rc;
+    if (n_images != ctx->n_images || (n_images > 0 && !xy)) return fail(ctx, SFMM_EINVAL, "set_points: image count differs from the descriptor set");
+    for (int32_t i = 0; i < n_images; ++i)
+        if (ctx->rows[i] > 0 && !xy[i]) return fail(ctx, SFMM_EINVAL, "set_points: NULL point list");
+    if ((rc = bind_device(ctx))) return rc;
+    if ((rc = sync_all(ctx))) return rc;
+    clear_results(ctx);
+    CU_TRY(ctx, ctx->d_points.ensure(std::max<uint64_t>(1, ctx->total_rows) * sizeof(double2)));
+    cudaStream_t st = ctx->slot[0].stream;
+    for (int32_t i = 0; i < n_images; ++i)
+        if (ctx->rows[i] > 0) {
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->d_points.as<double2>() + ctx->row0[i], xy[i], static_cast<size_t>(ctx->rows[i]) * sizeof(double2),
+                                        cudaMemcpyHostToDevice, st));
+            ctx->stats.h2d_bytes += static_cast<int64_t>(ctx->rows[i]) * static_cast<int64_t>(sizeof(double2));
+        }
+    CU_TRY(ctx, cudaStreamSynchronize(st));
+    ctx->have_points = true;
+    return SFMM_OK;
+}
+
+SFMM_API int sfmm_get_pair_points(const SfmmCtx* ctx, int32_t q, int32_t t, const double** left_xy, const double** right_xy, int32_t* count) {
+    int rc = require_descriptors(ctx);
+    if (rc) return rc;
+    if (!left_xy || !right_xy || !count) return fail(ctx, SFMM_EINVAL, "get_pair_points: NULL argument");
+    if (q < 0 || q >= ctx->n_images || t < 0 || t >= ctx->n_images) return fail(ctx, SFMM_ERANGE, "get_pair_points: image index out of range");
+    auto it = ctx->index.find(pair_key(q, t));
+    if (it == ctx->index.end()) return fail(ctx, SFMM_ESTATE, "get_pair_points: pair has not been matched");
+    if (ctx->pts_left.size() != ctx->table.size()) return fail(ctx, SFMM_ESTATE, "get_pair_points: sfmm_set_points was not called before matching");
+    const PairSlot& s = ctx->res_slots[static_cast<size_t>(it->second)];
+    *left_xy = reinterpret_cast<const double*>(ctx->pts_left.data() + s.offset);
+    *right_xy = reinterpret_cast<const double*>(ctx->pts_right.data() + s.offset);
+    *count = s.count;
+    return SFMM_OK;
+}
+
+namespace {
+struct TableHeader {  // 64 bytes, little endian
+    char magic[8];    // "SFMMTBL1"
+    int32_t n_images, norm, cross_check, elem_type;
+    float ratio;
+    int32_t cols;
+    int64_t n_pairs, n_matches;
+    int32_t reserved[4];
+};
+static_assert(sizeof(TableHeader) == 64, "table header is 64 bytes");
+}  // namespace
+
+SFMM_API int sfmm_save_table(const SfmmCtx* ctx, const char* path) {
+    int rc = require_descriptors(ctx);
+    if (rc) return rc;
+    if (!path) return fail(ctx, SFMM_EINVAL, "save_table: NULL path");
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(ctx, SFMM_EINVAL, std::string("save_table: cannot open ") + path);
+    TableHeader h{};
+    std::memcpy(h.magic, "SFMMTBL1", 8);
+    h.n_images = ctx->n_images; h.norm = ctx->cfg.norm; h.cross_check = ctx->cfg.cross_check; h.elem_type = ctx->elem_type;
+    h.ratio = ctx->cfg.ratio; h.cols = ctx->cols;
+    h.n_pairs = static_cast<int64_t>(ctx->res_counts.size()); h.n_matches = ctx->n_matches;
+    bool ok = std::fwrite(&h, sizeof h, 1, f) == 1;
+    auto put = [&](const void* p, size_t bytes) { ok = ok && (bytes == 0 || std::fwrite(p, 1, bytes, f) == bytes); };
+    put(ctx->rows.data(), ctx->rows.size() * sizeof(int32_t));
+    put(ctx->res_qt.data(), ctx->res_qt.size() * sizeof(int32_t));
+    put(ctx->res_counts.data(), ctx->res_counts.size() * sizeof(int32_t));
+    put(ctx->res_offsets.data(), ctx->res_offsets.size() * sizeof(int64_t));
+    put(ctx->table.data(), ctx->table.size() * sizeof(SfmDMatch));
+    ok = (std::fclose(f) == 0) && ok;
+    return ok ? SFMM_OK : fail(ctx, SFMM_EINVAL, std::string("save_table: short write to ") + path);
+}
+
+SFMM_API int sfmm_load_table(SfmmCtx* ctx, const char* path) {
+    int rc = require_descriptors(ctx);
+    if (rc) return rc;
+    if (!path) return fail(ctx, SFMM_EINVAL, "load_table: NULL path");
+    FILE* f = std::fopen(path, "rb");
+    if (!f) return fail(ctx, SFMM_EINVAL, std::string("load_table: cannot open ") + path);
+    TableHeader h{};
+    bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "SFMMTBL1", 8) == 0;
+    if (ok && (h.n_images != ctx->n_images || h.norm != ctx->cfg.norm || h.elem_type != ctx->elem_type || h.cols != ctx->cols ||
+               h.n_pairs < 0 || h.n_matches < 0)) {
+        std::fclose(f);
+        return fail(ctx, SFMM_EINVAL, "load_table: the file belongs to a different descriptor set / norm");
+    }
+    std::vector<int32_t> rows(ok ? h.n_images : 0), qt, counts;
+    std::vector<int64_t> offsets;
+    std::vector<SfmDMatch> table;
+    auto get = [&](void* p, size_t bytes) { ok = ok && (bytes == 0 || std::fread(p, 1, bytes, f) == bytes); };
+    if (ok) {
+        try {
+            qt.resize(2 * static_cast<size_t>(h.n_pairs)); counts.resize(h.n_pairs); offsets.resize(h.n_pairs); table.resize(h.n_matches);
+        } catch (const std::bad_alloc&) {
+            std::fclose(f);
+            return fail(ctx, SFMM_ENOMEM, "load_table: out of host memory");
+        }
+        get(rows.data(), rows.size() * sizeof(int32_t));
+        get(qt.data(), qt.size() * sizeof(int32_t));
+        get(counts.data(), counts.size() * sizeof(int32_t));
+        get(offsets.data(), offsets.size() * sizeof(int64_t));
+        get(table.data(), table.size() * sizeof(SfmDMatch));
+    }
+    std::fclose(f);
+    if (!ok) return fail(ctx, SFMM_EINVAL, std::string("load_table: not a match table or truncated: ") + path);
+    if (rows != ctx->rows) return fail(ctx, SFMM_EINVAL, "load_table: per-image row counts differ from the current descriptor set");
+    for (int64_t i = 0; i < h.n_pairs; ++i) {
+        const int32_t q = qt[2 * i], t = qt[2 * i + 1];
+        if (q < 0 || q >= ctx->n_images || t < 0 || t >= ctx->n_images || counts[i] < 0 || offsets[i] < 0 ||
+            offsets[i] + counts[i] > h.n_matches)
+            return fail(ctx, SFMM_EINVAL, "load_table: corrupt pair directory");
+    }
+    clear_results(ctx);
+    ctx->res_qt = std::move(qt);
+    ctx->res_counts = std::move(counts);
+    ctx->res_offsets = std::move(offsets);
+    ctx->table = std::move(table);
+    ctx->n_matches = h.n_matches;
+    ctx->res_slots.reserve(static_cast<size_t>(h.n_pairs));
+    for (int64_t i = 0; i < h.n_pairs; ++i) {
+        ctx->index[pair_key(ctx->res_qt[2 * i], ctx->res_qt[2 * i + 1])] = i;
+        ctx->res_slots.push_back(PairSlot{ctx->res_offsets[i], ctx->res_counts[i]});
+    }
     return SFMM_OK;
 }
 

@@ -165,6 +165,35 @@ class Matcher:
         return (arr(qt, 2 * n.value, np.int32).reshape(-1, 2), arr(cnt, n.value, np.int32),
                 arr(off, n.value, np.int64), arr(mat, m.value, DMATCH_DTYPE))
 
+    # -- next rows of the path ------------------------------------------
+    def set_points(self, points):
+        """imagesPts2D: one (rows_i, 2) float64 array per image (cv::Point2d).  Call after
+        set_descriptors; matching then also gathers AlignedPointsFromMatch's lists on the GPU."""
+        keep = [np.ascontiguousarray(p, np.float64).reshape(-1, 2) for p in points]
+        if [len(p) for p in keep] != list(self.rows):
+            raise SfmmError(_lib.SFMM_EINVAL, "one point per descriptor row is required")
+        ptrs = (C.c_void_p * max(len(keep), 1))(*[p.ctypes.data if len(p) else None for p in keep])
+        self._check(self._L.sfmm_set_points(self._ctx, len(keep), ptrs))
+
+    def aligned_points(self, idx_query: int, idx_train: int):
+        """(alignedL, alignedR): (count, 2) float64 arrays in match order (src/Sfm.cpp:694-711)."""
+        l, r, n = C.c_void_p(), C.c_void_p(), C.c_int32()
+        self._check(self._L.sfmm_get_pair_points(self._ctx, int(idx_query), int(idx_train), C.byref(l), C.byref(r), C.byref(n)))
+        if n.value == 0:
+            return np.zeros((0, 2)), np.zeros((0, 2))
+
+        def arr(p):
+            buf = (C.c_char * (n.value * 16)).from_address(p.value)
+            return np.frombuffer(buf, np.float64).reshape(-1, 2).copy()
+
+        return arr(l), arr(r)
+
+    def save_table(self, path: str):
+        self._check(self._L.sfmm_save_table(self._ctx, str(path).encode()))
+
+    def load_table(self, path: str):
+        self._check(self._L.sfmm_load_table(self._ctx, str(path).encode()))
+
     def clear_results(self):
         self._check(self._L.sfmm_clear_results(self._ctx))
 

@@ -3,6 +3,7 @@
 // expected lists from a flat binary file written by tests/test_cpp_adapter.py (oracle output).
 // exit 0 = identical, 1 = mismatch, 2 = usage/io, 77 = no GPU.
 #include <cstdio>
+#include <string>
 #include <vector>
 #include "sfm_match_opencv.hpp"
 
@@ -38,6 +39,35 @@ int main(int argc, char** argv) {
                 if (static_cast<int>(good.size()) != cnt + 1 || good[0].queryIdx != -1) { printf("size mismatch %d,%d\n", q, t); return 1; }
                 if (cnt && memcmp(static_cast<const void*>(good.data() + 1), expect.data(), sizeof(cv::DMatch) * cnt)) { printf("content mismatch %d,%d\n", q, t); return 1; }
             }
+        {   // next rows: aligned points gathered on the GPU + persisted table, through the adapter
+            std::vector<std::vector<cv::Point2d> > pts(n);
+            for (int i = 0; i < n; ++i)
+                for (int r = 0; r < rows[i]; ++r) pts[i].push_back(cv::Point2d(i * 1000.0 + r, -0.5 * r));
+            sfmm::AllPairsMatcher m2(hdr[2] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
+            m2.compute(imagesDescriptors, pts);
+            for (int q = 0; q < n - 1; ++q)
+                for (int t = q + 1; t < n; ++t) {
+                    std::vector<cv::DMatch> mm;
+                    std::vector<cv::Point2d> L, R;
+                    m2.getMatching(q, t, &mm);
+                    m2.getAlignedPoints(q, t, L, R);
+                    if (L.size() != mm.size() || R.size() != mm.size()) { printf("aligned size mismatch %d,%d\n", q, t); return 1; }
+                    for (size_t i = 0; i < mm.size(); ++i)  // AlignedPoints, src/Sfm.cpp:700-711
+                        if (L[i].x != pts[q][mm[i].queryIdx].x || L[i].y != pts[q][mm[i].queryIdx].y ||
+                            R[i].x != pts[t][mm[i].trainIdx].x || R[i].y != pts[t][mm[i].trainIdx].y) { printf("aligned mismatch %d,%d\n", q, t); return 1; }
+                }
+            const std::string path = std::string(argv[1]) + ".tbl";
+            m2.saveTable(path);
+            sfmm::AllPairsMatcher m3(hdr[2] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
+            m3.loadTable(imagesDescriptors, path);
+            for (int q = 0; q < n - 1; ++q)
+                for (int t = q + 1; t < n; ++t) {
+                    std::vector<cv::DMatch> a, b;
+                    m2.getMatching(q, t, &a);
+                    m3.getMatching(q, t, &b);
+                    if (a.size() != b.size() || (a.size() && memcmp(static_cast<const void*>(a.data()), b.data(), a.size() * sizeof(cv::DMatch)))) { printf("table mismatch %d,%d\n", q, t); return 1; }
+                }
+        }
         std::vector<cv::DMatch> rev;  // q>t is never asked by the reference; the adapter computes it on demand
         matcher.getMatching(1, 0, &rev);
         printf("adapter ok: %d images, reverse pair gave %zu matches\n", n, rev.size());

@@ -15,6 +15,11 @@ struct DMatch {
     int queryIdx, trainIdx, imgIdx;
     float distance;
 };
+struct Point2d {
+    Point2d() : x(0), y(0) {}
+    Point2d(double x_, double y_) : x(x_), y(y_) {}
+    double x, y;
+};
 struct Mat {  // continuous row-major matrix header over caller memory
     Mat() : rows(0), cols(0), data(nullptr), step(0), depth_(CV_8U) {}
     Mat(int r, int c, int depth, void* d, size_t s = 0)
