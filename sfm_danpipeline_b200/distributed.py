@@ -156,6 +156,39 @@ def gather_results(pairs: np.ndarray, shards: list[np.ndarray], local_counts: to
     return PairTable(pairs, counts, offsets, host)
 
 
+# --------------------------------------------------------------------------- one rank's shard
+_SHARD_BUF: dict = {}
+
+
+def match_shard(matcher, mine: np.ndarray, rows, fraction: float = 0.25):
+    """Step 3: match this rank's pairs, results left in torch-owned device buffers.
+
+    The worst case is one record per query row (16 B each: 20 GB per rank at cfg-5), so the buffer
+    is first sized for `fraction` of that (synthetic and real data keep ~1/8) and the call is
+    repeated with the full size if the library reports SFMM_ERANGE.  Buffers are cached per device.
+    Returns (counts int32[len(mine)], matches int32[n,4], n)."""
+    from ._lib import SFMM_ERANGE, SfmmError
+    dev = torch.device("cuda", matcher.device)
+    worst = int(np.asarray(rows, np.int64)[mine[:, 0]].sum()) if len(mine) else 0
+    cap = min(worst, max(int(worst * fraction), 1 << 20))
+    while True:
+        key = (matcher.device,)
+        buf = _SHARD_BUF.get(key)
+        if buf is None or buf[0].numel() < max(len(mine), 1) or buf[1].shape[0] < max(cap, 1):
+            buf = (torch.empty(max(len(mine), 1), dtype=torch.int32, device=dev),
+                   torch.empty((max(cap, 1), 4), dtype=torch.int32, device=dev))
+            _SHARD_BUF[key] = buf
+        d_counts, d_matches = buf
+        torch.cuda.current_stream(dev).synchronize()
+        try:
+            n = matcher.match_pairs_device(mine, d_counts.data_ptr(), d_matches.data_ptr(), cap)
+            return d_counts[: len(mine)], d_matches[:n], n
+        except SfmmError as e:
+            if e.code != SFMM_ERANGE or cap >= worst:
+                raise
+            cap = worst
+
+
 # --------------------------------------------------------------------------- the whole job
 def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, resident: bool = False):
     """Steps 1-4 on every rank of the default (NCCL) group.  `descriptors` is read on rank `dst`
@@ -168,11 +201,6 @@ def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, 
     pairs = all_pairs(len(rows))
     shards = shard_pairs(pairs, rows, world)
     mine = pairs[shards[rank]]
-    dev = torch.device("cuda", matcher.device)
-    cap = int(np.asarray(rows, np.int64)[mine[:, 0]].sum()) if len(mine) else 0
-    d_counts = torch.empty(max(len(mine), 1), dtype=torch.int32, device=dev)
-    d_matches = torch.empty((max(cap, 1), 4), dtype=torch.int32, device=dev)
-    torch.cuda.current_stream(dev).synchronize()
-    n = matcher.match_pairs_device(mine, d_counts.data_ptr(), d_matches.data_ptr(), cap)
-    table = gather_results(pairs, shards, d_counts[: len(mine)], d_matches[:n], dst, group)
+    d_counts, d_matches, n = match_shard(matcher, mine, rows)
+    table = gather_results(pairs, shards, d_counts, d_matches, dst, group)
     return table, {"pairs_local": len(mine), "matches_local": n}
