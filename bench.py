@@ -201,6 +201,8 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cross-check", action="store_true")
     ap.add_argument("--float-mode", default="auto", choices=["auto", "exact", "tensor"])
+    ap.add_argument("--binary-engine", default="popc", choices=["popc", "tensor"],
+                    help="popc = XOR+CSA+POPC kernel (default, the north-star design); tensor = opt-in tcgen05 kind::i8 engine")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
@@ -240,7 +242,8 @@ def main():
     dev = torch.device("cuda", local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
-    m = Matcher(norm, 0.8, args.cross_check, device=local, float_mode={"auto": 0, "exact": 1, "tensor": 2}[args.float_mode])
+    m = Matcher(norm, 0.8, args.cross_check, device=local, float_mode={"auto": 0, "exact": 1, "tensor": 2}[args.float_mode],
+                binary_engine={"popc": 0, "tensor": 1}[args.binary_engine])
     # ---- resident arm: descriptors in HBM before the timed region -------------------------
     if world > 1:
         D.broadcast_descriptors(m, descs, 0)
@@ -329,7 +332,16 @@ def main():
         sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
         n_sm = torch.cuda.get_device_properties(local).multi_processor_count
         knn_s = knn_ms * 1e-3
-        if norm == 0:
+        if norm == 0 and args.binary_engine == "tensor":
+            i8 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))  # int8 dense = twice the measured bf16 cuBLAS rate
+            macs = knn_work / 16.0 * 512.0  # 512 u8 MACs per 16 algorithmic POPC32 (one 486-bit distance)
+            roof = {"bound": "tensor", "achieved": 2.0 * macs / knn_s / 1e12, "peak": i8, "unit": "TOP/s",
+                    "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (int8 dense is twice bf16); ops = 2*Nq*Nt*512 per pair, "
+                                   "tcgen05 kind::i8 on bits unpacked to bytes",
+                    "popc_equivalent": {"achieved_GPOPC32": knn_work / knn_s / 1e9,
+                                        "x_nominal_popc_roofline": knn_work / knn_s / 1e9 / (n_sm * 16 * sm_max_mhz * 1e6 / 1e9)},
+                    "traffic": None}
+        elif norm == 0:
             peak = n_sm * 16 * sm_max_mhz * 1e6 / 1e9  # GPOPC32/s: 16 POPC/clk/SM x SMs x max SM clock
             roof = {"bound": "popc", "achieved": knn_work / knn_s / 1e9, "peak": peak, "unit": "GPOPC32/s",
                     "peak_source": f"nominal 16 POPC/clk/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
@@ -360,7 +372,8 @@ def main():
             "dtype": "u8" if norm == 0 else "f32", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {n_images} images x {n_desc} x "
                                    f"{'486-bit AKAZE-shape' if kind == 'binary' else ('256-bit ORB-shape' if kind == 'orb' else '128-d f32 SIFT-shape')}"
-                                   f" descriptors, all {len(pairs)} pairs q<t, ratio 0.8, cross_check={bool(args.cross_check)}",
+                                   f" descriptors, all {len(pairs)} pairs q<t, ratio 0.8, cross_check={bool(args.cross_check)}"
+                                   + (", binary_engine=tensor(i8)" if norm == 0 and args.binary_engine == "tensor" else ""),
                        "pairs": int(len(pairs)), "pairs_per_gpu": int(len(mine)), "matches_per_step": total_matches,
                        "l2": "flushed between steps (256 MiB memset outside the timed events)",
                        "parallelism": f"pairs sharded over {world} rank(s); NCCL broadcast + gather only in e2e"},

@@ -77,6 +77,12 @@ enum {
     SFMM_FLOAT_TENSOR = 2  /* tcgen05 TF32 |a|^2+|b|^2-2ab ranking + fp32 refinement of the winners */
 };
 
+/* Which pipe evaluates Hamming distances.  Results are bit-identical. */
+enum {
+    SFMM_BINARY_POPC = 0,   /* default, the north-star design: XOR + carry-save + POPC on the integer pipes */
+    SFMM_BINARY_TENSOR = 1  /* opt-in: bits unpacked to bytes, tcgen05 kind::i8 contraction (descriptors <= 512 bit) */
+};
+
 typedef struct SfmmConfig {
     int32_t struct_size;  /* = sizeof(SfmmConfig); set by sfmm_default_config */
     int32_t device;       /* CUDA device ordinal this context lives on */
@@ -86,7 +92,7 @@ typedef struct SfmmConfig {
                              1 = additionally require q == lowest-index argmin_q' d(q',t) */
     int32_t float_mode;   /* SFMM_FLOAT_* */
     int32_t pair_batch;   /* max image pairs per kernel launch; 0 = automatic */
-    int32_t reserved;
+    int32_t binary_engine; /* SFMM_BINARY_* (Hamming only) */
 } SfmmConfig;
 
 typedef struct SfmmStats {
@@ -98,7 +104,8 @@ typedef struct SfmmStats {
     double last_knn_ms;        /* of which: the 2-NN distance kernel(s) */
     double last_knn_work;      /* algorithmic work of those launches: POPC32 ops (Hamming) or FLOPs (L2) */
     int64_t last_knn_launches; /* number of 2-NN kernel launches behind last_knn_ms */
-    int64_t float_path;        /* L2 only: 0 = not decided yet, SFMM_FLOAT_EXACT or SFMM_FLOAT_TENSOR = the kernel in use */
+    int64_t float_path;        /* L2: 0 = not decided yet, SFMM_FLOAT_EXACT or SFMM_FLOAT_TENSOR = the kernel in use;
+                                  Hamming: SFMM_FLOAT_TENSOR when the SFMM_BINARY_TENSOR engine is active, else 0 */
 } SfmmStats;
 
 typedef struct SfmmCtx SfmmCtx;

@@ -13,6 +13,7 @@ SFMM_OK, SFMM_EINVAL, SFMM_ENOMEM, SFMM_ECUDA, SFMM_ESTATE, SFMM_ERANGE, SFMM_EN
 NORM_HAMMING, NORM_L2 = 0, 1
 U8, F32 = 0, 1
 FLOAT_AUTO, FLOAT_EXACT, FLOAT_TENSOR = 0, 1, 2
+BINARY_POPC, BINARY_TENSOR = 0, 1
 
 #: numpy view of SfmDMatch == cv::DMatch
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])
@@ -30,7 +31,7 @@ EXPORTS = (
 class SfmmConfig(C.Structure):
     _fields_ = [("struct_size", C.c_int32), ("device", C.c_int32), ("norm", C.c_int32), ("ratio", C.c_float),
                 ("cross_check", C.c_int32), ("float_mode", C.c_int32), ("pair_batch", C.c_int32),
-                ("reserved", C.c_int32)]
+                ("binary_engine", C.c_int32)]
 
 
 class SfmmStats(C.Structure):

@@ -23,6 +23,12 @@
 // sqrtf(sum (a-b)^2), and candidates are inserted in ascending train index with a strict '<'
 // -- OpenCV's own insertion rule -- so indices, distances and ties are bit-exact.  Anything else
 // (arbitrary floats) is routed to float_exact.cuh by SFMM_FLOAT_AUTO.
+//
+// INT8 = true instantiates the same pipeline for BINARY descriptors (opt-in engine
+// SFMM_BINARY_TENSOR): bits unpacked to {0,1} bytes, tcgen05.mma kind::i8 (u8 x u8 -> s32, exact),
+// hamming(q,t) = popc(q) + popc(t) - 2 q.t, same key/top-2 epilogue in integer arithmetic.  The
+// default binary engine remains the XOR+POPC kernel of binary_knn.cuh (the north-star design);
+// this one trades 8x the descriptor bytes for the tensor pipe.
 #pragma once
 #include <cuda.h>
 
@@ -58,16 +64,26 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
                  : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate; M=128, N=128, K=8 per instruction.
-__device__ __forceinline__ void tc_mma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                            uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d),
-        "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-        : "memory");
+template <bool INT8>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+    if constexpr (INT8)  // u8 x u8 -> s32, K = 32 per instruction
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else  // tf32 x tf32 -> f32, K = 8 per instruction
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -98,6 +114,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 // Instruction descriptor (cute::UMMA::InstrDescriptor): D=F32 (bits 4-5 = 1), A=B=TF32 (bits 7-9,
 // 10-12 = 2), both K-major, N>>3 in bits [17,23), M>>4 in bits [24,29).
 static constexpr uint32_t FT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((FT_N >> 3) << 17) | ((FT_M >> 4) << 24);
+// kind::i8: D=S32 (bits 4-5 = 2), A=B=UINT8 (format 0), both K-major.
+static constexpr uint32_t FT_IDESC_I8 = (2u << 4) | (0u << 7) | (0u << 10) | ((FT_N >> 3) << 17) | ((FT_M >> 4) << 24);
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;
@@ -129,6 +147,35 @@ __global__ void float_prepare_kernel(const float* __restrict__ blob, int kq, uin
         if (bad) atomicOr(&flags[0], 1u);
         atomicMax(&flags[1], __float_as_uint(acc));
     }
+}
+
+// ------------------------------------------------------------------ prepare (binary tensor engine)
+// Bits -> {0,1} bytes, kbytes per row (a multiple of 128: whole swizzle rows), plus popcount per row.
+// One warp per row; lane l expands the 16 bits [16l, 16l+16) of every 512-bit group.
+__global__ void binary_unpack_kernel(const uint32_t* __restrict__ blob, int words, uint32_t total_rows, int kbytes,
+                                     uint8_t* __restrict__ out, int32_t* __restrict__ norms) {
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t* src = blob + (size_t)row * words;
+    int pc = 0;
+    for (int base = 0; base < kbytes; base += 512) {
+        const int w = base / 32 + lane / 2;  // word holding this lane's 16 bits
+        const uint32_t word = w < words ? src[w] : 0u;
+        const uint32_t half = (word >> (16 * (lane & 1))) & 0xFFFFu;
+        pc += __popc(half);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const uint32_t nib = (half >> (4 * j)) & 0xFu;
+            o[j] = (nib & 1u) | ((nib & 2u) << 7) | ((nib & 4u) << 14) | ((nib & 8u) << 21);
+        }
+        if (base + lane * 16 < kbytes)
+            *reinterpret_cast<uint4*>(out + (size_t)row * kbytes + base + lane * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) pc += __shfl_xor_sync(0xFFFFFFFFu, pc, d);
+    if (lane == 0) norms[row] = pc;
 }
 
 // ------------------------------------------------------------------ the kernel
@@ -197,7 +244,7 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     return v;
 }
 
-template <bool PARTIAL>
+template <bool PARTIAL, bool INT8>
 __device__ __forceinline__ void tile_top2(const uint32_t (&acc)[2][32], uint32_t nb_saddr, float cq, uint32_t key_mul,
                                           uint32_t col0, uint32_t n_rows, uint32_t& m1, uint32_t& m2) {
 #pragma unroll
@@ -209,7 +256,16 @@ __device__ __forceinline__ void tile_top2(const uint32_t (&acc)[2][32], uint32_t
             uint32_t k[4];
 #pragma unroll
             for (int i = 0; i < 4; ++i) {
-                const uint32_t bits = __float_as_uint(fmaf(__uint_as_float(acc[c][e + i]), -2.f, nbv[i] + cq));
+                uint32_t bits;
+                if constexpr (INT8) {
+                    // hamming = (popc(t) + popc(q)) - 2 q.t in s32; the IMADs keep it off the ALU pipe
+                    // (cq carries popc(q) as integer bits, nbv popc(t) as integer bits; key_mul - 514 = -2)
+                    uint32_t nbq;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nbq) : "r"(__float_as_uint(nbv[i])), "r"(key_mul - 511u), "r"(__float_as_uint(cq)));
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(bits) : "r"(acc[c][e + i]), "r"(key_mul - 514u), "r"(nbq));
+                } else {
+                    bits = __float_as_uint(fmaf(__uint_as_float(acc[c][e + i]), -2.f, nbv[i] + cq));
+                }
                 const uint32_t lc = c * 32 + e + i;  // column inside this thread's 64-wide half of the tile
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(bits), "r"(key_mul), "r"(lc));
                 if (PARTIAL) k[i] = col0 + c * 32 + e + i < n_rows ? k[i] : 0xFFFFFFFFu;
@@ -220,9 +276,9 @@ __device__ __forceinline__ void tile_top2(const uint32_t (&acc)[2][32], uint32_t
     }
 }
 
-template <int KB /* K-blocks of 32 floats: 4 for 128-d, 2 for 64-d */>
+template <int KB /* 128-byte K-blocks per row: 4 for 128-d float / 512-bit binary */, bool INT8>
 __global__ void __launch_bounds__(FT_THREADS, 1)
-float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ norms,
+tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ norms /* int32 popcounts when INT8 */,
                          const KnnTile* __restrict__ tiles, const PairDesc* __restrict__ pairs,
                          KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */) {
     extern __shared__ unsigned char ft_smem_raw[];
@@ -278,7 +334,7 @@ float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* 
             mbar_expect_tx(&sm.a_full, KB * FT_KBLOCK_BYTES);
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
-                tma_load_2d(sA + kb * FT_KBLOCK_BYTES, &tmap, kb * FT_KB_ELEMS, (int)(pd.q_row0 + tile.q0), &sm.a_full);
+                tma_load_2d(sA + kb * FT_KBLOCK_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS), (int)(pd.q_row0 + tile.q0), &sm.a_full);
             for (uint32_t j = 0; j < n_tiles; ++j) {
                 const uint32_t s = j % FT_B_STAGES;
                 const uint32_t a = j % FT_ACC_STAGES;
@@ -292,7 +348,7 @@ float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* 
                 unsigned char* dst = sB + (size_t)s * KB * FT_KBLOCK_BYTES;
                 const int row = (int)(pd.t_row0 + tile.t0 + j * FT_N);
 #pragma unroll
-                for (int kb = 0; kb < KB; ++kb) tma_load_2d(dst + kb * FT_KBLOCK_BYTES, &tmap, kb * FT_KB_ELEMS, row, &sm.b_full[s]);
+                for (int kb = 0; kb < KB; ++kb) tma_load_2d(dst + kb * FT_KBLOCK_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS), row, &sm.b_full[s]);
             }
         }
     } else if (warp == 1) {
@@ -312,7 +368,7 @@ float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* 
                     for (int k = 0; k < 4; ++k) {  // 4 x (K=8 tf32 = 32 bytes) inside the 128-byte swizzle row
                         const uint64_t da = umma_desc_sw128(a_addr + kb * FT_KBLOCK_BYTES + k * 32);
                         const uint64_t db = umma_desc_sw128(b_addr + kb * FT_KBLOCK_BYTES + k * 32);
-                        tc_mma_tf32(d_tmem, da, db, FT_IDESC, (kb | k) ? 1u : 0u);
+                        tc_mma<INT8>(d_tmem, da, db, INT8 ? FT_IDESC_I8 : FT_IDESC, (kb | k) ? 1u : 0u);
                     }
                 tc_commit(&sm.b_empty[s]);   // smem stage reusable once these MMAs have read it
                 tc_commit(&sm.acc_full[a]);  // accumulator ready for the epilogue
@@ -325,7 +381,7 @@ float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* 
         const uint32_t row = quarter * 32 + lane;          // row of the query tile == TMEM lane
         const uint32_t qrow = tile.q0 + row;
         const float nq2 = qrow < pd.nq ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
-        const float cq = nq2 + 8388608.f;  // |q|^2 + 2^23 (exact): see Top2
+        const float cq = INT8 ? nq2 /* popc(q), integer bits */ : nq2 + 8388608.f;  // |q|^2 + 2^23 (exact): see Top2
         Top2 best;
         best.init();
         for (uint32_t j = 0; j < n_tiles; ++j) {
@@ -345,8 +401,8 @@ float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* 
             const uint32_t col0 = j * FT_N + half * 64;   // first column of this thread, relative to tile.t0
             const uint32_t nb_saddr = smem_u32(&sm.nb[a][half * 64]);
             uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;   // two smallest keys of this tile
-            if (col0 + 64 <= n_rows) tile_top2<false>(acc, nb_saddr, cq, key_mul, col0, n_rows, m1, m2);
-            else tile_top2<true>(acc, nb_saddr, cq, key_mul, col0, n_rows, m1, m2);  // last tile only (warp-uniform)
+            if (col0 + 64 <= n_rows) tile_top2<false, INT8>(acc, nb_saddr, cq, key_mul, col0, n_rows, m1, m2);
+            else tile_top2<true, INT8>(acc, nb_saddr, cq, key_mul, col0, n_rows, m1, m2);  // last tile only (warp-uniform)
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.nb_empty[a]);
             // merge the tile's two best into the running pair (ascending tiles = arrival order)
@@ -372,9 +428,14 @@ float_tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* 
                 if (k1 != KEY_NONE) atomicMin(colmin + pd.col_off + qrow, k1);
                 return_early = true;
             }
-            KnnEntry e;  // integer d^2 -> float bits of d
-            e.x = k1 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32))), (uint32_t)k1);
-            e.y = k2 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k2 >> 32))), (uint32_t)k2);
+            KnnEntry e;
+            if constexpr (INT8) {  // Hamming distance stays an integer in the key (binary_knn.cuh's convention)
+                e.x = k1;
+                e.y = k2;
+            } else {  // integer d^2 -> float bits of d
+                e.x = k1 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32))), (uint32_t)k1);
+                e.y = k2 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k2 >> 32))), (uint32_t)k2);
+            }
             if (!return_early) knn[pd.knn_off + (size_t)tile.split * pd.nq + qrow] = e;
         }
     }

@@ -153,9 +153,11 @@ struct SfmmCtx {
     // float path state (norms + TF32-exactness proof, see float_tensor.cuh)
     bool float_prepared = false;
     bool tensor_eligible = false;
-    bool use_tensor = false;
+    bool use_tensor = false;   // a tcgen05 kernel is in use (float TF32, or binary through kind::i8)
+    int tensor_kblocks = 0;    // 128-byte K-blocks per operand row
     CUtensorMap tmap{};
     DevBuf d_norms, d_flags;
+    DevBuf d_unpacked;  // SFMM_BINARY_TENSOR: one byte per descriptor bit
 
     // descriptors (imagesDescriptors, include/Sfm.h:29)
     int32_t n_images = 0;
@@ -229,7 +231,8 @@ void clear_results(SfmmCtx* ctx) {
 inline uint64_t pair_key(int32_t q, int32_t t) { return (static_cast<uint64_t>(static_cast<uint32_t>(q)) << 32) | static_cast<uint32_t>(t); }
 
 uint32_t query_tile_rows(const SfmmCtx* ctx) {
-    if (ctx->elem_type == SFMM_F32) return ctx->use_tensor ? FT_M : FX_BQ;
+    if (ctx->use_tensor) return FT_M;
+    if (ctx->elem_type == SFMM_F32) return FX_BQ;
     return BK_THREADS * (binary_words(ctx->cols) >= 16 ? 2 : 4);
 }
 
@@ -239,7 +242,7 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
     plan.clear();
     const bool is_float = ctx->elem_type == SFMM_F32;
     const uint32_t q_tile = query_tile_rows(ctx);
-    const uint32_t t_gran = is_float ? (ctx->use_tensor ? FT_N : FX_BT) : BK_TT;
+    const uint32_t t_gran = ctx->use_tensor ? FT_N : (is_float ? FX_BT : BK_TT);
     plan.pairs.resize(n);
     uint64_t base_tiles = 0;
     for (int64_t i = 0; i < n; ++i) {
@@ -285,7 +288,7 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
                 plan.tiles.push_back(kt);
             }
         if (ctx->use_tensor && ctx->cfg.cross_check) {
-            // tensor path: the cross-check's column minima come from "reverse" tiles (roles swapped,
+            // tensor kernels: the cross-check's column minima come from "reverse" tiles (roles swapped,
             // bit 31 of split), see float_tensor.cuh; rows = train rows, streamed = query rows
             uint32_t rsplits = std::min<uint32_t>(splits_wanted, std::max<uint32_t>(1, pd.nq / (2 * t_gran)));
             const uint32_t rper = ((pd.nq + rsplits - 1) / rsplits + t_gran - 1) / t_gran * t_gran;
@@ -351,30 +354,82 @@ cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     return cudaGetLastError();
 }
 
-template <int KB>
-cudaError_t launch_float_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
+template <int KB, bool INT8>
+cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     const size_t smem = float_tensor_smem_bytes(KB);
-    cudaError_t e = cudaFuncSetAttribute(float_tensor_knn2_kernel<KB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(tensor_knn2_kernel<KB, INT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    float_tensor_knn2_kernel<KB><<<n_tiles, FT_THREADS, smem, sl.stream>>>(
+    tensor_knn2_kernel<KB, INT8><<<n_tiles, FT_THREADS, smem, sl.stream>>>(
         ctx->tmap, ctx->d_norms.as<float>(), sl.d_tiles.as<KnnTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
         sl.d_colmin.as<unsigned long long>(), 512u);
     return cudaGetLastError();
 }
 
-cudaError_t launch_float_tensor(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
-    switch (ctx->cols / FT_KB_ELEMS) {
-        case 1: return launch_float_tensor_t<1>(ctx, sl, n_tiles);
-        case 2: return launch_float_tensor_t<2>(ctx, sl, n_tiles);
-        case 3: return launch_float_tensor_t<3>(ctx, sl, n_tiles);
-        case 4: return launch_float_tensor_t<4>(ctx, sl, n_tiles);
+template <bool INT8>
+cudaError_t launch_tensor(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks) {
+    switch (kblocks) {
+        case 1: return launch_tensor_t<1, INT8>(ctx, sl, n_tiles);
+        case 2: return launch_tensor_t<2, INT8>(ctx, sl, n_tiles);
+        case 3: return launch_tensor_t<3, INT8>(ctx, sl, n_tiles);
+        case 4: return launch_tensor_t<4, INT8>(ctx, sl, n_tiles);
     }
     return cudaErrorInvalidValue;
+}
+
+typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                      const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                      CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+// 2-D tensor map over a row-major matrix of `row_bytes`-byte rows: boxes of 128 bytes x 128 rows, 128-byte swizzle.
+int make_tensor_map(SfmmCtx* ctx, void* base, CUtensorMapDataType dtype, size_t elem_bytes, size_t row_bytes, uint64_t rows) {
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CU_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+    if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, SFMM_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
+    const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(row_bytes / elem_bytes), static_cast<cuuint64_t>(rows)};
+    const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(row_bytes)};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), FT_M};
+    const cuuint32_t estr[2] = {1, 1};
+    const CUresult r = reinterpret_cast<TensorMapEncodeFn>(fn)(&ctx->tmap, dtype, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                                                               CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) return fail(ctx, SFMM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+    return SFMM_OK;
+}
+
+// SFMM_BINARY_TENSOR: unpack the bit rows to bytes once per descriptor set (lazily, like prepare_float).
+int prepare_binary_tensor(SfmmCtx* ctx) {
+    if (ctx->elem_type != SFMM_U8 || ctx->float_prepared) return SFMM_OK;
+    ctx->use_tensor = false;
+    if (ctx->cfg.binary_engine == SFMM_BINARY_TENSOR) {
+        const int words = binary_words(ctx->cols);
+        const int kbytes = (words * 32 + 127) / 128 * 128;
+        if (kbytes > 512) return fail(ctx, SFMM_EINVAL, "SFMM_BINARY_TENSOR supports descriptors of at most 512 bits");
+        if (ctx->total_rows > 0) {
+            cudaStream_t st = ctx->slot[0].stream;
+            CU_TRY(ctx, ctx->d_unpacked.ensure(static_cast<size_t>(ctx->total_rows) * kbytes));
+            CU_TRY(ctx, ctx->d_norms.ensure((static_cast<size_t>(ctx->total_rows) + 2 * FT_N) * sizeof(int32_t)));
+            const uint32_t rows = static_cast<uint32_t>(ctx->total_rows);
+            binary_unpack_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ctx->blob.as<uint32_t>(), words, rows, kbytes, ctx->d_unpacked.as<uint8_t>(),
+                                                                 ctx->d_norms.as<int32_t>());
+            CU_TRY(ctx, cudaGetLastError());
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            ctx->stats.kernel_launches += 1;
+            int rc = make_tensor_map(ctx, ctx->d_unpacked.p, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, static_cast<size_t>(kbytes), ctx->total_rows);
+            if (rc) return rc;
+            ctx->tensor_kblocks = kbytes / 128;
+            ctx->use_tensor = true;
+        }
+    }
+    ctx->float_prepared = true;
+    ctx->stats.float_path = ctx->use_tensor ? SFMM_FLOAT_TENSOR : 0;
+    return SFMM_OK;
 }
 
 // Float descriptors only, once per descriptor set (lazily, so that a blob filled by an NCCL
 // broadcast is seen): row norms, the TF32-exactness proof and the TMA tensor map; picks the path.
 int prepare_float(SfmmCtx* ctx) {
+    if (ctx->elem_type == SFMM_U8) return prepare_binary_tensor(ctx);
     if (ctx->elem_type != SFMM_F32 || ctx->float_prepared) return SFMM_OK;
     cudaStream_t st = ctx->slot[0].stream;
     ctx->tensor_eligible = false;
@@ -396,21 +451,9 @@ int prepare_float(SfmmCtx* ctx) {
         std::memcpy(&max_norm2, &flags[1], sizeof(float));
         ctx->tensor_eligible = flags[0] == 0 && max_norm2 <= 1048576.f;  // integers, |v|<=2047, |x|^2 <= 2^20
         if (ctx->tensor_eligible) {
-            typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                         const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                         CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-            void* fn = nullptr;
-            cudaDriverEntryPointQueryResult qres;
-            CU_TRY(ctx, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
-            if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, SFMM_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
-            const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(ctx->pitch / 4), static_cast<cuuint64_t>(ctx->total_rows)};
-            const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(ctx->pitch)};
-            const cuuint32_t box[2] = {FT_KB_ELEMS, FT_M};
-            const cuuint32_t estr[2] = {1, 1};
-            const CUresult r = reinterpret_cast<EncodeFn>(fn)(&ctx->tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, ctx->blob.p, gdim, gstride, box, estr,
-                                                              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-            if (r != CUDA_SUCCESS) return fail(ctx, SFMM_ECUDA, "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r));
+            int rc = make_tensor_map(ctx, ctx->blob.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ctx->pitch, ctx->total_rows);
+            if (rc) return rc;
+            ctx->tensor_kblocks = ctx->cols / FT_KB_ELEMS;
             ctx->use_tensor = true;
         }
     }
@@ -476,7 +519,8 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
     if (!plan.tiles.empty()) {
         const uint32_t nt = static_cast<uint32_t>(plan.tiles.size());
         cudaError_t e;
-        if (ctx->elem_type == SFMM_F32) e = ctx->use_tensor ? launch_float_tensor(ctx, sl, nt) : launch_float_exact(ctx, sl, nt);
+        if (ctx->elem_type == SFMM_F32) e = ctx->use_tensor ? launch_tensor<false>(ctx, sl, nt, ctx->tensor_kblocks) : launch_float_exact(ctx, sl, nt);
+        else if (ctx->use_tensor) e = launch_tensor<true>(ctx, sl, nt, ctx->tensor_kblocks);
         else e = cross ? launch_binary<true>(ctx, sl, nt) : launch_binary<false>(ctx, sl, nt);
         CU_TRY(ctx, e);
         ctx->stats.kernel_launches += 1;
@@ -691,6 +735,7 @@ SFMM_API void sfmm_default_config(SfmmConfig* cfg) {
     cfg->cross_check = 0;      // src/Sfm.cpp:593 (crossCheck=false)
     cfg->float_mode = SFMM_FLOAT_AUTO;
     cfg->pair_batch = 0;
+    cfg->binary_engine = SFMM_BINARY_POPC;
 }
 
 SFMM_API const char* sfmm_last_error(const SfmmCtx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -705,6 +750,8 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     if (!(cfg->ratio >= 0.f)) return fail(nullptr, SFMM_EINVAL, "sfmm_create: ratio must be >= 0");
     if (cfg->float_mode < SFMM_FLOAT_AUTO || cfg->float_mode > SFMM_FLOAT_TENSOR)
         return fail(nullptr, SFMM_EINVAL, "sfmm_create: unknown float_mode");
+    if (cfg->binary_engine != SFMM_BINARY_POPC && cfg->binary_engine != SFMM_BINARY_TENSOR)
+        return fail(nullptr, SFMM_EINVAL, "sfmm_create: unknown binary_engine");
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
     if (e != cudaSuccess || n_dev == 0) {
@@ -752,7 +799,7 @@ SFMM_API void sfmm_destroy(SfmmCtx* ctx) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
-    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points}) b->release();
+    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked}) b->release();
     for (PinBuf& p : ctx->pack) p.release();
     for (cudaEvent_t ev : {ctx->ev_begin, ctx->ev_end, ctx->ev_pack[0], ctx->ev_pack[1]})
         if (ev) cudaEventDestroy(ev);

@@ -28,12 +28,13 @@ class Matcher:
     """
 
     def __init__(self, norm: int = NORM_L2, ratio: float = 0.8, cross_check: bool = False, device: int = 0,
-                 float_mode: int = _lib.FLOAT_AUTO, pair_batch: int = 0):
+                 float_mode: int = _lib.FLOAT_AUTO, pair_batch: int = 0, binary_engine: int = _lib.BINARY_POPC):
         self._L = _lib.load()
         cfg = _lib.SfmmConfig()
         self._L.sfmm_default_config(C.byref(cfg))
         cfg.device, cfg.norm, cfg.ratio = int(device), int(norm), float(ratio)
         cfg.cross_check, cfg.float_mode, cfg.pair_batch = int(bool(cross_check)), int(float_mode), int(pair_batch)
+        cfg.binary_engine = int(binary_engine)
         self._ctx = C.c_void_p()
         rc = self._L.sfmm_create(C.byref(cfg), C.byref(self._ctx))
         if rc != 0:

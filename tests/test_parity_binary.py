@@ -163,3 +163,55 @@ def test_full_size_properties_cfg2():
         assert same.mean() > 0.95
         idx, dist = m.knn_pair(1, 1)
         assert (dist[:, 0] == 0).all()
+
+
+# ----------------------------------------------------------------- opt-in tensor-core engine (tcgen05 kind::i8)
+from sfm_danpipeline_b200 import BINARY_TENSOR  # noqa: E402
+
+
+@pytest.mark.parametrize("name", ["temple_akaze", "temple_orb", "synth_binary"])
+@pytest.mark.parametrize("cross", [False, True])
+def test_tensor_engine_equals_cv2_golden(name, cross):
+    g = GoldenSet(name)
+    with Matcher(NORM_HAMMING, 0.8, cross, binary_engine=BINARY_TENSOR) as m:
+        m.set_descriptors(g.descs)
+        m.match_all_pairs()
+        assert m.stats()["float_path"] == 2  # the tcgen05 kernel really ran
+        for p, (q, t, kd, ki, *_r) in enumerate(g.pairs):
+            got = m.getMatching(q, t)
+            eq, et, ed = g.expected(p, cross)
+            assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all(), (name, q, t)
+            assert (got["distance"] == ed).all() and (got["imgIdx"] == 0).all()
+        for q, t, kd, ki, *_r in g.pairs[::9]:
+            idx, dist = m.knn_pair(q, t)
+            assert (idx == ki).all() and (dist == kd).all()
+
+
+@pytest.mark.parametrize("cols", [16, 32, 61, 64])
+def test_tensor_engine_widths_ties_ragged(cols):
+    rng = np.random.default_rng(cols)
+    descs = [rng.integers(0, 2, (n, cols), dtype=np.uint8) * 255 for n in (700, 513, 1024, 3, 0, 129)]
+    descs[4] = np.zeros((0, cols), np.uint8)
+    for cross in (False, True):
+        with Matcher(NORM_HAMMING, 0.8, cross, binary_engine=BINARY_TENSOR) as m, Matcher(NORM_HAMMING, 0.8, cross) as ref:
+            m.set_descriptors(descs)
+            ref.set_descriptors(descs)
+            m.match_all_pairs()
+            ref.match_all_pairs()
+            for a, b in zip(m.result_table(), ref.result_table()):
+                assert a.tobytes() == b.tobytes()  # both engines: identical tables
+            _expect_equal(m.getMatching(0, 2), oracle.match_pair(descs[0], descs[2], 0, 0.8, cross, threads=4))
+
+
+def test_tensor_engine_cfg2_shape_and_limits():
+    descs = synth.binary_images(4, 5000, seed=0)
+    with Matcher(NORM_HAMMING, binary_engine=BINARY_TENSOR) as m:
+        m.set_descriptors(descs)
+        m.match_all_pairs()
+        for (q, t) in [(0, 1), (2, 3)]:
+            _expect_equal(m.getMatching(q, t), oracle.match_pair(descs[q], descs[t], 0, 0.8, False, threads=8))
+    with Matcher(NORM_HAMMING, binary_engine=BINARY_TENSOR) as m:
+        m.set_descriptors([np.zeros((10, 100), np.uint8)] * 2)  # 800 bit: beyond the engine's 512
+        with pytest.raises(SfmmError) as e:
+            m.match_all_pairs()
+        assert e.value.code == -1
