@@ -7,12 +7,13 @@
 // (tcgen05.mma kind::tf32, operands staged in shared memory by TMA with the 128-byte swizzle,
 // fp32 accumulators in TMEM), the rest is a fused epilogue that never writes the distance matrix:
 //
-//   warp 0      TMA producer : query tile once, then train tiles through a 2-stage smem ring
+//   warp 0      TMA producer : query tile once, then 128-row train tiles through a 2-stage smem ring
 //   warp 1      MMA issuer   : one elected lane, 4*KB tcgen05.mma (M=128,N=128,K=8) per train tile
 //                              into a 4-stage TMEM ring (4 x 128 columns = all 512 columns)
 //   warp 2      TMEM allocator
-//   warps 4-11  epilogue     : tcgen05.ld 32x32b.x32 -> d^2 (one FADD + one FFMA) -> packed integer key
-//                              (one IMAD) -> branch-free top-2 (2.5 VIMNMX per column); see Top2
+//   warps 4-11  epilogue     : two groups of four warps on alternate tiles; tcgen05.ld 32x32b.x32 (register
+//                              double buffer) -> d^2 (one FADD + one FFMA) -> packed integer key (one IMAD)
+//                              -> branch-free top-2 (2.5 VIMNMX per column); see Top2
 //
 // Exactness contract.  This mode is selected only for descriptor sets the prepare kernel proved
 // "TF32-exact": every value an integer with |v| <= 2047 (11 significant bits: exactly
@@ -38,13 +39,16 @@
 namespace sfmm {
 
 static constexpr int FT_M = 128;         // query rows per CTA (UMMA M)
-static constexpr int FT_N = 128;         // train rows per MMA tile (UMMA N)
+static constexpr int FT_N = 128;         // train rows per MMA tile (UMMA N); 64 was measured slower (per-tile costs double)
 static constexpr int FT_KB_ELEMS = 32;   // floats per 128-byte swizzle row
-static constexpr int FT_B_STAGES = 2;
+static constexpr int FT_B_STAGES = 2;    // train tiles in shared memory (2 x 64 KB next to the 64 KB query tile)
 static constexpr int FT_ACC_STAGES = 4;  // 4 x 128 fp32 columns = 512 TMEM columns
 static constexpr int FT_THREADS = 384;   // 4 control warps + 8 epilogue warps
 static constexpr int FT_EPI_WARPS = 8;
-static constexpr uint32_t FT_KBLOCK_BYTES = FT_M * 128;  // one K-block of a 128-row tile: 16 KB
+static constexpr uint32_t FT_KBLOCK_BYTES = FT_M * 128;  // one K-block of the 128-row query tile: 16 KB
+static constexpr uint32_t FT_B_KBLOCK_BYTES = FT_N * 128;  // one K-block of a train tile
+static constexpr int FT_BOX_ROWS = 64;                   // TMA box: 128 bytes x 64 rows (half a K-block)
+static constexpr uint32_t FT_BOX_BYTES = FT_BOX_ROWS * 128;
 
 // ------------------------------------------------------------------ tcgen05 / TMA PTX
 __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
@@ -54,36 +58,83 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
+// Same, delivered to the same shared-memory offsets (data and mbarrier) of every CTA in cta_mask.
+__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// commit that arrives on the barrier at this offset in every CTA of cta_mask
+__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
+                 "h"(cta_mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate; M=128, N=128, K=8 per instruction.
-template <bool INT8>
-__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+// Called by the WHOLE warp with warp-uniform operands; one elected lane issues.  (Issuing from inside
+// an `if (lane == 0)` made ptxas wrap every MMA in a R2UR.BROADCAST / BRA.U.ANY uniformisation loop
+// and recompute the descriptors: ~90 cycles per instruction for 64 cycles of tensor work.)
+template <bool INT8, bool ACCUMULATE>
+__device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
     if constexpr (INT8)  // u8 x u8 -> s32, K = 32 per instruction
         asm volatile(
             "{\n\t"
-            ".reg .pred p;\n\t"
+            ".reg .pred pe, p;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n\t"
             "}" ::"r"(tmem_d),
-            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(ACCUMULATE ? 1 : 0)
             : "memory");
     else  // tf32 x tf32 -> f32, K = 8 per instruction
         asm volatile(
             "{\n\t"
-            ".reg .pred p;\n\t"
+            ".reg .pred pe, p;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t"
             "}" ::"r"(tmem_d),
-            "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(ACCUMULATE ? 1 : 0)
             : "memory");
+}
+__device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+        "}" ::"r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tc_commit_mcast_elect(uint64_t* bar, uint16_t cta_mask) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred pe;\n\t"
+        "elect.sync _|pe, 0xffffffff;\n\t"
+        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "h"(cta_mask)
+        : "memory");
 }
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -97,7 +148,17 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// Waits for this thread's outstanding tcgen05.ld; the registers are listed as in/out operands so that
+// the compiler cannot schedule a use of them above the wait (the loads complete asynchronously).
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]), "+r"(r[17]), "+r"(r[18]),
+                   "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]),
+                   "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 
 // Shared-memory matrix descriptor, K-major operand, 128-byte swizzle (cute::UMMA::SmemDescriptor):
 // start address >> 4 in bits [0,14), LBO bits [16,30) (unused for swizzled K-major), SBO >> 4 in
@@ -190,11 +251,11 @@ struct FtSmem {  // after the 1024-byte aligned operand area
     uint32_t tmem_base;
     uint32_t pad;
     alignas(16) float nb[FT_ACC_STAGES][FT_N];  // |t|^2 of the train tile, bulk-copied next to the operands
-    uint4 merge[FT_M];                          // (d2_1, i1, d2_2, i2) of the upper column half
+    uint4 merge[FT_M];                          // (d2_1, i1, d2_2, i2) of the group that took the odd tiles
 };
 
 static inline size_t float_tensor_smem_bytes(int kblocks) {
-    return 1024 /*alignment slack*/ + (size_t)(1 + FT_B_STAGES) * kblocks * FT_KBLOCK_BYTES + sizeof(FtSmem);
+    return 1024 /*alignment slack*/ + (size_t)kblocks * (FT_KBLOCK_BYTES + FT_B_STAGES * FT_B_KBLOCK_BYTES) + sizeof(FtSmem);
 }
 
 // Top-2 bookkeeping of the epilogue.
@@ -245,38 +306,41 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
 }
 
 template <bool PARTIAL, bool INT8>
-__device__ __forceinline__ void tile_top2(const uint32_t (&acc)[2][32], uint32_t nb_saddr, float cq, uint32_t key_mul,
-                                          uint32_t col0, uint32_t n_rows, uint32_t& m1, uint32_t& m2) {
+__device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[32], uint32_t nb_saddr, float cq, uint32_t key_mul,
+                                           uint32_t lc0 /* first column of the chunk inside the tile */, uint32_t col0 /* same, relative to t0 */,
+                                           uint32_t n_rows, uint32_t& m1, uint32_t& m2) {
 #pragma unroll
-    for (int c = 0; c < 2; ++c) {
+    for (int e = 0; e < 32; e += 4) {
+        const float4 nb = lds128(nb_saddr + e * 4);  // same address in every lane: broadcast
+        const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+        uint32_t k[4];
 #pragma unroll
-        for (int e = 0; e < 32; e += 4) {
-            const float4 nb = lds128(nb_saddr + (c * 32 + e) * 4);  // same address in every lane: broadcast
-            const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
-            uint32_t k[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                uint32_t bits;
-                if constexpr (INT8) {
-                    // hamming = (popc(t) + popc(q)) - 2 q.t in s32; the IMADs keep it off the ALU pipe
-                    // (cq carries popc(q) as integer bits, nbv popc(t) as integer bits; key_mul - 514 = -2)
-                    uint32_t nbq;
-                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nbq) : "r"(__float_as_uint(nbv[i])), "r"(key_mul - 511u), "r"(__float_as_uint(cq)));
-                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(bits) : "r"(acc[c][e + i]), "r"(key_mul - 514u), "r"(nbq));
-                } else {
-                    bits = __float_as_uint(fmaf(__uint_as_float(acc[c][e + i]), -2.f, nbv[i] + cq));
-                }
-                const uint32_t lc = c * 32 + e + i;  // column inside this thread's 64-wide half of the tile
-                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(bits), "r"(key_mul), "r"(lc));
-                if (PARTIAL) k[i] = col0 + c * 32 + e + i < n_rows ? k[i] : 0xFFFFFFFFu;
+        for (int i = 0; i < 4; ++i) {
+            uint32_t bits;
+            if constexpr (INT8) {
+                // hamming = (popc(t) + popc(q)) - 2 q.t in s32; the IMADs keep it off the ALU pipe
+                // (cq carries popc(q) as integer bits, nbv popc(t) as integer bits; key_mul - 514 = -2)
+                uint32_t nbq;
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nbq) : "r"(__float_as_uint(nbv[i])), "r"(key_mul - 511u), "r"(__float_as_uint(cq)));
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(bits) : "r"(acc[e + i]), "r"(key_mul - 514u), "r"(nbq));
+            } else {
+                bits = __float_as_uint(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i] + cq));
             }
-            top2_pair(m1, m2, k[0], k[1]);
-            top2_pair(m1, m2, k[2], k[3]);
+            const uint32_t lc = lc0 + e + i;  // column inside the 128-wide tile
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(bits), "r"(key_mul), "r"(lc));
+            if (PARTIAL) k[i] = col0 + e + i < n_rows ? k[i] : 0xFFFFFFFFu;
         }
+        top2_pair(m1, m2, k[0], k[1]);
+        top2_pair(m1, m2, k[2], k[3]);
     }
 }
 
-template <int KB /* 128-byte K-blocks per row: 4 for 128-d float / 512-bit binary */, bool INT8>
+// CL = 2: thread-block cluster of two CTAs working on neighbouring query tiles of the same pair.
+// Each CTA fetches HALF of every train tile and TMA-multicasts it into both CTAs' shared memory,
+// halving the L2 -> SM operand traffic that bounds the single-CTA version (9 TB/s measured at
+// 51 % tensor-pipe activity, profiles/ncu_float_tensor_r01d.txt).  A stage is recycled only when
+// BOTH CTAs' MMAs have consumed it (tcgen05.commit multicast onto both b_empty barriers).
+template <int KB /* 128-byte K-blocks per row: 4 for 128-d float / 512-bit binary */, bool INT8, int CL>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ norms /* int32 popcounts when INT8 */,
                          const KnnTile* __restrict__ tiles, const PairDesc* __restrict__ pairs,
@@ -284,8 +348,8 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                   // KB x 16 KB
-    unsigned char* sB = base + (size_t)KB * FT_KBLOCK_BYTES;    // FT_B_STAGES x KB x 16 KB
-    FtSmem& sm = *reinterpret_cast<FtSmem*>(base + (size_t)(1 + FT_B_STAGES) * KB * FT_KBLOCK_BYTES);
+    unsigned char* sB = base + (size_t)KB * FT_KBLOCK_BYTES;    // FT_B_STAGES x KB x 8 KB
+    FtSmem& sm = *reinterpret_cast<FtSmem*>(base + (size_t)KB * (FT_KBLOCK_BYTES + FT_B_STAGES * FT_B_KBLOCK_BYTES));
 
     KnnTile tile = tiles[blockIdx.x];
     PairDesc pd = pairs[tile.pair];
@@ -307,13 +371,13 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
         mbar_init(&sm.a_full, 1);
         for (int s = 0; s < FT_B_STAGES; ++s) {
             mbar_init(&sm.b_full[s], 1);
-            mbar_init(&sm.b_empty[s], 1);
+            mbar_init(&sm.b_empty[s], CL);
         }
         for (int s = 0; s < FT_ACC_STAGES; ++s) {
             mbar_init(&sm.acc_full[s], 1);
-            mbar_init(&sm.acc_empty[s], FT_EPI_WARPS);
+            mbar_init(&sm.acc_empty[s], FT_EPI_WARPS / 2);  // the four warps of the group that owns the tile
             mbar_init(&sm.nb_full[s], 1);
-            mbar_init(&sm.nb_empty[s], FT_EPI_WARPS);
+            mbar_init(&sm.nb_empty[s], FT_EPI_WARPS / 2);
         }
         mbar_fence_init();
     }
@@ -324,8 +388,10 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
     }
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
+    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
@@ -334,7 +400,10 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             mbar_expect_tx(&sm.a_full, KB * FT_KBLOCK_BYTES);
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb)
-                tma_load_2d(sA + kb * FT_KBLOCK_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS), (int)(pd.q_row0 + tile.q0), &sm.a_full);
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+                    tma_load_2d(sA + kb * FT_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS),
+                                (int)(pd.q_row0 + tile.q0) + h * FT_BOX_ROWS, &sm.a_full);
             for (uint32_t j = 0; j < n_tiles; ++j) {
                 const uint32_t s = j % FT_B_STAGES;
                 const uint32_t a = j % FT_ACC_STAGES;
@@ -344,65 +413,85 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 // the norms array is padded so that the copy may run past the image's last row
                 tma_load_1d(sm.nb[a], norms + pd.t_row0 + tile.t0 + j * FT_N, FT_N * sizeof(float), &sm.nb_full[a]);
                 mbar_wait(&sm.b_empty[s], ((j / FT_B_STAGES) & 1) ^ 1);
-                mbar_expect_tx(&sm.b_full[s], KB * FT_KBLOCK_BYTES);
-                unsigned char* dst = sB + (size_t)s * KB * FT_KBLOCK_BYTES;
+                mbar_expect_tx(&sm.b_full[s], KB * FT_B_KBLOCK_BYTES);
+                unsigned char* dst = sB + (size_t)s * KB * FT_B_KBLOCK_BYTES;
                 const int row = (int)(pd.t_row0 + tile.t0 + j * FT_N);
-#pragma unroll
-                for (int kb = 0; kb < KB; ++kb) tma_load_2d(dst + kb * FT_KBLOCK_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS), row, &sm.b_full[s]);
-            }
-        }
-    } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            mbar_wait(&sm.a_full, 0);
-            for (uint32_t j = 0; j < n_tiles; ++j) {
-                const uint32_t s = j % FT_B_STAGES, a = j % FT_ACC_STAGES;
-                mbar_wait(&sm.b_full[s], (j / FT_B_STAGES) & 1);
-                mbar_wait(&sm.acc_empty[a], ((j / FT_ACC_STAGES) & 1) ^ 1);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA), b_addr = smem_u32(sB + (size_t)s * KB * FT_KBLOCK_BYTES);
-                const uint32_t d_tmem = tmem_base + a * FT_N;
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {  // 4 x (K=8 tf32 = 32 bytes) inside the 128-byte swizzle row
-                        const uint64_t da = umma_desc_sw128(a_addr + kb * FT_KBLOCK_BYTES + k * 32);
-                        const uint64_t db = umma_desc_sw128(b_addr + kb * FT_KBLOCK_BYTES + k * 32);
-                        tc_mma<INT8>(d_tmem, da, db, INT8 ? FT_IDESC_I8 : FT_IDESC, (kb | k) ? 1u : 0u);
+                    for (int h = 0; h < FT_N / FT_BOX_ROWS; ++h) {
+                        unsigned char* d = dst + kb * FT_B_KBLOCK_BYTES + h * FT_BOX_BYTES;
+                        if constexpr (CL > 1) {  // the 64-row boxes are dealt to the two CTAs; each is delivered to both
+                            if (((kb * (FT_N / FT_BOX_ROWS) + h) & 1) == (int)cta_rank)
+                                tma_load_2d_mcast(d, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS), row + h * FT_BOX_ROWS, &sm.b_full[s], (uint16_t)0x3);
+                        } else {
+                            tma_load_2d(d, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS), row + h * FT_BOX_ROWS, &sm.b_full[s]);
+                        }
                     }
-                tc_commit(&sm.b_empty[s]);   // smem stage reusable once these MMAs have read it
-                tc_commit(&sm.acc_full[a]);  // accumulator ready for the epilogue
             }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp, uniform; one elected lane issues) =====================
+        const uint32_t tb = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
+        const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
+        const uint32_t idesc = INT8 ? FT_IDESC_I8 : FT_IDESC;
+        mbar_wait(&sm.a_full, 0);
+        for (uint32_t j = 0; j < n_tiles; ++j) {
+            const uint32_t s = j % FT_B_STAGES, a = j % FT_ACC_STAGES;
+            mbar_wait(&sm.b_full[s], (j / FT_B_STAGES) & 1);
+            mbar_wait(&sm.acc_empty[a], ((j / FT_ACC_STAGES) & 1) ^ 1);
+            tc_fence_after();
+            const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB + (size_t)s * KB * FT_B_KBLOCK_BYTES));
+            const uint32_t d_tmem = tb + a * FT_N;
+            // the start-address field counts 16-byte units: stepping inside the tile is an integer add
+            tc_mma<INT8, false>(d_tmem, a_desc0, b_desc0, idesc);
+#pragma unroll
+            for (int i = 1; i < 4 * KB; ++i) {  // i = kb*4 + k: 4 x (32 bytes of K) inside each 128-byte swizzle row
+                const int kb = i >> 2, k = i & 3;
+                tc_mma<INT8, true>(d_tmem, a_desc0 + ((kb * FT_KBLOCK_BYTES + k * 32) >> 4), b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
+            }
+            if constexpr (CL > 1) tc_commit_mcast_elect(&sm.b_empty[s], (uint16_t)0x3);  // both CTAs' producers learn that I am done with it
+            else tc_commit_elect(&sm.b_empty[s]);  // smem stage reusable once these MMAs have read it
+            tc_commit_elect(&sm.acc_full[a]);      // accumulator ready for the epilogue
         }
     } else if (warp >= 4) {
         // ===================== epilogue: fused top-2 =====================
+        // Two groups of four warps (one warp per TMEM lane quarter) take alternate train tiles, so that on
+        // every SM sub-partition one warp computes while the other waits for its barrier / TMEM load.
         const uint32_t ew = warp - 4;
-        const uint32_t quarter = ew & 3, half = ew >> 2;   // TMEM lanes 32*quarter.., columns 64*half..
+        const uint32_t quarter = ew & 3, half = ew >> 2;   // TMEM lanes 32*quarter..; group `half` owns tiles j = half, half+2, ...
         const uint32_t row = quarter * 32 + lane;          // row of the query tile == TMEM lane
         const uint32_t qrow = tile.q0 + row;
         const float nq2 = qrow < pd.nq ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
         const float cq = INT8 ? nq2 /* popc(q), integer bits */ : nq2 + 8388608.f;  // |q|^2 + 2^23 (exact): see Top2
         Top2 best;
         best.init();
-        for (uint32_t j = 0; j < n_tiles; ++j) {
+        for (uint32_t j = half; j < n_tiles; j += 2) {
             const uint32_t a = j % FT_ACC_STAGES;
             mbar_wait(&sm.acc_full[a], (j / FT_ACC_STAGES) & 1);
             tc_fence_after();
-            uint32_t acc[2][32];
-            const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + a * FT_N + half * 64;
+            uint32_t acc[2][32];  // register double buffer: chunk c+1 streams in from TMEM while chunk c is folded
+            const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + a * FT_N;
             tc_ld_32x32(taddr, acc[0]);
-            tc_ld_32x32(taddr + 32, acc[1]);
-            tc_wait_ld();
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.acc_empty[a]);  // TMEM stage free: the MMA of tile j+4 may start
             mbar_wait(&sm.nb_full[a], (j / FT_ACC_STAGES) & 1);
-
-            const uint32_t col0 = j * FT_N + half * 64;   // first column of this thread, relative to tile.t0
-            const uint32_t nb_saddr = smem_u32(&sm.nb[a][half * 64]);
+            tc_wait_ld(acc[0]);
+            const uint32_t col0 = j * FT_N;                // first column of the tile, relative to tile.t0
+            const bool partial = col0 + FT_N > n_rows;     // warp-uniform: only the last tile
             uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;   // two smallest keys of this tile
-            if (col0 + 64 <= n_rows) tile_top2<false, INT8>(acc, nb_saddr, cq, key_mul, col0, n_rows, m1, m2);
-            else tile_top2<true, INT8>(acc, nb_saddr, cq, key_mul, col0, n_rows, m1, m2);  // last tile only (warp-uniform)
+            constexpr int NCH = FT_N / 32;  // 32-column chunks per tile
+#pragma unroll
+            for (int c = 0; c < NCH; ++c) {
+                if (c < NCH - 1) tc_ld_32x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
+                const uint32_t nb_saddr = smem_u32(&sm.nb[a][c * 32]);
+                if (!partial) chunk_top2<false, INT8>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
+                else chunk_top2<true, INT8>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
+                if (c < NCH - 1) tc_wait_ld(acc[(c + 1) & 1]);
+                if (c == (NCH > 1 ? NCH - 2 : 0)) {  // the last TMEM read of this tile has landed: the MMA that reuses the stage may start
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
+                }
+            }
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.nb_empty[a]);
             // merge the tile's two best into the running pair (ascending tiles = arrival order)
@@ -410,7 +499,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             if (m1 != 0xFFFFFFFFu) best.offer(m1 >> 9, tbase + (int)(m1 & 511u));
             if (m2 != 0xFFFFFFFFu) best.offer(m2 >> 9, tbase + (int)(m2 & 511u));
         }
-        // merge the two column halves of each row: lexicographic (d^2, index), then d = sqrtf(d^2)
+        // merge the two groups' lists of each row (even / odd tiles): lexicographic (d^2, index), then d = sqrtf(d^2)
         // (an exact integer under the root: bit-identical to OpenCV's sqrtf(sum (a-b)^2))
         if (half == 1) sm.merge[row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
@@ -443,6 +532,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
     __syncwarp();
     tc_fence_before();
     __syncthreads();
+    if constexpr (CL > 1) cluster_sync_all();  // nobody exits while the peer may still multicast to it
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");

@@ -155,6 +155,7 @@ struct SfmmCtx {
     bool tensor_eligible = false;
     bool use_tensor = false;   // a tcgen05 kernel is in use (float TF32, or binary through kind::i8)
     int tensor_kblocks = 0;    // 128-byte K-blocks per operand row
+    int tensor_cluster = 1;    // CTAs per cluster sharing train tiles by TMA multicast (1 or 2); 2 measured no faster: not L2-bound
     CUtensorMap tmap{};
     DevBuf d_norms, d_flags;
     DevBuf d_unpacked;  // SFMM_BINARY_TENSOR: one byte per descriptor bit
@@ -277,25 +278,31 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
         const uint32_t per = ((pd.nt + splits - 1) / splits + t_gran - 1) / t_gran * t_gran;
         splits = (pd.nt + per - 1) / per;
         pd.n_splits = splits;
-        for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile)
-            for (uint32_t s = 0; s < splits; ++s) {
-                KnnTile kt;
-                kt.pair = static_cast<uint32_t>(i);
-                kt.q0 = q0;
-                kt.t0 = s * per;
-                kt.t1 = std::min(pd.nt, (s + 1) * per);
-                kt.split = s;
-                plan.tiles.push_back(kt);
-            }
+        // tensor kernels run as clusters of `cl` CTAs that share train tiles: consecutive tiles of the list
+        // must differ in q0 only; a row count that is not a multiple of cl*128 gets a tile past the image
+        // (it computes on rows nobody reads and writes nothing)
+        const uint32_t cl = ctx->use_tensor ? static_cast<uint32_t>(ctx->tensor_cluster) : 1;
+        for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile * cl)
+            for (uint32_t s = 0; s < splits; ++s)
+                for (uint32_t c = 0; c < cl; ++c) {
+                    KnnTile kt;
+                    kt.pair = static_cast<uint32_t>(i);
+                    kt.q0 = q0 + c * q_tile;
+                    kt.t0 = s * per;
+                    kt.t1 = std::min(pd.nt, (s + 1) * per);
+                    kt.split = s;
+                    plan.tiles.push_back(kt);
+                }
         if (ctx->use_tensor && ctx->cfg.cross_check) {
             // tensor kernels: the cross-check's column minima come from "reverse" tiles (roles swapped,
             // bit 31 of split), see float_tensor.cuh; rows = train rows, streamed = query rows
             uint32_t rsplits = std::min<uint32_t>(splits_wanted, std::max<uint32_t>(1, pd.nq / (2 * t_gran)));
             const uint32_t rper = ((pd.nq + rsplits - 1) / rsplits + t_gran - 1) / t_gran * t_gran;
             rsplits = (pd.nq + rper - 1) / rper;
-            for (uint32_t r0 = 0; r0 < pd.nt; r0 += q_tile)
+            for (uint32_t r0 = 0; r0 < pd.nt; r0 += q_tile * cl)
                 for (uint32_t s2 = 0; s2 < rsplits; ++s2)
-                    plan.tiles.push_back(KnnTile{static_cast<uint32_t>(i), r0, s2 * rper, std::min(pd.nq, (s2 + 1) * rper), s2 | 0x80000000u});
+                    for (uint32_t c = 0; c < cl; ++c)
+                        plan.tiles.push_back(KnnTile{static_cast<uint32_t>(i), r0 + c * q_tile, s2 * rper, std::min(pd.nq, (s2 + 1) * rper), s2 | 0x80000000u});
         }
         pd.n_ftiles = (pd.nq + FILTER_TILE - 1) / FILTER_TILE;
         for (uint32_t f = 0; f < pd.n_ftiles; ++f) plan.ftiles.push_back(FilterTile{static_cast<uint32_t>(i), f * FILTER_TILE});
@@ -354,26 +361,42 @@ cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     return cudaGetLastError();
 }
 
-template <int KB, bool INT8>
+template <int KB, bool INT8, int CL>
 cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     const size_t smem = float_tensor_smem_bytes(KB);
-    cudaError_t e = cudaFuncSetAttribute(tensor_knn2_kernel<KB, INT8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto kern = tensor_knn2_kernel<KB, INT8, CL>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    tensor_knn2_kernel<KB, INT8><<<n_tiles, FT_THREADS, smem, sl.stream>>>(
-        ctx->tmap, ctx->d_norms.as<float>(), sl.d_tiles.as<KnnTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
-        sl.d_colmin.as<unsigned long long>(), 512u);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(n_tiles);
+    cfg.blockDim = dim3(FT_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = sl.stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, ctx->tmap, (const float*)ctx->d_norms.as<float>(), (const KnnTile*)sl.d_tiles.as<KnnTile>(),
+                              (const PairDesc*)sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u);
+}
+
+template <bool INT8, int CL>
+cudaError_t launch_tensor_c(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks) {
+    switch (kblocks) {
+        case 1: return launch_tensor_t<1, INT8, CL>(ctx, sl, n_tiles);
+        case 2: return launch_tensor_t<2, INT8, CL>(ctx, sl, n_tiles);
+        case 3: return launch_tensor_t<3, INT8, CL>(ctx, sl, n_tiles);
+        case 4: return launch_tensor_t<4, INT8, CL>(ctx, sl, n_tiles);
+    }
+    return cudaErrorInvalidValue;
 }
 
 template <bool INT8>
 cudaError_t launch_tensor(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks) {
-    switch (kblocks) {
-        case 1: return launch_tensor_t<1, INT8>(ctx, sl, n_tiles);
-        case 2: return launch_tensor_t<2, INT8>(ctx, sl, n_tiles);
-        case 3: return launch_tensor_t<3, INT8>(ctx, sl, n_tiles);
-        case 4: return launch_tensor_t<4, INT8>(ctx, sl, n_tiles);
-    }
-    return cudaErrorInvalidValue;
+    return ctx->tensor_cluster == 2 ? launch_tensor_c<INT8, 2>(ctx, sl, n_tiles, kblocks) : launch_tensor_c<INT8, 1>(ctx, sl, n_tiles, kblocks);
 }
 
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -388,7 +411,7 @@ int make_tensor_map(SfmmCtx* ctx, void* base, CUtensorMapDataType dtype, size_t 
     if (!fn || qres != cudaDriverEntryPointSuccess) return fail(ctx, SFMM_ECUDA, "cuTensorMapEncodeTiled is not available in this driver");
     const cuuint64_t gdim[2] = {static_cast<cuuint64_t>(row_bytes / elem_bytes), static_cast<cuuint64_t>(rows)};
     const cuuint64_t gstride[1] = {static_cast<cuuint64_t>(row_bytes)};
-    const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), FT_M};
+    const cuuint32_t box[2] = {static_cast<cuuint32_t>(128 / elem_bytes), FT_BOX_ROWS};
     const cuuint32_t estr[2] = {1, 1};
     const CUresult r = reinterpret_cast<TensorMapEncodeFn>(fn)(&ctx->tmap, dtype, 2, base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                                                                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -494,7 +517,9 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
         PairDesc& pd = plan.pairs[0];  // nt == 1: planned as "no matches"; the raw list still has one neighbour
         pd.n_splits = 1;
         const uint32_t q_tile = query_tile_rows(ctx);
-        for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile) plan.tiles.push_back(KnnTile{0, q0, 0, pd.nt, 0});
+        const uint32_t cl = ctx->use_tensor ? static_cast<uint32_t>(ctx->tensor_cluster) : 1;
+        for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile * cl)
+            for (uint32_t c = 0; c < cl; ++c) plan.tiles.push_back(KnnTile{0, q0 + c * q_tile, 0, pd.nt, 0});
         plan.knn_entries = pd.nq;
         plan.col_entries = pd.nt;
     }
@@ -771,6 +796,7 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     ctx->cfg = *cfg;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* s = std::getenv("SFMM_CSA_LEVEL")) ctx->csa_level = std::max(0, std::min(3, std::atoi(s)));
+    if (const char* s = std::getenv("SFMM_TENSOR_CLUSTER")) ctx->tensor_cluster = std::atoi(s) == 2 ? 2 : 1;
     bool ok = (e = cudaSetDevice(cfg->device)) == cudaSuccess;
     for (Slot& sl : ctx->slot) {
         ok = ok && (e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) == cudaSuccess;
