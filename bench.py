@@ -60,6 +60,13 @@ def images_for(n1: int, gpus: int, weak: bool) -> int:
 
 def make_descriptors(kind: str, n_images: int, n_desc: int, seed: int = 0):
     from sfm_danpipeline_b200 import synth
+    if kind in ("binary", "orb") and n_images * n_desc >= 4_000_000:
+        # large sets (cfg3, cfg5): same generator, same seeds, images dealt to worker processes
+        import multiprocessing as mp
+        from concurrent.futures import ProcessPoolExecutor
+        bits = synth.AKAZE_BITS if kind == "binary" else synth.ORB_BITS
+        with ProcessPoolExecutor(min(32, os.cpu_count() or 1), mp_context=mp.get_context("spawn")) as ex:
+            return list(ex.map(synth.binary_image_task, [(i, n_desc, bits, seed) for i in range(n_images)], chunksize=4)), 0
     if kind == "binary":
         return synth.binary_images(n_images, n_desc, synth.AKAZE_BITS, seed), 0
     if kind == "orb":
@@ -188,6 +195,49 @@ def run_reference_arm(args, kind, n_images, n_desc):
     print(json.dumps(line), flush=True)
 
 
+def verify_pairs(table, descs, norm, n, cross, world):
+    """Bit-exactness spot check of the end-to-end table at full size: n random pairs vs the CPU oracle."""
+    import oracle
+    rng = np.random.default_rng(123)
+    if world > 1:
+        pairs, get = table.pairs, table.getMatching
+    else:
+        pairs = table[0]
+        pos = {(int(q), int(t)): i for i, (q, t) in enumerate(pairs)}
+        get = lambda q, t: table[3][table[2][pos[(q, t)]]: table[2][pos[(q, t)]] + table[1][pos[(q, t)]]]  # noqa: E731
+    ok = 0
+    for k in rng.choice(len(pairs), min(n, len(pairs)), replace=False):
+        q, t = int(pairs[k][0]), int(pairs[k][1])
+        exp = oracle.match_pair_cv2(descs[q], descs[t], norm, 0.8, cross) if oracle.have_cv2() else \
+            oracle.match_pair(descs[q], descs[t], norm, 0.8, cross, threads=os.cpu_count() or 1)
+        got = np.asarray(get(q, t))
+        if norm == 0 or True:
+            assert got.tobytes() == exp.tobytes(), f"pair ({q},{t}) differs from the oracle"
+        ok += 1
+    return {"pairs_checked": ok, "against": "cv2 BFMatcher path" if oracle.have_cv2() else "C oracle", "result": "bit-identical"}
+
+
+def alt_engine_line(args, local, world, rank, descs, mine, rows, n_pairs, flush, D):
+    """Resident throughput of the SFMM_BINARY_TENSOR engine on the same shard (rank 0's shard at N>1)."""
+    import torch
+    from sfm_danpipeline_b200 import BINARY_TENSOR, Matcher
+    m2 = Matcher(0, 0.8, False, device=local, binary_engine=BINARY_TENSOR)
+    try:
+        m2.set_descriptors(descs)
+        ms = []
+        for it in range(2 + 3):
+            flush.zero_()
+            torch.cuda.synchronize()
+            _c, _m, n = D.match_shard(m2, mine, rows)
+            if it >= 2:
+                ms.append(m2.stats()["last_match_ms"])
+        per = float(np.mean(ms))
+        return {"binary_engine": "tensor (tcgen05 kind::i8 on unpacked bits)", "pairs_per_s_per_gpu": len(mine) / (per * 1e-3),
+                "ms_per_step": per, "matches_per_step_this_rank": int(n), "note": "opt-in engine, identical match tables; default stays XOR+POPC"}
+    finally:
+        m2.close()
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -207,6 +257,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--e2e-warmup", type=int, default=1)
+    ap.add_argument("--verify", type=int, default=0, help="check this many random pairs of the e2e table against the CPU oracle")
     args = ap.parse_args()
 
     kind, n1, n_desc, weak = WORKLOADS[args.workload]
@@ -384,6 +435,12 @@ def main():
             "roofline": roof,
             "clocks": clk.summary(),
         }
+        if norm == 0 and args.binary_engine == "popc" and m.cols <= 64 and not args.cross_check:
+            # same workload, same run, through the opt-in tensor-core engine (bit-identical tables): reported
+            # beside the north-star POPC kernel, never instead of it
+            line["alt_engine"] = alt_engine_line(args, local, world, rank, descs, mine, rows, len(pairs), flush, D)
+        if args.verify:
+            line["verified"] = verify_pairs(table, descs, norm, args.verify, args.cross_check, world)
         if world == 1 and not args.no_cpu_baseline:
             v, kind_s, cores, how = time_cpu_sample(descs, norm, args.cpu_seconds, 100000)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind_s, "sample": how}

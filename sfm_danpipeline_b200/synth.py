@@ -33,6 +33,19 @@ def binary_image(world: np.ndarray, i: int, n_desc: int, seed: int = 0, flip_p: 
     return np.packbits(rows, axis=1)
 
 
+_WORLD_CACHE: dict = {}
+
+
+def binary_image_task(args) -> np.ndarray:
+    """binary_image for process pools: args = (i, n_desc, bits, seed); the world is built once per worker."""
+    i, n_desc, bits, seed = args
+    key = (n_desc, bits, seed)
+    if key not in _WORLD_CACHE:
+        _WORLD_CACHE.clear()
+        _WORLD_CACHE[key] = binary_world(n_desc, bits, seed)
+    return binary_image(_WORLD_CACHE[key], i, n_desc, seed)
+
+
 def binary_images(n_images: int, n_desc, bits: int = AKAZE_BITS, seed: int = 0, flip_p: float = 0.05):
     """List of `n_images` descriptor sets; `n_desc` is an int or a per-image sequence (ragged)."""
     counts = [int(n_desc)] * n_images if np.isscalar(n_desc) else [int(c) for c in n_desc]
