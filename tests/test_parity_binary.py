@@ -215,3 +215,26 @@ def test_tensor_engine_cfg2_shape_and_limits():
         with pytest.raises(SfmmError) as e:
             m.match_all_pairs()
         assert e.value.code == -1
+
+
+def test_incremental_match_pairs_like_addmoreviews():
+    # addMoreViews / find2D3DMatches (src/Sfm.cpp:964-977, 1020-1042) ask for one new view against the done views:
+    # the table grows call by call and earlier pairs stay addressable
+    descs = synth.binary_images(5, [400, 380, 512, 90, 700], seed=17)
+    with Matcher(NORM_HAMMING) as m:
+        m.set_descriptors(descs)
+        m.match_pairs([(0, 1)])
+        first = m.getMatching(0, 1)
+        m.match_pairs([(0, 2), (1, 2)])
+        m.match_pairs([(2, 4), (0, 4), (1, 4)])
+        assert m.getMatching(0, 1).tobytes() == first.tobytes()
+        for (q, t) in [(0, 1), (0, 2), (1, 2), (2, 4), (0, 4), (1, 4)]:
+            _expect_equal(m.getMatching(q, t), oracle.match_pair(descs[q], descs[t], 0))
+        pairs, counts, offs, mat = m.result_table()
+        assert pairs.tolist() == [[0, 1], [0, 2], [1, 2], [2, 4], [0, 4], [1, 4]]
+        assert int(counts.sum()) == len(mat) and (np.diff(offs) == counts[:-1]).all()
+        with pytest.raises(SfmmError):
+            m.getMatching(3, 4)  # never asked
+        m.clear_results()
+        with pytest.raises(SfmmError):
+            m.getMatching(0, 1)
