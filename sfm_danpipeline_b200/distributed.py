@@ -127,31 +127,42 @@ def gather_results(pairs: np.ndarray, shards: list[np.ndarray], local_counts: to
     dist.all_gather_into_tensor(totals, mine, group=group) if dev.type == "cuda" else \
         dist.all_gather(list(totals.split(1)), mine, group=group)
     totals_h = totals.cpu().numpy()
+    # every ragged segment moves in ONE grouped point-to-point launch (batch_isend_irecv): unbatched
+    # send/recv pairs are serialised as separate collectives by the NCCL process group
     if rank != dst:
+        ops = []
         if len(shards[rank]):
-            dist.send(local_counts, dst, group=group)
+            ops.append(dist.P2POp(dist.isend, local_counts, dst, group))
         if totals_h[rank]:
-            dist.send(local_matches, dst, group=group)
+            ops.append(dist.P2POp(dist.isend, local_matches, dst, group))
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
         return None
     base = np.concatenate([[0], np.cumsum(totals_h)]).astype(np.int64)
     all_matches = torch.empty((int(base[-1]), 4), dtype=torch.int32, device=dev)
     counts = np.zeros(len(pairs), np.int32)
     offsets = np.zeros(len(pairs), np.int64)
+    cbase = np.concatenate([[0], np.cumsum([len(sh) for sh in shards])]).astype(np.int64)
+    all_counts = torch.empty(int(cbase[-1]), dtype=torch.int32, device=dev)
+    ops = []
     for r in range(world):
-        n_r = len(shards[r])
         if r == rank:
-            c_r = local_counts
+            all_counts[cbase[r]: cbase[r + 1]] = local_counts
             if totals_h[r]:
                 all_matches[base[r]: base[r + 1]] = local_matches
         else:
-            c_r = torch.empty(n_r, dtype=torch.int32, device=dev)
-            if n_r:
-                dist.recv(c_r, r, group=group)
+            if len(shards[r]):
+                ops.append(dist.P2POp(dist.irecv, all_counts[cbase[r]: cbase[r + 1]], r, group))
             if totals_h[r]:
-                dist.recv(all_matches[base[r]: base[r + 1]], r, group=group)
-        c_h = c_r.cpu().numpy()
-        counts[shards[r]] = c_h
-        offsets[shards[r]] = base[r] + np.concatenate([[0], np.cumsum(c_h[:-1], dtype=np.int64)]) if n_r else []
+                ops.append(dist.P2POp(dist.irecv, all_matches[base[r]: base[r + 1]], r, group))
+    for w in (dist.batch_isend_irecv(ops) if ops else []):
+        w.wait()
+    counts_h = all_counts.cpu().numpy()
+    for r in range(world):
+        c_h = counts_h[cbase[r]: cbase[r + 1]]
+        if len(c_h):
+            counts[shards[r]] = c_h
+            offsets[shards[r]] = base[r] + np.concatenate([[0], np.cumsum(c_h[:-1], dtype=np.int64)])
     host = _to_host(all_matches).view(DMATCH_DTYPE).reshape(-1)  # the one device->host read (view of a reused pinned buffer)
     return PairTable(pairs, counts, offsets, host)
 
@@ -194,13 +205,25 @@ def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, 
     """Steps 1-4 on every rank of the default (NCCL) group.  `descriptors` is read on rank `dst`
     only; `resident=True` skips step 1 (descriptors already broadcast).  Returns
     (PairTable on dst | None, info dict)."""
+    import os
+    import time
+    trace = os.environ.get("SFMM_TRACE") == "1"
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    t0 = time.perf_counter()
     if not resident:
         broadcast_descriptors(matcher, descriptors, dst, group)
+    t1 = time.perf_counter()
     rows = matcher.rows
     pairs = all_pairs(len(rows))
     shards = shard_pairs(pairs, rows, world)
     mine = pairs[shards[rank]]
+    t2 = time.perf_counter()
     d_counts, d_matches, n = match_shard(matcher, mine, rows)
+    t3 = time.perf_counter()
     table = gather_results(pairs, shards, d_counts, d_matches, dst, group)
-    return table, {"pairs_local": len(mine), "matches_local": n}
+    t4 = time.perf_counter()
+    info = {"pairs_local": len(mine), "matches_local": n,
+            "ms": {"broadcast": 1e3 * (t1 - t0), "shard": 1e3 * (t2 - t1), "match": 1e3 * (t3 - t2), "gather": 1e3 * (t4 - t3)}}
+    if trace and rank == dst:
+        print("[sfmm trace]", info["ms"], flush=True)
+    return table, info
