@@ -9,9 +9,14 @@
 #ifndef SFM_MATCH_OPENCV_HPP_
 #define SFM_MATCH_OPENCV_HPP_
 
+#include <algorithm>
 #include <cstring>
+#include <memory>
+#include <numeric>
 #include <stdexcept>
 #include <string>
+#include <thread>
+#include <utility>
 #include <vector>
 
 #include <opencv2/core.hpp>
@@ -55,7 +60,9 @@ class AllPairsMatcher {
         check(sfmm_match_all_pairs(ctx_));
     }
 
-  private:
+    // Building blocks (also used by MultiGpuMatcher): descriptors to this device; match an explicit
+    // list of ordered pairs (q0,t0,q1,t1,...) -- the unit that is sharded across devices.
+    void matchPairs(const std::vector<int32_t>& qt) { check(sfmm_match_pairs(ctx_, qt.data(), static_cast<int64_t>(qt.size() / 2))); }
     void upload(const std::vector<cv::Mat>& imagesDescriptors) {
         const int n = static_cast<int>(imagesDescriptors.size());
         std::vector<const void*> data(n);
@@ -146,6 +153,85 @@ class AllPairsMatcher {
         if (rc != SFMM_OK) throw Error(rc, sfmm_last_error(ctx_));
     }
     SfmmCtx* ctx_;
+};
+
+// All GPUs of the box from ONE host process -- the shape of the reference (a single C++ program).
+// Every device gets the descriptors (its own H2D over its own PCIe link, in parallel host threads),
+// the q<t pairs are dealt by descending cost rows_q*rows_t in a snake order (the same rule as
+// sfm_danpipeline_b200/distributed.py, so shards are balanced and deterministic), each device
+// matches its shard into its own host table, and getMatching() looks the pair up in the owning
+// context.  No inter-GPU traffic is needed: results are wanted in host memory anyway.  (The
+// multi-PROCESS variant -- NCCL broadcast + gather to rank 0 -- lives in distributed.py.)
+class MultiGpuMatcher {
+  public:
+    explicit MultiGpuMatcher(int nDevices, int normType = cv::NORM_L2, float ratio = 0.8f, bool crossCheck = false) {
+        if (nDevices < 1) throw Error(SFMM_EINVAL, "MultiGpuMatcher: need at least one device");
+        for (int d = 0; d < nDevices; ++d) dev_.emplace_back(new AllPairsMatcher(normType, ratio, crossCheck, d));
+    }
+
+    void compute(const std::vector<cv::Mat>& imagesDescriptors) {
+        const int n = static_cast<int>(imagesDescriptors.size()), nd = static_cast<int>(dev_.size());
+        // findBestPair's enumeration (src/Sfm.cpp:511-512), then the cost-sorted snake deal
+        std::vector<std::pair<int, int> > pairs;
+        for (int q = 0; q + 1 < n; ++q)
+            for (int t = q + 1; t < n; ++t) pairs.push_back(std::make_pair(q, t));
+        std::vector<size_t> order(pairs.size());
+        std::iota(order.begin(), order.end(), size_t(0));
+        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
+            const long long ca = 1LL * imagesDescriptors[pairs[a].first].rows * imagesDescriptors[pairs[a].second].rows;
+            const long long cb = 1LL * imagesDescriptors[pairs[b].first].rows * imagesDescriptors[pairs[b].second].rows;
+            return ca > cb;
+        });
+        owner_.assign(static_cast<size_t>(n) * n, -1);
+        std::vector<std::vector<int32_t> > shard(nd);
+        std::vector<std::vector<size_t> > members(nd);
+        for (size_t pos = 0; pos < order.size(); ++pos) {
+            const size_t lap = pos / nd, off = pos % nd;
+            members[(lap % 2 == 0) ? off : nd - 1 - off].push_back(order[pos]);
+        }
+        for (int d = 0; d < nd; ++d) {
+            std::sort(members[d].begin(), members[d].end());  // ascending pair order inside a device
+            for (size_t k : members[d]) {
+                shard[d].push_back(pairs[k].first);
+                shard[d].push_back(pairs[k].second);
+                owner_[static_cast<size_t>(pairs[k].first) * n + pairs[k].second] = d;
+            }
+        }
+        n_images_ = n;
+        std::vector<std::string> errors(nd);
+        std::vector<int> codes(nd, SFMM_OK);
+        std::vector<std::thread> pool;
+        for (int d = 0; d < nd; ++d)
+            pool.emplace_back([&, d]() {
+                try {
+                    dev_[d]->upload(imagesDescriptors);
+                    dev_[d]->matchPairs(shard[d]);
+                } catch (const Error& e) {
+                    codes[d] = e.code;
+                    errors[d] = e.what();
+                }
+            });
+        for (auto& t : pool) t.join();
+        for (int d = 0; d < nd; ++d)
+            if (codes[d] != SFMM_OK) throw Error(codes[d], "device " + std::to_string(d) + ": " + errors[d]);
+    }
+
+    // Drop-in body of StructFromMotion::getMatching (appends).
+    void getMatching(const int& idx_query, const int& idx_train, std::vector<cv::DMatch>* goodMatches) {
+        int d = 0;
+        if (idx_query >= 0 && idx_train >= 0 && idx_query < n_images_ && idx_train < n_images_) {
+            const int o = owner_[static_cast<size_t>(idx_query) * n_images_ + idx_train];
+            if (o >= 0) d = o;  // pairs outside the table are computed on demand by device 0
+        }
+        dev_[d]->getMatching(idx_query, idx_train, goodMatches);
+    }
+
+    int devices() const { return static_cast<int>(dev_.size()); }
+
+  private:
+    std::vector<std::unique_ptr<AllPairsMatcher> > dev_;
+    std::vector<int> owner_;
+    int n_images_ = 0;
 };
 
 }  // namespace sfmm

@@ -3,6 +3,7 @@
 // expected lists from a flat binary file written by tests/test_cpp_adapter.py (oracle output).
 // exit 0 = identical, 1 = mismatch, 2 = usage/io, 77 = no GPU.
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "sfm_match_opencv.hpp"
@@ -67,6 +68,22 @@ int main(int argc, char** argv) {
                     m3.getMatching(q, t, &b);
                     if (a.size() != b.size() || (a.size() && memcmp(static_cast<const void*>(a.data()), b.data(), a.size() * sizeof(cv::DMatch)))) { printf("table mismatch %d,%d\n", q, t); return 1; }
                 }
+        }
+        {   // single process, several devices (as many as the box has, at most 2 here): same lists
+            int n_dev = 1;
+            if (argc > 2) n_dev = atoi(argv[2]);
+            sfmm::MultiGpuMatcher multi(n_dev, hdr[2] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0);
+            multi.compute(imagesDescriptors);
+            sfmm::AllPairsMatcher single(hdr[2] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
+            single.compute(imagesDescriptors);
+            for (int q = 0; q < n - 1; ++q)
+                for (int t = q + 1; t < n; ++t) {
+                    std::vector<cv::DMatch> a, b;
+                    multi.getMatching(q, t, &a);
+                    single.getMatching(q, t, &b);
+                    if (a.size() != b.size() || (a.size() && memcmp(static_cast<const void*>(a.data()), b.data(), a.size() * sizeof(cv::DMatch)))) { printf("multi-gpu mismatch %d,%d\n", q, t); return 1; }
+                }
+            printf("multi-gpu ok on %d device(s)\n", multi.devices());
         }
         std::vector<cv::DMatch> rev;  // q>t is never asked by the reference; the adapter computes it on demand
         matcher.getMatching(1, 0, &rev);

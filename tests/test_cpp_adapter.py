@@ -18,7 +18,7 @@ def _build():
     lib_dir = os.path.dirname(_lib.LIB_PATH)
     if not os.path.exists(EXE) or os.path.getmtime(EXE) < max(os.path.getmtime(SRC), os.path.getmtime(
             os.path.join(ROOT, "include", "sfm_match_opencv.hpp"))):
-        subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-I", os.path.join(ROOT, "include"),
+        subprocess.check_call(["g++", "-std=c++11", "-O1", "-Wall", "-pthread", "-I", os.path.join(ROOT, "include"),
                                "-I", os.path.join(ROOT, "tests", "cpp", "mock_opencv"), SRC, "-o", EXE,
                                "-L", lib_dir, "-lsfmmatch", "-Wl,-rpath," + lib_dir])
     return EXE
@@ -52,6 +52,8 @@ def test_patched_getmatching_equals_oracle(tmp_path, kind, cross):
         descs, norm = synth.float_images(3, [300, 200, 150], seed=22), 1
     case = str(tmp_path / "case.bin")
     _write_case(case, descs, norm, cross)
-    r = subprocess.run([exe, case], capture_output=True, text=True)
+    import torch
+    n_dev = min(torch.cuda.device_count(), 2)
+    r = subprocess.run([exe, case, str(n_dev)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "adapter ok" in r.stdout
+    assert "adapter ok" in r.stdout and f"multi-gpu ok on {n_dev} device(s)" in r.stdout
