@@ -409,6 +409,12 @@ def main():
             roof = {"bound": "fp32", "achieved": knn_work / knn_s / 1e12, "peak": peak, "unit": "TFLOP/s",
                     "peak_source": f"128 FFMA lanes/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz; algorithmic FLOPs = 2*Nq*Nt*128",
                     "traffic": None}
+        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
+        # `ncu --set full` captures of exactly this workload (profiles/ncu_*_r01*.txt); null when not captured
+        ncu_traffic = {("cfg2", "popc", 1): 18.847e6 + 46.489e6,    # profiles/ncu_binary_r01c_tq2.txt
+                       ("cfg2", "tensor", 1): 2413.4e6 + 88.4e6}    # profiles/ncu_tensor_i8_r01.txt
+        if n_images == WORKLOADS[args.workload][1] and not args.cross_check:
+            roof["traffic"] = ncu_traffic.get((args.workload, args.binary_engine if norm == 0 else "float", world))
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["kernel_ms_per_launch"] = knn_ms / max(knn_launches, 1)
         roof["kernel_share_of_step"] = knn_ms / max(dev_ms, 1e-9)
