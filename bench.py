@@ -45,6 +45,9 @@ WORKLOADS = {
     "orb": ("orb", 100, 2000, True),        # ORB shape: 256 bit
     "float2": ("float", 40, 4000, True),
     "cfg4s": ("float", 60, 8000, True),     # cfg4's pair shape (8k x 8k x 128 f32) on a 60-image subset
+    # configs[0]: the reference's own fixture (data/temple, 10 images, 45 pairs) through the committed cv2 descriptors
+    "temple_sift": ("golden:temple_sift", 10, 850, False),
+    "temple_akaze": ("golden:temple_akaze", 10, 700, False),
 }
 
 
@@ -60,6 +63,12 @@ def images_for(n1: int, gpus: int, weak: bool) -> int:
 
 def make_descriptors(kind: str, n_images: int, n_desc: int, seed: int = 0):
     from sfm_danpipeline_b200 import synth
+    if kind.startswith("golden:"):  # descriptors cv2 extracted from /root/reference/data/temple (tests/golden/make_golden.py)
+        z = np.load(os.path.join(ROOT, "tests", "golden", kind.split(":")[1] + ".npz"))
+        offs = np.concatenate([[0], np.cumsum(z["rows"])])
+        is_f = "sift" in kind
+        d = z["desc"].astype(np.float32 if is_f else np.uint8)
+        return [np.ascontiguousarray(d[offs[i]:offs[i + 1]]) for i in range(len(z["rows"]))], (1 if is_f else 0)
     if kind in ("binary", "orb") and n_images * n_desc >= 4_000_000:
         # large sets (cfg3, cfg5): same generator, same seeds, images dealt to worker processes
         import multiprocessing as mp
@@ -288,7 +297,7 @@ def main():
         torch.cuda.synchronize()
 
     # synthetic descriptors exist on rank 0 only; the other ranks receive them by NCCL broadcast
-    norm = 0 if kind in ("binary", "orb") else 1
+    norm = 0 if kind in ("binary", "orb", "golden:temple_akaze") else 1
     descs = make_descriptors(kind, n_images, n_desc, args.seed)[0] if rank == 0 else None
     dev = torch.device("cuda", local)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
@@ -422,13 +431,14 @@ def main():
         alg_bytes = float(sum((rows[q] + rows[t]) * row_bytes for q, t in mine)) * args.steps + 16.0 * n_matches * args.steps
         roof["hbm"] = {"algorithmic_GBps": alg_bytes / knn_s / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
                        "note": "compute-bound path: HBM is reported, not the binding roof"}
+        desc_shape = ("486-bit AKAZE" if kind in ("binary", "golden:temple_akaze") else ("256-bit ORB" if kind == "orb" else "128-d f32 SIFT")) \
+            + ("-shape" if not kind.startswith("golden:") else " (real, about that many rows per image)")
         line = {
             "metric": "image-pair matches/sec (all-pairs 2-NN + ratio test)", "value": value, "unit": "pairs/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
             "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
-            "dtype": "u8" if norm == 0 else "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {n_images} images x {n_desc} x "
-                                   f"{'486-bit AKAZE-shape' if kind == 'binary' else ('256-bit ORB-shape' if kind == 'orb' else '128-d f32 SIFT-shape')}"
+            "dtype": "u8" if norm == 0 else "f32", "data": "synthetic" if not kind.startswith("golden:") else "cv2 descriptors of the reference's data/temple fixture",
+            "config": {"workload": f"{args.workload}: {n_images} images x {n_desc} x " + desc_shape +
                                    f" descriptors, all {len(pairs)} pairs q<t, ratio 0.8, cross_check={bool(args.cross_check)}"
                                    + (", binary_engine=tensor(i8)" if norm == 0 and args.binary_engine == "tensor" else ""),
                        "pairs": int(len(pairs)), "pairs_per_gpu": int(len(mine)), "matches_per_step": total_matches,
