@@ -45,6 +45,7 @@ WORKLOADS = {
     "orb": ("orb", 100, 2000, True),        # ORB shape: 256 bit
     "float2": ("float", 40, 4000, True),
     "cfg4s": ("float", 60, 8000, True),     # cfg4's pair shape (8k x 8k x 128 f32) on a 60-image subset
+    "cfg4x": ("floatx", 60, 8000, True),    # same shape, NON-integer values: TF32 ranking + exact refinement path
     # configs[0]: the reference's own fixture (data/temple, 10 images, 45 pairs) through the committed cv2 descriptors
     "temple_sift": ("golden:temple_sift", 10, 850, False),
     "temple_akaze": ("golden:temple_akaze", 10, 700, False),
@@ -80,7 +81,7 @@ def make_descriptors(kind: str, n_images: int, n_desc: int, seed: int = 0):
         return synth.binary_images(n_images, n_desc, synth.AKAZE_BITS, seed), 0
     if kind == "orb":
         return synth.binary_images(n_images, n_desc, synth.ORB_BITS, seed), 0
-    return synth.float_images(n_images, n_desc, 128, seed, integer=True), 1
+    return synth.float_images(n_images, n_desc, 128, seed, integer=(kind != "floatx")), 1
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -407,7 +408,7 @@ def main():
                     "peak_source": f"nominal 16 POPC/clk/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
                                    "measured issue rates in profiles/pipe_bench_r01.txt",
                     "traffic": None}
-        elif m.stats()["float_path"] == 2:
+        elif m.stats()["float_path"] in (2, 3):
             tf32 = 0.5 * float(peaks.get("bf16_tflops", 1590.0))  # TF32 dense = half the measured bf16 cuBLAS rate
             roof = {"bound": "tensor", "achieved": knn_work / knn_s / 1e12, "peak": tf32, "unit": "TFLOP/s",
                     "peak_source": "0.5 x MEASURED_PEAKS.json bf16_tflops (TF32 dense is half the bf16 rate); "

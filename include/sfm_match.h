@@ -72,7 +72,8 @@ enum { SFMM_NORM_HAMMING = 0, SFMM_NORM_L2 = 1 };
 enum { SFMM_U8 = 0, SFMM_F32 = 1 };
 /* How the L2 path ranks candidates (distances REPORTED are always fp32 direct-difference). */
 enum {
-    SFMM_FLOAT_AUTO = 0,   /* tensor-core ranking when the data allows, else exact */
+    SFMM_FLOAT_AUTO = 0,   /* tensor cores whenever the shape allows (exact keys for integer-valued data such as SIFT,
+                              TF32 ranking + exact fp32 refinement of the candidates otherwise), else the exact kernel */
     SFMM_FLOAT_EXACT = 1,  /* fp32 CUDA-core direct difference for every candidate */
     SFMM_FLOAT_TENSOR = 2  /* tcgen05 TF32 |a|^2+|b|^2-2ab ranking + fp32 refinement of the winners */
 };
@@ -104,7 +105,8 @@ typedef struct SfmmStats {
     double last_knn_ms;        /* of which: the 2-NN distance kernel(s) */
     double last_knn_work;      /* algorithmic work of those launches: POPC32 ops (Hamming) or FLOPs (L2) */
     int64_t last_knn_launches; /* number of 2-NN kernel launches behind last_knn_ms */
-    int64_t float_path;        /* L2: 0 = not decided yet, SFMM_FLOAT_EXACT or SFMM_FLOAT_TENSOR = the kernel in use;
+    int64_t float_path;        /* L2: 0 = not decided yet, SFMM_FLOAT_EXACT or SFMM_FLOAT_TENSOR = the kernel in use,
+                                  3 = tensor-core TF32 ranking + exact refinement (arbitrary floats);
                                   Hamming: SFMM_FLOAT_TENSOR when the SFMM_BINARY_TENSOR engine is active, else 0 */
 } SfmmStats;
 

@@ -22,6 +22,8 @@ struct PairDesc {
     uint32_t n_splits;    // how many train-range splits produced partial 2-NN lists
     uint32_t first_ftile; // index of this pair's first filter tile
     uint32_t n_ftiles;    // number of filter tiles (ceil(nq / FILTER_TILE))
+    uint32_t q_off;       // first query row of this pair in per-launch row-indexed scratch (candidate lists)
+    float t_maxnorm2;     // max |t|^2 over the train image (error bound of the TF32 ranking pass)
     uint32_t pad;
 };
 

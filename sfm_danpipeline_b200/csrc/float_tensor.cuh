@@ -35,8 +35,20 @@
 
 #include "binary_knn.cuh"  // mbarrier / PTX helpers
 #include "common.cuh"
+#include "float_exact.cuh"  // top2_insert
 
 namespace sfmm {
+
+// What the kernel computes (template parameter MODE):
+enum TensorMode {
+    TM_TF32_EXACT = 0,    // TF32-exact float data: keys carry the exact integer d^2, result is final
+    TM_I8 = 1,            // binary descriptors unpacked to bytes (kind::i8), result is final
+    TM_TF32_RANK = 2,     // arbitrary floats, pass 1: approximate d^2 (TF32 truncation) -> approximate top-2 per row
+    TM_TF32_COLLECT = 3   // arbitrary floats, pass 2: every column whose approximate d^2 can still be in the exact
+                          // top-2 (<= m2 + 2*eps, a rigorous bound) is appended to the row's candidate list, which
+                          // float_refine_kernel then evaluates exactly (fp32 direct difference, float_exact.cuh's arithmetic)
+};
+static constexpr int FT_CAND_CAP = 32;  // candidates kept per query row; more => that row is rescanned exactly
 
 static constexpr int FT_M = 128;         // query rows per CTA (UMMA M)
 static constexpr int FT_N = 128;         // train rows per MMA tile (UMMA N); 64 was measured slower (per-tile costs double)
@@ -305,7 +317,7 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     return v;
 }
 
-template <bool PARTIAL, bool INT8>
+template <bool PARTIAL, int MODE>
 __device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[32], uint32_t nb_saddr, float cq, uint32_t key_mul,
                                            uint32_t lc0 /* first column of the chunk inside the tile */, uint32_t col0 /* same, relative to t0 */,
                                            uint32_t n_rows, uint32_t& m1, uint32_t& m2) {
@@ -317,12 +329,15 @@ __device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[32], uint32_t n
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             uint32_t bits;
-            if constexpr (INT8) {
+            if constexpr (MODE == TM_I8) {
                 // hamming = (popc(t) + popc(q)) - 2 q.t in s32; the IMADs keep it off the ALU pipe
                 // (cq carries popc(q) as integer bits, nbv popc(t) as integer bits; key_mul - 514 = -2)
                 uint32_t nbq;
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nbq) : "r"(__float_as_uint(nbv[i])), "r"(key_mul - 511u), "r"(__float_as_uint(cq)));
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(bits) : "r"(acc[e + i]), "r"(key_mul - 514u), "r"(nbq));
+            } else if constexpr (MODE == TM_TF32_RANK) {
+                // approximate d^2 (clamped at 0), truncated to its upper 23 bits: a monotone 23-bit code
+                bits = __float_as_uint(fmaxf(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i] + cq), 0.f)) >> 8;
             } else {
                 bits = __float_as_uint(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i] + cq));
             }
@@ -335,16 +350,38 @@ __device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[32], uint32_t n
     }
 }
 
+// TM_TF32_COLLECT: append every column of the chunk whose approximate d^2 is <= tau to the row's candidate list.
+__device__ __forceinline__ void chunk_collect(const uint32_t (&acc)[32], uint32_t nb_saddr, float nq2, float tau, uint32_t col0,
+                                              uint32_t n_rows, uint32_t t_first, uint32_t* cand_count_row, uint32_t* cand_idx_row) {
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+        const float4 nb = lds128(nb_saddr + e * 4);
+        const float x0 = fmaf(__uint_as_float(acc[e + 0]), -2.f, nb.x + nq2), x1 = fmaf(__uint_as_float(acc[e + 1]), -2.f, nb.y + nq2);
+        const float x2 = fmaf(__uint_as_float(acc[e + 2]), -2.f, nb.z + nq2), x3 = fmaf(__uint_as_float(acc[e + 3]), -2.f, nb.w + nq2);
+        if (fminf(fmin3(x0, x1, x2), x3) <= tau) {  // rare: a handful of columns per row over the whole train set
+            const float xs[4] = {x0, x1, x2, x3};
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                if (xs[i] <= tau && col0 + e + i < n_rows) {
+                    const uint32_t pos = atomicAdd(cand_count_row, 1u);
+                    if (pos < FT_CAND_CAP) cand_idx_row[pos] = t_first + e + i;
+                }
+        }
+    }
+}
+
 // CL = 2: thread-block cluster of two CTAs working on neighbouring query tiles of the same pair.
 // Each CTA fetches HALF of every train tile and TMA-multicasts it into both CTAs' shared memory,
 // halving the L2 -> SM operand traffic that bounds the single-CTA version (9 TB/s measured at
 // 51 % tensor-pipe activity, profiles/ncu_float_tensor_r01d.txt).  A stage is recycled only when
 // BOTH CTAs' MMAs have consumed it (tcgen05.commit multicast onto both b_empty barriers).
-template <int KB /* 128-byte K-blocks per row: 4 for 128-d float / 512-bit binary */, bool INT8, int CL>
+template <int KB /* 128-byte K-blocks per row: 4 for 128-d float / 512-bit binary */, int MODE, int CL>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ norms /* int32 popcounts when INT8 */,
                          const KnnTile* __restrict__ tiles, const PairDesc* __restrict__ pairs,
-                         KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */) {
+                         KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */,
+                         uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
+    constexpr bool INT8 = MODE == TM_I8;
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                   // KB x 16 KB
@@ -463,9 +500,35 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
         const uint32_t row = quarter * 32 + lane;          // row of the query tile == TMEM lane
         const uint32_t qrow = tile.q0 + row;
         const float nq2 = qrow < pd.nq ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
-        const float cq = INT8 ? nq2 /* popc(q), integer bits */ : nq2 + 8388608.f;  // |q|^2 + 2^23 (exact): see Top2
+        const float cq = (MODE == TM_TF32_EXACT) ? nq2 + 8388608.f  // |q|^2 + 2^23 (exact): see Top2
+                                                 : nq2;            // popc(q) as integer bits (i8) / |q|^2 (rank, collect)
         Top2 best;
         best.init();
+        [[maybe_unused]] float tau = 0.f;
+        [[maybe_unused]] uint32_t* cand_count_row = nullptr;
+        [[maybe_unused]] uint32_t* cand_idx_row = nullptr;
+        if constexpr (MODE == TM_TF32_COLLECT) {
+            // m2 = approximate second-smallest d^2 of this row from pass 1 (merged over the splits; a truncated
+            // 23-bit code: (code+1) << 8 bounds it from above).  |approx - exact| <= eps with
+            // eps = 2^-8 |q| max|t| (both operands truncated to TF32: relative error < 2^-10 each, Cauchy-Schwarz)
+            // + accumulation / norm rounding slack; every column of the exact top-2 has approx <= m2 + 2 eps.
+            if (qrow < pd.nq) {
+                unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
+                for (uint32_t sidx = 0; sidx < pd.n_splits; ++sidx) {
+                    const KnnEntry e = knn[pd.knn_off + (size_t)sidx * pd.nq + qrow];
+                    const unsigned long long hi = max(k1, e.x);
+                    k1 = min(k1, e.x);
+                    k2 = min(min(k2, hi), e.y);
+                }
+                const float m2 = k2 == KEY_NONE ? __int_as_float(0x7f7fffff) : __uint_as_float((static_cast<uint32_t>(k2 >> 32) + 1u) << 8);
+                const float eps = 0.00390625f * 1.02f * sqrtf(nq2) * sqrtf(pd.t_maxnorm2) + 1e-6f * (nq2 + pd.t_maxnorm2);
+                tau = m2 + 2.f * eps;
+            } else {
+                tau = -1.f;  // rows past the image collect nothing
+            }
+            cand_count_row = cand_count + pd.q_off + min(qrow, pd.nq - 1);
+            cand_idx_row = cand_idx + (size_t)(pd.q_off + min(qrow, pd.nq - 1)) * FT_CAND_CAP;
+        }
         for (uint32_t j = half; j < n_tiles; j += 2) {
             const uint32_t a = j % FT_ACC_STAGES;
             mbar_wait(&sm.acc_full[a], (j / FT_ACC_STAGES) & 1);
@@ -483,8 +546,12 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             for (int c = 0; c < NCH; ++c) {
                 if (c < NCH - 1) tc_ld_32x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
                 const uint32_t nb_saddr = smem_u32(&sm.nb[a][c * 32]);
-                if (!partial) chunk_top2<false, INT8>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
-                else chunk_top2<true, INT8>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
+                if constexpr (MODE == TM_TF32_COLLECT) {
+                    chunk_collect(acc[c & 1], nb_saddr, nq2, tau, col0 + c * 32, n_rows, tile.t0 + col0 + c * 32, cand_count_row, cand_idx_row);
+                } else {
+                    if (!partial) chunk_top2<false, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
+                    else chunk_top2<true, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
+                }
                 if (c < NCH - 1) tc_wait_ld(acc[(c + 1) & 1]);
                 if (c == (NCH > 1 ? NCH - 2 : 0)) {  // the last TMEM read of this tile has landed: the MMA that reuses the stage may start
                     tc_fence_before();
@@ -503,7 +570,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
         // (an exact integer under the root: bit-identical to OpenCV's sqrtf(sum (a-b)^2))
         if (half == 1) sm.merge[row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
         asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-        if (half == 0 && qrow < pd.nq) {
+        if (MODE != TM_TF32_COLLECT && half == 0 && qrow < pd.nq) {
             bool return_early = false;
             const uint4 o = sm.merge[row];
             unsigned long long k1 = best.i1 < 0 ? KEY_NONE : make_key(best.d1, (uint32_t)best.i1);
@@ -518,7 +585,9 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 return_early = true;
             }
             KnnEntry e;
-            if constexpr (INT8) {  // Hamming distance stays an integer in the key (binary_knn.cuh's convention)
+            if constexpr (MODE == TM_I8 || MODE == TM_TF32_RANK) {
+                // i8: the Hamming distance stays an integer in the key (binary_knn.cuh's convention);
+                // rank pass: the 23-bit code of the approximate d^2 (only pass 2 reads it)
                 e.x = k1;
                 e.y = k2;
             } else {  // integer d^2 -> float bits of d
@@ -536,6 +605,53 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+// ------------------------------------------------------------------ pass 3: exact refinement of the candidates
+// One warp per query row of the launch.  The candidates (or, if the list overflowed, the whole train
+// image) are evaluated with exactly float_exact_knn2_kernel's arithmetic -- acc = fmaf(a-b, a-b, acc)
+// over ascending k, then sqrtf -- so the result is bit-identical to SFMM_FLOAT_EXACT; top-2 by the
+// same (float bits << 32 | index) key.  The entry goes to split 0; the other splits are neutralised.
+__global__ void float_refine_kernel(const float* __restrict__ blob, int kq, const PairDesc* __restrict__ pairs, uint32_t n_pairs,
+                                    const uint32_t* __restrict__ pair_of_row, const uint32_t* __restrict__ cand_count,
+                                    const uint32_t* __restrict__ cand_idx, KnnEntry* __restrict__ knn, uint32_t total_rows) {
+    const uint32_t grow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row index in the launch
+    if (grow >= total_rows) return;
+    const uint32_t lane = threadIdx.x & 31;
+    const PairDesc pd = pairs[pair_of_row[grow]];
+    const uint32_t q = grow - pd.q_off;
+    const uint32_t count = cand_count[grow];
+    const bool overflow = count > FT_CAND_CAP;
+    const uint32_t n_items = overflow ? pd.nt : count;
+    const float4* qa = reinterpret_cast<const float4*>(blob) + (size_t)(pd.q_row0 + q) * kq;
+    unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
+    for (uint32_t i = lane; i < n_items; i += 32) {
+        const uint32_t t = overflow ? i : cand_idx[(size_t)grow * FT_CAND_CAP + i];
+        const float4* tb = reinterpret_cast<const float4*>(blob) + (size_t)(pd.t_row0 + t) * kq;
+        float acc = 0.f;
+        for (int c = 0; c < kq; ++c) {
+            const float4 a = __ldg(qa + c), b = __ldg(tb + c);
+            float d;
+            d = a.x - b.x; acc = fmaf(d, d, acc);
+            d = a.y - b.y; acc = fmaf(d, d, acc);
+            d = a.z - b.z; acc = fmaf(d, d, acc);
+            d = a.w - b.w; acc = fmaf(d, d, acc);
+        }
+        top2_insert(k1, k2, make_key(__float_as_uint(sqrtf(acc)), t));
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, d);
+        const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, d);
+        top2_insert(k1, k2, o1);
+        k2 = min(k2, o2);
+    }
+    for (uint32_t sidx = lane; sidx < pd.n_splits; sidx += 32) {
+        KnnEntry e;
+        e.x = sidx == 0 ? k1 : KEY_NONE;
+        e.y = sidx == 0 ? k2 : KEY_NONE;
+        knn[pd.knn_off + (size_t)sidx * pd.nq + q] = e;
     }
 }
 

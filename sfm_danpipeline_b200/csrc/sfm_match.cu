@@ -11,6 +11,7 @@
 // device->host copy and host-side bookkeeping of chunk k overlap the kernels of chunk k+1.
 #include <algorithm>
 #include <cfloat>
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -101,12 +102,13 @@ struct ChunkPlan {
     std::vector<PairDesc> pairs;
     std::vector<KnnTile> tiles;
     std::vector<FilterTile> ftiles;
+    std::vector<uint32_t> pair_of_row;  // TF32 rank + refine path: owning pair of every query row of the launch
     uint64_t knn_entries = 0;
     uint64_t col_entries = 0;
     uint64_t max_matches = 0;
     double work = 0;  // algorithmic POPC32 ops / FLOPs of the knn launch
     void clear() {
-        pairs.clear(); tiles.clear(); ftiles.clear();
+        pairs.clear(); tiles.clear(); ftiles.clear(); pair_of_row.clear();
         knn_entries = col_entries = max_matches = 0;
         work = 0;
     }
@@ -117,6 +119,7 @@ struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_knn0 = nullptr, ev_knn1 = nullptr, ev_done = nullptr;
     DevBuf d_pairs, d_tiles, d_ftiles, d_knn, d_colmin, d_tile_count, d_tile_off, d_pair_count, d_pair_off, d_matches, d_left, d_right;
+    DevBuf d_cand_count, d_cand_idx, d_pair_of_row;  // TF32 rank + refine path
     PinBuf meta;     // [total u64][pair_off u64 x n][pair_count i32 x n]
     PinBuf records;  // SfmDMatch staging
     PinBuf points;   // aligned-point staging (left then right)
@@ -124,7 +127,8 @@ struct Slot {
     int64_t first = 0, n = 0;  // pair range [first, first+n) of the caller's list
     bool busy = false;
     void release() {
-        for (DevBuf* b : {&d_pairs, &d_tiles, &d_ftiles, &d_knn, &d_colmin, &d_tile_count, &d_tile_off, &d_pair_count, &d_pair_off, &d_matches, &d_left, &d_right})
+        for (DevBuf* b : {&d_pairs, &d_tiles, &d_ftiles, &d_knn, &d_colmin, &d_tile_count, &d_tile_off, &d_pair_count, &d_pair_off, &d_matches, &d_left, &d_right,
+                          &d_cand_count, &d_cand_idx, &d_pair_of_row})
             b->release();
         meta.release();
         records.release();
@@ -155,6 +159,8 @@ struct SfmmCtx {
     bool tensor_eligible = false;
     bool use_tensor = false;   // a tcgen05 kernel is in use (float TF32, or binary through kind::i8)
     int tensor_kblocks = 0;    // 128-byte K-blocks per operand row
+    bool tensor_refine = false; // arbitrary floats: TF32 ranking pass + candidate collection + exact refinement
+    std::vector<float> img_maxnorm2;  // per image max |x|^2 (error bound of the ranking pass)
     int tensor_cluster = 1;    // CTAs per cluster sharing train tiles by TMA multicast (1 or 2); 2 measured no faster: not L2-bound
     CUtensorMap tmap{};
     DevBuf d_norms, d_flags;
@@ -273,7 +279,10 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
         pd.first_ftile = static_cast<uint32_t>(plan.ftiles.size());
         pd.n_ftiles = 0;
         pd.pad = 0;
+        pd.q_off = static_cast<uint32_t>(plan.pair_of_row.size());
+        pd.t_maxnorm2 = ctx->tensor_refine ? ctx->img_maxnorm2[t] : 0.f;
         if (pd.nq == 0 || pd.nt < 2) continue;  // defined: no matches (see sfm_match.h)
+        if (ctx->tensor_refine) plan.pair_of_row.insert(plan.pair_of_row.end(), pd.nq, static_cast<uint32_t>(i));
         uint32_t splits = std::min<uint32_t>(splits_wanted, std::max<uint32_t>(1, pd.nt / (2 * t_gran)));
         const uint32_t per = ((pd.nt + splits - 1) / splits + t_gran - 1) / t_gran * t_gran;
         splits = (pd.nt + per - 1) / per;
@@ -361,10 +370,10 @@ cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     return cudaGetLastError();
 }
 
-template <int KB, bool INT8, int CL>
+template <int KB, int MODE, int CL>
 cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     const size_t smem = float_tensor_smem_bytes(KB);
-    auto kern = tensor_knn2_kernel<KB, INT8, CL>;
+    auto kern = tensor_knn2_kernel<KB, MODE, CL>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     cudaLaunchConfig_t cfg{};
@@ -380,23 +389,42 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, ctx->tmap, (const float*)ctx->d_norms.as<float>(), (const KnnTile*)sl.d_tiles.as<KnnTile>(),
-                              (const PairDesc*)sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u);
+                              (const PairDesc*)sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u,
+                              sl.d_cand_count.as<uint32_t>(), sl.d_cand_idx.as<uint32_t>());
 }
 
-template <bool INT8, int CL>
+template <int MODE, int CL>
 cudaError_t launch_tensor_c(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks) {
     switch (kblocks) {
-        case 1: return launch_tensor_t<1, INT8, CL>(ctx, sl, n_tiles);
-        case 2: return launch_tensor_t<2, INT8, CL>(ctx, sl, n_tiles);
-        case 3: return launch_tensor_t<3, INT8, CL>(ctx, sl, n_tiles);
-        case 4: return launch_tensor_t<4, INT8, CL>(ctx, sl, n_tiles);
+        case 1: return launch_tensor_t<1, MODE, CL>(ctx, sl, n_tiles);
+        case 2: return launch_tensor_t<2, MODE, CL>(ctx, sl, n_tiles);
+        case 3: return launch_tensor_t<3, MODE, CL>(ctx, sl, n_tiles);
+        case 4: return launch_tensor_t<4, MODE, CL>(ctx, sl, n_tiles);
     }
     return cudaErrorInvalidValue;
 }
 
-template <bool INT8>
+template <int MODE>
 cudaError_t launch_tensor(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks) {
-    return ctx->tensor_cluster == 2 ? launch_tensor_c<INT8, 2>(ctx, sl, n_tiles, kblocks) : launch_tensor_c<INT8, 1>(ctx, sl, n_tiles, kblocks);
+    if constexpr (MODE == TM_TF32_EXACT || MODE == TM_I8)
+        if (ctx->tensor_cluster == 2) return launch_tensor_c<MODE, 2>(ctx, sl, n_tiles, kblocks);
+    return launch_tensor_c<MODE, 1>(ctx, sl, n_tiles, kblocks);
+}
+
+// Arbitrary float data: TF32 ranking pass -> candidate collection (same tiles) -> exact refinement.
+cudaError_t launch_tensor_refine(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks) {
+    const uint32_t rows = static_cast<uint32_t>(sl.plan.pair_of_row.size());
+    cudaError_t e = cudaMemsetAsync(sl.d_cand_count.p, 0, std::max<size_t>(1, rows) * sizeof(uint32_t), sl.stream);
+    if (e != cudaSuccess) return e;
+    if ((e = launch_tensor<TM_TF32_RANK>(ctx, sl, n_tiles, kblocks)) != cudaSuccess) return e;
+    if ((e = launch_tensor<TM_TF32_COLLECT>(ctx, sl, n_tiles, kblocks)) != cudaSuccess) return e;
+    if (rows)
+        float_refine_kernel<<<(rows + 7) / 8, 256, 0, sl.stream>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), sl.d_pairs.as<PairDesc>(),
+                                                                  static_cast<uint32_t>(sl.plan.pairs.size()), sl.d_pair_of_row.as<uint32_t>(),
+                                                                  sl.d_cand_count.as<uint32_t>(), sl.d_cand_idx.as<uint32_t>(),
+                                                                  sl.d_knn.as<KnnEntry>(), rows);
+    ctx->stats.kernel_launches += 2;
+    return cudaGetLastError();
 }
 
 typedef CUresult (*TensorMapEncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -473,19 +501,32 @@ int prepare_float(SfmmCtx* ctx) {
         float max_norm2;
         std::memcpy(&max_norm2, &flags[1], sizeof(float));
         ctx->tensor_eligible = flags[0] == 0 && max_norm2 <= 1048576.f;  // integers, |v|<=2047, |x|^2 <= 2^20
-        if (ctx->tensor_eligible) {
+        ctx->tensor_refine = false;
+        const bool finite = std::isfinite(max_norm2);  // NaN / inf rows: leave those sets to the exact kernel
+        if (ctx->tensor_eligible || (finite && !ctx->cfg.cross_check)) {
             int rc = make_tensor_map(ctx, ctx->blob.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ctx->pitch, ctx->total_rows);
             if (rc) return rc;
             ctx->tensor_kblocks = ctx->cols / FT_KB_ELEMS;
             ctx->use_tensor = true;
+            if (!ctx->tensor_eligible) {
+                // arbitrary floats: the TF32 pass only ranks; per-image max |x|^2 feeds its error bound
+                ctx->tensor_refine = true;
+                std::vector<float> h(static_cast<size_t>(ctx->total_rows));
+                CU_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->d_norms.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
+                CU_TRY(ctx, cudaStreamSynchronize(st));
+                ctx->stats.d2h_bytes += static_cast<int64_t>(h.size() * sizeof(float));
+                ctx->img_maxnorm2.assign(static_cast<size_t>(ctx->n_images), 0.f);
+                for (int32_t i = 0; i < ctx->n_images; ++i)
+                    for (int32_t r = 0; r < ctx->rows[i]; ++r) ctx->img_maxnorm2[i] = std::max(ctx->img_maxnorm2[i], h[ctx->row0[i] + r]);
+            }
         }
     }
     if (ctx->cfg.float_mode == SFMM_FLOAT_TENSOR && !ctx->use_tensor)
         return fail(ctx, SFMM_EINVAL,
-                    "SFMM_FLOAT_TENSOR needs TF32-exact descriptors (integer values |v|<=2047, row norm^2 <= 2^20), a width that is a "
-                    "multiple of 32 up to 128; use SFMM_FLOAT_AUTO or SFMM_FLOAT_EXACT");
+                    "SFMM_FLOAT_TENSOR needs a descriptor width that is a multiple of 32 up to 128, finite values, and -- with cross_check -- "
+                    "TF32-exact descriptors (integer values |v|<=2047, row norm^2 <= 2^20); use SFMM_FLOAT_AUTO or SFMM_FLOAT_EXACT");
     ctx->float_prepared = true;
-    ctx->stats.float_path = ctx->use_tensor ? SFMM_FLOAT_TENSOR : SFMM_FLOAT_EXACT;
+    ctx->stats.float_path = ctx->use_tensor ? (ctx->tensor_refine ? 3 : SFMM_FLOAT_TENSOR) : SFMM_FLOAT_EXACT;
     return SFMM_OK;
 }
 
@@ -522,6 +563,10 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
             for (uint32_t c = 0; c < cl; ++c) plan.tiles.push_back(KnnTile{0, q0 + c * q_tile, 0, pd.nt, 0});
         plan.knn_entries = pd.nq;
         plan.col_entries = pd.nt;
+        if (ctx->tensor_refine) {
+            pd.q_off = 0;
+            plan.pair_of_row.assign(pd.nq, 0u);
+        }
     }
     sl.first = first;
     sl.n = n;
@@ -540,12 +585,23 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
     ctx->stats.h2d_bytes += np * sizeof(PairDesc) + plan.tiles.size() * sizeof(KnnTile) + nft * sizeof(FilterTile);
     if (cross && plan.col_entries)
         CU_TRY(ctx, cudaMemsetAsync(sl.d_colmin.p, 0xFF, plan.col_entries * sizeof(unsigned long long), sl.stream));
+    if (ctx->tensor_refine) {
+        const size_t rows = std::max<size_t>(1, plan.pair_of_row.size());
+        CU_TRY(ctx, sl.d_cand_count.ensure(rows * sizeof(uint32_t)));
+        CU_TRY(ctx, sl.d_cand_idx.ensure(rows * FT_CAND_CAP * sizeof(uint32_t)));
+        CU_TRY(ctx, sl.d_pair_of_row.ensure(rows * sizeof(uint32_t)));
+        if (!plan.pair_of_row.empty())
+            CU_TRY(ctx, cudaMemcpyAsync(sl.d_pair_of_row.p, plan.pair_of_row.data(), plan.pair_of_row.size() * sizeof(uint32_t),
+                                        cudaMemcpyHostToDevice, sl.stream));
+        ctx->stats.h2d_bytes += static_cast<int64_t>(plan.pair_of_row.size() * sizeof(uint32_t));
+    }
     CU_TRY(ctx, cudaEventRecord(sl.ev_knn0, sl.stream));
     if (!plan.tiles.empty()) {
         const uint32_t nt = static_cast<uint32_t>(plan.tiles.size());
         cudaError_t e;
-        if (ctx->elem_type == SFMM_F32) e = ctx->use_tensor ? launch_tensor<false>(ctx, sl, nt, ctx->tensor_kblocks) : launch_float_exact(ctx, sl, nt);
-        else if (ctx->use_tensor) e = launch_tensor<true>(ctx, sl, nt, ctx->tensor_kblocks);
+        if (ctx->elem_type == SFMM_F32 && ctx->use_tensor && ctx->tensor_refine) e = launch_tensor_refine(ctx, sl, nt, ctx->tensor_kblocks);
+        else if (ctx->elem_type == SFMM_F32) e = ctx->use_tensor ? launch_tensor<TM_TF32_EXACT>(ctx, sl, nt, ctx->tensor_kblocks) : launch_float_exact(ctx, sl, nt);
+        else if (ctx->use_tensor) e = launch_tensor<TM_I8>(ctx, sl, nt, ctx->tensor_kblocks);
         else e = cross ? launch_binary<true>(ctx, sl, nt) : launch_binary<false>(ctx, sl, nt);
         CU_TRY(ctx, e);
         ctx->stats.kernel_launches += 1;
@@ -870,6 +926,7 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
     ctx->elem_type = -1;
     ctx->float_prepared = false;
     ctx->use_tensor = false;
+    ctx->tensor_refine = false;
     ctx->have_points = false;
     ctx->stats.float_path = 0;
     const size_t bytes = static_cast<size_t>(total) * pitch;
@@ -1080,7 +1137,7 @@ SFMM_API int sfmm_match_pairs_device(SfmmCtx* ctx, const int32_t* qt, int64_t n_
     int64_t done = 0;
     uint64_t written = 0;
     while (done < n_pairs) {
-        const int64_t n = chunk_extent(ctx, qt, done, n_pairs, MAX_CHUNK_ROWS);
+        const int64_t n = chunk_extent(ctx, qt, done, n_pairs, ctx->tensor_refine ? MAX_CHUNK_ROWS / 4 : MAX_CHUNK_ROWS);
         const uint64_t room = static_cast<uint64_t>(match_capacity) - std::min<uint64_t>(written, match_capacity);
         if ((rc = launch_chunk(ctx, sl, qt, done, n, d_counts + done, d_matches ? d_matches + written : nullptr, d_matches ? room : 0))) return rc;
         uint64_t total = 0;
@@ -1117,7 +1174,7 @@ SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) 
         if (q >= 0 && q < ctx->n_images) q_rows += static_cast<uint64_t>(ctx->rows[q]);
     }
     const uint64_t min_rows = static_cast<uint64_t>(query_tile_rows(ctx)) * ctx->sm_count * 8;
-    const uint64_t budget = std::min<uint64_t>(MAX_CHUNK_ROWS, std::max<uint64_t>(min_rows, q_rows / 8 + 1));
+    const uint64_t budget = std::min<uint64_t>(ctx->tensor_refine ? MAX_CHUNK_ROWS / 4 : MAX_CHUNK_ROWS, std::max<uint64_t>(min_rows, q_rows / 8 + 1));
     int64_t next = 0;
     int k = 0;
     int pending[2] = {-1, -1};  // slot indices in launch order

@@ -151,17 +151,64 @@ def test_tensor_mode_other_widths(cols):
             assert m.getMatching(q, t).tobytes() == oracle.match_pair(descs[q], descs[t], 1).tobytes()
 
 
-def test_auto_falls_back_to_exact_kernel_for_arbitrary_floats():
+# ----------------------------------------------------------------- arbitrary floats: TF32 ranking + exact refinement
+def _tables_equal(a, b):
+    for x, y in zip(a.result_table(), b.result_table()):
+        assert x.tobytes() == y.tobytes()
+
+
+def test_arbitrary_floats_use_rank_and_refine_and_equal_the_exact_kernel():
     g = GoldenSet("synth_float")  # non-integer values: not TF32-exact
-    with Matcher(NORM_L2, float_mode=FLOAT_AUTO) as m:
+    for mode in (FLOAT_AUTO, FLOAT_TENSOR):
+        with Matcher(NORM_L2, float_mode=mode) as m, Matcher(NORM_L2, float_mode=FLOAT_EXACT) as mx:
+            m.set_descriptors(g.descs)
+            mx.set_descriptors(g.descs)
+            m.match_all_pairs()
+            mx.match_all_pairs()
+            assert m.stats()["float_path"] == 3 and mx.stats()["float_path"] == FLOAT_EXACT
+            _tables_equal(m, mx)  # the refinement uses the exact kernel's arithmetic: bit-identical
+            for p, (q, t, kd, ki, *_r) in enumerate(g.pairs):
+                idx, dist = m.knn_pair(q, t)
+                _check_knn_within_tolerance(idx, dist, ki, kd)  # and within 1e-4 of OpenCV
+    with Matcher(NORM_L2, 0.8, True, float_mode=FLOAT_AUTO) as m:  # cross-check on arbitrary floats: exact kernel
         m.set_descriptors(g.descs)
         m.match_all_pairs()
         assert m.stats()["float_path"] == FLOAT_EXACT
-    with Matcher(NORM_L2, float_mode=FLOAT_TENSOR) as m:
-        m.set_descriptors(g.descs)
-        with pytest.raises(SfmmError) as e:
-            m.match_all_pairs()
-        assert e.value.code == -1 and "TF32-exact" in str(e.value)
+
+
+def test_rank_and_refine_at_cfg4_size_near_duplicates_and_ties():
+    rng = np.random.default_rng(3)
+    a = synth.float_images(2, [8000, 4100], seed=6, integer=False)  # SIFT-scale non-integer values
+    near = (a[0][:1500] + rng.normal(0, 1e-3, (1500, 128))).astype(np.float32)  # near-duplicates: d ~ 1e-2 vs |x| ~ 500
+    dup = np.repeat(a[1][:3], 40, axis=0)  # 120 identical rows: candidate lists overflow -> exact rescan of the row
+    sets = [a[0], np.concatenate([a[1], near, dup]), near[:130], a[1][:1]]
+    with Matcher(NORM_L2, float_mode=FLOAT_TENSOR) as m, Matcher(NORM_L2, float_mode=FLOAT_EXACT) as mx:
+        m.set_descriptors(sets)
+        mx.set_descriptors(sets)
+        m.match_all_pairs()
+        mx.match_all_pairs()
+        assert m.stats()["float_path"] == 3
+        _tables_equal(m, mx)
+        for (q, t) in [(0, 1), (2, 1), (1, 0), (0, 3)]:
+            ia, da = m.knn_pair(q, t)
+            ib, db = mx.knn_pair(q, t)
+            assert (ia == ib).all() and (da == db).all(), (q, t)
+        exp = oracle.match_pair(sets[2], sets[1], 1, 0.8, False, threads=8)
+        got = m.match_pair(2, 1)
+        assert (got["queryIdx"] == exp["queryIdx"]).all() and (got["trainIdx"] == exp["trainIdx"]).all()
+        np.testing.assert_allclose(got["distance"], exp["distance"], rtol=RTOL)
+
+
+def test_rank_and_refine_small_scale_values_and_negative_entries():
+    rng = np.random.default_rng(9)
+    descs = [rng.normal(0, 0.1, (n, 64)).astype(np.float32) for n in (700, 650, 129)]  # SURF-like: signed, |x| ~ 1
+    with Matcher(NORM_L2, 0.9, float_mode=FLOAT_AUTO) as m, Matcher(NORM_L2, 0.9, float_mode=FLOAT_EXACT) as mx:
+        m.set_descriptors(descs)
+        mx.set_descriptors(descs)
+        m.match_all_pairs()
+        mx.match_all_pairs()
+        assert m.stats()["float_path"] == 3
+        _tables_equal(m, mx)
 
 
 def test_tensor_mode_cross_check_temple_and_ragged():
