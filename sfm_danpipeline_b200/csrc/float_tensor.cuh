@@ -48,7 +48,7 @@ enum TensorMode {
                           // top-2 (<= m2 + 2*eps, a rigorous bound) is appended to the row's candidate list, which
                           // float_refine_kernel then evaluates exactly (fp32 direct difference, float_exact.cuh's arithmetic)
 };
-static constexpr int FT_CAND_CAP = 32;  // candidates kept per query row; more => that row is rescanned exactly
+static constexpr int FT_CAND_CAP = 32;  // candidate slots per query row (two halves of 16); a half overflowing => exact rescan of the row
 
 static constexpr int FT_M = 128;         // query rows per CTA (UMMA M)
 static constexpr int FT_N = 128;         // train rows per MMA tile (UMMA N); 64 was measured slower (per-tile costs double)
@@ -328,16 +328,13 @@ __device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[32], uint32_t n
         uint32_t k[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            uint32_t bits;
+            [[maybe_unused]] uint32_t bits = 0;
             if constexpr (MODE == TM_I8) {
                 // hamming = (popc(t) + popc(q)) - 2 q.t in s32; the IMADs keep it off the ALU pipe
                 // (cq carries popc(q) as integer bits, nbv popc(t) as integer bits; key_mul - 514 = -2)
                 uint32_t nbq;
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nbq) : "r"(__float_as_uint(nbv[i])), "r"(key_mul - 511u), "r"(__float_as_uint(cq)));
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(bits) : "r"(acc[e + i]), "r"(key_mul - 514u), "r"(nbq));
-            } else if constexpr (MODE == TM_TF32_RANK) {
-                // approximate d^2 (clamped at 0), truncated to its upper 23 bits: a monotone 23-bit code
-                bits = __float_as_uint(fmaxf(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i] + cq), 0.f)) >> 8;
             } else {
                 bits = __float_as_uint(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i] + cq));
             }
@@ -350,22 +347,74 @@ __device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[32], uint32_t n
     }
 }
 
-// TM_TF32_COLLECT: append every column of the chunk whose approximate d^2 is <= tau to the row's candidate list.
-__device__ __forceinline__ void chunk_collect(const uint32_t (&acc)[32], uint32_t nb_saddr, float nq2, float tau, uint32_t col0,
-                                              uint32_t n_rows, uint32_t t_first, uint32_t* cand_count_row, uint32_t* cand_idx_row) {
+// TM_TF32_RANK: only the two smallest VALUES of the row matter (pass 2 re-derives the columns), so the key is
+// the raw float, ordered as a signed integer: the float order for values >= 0.  Slightly negative values (only
+// possible within the error bound of 0) sort first in scrambled order; the caller clamps the result at 0, which
+// keeps the threshold an upper bound (see the COLLECT prologue).  FADD + FFMA + 2.5 VIMNMX per column.
+__device__ __forceinline__ void top2_pair_s32(int& m1, int& m2, int a, int b) {
+    const int lo = min(a, b), hi = max(a, b);
+    const int loser = max(m1, lo);
+    m1 = min(m1, lo);
+    m2 = __vimin3_s32(m2, loser, hi);
+}
+
+template <bool PARTIAL>
+__device__ __forceinline__ void chunk_rank(const uint32_t (&acc)[32], uint32_t nb_saddr, float cq, uint32_t col0,
+                                           uint32_t n_rows, int& m1, int& m2) {
 #pragma unroll
     for (int e = 0; e < 32; e += 4) {
         const float4 nb = lds128(nb_saddr + e * 4);
-        const float x0 = fmaf(__uint_as_float(acc[e + 0]), -2.f, nb.x + nq2), x1 = fmaf(__uint_as_float(acc[e + 1]), -2.f, nb.y + nq2);
-        const float x2 = fmaf(__uint_as_float(acc[e + 2]), -2.f, nb.z + nq2), x3 = fmaf(__uint_as_float(acc[e + 3]), -2.f, nb.w + nq2);
-        if (fminf(fmin3(x0, x1, x2), x3) <= tau) {  // rare: a handful of columns per row over the whole train set
-            const float xs[4] = {x0, x1, x2, x3};
+        const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+        int k[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i)
-                if (xs[i] <= tau && col0 + e + i < n_rows) {
-                    const uint32_t pos = atomicAdd(cand_count_row, 1u);
-                    if (pos < FT_CAND_CAP) cand_idx_row[pos] = t_first + e + i;
-                }
+        for (int i = 0; i < 4; ++i) {
+            k[i] = __float_as_int(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i] + cq));
+            if (PARTIAL) k[i] = col0 + e + i < n_rows ? k[i] : 0x7FFFFFFF;
+        }
+        top2_pair_s32(m1, m2, k[0], k[1]);
+        top2_pair_s32(m1, m2, k[2], k[3]);
+    }
+}
+
+// TM_TF32_COLLECT: append every column of the chunk whose approximate d^2 is <= tau to this thread's
+// half of the row's candidate list (FT_CAND_CAP/2 slots per epilogue group).  One FFMA + ~half an FMNMX
+// per column and ONE branch per 32 columns: hits are rare (a handful of columns per row over the whole
+// train set), and a data-dependent branch cannot be scheduled across -- a branch every 4 columns left the
+// epilogue latency-bound at 19 % issue utilisation (profiles/ncu_float_refine_r01.txt).
+// The slow path is kept SMALL: it only builds a per-thread bit mask of the hits (FSETP + predicated OR per
+// column); the appends run in a rolled loop over the set bits.  The first version appended inline, column by
+// column -- 6 instructions x 32 columns x 4 chunks x 2 variants = an 88 KB kernel whose warps stalled on
+// instruction fetch (stall_no_inst on every opcode, same profile).
+// With one split per pair the two owners of a row are the only writers, so the fill count lives in a
+// register (`shared_fill` false); with several splits it is a global counter.
+__device__ __forceinline__ void chunk_collect(const uint32_t (&acc)[32], uint32_t nb_saddr, float tau, uint32_t valid /* bit i: column i is a train row */,
+                                              uint32_t t_first, bool shared_fill, uint32_t& fill, uint32_t* fill_global,
+                                              uint32_t* __restrict__ list) {
+    float x[32];
+#pragma unroll
+    for (int e = 0; e < 32; e += 4) {
+        const float4 nb = lds128(nb_saddr + e * 4);
+        // tau already has |q|^2 subtracted: compare |t|^2 - 2 q.t, one FFMA per column
+        x[e + 0] = fmaf(__uint_as_float(acc[e + 0]), -2.f, nb.x);
+        x[e + 1] = fmaf(__uint_as_float(acc[e + 1]), -2.f, nb.y);
+        x[e + 2] = fmaf(__uint_as_float(acc[e + 2]), -2.f, nb.z);
+        x[e + 3] = fmaf(__uint_as_float(acc[e + 3]), -2.f, nb.w);
+    }
+    float mn = fmin3(x[0], x[1], x[2]);
+#pragma unroll
+    for (int e = 3; e < 31; e += 2) mn = fmin3(mn, x[e], x[e + 1]);
+    mn = fminf(mn, x[31]);
+    if (mn <= tau) {
+        uint32_t h[4] = {0, 0, 0, 0};  // four independent chains
+#pragma unroll
+        for (int i = 0; i < 32; ++i) h[i & 3] |= x[i] <= tau ? (1u << i) : 0u;
+        uint32_t hits = ((h[0] | h[1]) | (h[2] | h[3])) & valid;
+#pragma unroll 1
+        while (hits) {
+            const uint32_t i = __ffs(hits) - 1;
+            hits &= hits - 1;
+            const uint32_t pos = shared_fill ? atomicAdd(fill_global, 1u) : fill++;
+            if (pos < FT_CAND_CAP / 2) list[pos] = t_first + i;
         }
     }
 }
@@ -507,9 +556,13 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
         [[maybe_unused]] float tau = 0.f;
         [[maybe_unused]] uint32_t* cand_count_row = nullptr;
         [[maybe_unused]] uint32_t* cand_idx_row = nullptr;
+        [[maybe_unused]] uint32_t fill = 0;
+        [[maybe_unused]] int r1 = 0x7FFFFFFF, r2 = 0x7FFFFFFF;  // TM_TF32_RANK: two smallest approximate d^2 (float bits), over all tiles
         if constexpr (MODE == TM_TF32_COLLECT) {
-            // m2 = approximate second-smallest d^2 of this row from pass 1 (merged over the splits; a truncated
-            // 23-bit code: (code+1) << 8 bounds it from above).  |approx - exact| <= eps with
+            // m2 = approximate second-smallest d^2 of this row from pass 1 (merged over the splits, clamped at 0:
+            // if two or more approximations were negative, pass 1's signed-integer order may have kept the wrong
+            // two of them, but then every one of them -- and the true second-smallest -- is <= 0 + eps).
+            // |approx - exact| <= eps with
             // eps = 2^-8 |q| max|t| (both operands truncated to TF32: relative error < 2^-10 each, Cauchy-Schwarz)
             // + accumulation / norm rounding slack; every column of the exact top-2 has approx <= m2 + 2 eps.
             if (qrow < pd.nq) {
@@ -520,14 +573,17 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                     k1 = min(k1, e.x);
                     k2 = min(min(k2, hi), e.y);
                 }
-                const float m2 = k2 == KEY_NONE ? __int_as_float(0x7f7fffff) : __uint_as_float((static_cast<uint32_t>(k2 >> 32) + 1u) << 8);
+                const uint32_t m2bits = static_cast<uint32_t>(k2 >> 32);
+                const float m2 = m2bits >= 0x7f800000u ? __int_as_float(0x7f7fffff) : __uint_as_float(m2bits);  // none / inf / NaN: collect all
                 const float eps = 0.00390625f * 1.02f * sqrtf(nq2) * sqrtf(pd.t_maxnorm2) + 1e-6f * (nq2 + pd.t_maxnorm2);
-                tau = m2 + 2.f * eps;
+                tau = m2 + 2.f * eps - nq2 + 1e-6f * (m2 + nq2);  // (|q|^2 moved to this side; last term: rounding of that move)
             } else {
-                tau = -1.f;  // rows past the image collect nothing
+                tau = __int_as_float(0xff800000);  // -inf: rows past the image collect nothing (their accumulators are
+                                                   // dot products with some other image's rows and can be anything)
             }
-            cand_count_row = cand_count + pd.q_off + min(qrow, pd.nq - 1);
-            cand_idx_row = cand_idx + (size_t)(pd.q_off + min(qrow, pd.nq - 1)) * FT_CAND_CAP;
+            // each epilogue group owns one counter and half of the row's list
+            cand_count_row = cand_count + 2 * (size_t)(pd.q_off + min(qrow, pd.nq - 1)) + half;
+            cand_idx_row = cand_idx + (size_t)(pd.q_off + min(qrow, pd.nq - 1)) * FT_CAND_CAP + half * (FT_CAND_CAP / 2);
         }
         for (uint32_t j = half; j < n_tiles; j += 2) {
             const uint32_t a = j % FT_ACC_STAGES;
@@ -547,7 +603,12 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 if (c < NCH - 1) tc_ld_32x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
                 const uint32_t nb_saddr = smem_u32(&sm.nb[a][c * 32]);
                 if constexpr (MODE == TM_TF32_COLLECT) {
-                    chunk_collect(acc[c & 1], nb_saddr, nq2, tau, col0 + c * 32, n_rows, tile.t0 + col0 + c * 32, cand_count_row, cand_idx_row);
+                    const uint32_t c0 = col0 + c * 32;  // columns at or past n_rows belong to another image / padding
+                    const uint32_t valid = c0 + 32 <= n_rows ? 0xFFFFFFFFu : (c0 < n_rows ? (1u << (n_rows - c0)) - 1u : 0u);
+                    chunk_collect(acc[c & 1], nb_saddr, tau, valid, tile.t0 + c0, pd.n_splits != 1, fill, cand_count_row, cand_idx_row);
+                } else if constexpr (MODE == TM_TF32_RANK) {
+                    if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
+                    else chunk_rank<true>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
                 } else {
                     if (!partial) chunk_top2<false, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
                     else chunk_top2<true, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
@@ -562,10 +623,18 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             __syncwarp();
             if (lane == 0) mbar_arrive(&sm.nb_empty[a]);
             // merge the tile's two best into the running pair (ascending tiles = arrival order)
-            const int tbase = (int)(tile.t0 + col0);
-            if (m1 != 0xFFFFFFFFu) best.offer(m1 >> 9, tbase + (int)(m1 & 511u));
-            if (m2 != 0xFFFFFFFFu) best.offer(m2 >> 9, tbase + (int)(m2 & 511u));
+            if constexpr (MODE != TM_TF32_RANK && MODE != TM_TF32_COLLECT) {
+                const int tbase = (int)(tile.t0 + col0);
+                if (m1 != 0xFFFFFFFFu) best.offer(m1 >> 9, tbase + (int)(m1 & 511u));
+                if (m2 != 0xFFFFFFFFu) best.offer(m2 >> 9, tbase + (int)(m2 & 511u));
+            }
         }
+        if constexpr (MODE == TM_TF32_RANK) {  // values only, clamped at 0; the index field is unused
+            if (r1 != 0x7FFFFFFF) { best.d1 = (uint32_t)max(r1, 0); best.i1 = 0; }
+            if (r2 != 0x7FFFFFFF) { best.d2 = (uint32_t)max(r2, 0); best.i2 = 0; }
+        }
+        if constexpr (MODE == TM_TF32_COLLECT)
+            if (pd.n_splits == 1 && qrow < pd.nq) *cand_count_row = fill;
         // merge the two groups' lists of each row (even / odd tiles): lexicographic (d^2, index), then d = sqrtf(d^2)
         // (an exact integer under the root: bit-identical to OpenCV's sqrtf(sum (a-b)^2))
         if (half == 1) sm.merge[row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
@@ -587,7 +656,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             KnnEntry e;
             if constexpr (MODE == TM_I8 || MODE == TM_TF32_RANK) {
                 // i8: the Hamming distance stays an integer in the key (binary_knn.cuh's convention);
-                // rank pass: the 23-bit code of the approximate d^2 (only pass 2 reads it)
+                // rank pass: float bits of the approximate d^2 (only pass 2 reads it)
                 e.x = k1;
                 e.y = k2;
             } else {  // integer d^2 -> float bits of d
@@ -609,27 +678,30 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
 }
 
 // ------------------------------------------------------------------ pass 3: exact refinement of the candidates
-// One warp per query row of the launch.  The candidates (or, if the list overflowed, the whole train
+// Four lanes per query row of the launch.  The candidates (or, if the list overflowed, the whole train
 // image) are evaluated with exactly float_exact_knn2_kernel's arithmetic -- acc = fmaf(a-b, a-b, acc)
 // over ascending k, then sqrtf -- so the result is bit-identical to SFMM_FLOAT_EXACT; top-2 by the
 // same (float bits << 32 | index) key.  The entry goes to split 0; the other splits are neutralised.
 __global__ void float_refine_kernel(const float* __restrict__ blob, int kq, const PairDesc* __restrict__ pairs, uint32_t n_pairs,
                                     const uint32_t* __restrict__ pair_of_row, const uint32_t* __restrict__ cand_count,
                                     const uint32_t* __restrict__ cand_idx, KnnEntry* __restrict__ knn, uint32_t total_rows) {
-    const uint32_t grow = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // row index in the launch
-    if (grow >= total_rows) return;
-    const uint32_t lane = threadIdx.x & 31;
+    // four lanes per query row (a list holds ~3 candidates): 8 rows per warp, one candidate per lane and step
+    const uint32_t lane = threadIdx.x & 31, sub = lane & 3;
+    const uint32_t grow_raw = (blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5)) * 8 + (lane >> 2);  // row index in the launch
+    const bool live = grow_raw < total_rows;
+    const uint32_t grow = live ? grow_raw : total_rows - 1;
     const PairDesc pd = pairs[pair_of_row[grow]];
     const uint32_t q = grow - pd.q_off;
-    const uint32_t count = cand_count[grow];
-    const bool overflow = count > FT_CAND_CAP;
-    const uint32_t n_items = overflow ? pd.nt : count;
+    const uint32_t c0 = cand_count[2 * (size_t)grow], c1 = cand_count[2 * (size_t)grow + 1];  // the two epilogue groups' halves
+    const bool overflow = c0 > FT_CAND_CAP / 2 || c1 > FT_CAND_CAP / 2;
+    const uint32_t n_items = live ? (overflow ? pd.nt : c0 + c1) : 0;
     const float4* qa = reinterpret_cast<const float4*>(blob) + (size_t)(pd.q_row0 + q) * kq;
     unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
-    for (uint32_t i = lane; i < n_items; i += 32) {
-        const uint32_t t = overflow ? i : cand_idx[(size_t)grow * FT_CAND_CAP + i];
+    for (uint32_t i = sub; i < n_items; i += 4) {
+        const uint32_t t = overflow ? i : cand_idx[(size_t)grow * FT_CAND_CAP + (i < c0 ? i : FT_CAND_CAP / 2 + (i - c0))];
         const float4* tb = reinterpret_cast<const float4*>(blob) + (size_t)(pd.t_row0 + t) * kq;
         float acc = 0.f;
+#pragma unroll 8
         for (int c = 0; c < kq; ++c) {
             const float4 a = __ldg(qa + c), b = __ldg(tb + c);
             float d;
@@ -641,18 +713,19 @@ __global__ void float_refine_kernel(const float* __restrict__ blob, int kq, cons
         top2_insert(k1, k2, make_key(__float_as_uint(sqrtf(acc)), t));
     }
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
+    for (int d = 1; d < 4; d <<= 1) {
         const unsigned long long o1 = __shfl_xor_sync(0xFFFFFFFFu, k1, d);
         const unsigned long long o2 = __shfl_xor_sync(0xFFFFFFFFu, k2, d);
         top2_insert(k1, k2, o1);
         k2 = min(k2, o2);
     }
-    for (uint32_t sidx = lane; sidx < pd.n_splits; sidx += 32) {
-        KnnEntry e;
-        e.x = sidx == 0 ? k1 : KEY_NONE;
-        e.y = sidx == 0 ? k2 : KEY_NONE;
-        knn[pd.knn_off + (size_t)sidx * pd.nq + q] = e;
-    }
+    if (live)
+        for (uint32_t sidx = sub; sidx < pd.n_splits; sidx += 4) {
+            KnnEntry e;
+            e.x = sidx == 0 ? k1 : KEY_NONE;
+            e.y = sidx == 0 ? k2 : KEY_NONE;
+            knn[pd.knn_off + (size_t)sidx * pd.nq + q] = e;
+        }
 }
 
 }  // namespace sfmm

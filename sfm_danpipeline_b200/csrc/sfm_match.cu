@@ -414,16 +414,28 @@ cudaError_t launch_tensor(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks)
 // Arbitrary float data: TF32 ranking pass -> candidate collection (same tiles) -> exact refinement.
 cudaError_t launch_tensor_refine(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks) {
     const uint32_t rows = static_cast<uint32_t>(sl.plan.pair_of_row.size());
-    cudaError_t e = cudaMemsetAsync(sl.d_cand_count.p, 0, std::max<size_t>(1, rows) * sizeof(uint32_t), sl.stream);
+    cudaError_t e = cudaMemsetAsync(sl.d_cand_count.p, 0, std::max<size_t>(1, rows) * 2 * sizeof(uint32_t), sl.stream);
     if (e != cudaSuccess) return e;
     if ((e = launch_tensor<TM_TF32_RANK>(ctx, sl, n_tiles, kblocks)) != cudaSuccess) return e;
     if ((e = launch_tensor<TM_TF32_COLLECT>(ctx, sl, n_tiles, kblocks)) != cudaSuccess) return e;
     if (rows)
-        float_refine_kernel<<<(rows + 7) / 8, 256, 0, sl.stream>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), sl.d_pairs.as<PairDesc>(),
+        float_refine_kernel<<<(rows + 63) / 64, 256, 0, sl.stream>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), sl.d_pairs.as<PairDesc>(),
                                                                   static_cast<uint32_t>(sl.plan.pairs.size()), sl.d_pair_of_row.as<uint32_t>(),
                                                                   sl.d_cand_count.as<uint32_t>(), sl.d_cand_idx.as<uint32_t>(),
                                                                   sl.d_knn.as<KnnEntry>(), rows);
     ctx->stats.kernel_launches += 2;
+    if (std::getenv("SFMM_DEBUG_CAND") && rows) {  // development aid: candidate-list statistics of this launch
+        std::vector<uint32_t> h(2 * static_cast<size_t>(rows));
+        cudaMemcpyAsync(h.data(), sl.d_cand_count.p, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, sl.stream);
+        cudaStreamSynchronize(sl.stream);
+        double sum = 0;
+        uint32_t mx = 0, over = 0;
+        for (uint32_t r = 0; r < rows; ++r) {
+            const uint32_t a = h[2 * r], b = h[2 * r + 1];
+            sum += a + b; mx = std::max(mx, a + b); over += a > FT_CAND_CAP / 2 || b > FT_CAND_CAP / 2;
+        }
+        std::fprintf(stderr, "[sfmm] candidates per row: mean %.2f max %u, rows over capacity %u of %u\n", sum / rows, mx, over, rows);
+    }
     return cudaGetLastError();
 }
 
@@ -587,7 +599,7 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
         CU_TRY(ctx, cudaMemsetAsync(sl.d_colmin.p, 0xFF, plan.col_entries * sizeof(unsigned long long), sl.stream));
     if (ctx->tensor_refine) {
         const size_t rows = std::max<size_t>(1, plan.pair_of_row.size());
-        CU_TRY(ctx, sl.d_cand_count.ensure(rows * sizeof(uint32_t)));
+        CU_TRY(ctx, sl.d_cand_count.ensure(rows * 2 * sizeof(uint32_t)));
         CU_TRY(ctx, sl.d_cand_idx.ensure(rows * FT_CAND_CAP * sizeof(uint32_t)));
         CU_TRY(ctx, sl.d_pair_of_row.ensure(rows * sizeof(uint32_t)));
         if (!plan.pair_of_row.empty())
