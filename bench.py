@@ -227,23 +227,38 @@ def verify_pairs(table, descs, norm, n, cross, world):
     return {"pairs_checked": ok, "against": "cv2 BFMatcher path" if oracle.have_cv2() else "C oracle", "result": "bit-identical"}
 
 
-def alt_engine_line(args, local, world, rank, descs, mine, rows, n_pairs, flush, D):
-    """Resident throughput of the SFMM_BINARY_TENSOR engine on the same shard (rank 0's shard at N>1)."""
+def alt_engine_line(args, local, world, rank, descs, mine, rows, n_pairs, flush, D, engine, n_sm, sm_max_mhz, peaks):
+    """Resident throughput of the OTHER Hamming engine on the same shard (rank 0's shard at N>1), with its own roofline."""
     import torch
-    from sfm_danpipeline_b200 import BINARY_TENSOR, Matcher
-    m2 = Matcher(0, 0.8, False, device=local, binary_engine=BINARY_TENSOR)
+    from sfm_danpipeline_b200 import BINARY_POPC, BINARY_TENSOR, Matcher
+    m2 = Matcher(0, 0.8, False, device=local, binary_engine=BINARY_TENSOR if engine == "tensor" else BINARY_POPC)
     try:
         m2.set_descriptors(descs)
-        ms = []
+        ms, knn, work = [], 0.0, 0.0
         for it in range(2 + 3):
             flush.zero_()
             torch.cuda.synchronize()
             _c, _m, n = D.match_shard(m2, mine, rows)
             if it >= 2:
-                ms.append(m2.stats()["last_match_ms"])
+                st = m2.stats()
+                ms.append(st["last_match_ms"])
+                knn += st["last_knn_ms"]
+                work += st["last_knn_work"]
         per = float(np.mean(ms))
-        return {"binary_engine": "tensor (tcgen05 kind::i8 on unpacked bits)", "pairs_per_s_per_gpu": len(mine) / (per * 1e-3),
-                "ms_per_step": per, "matches_per_step_this_rank": int(n), "note": "opt-in engine, identical match tables; default stays XOR+POPC"}
+        out = {"binary_engine": "tensor (tcgen05 kind::i8 on unpacked bits)" if engine == "tensor" else "popc (XOR + carry-save + POPC, packed bits)",
+               "pairs_per_s_per_gpu": len(mine) / (per * 1e-3), "ms_per_step": per, "matches_per_step_this_rank": int(n),
+               "note": "same workload, same run, identical match tables; selectable with SfmmConfig.binary_engine"}
+        if engine == "popc":
+            peak = n_sm * 16 * sm_max_mhz * 1e6 / 1e9
+            out["roofline"] = {"bound": "popc", "achieved": work / (knn * 1e-3) / 1e9, "peak": peak, "unit": "GPOPC32/s",
+                               "frac": work / (knn * 1e-3) / 1e9 / peak,
+                               "peak_source": f"nominal 16 POPC/clk/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz"}
+        else:
+            i8 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
+            ach = 2.0 * (work / 16.0 * 512.0) / (knn * 1e-3) / 1e12
+            out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": i8, "unit": "TOP/s", "frac": ach / i8,
+                               "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops"}
+        return out
     finally:
         m2.close()
 
@@ -261,8 +276,10 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cross-check", action="store_true")
     ap.add_argument("--float-mode", default="auto", choices=["auto", "exact", "tensor"])
-    ap.add_argument("--binary-engine", default="popc", choices=["popc", "tensor"],
-                    help="popc = XOR+CSA+POPC kernel (default, the north-star design); tensor = opt-in tcgen05 kind::i8 engine")
+    ap.add_argument("--binary-engine", default="auto", choices=["auto", "popc", "tensor"],
+                    help="auto = the library default (tensor engine for <= 512-bit descriptors); popc = XOR+CSA+POPC kernel "
+                         "(the north-star design); tensor = tcgen05 kind::i8 engine.  The other engine is reported as alt_engine")
+    ap.add_argument("--no-alt-engine", action="store_true")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
@@ -304,7 +321,7 @@ def main():
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     m = Matcher(norm, 0.8, args.cross_check, device=local, float_mode={"auto": 0, "exact": 1, "tensor": 2}[args.float_mode],
-                binary_engine={"popc": 0, "tensor": 1}[args.binary_engine])
+                binary_engine={"auto": 0, "popc": 1, "tensor": 2}[args.binary_engine])
     # ---- resident arm: descriptors in HBM before the timed region -------------------------
     if world > 1:
         D.broadcast_descriptors(m, descs, 0)
@@ -393,7 +410,9 @@ def main():
         sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
         n_sm = torch.cuda.get_device_properties(local).multi_processor_count
         knn_s = knn_ms * 1e-3
-        if norm == 0 and args.binary_engine == "tensor":
+        # the engine the library actually ran (AUTO resolves to the tensor engine for <= 512-bit descriptors)
+        engine = ("tensor" if m.stats()["float_path"] == 2 else "popc") if norm == 0 else "float"
+        if engine == "tensor":
             i8 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))  # int8 dense = twice the measured bf16 cuBLAS rate
             macs = knn_work / 16.0 * 512.0  # 512 u8 MACs per 16 algorithmic POPC32 (one 486-bit distance)
             roof = {"bound": "tensor", "achieved": 2.0 * macs / knn_s / 1e12, "peak": i8, "unit": "TOP/s",
@@ -424,7 +443,7 @@ def main():
         ncu_traffic = {("cfg2", "popc", 1): 18.847e6 + 46.489e6,    # profiles/ncu_binary_r01c_tq2.txt
                        ("cfg2", "tensor", 1): 2413.4e6 + 88.4e6}    # profiles/ncu_tensor_i8_r01.txt
         if n_images == WORKLOADS[args.workload][1] and not args.cross_check:
-            roof["traffic"] = ncu_traffic.get((args.workload, args.binary_engine if norm == 0 else "float", world))
+            roof["traffic"] = ncu_traffic.get((args.workload, engine, world))
         roof["frac"] = roof["achieved"] / roof["peak"]
         roof["kernel_ms_per_launch"] = knn_ms / max(knn_launches, 1)
         roof["kernel_share_of_step"] = knn_ms / max(dev_ms, 1e-9)
@@ -441,7 +460,7 @@ def main():
             "dtype": "u8" if norm == 0 else "f32", "data": "synthetic" if not kind.startswith("golden:") else "cv2 descriptors of the reference's data/temple fixture",
             "config": {"workload": f"{args.workload}: {n_images} images x {n_desc} x " + desc_shape +
                                    f" descriptors, all {len(pairs)} pairs q<t, ratio 0.8, cross_check={bool(args.cross_check)}"
-                                   + (", binary_engine=tensor(i8)" if norm == 0 and args.binary_engine == "tensor" else ""),
+                                   + (f", binary_engine={engine}" if norm == 0 else ""),
                        "pairs": int(len(pairs)), "pairs_per_gpu": int(len(mine)), "matches_per_step": total_matches,
                        "l2": "flushed between steps (256 MiB memset outside the timed events)",
                        "parallelism": f"pairs sharded over {world} rank(s); NCCL broadcast + gather only in e2e"},
@@ -452,10 +471,11 @@ def main():
             "roofline": roof,
             "clocks": clk.summary(),
         }
-        if norm == 0 and args.binary_engine == "popc" and m.cols <= 64 and not args.cross_check:
-            # same workload, same run, through the opt-in tensor-core engine (bit-identical tables): reported
-            # beside the north-star POPC kernel, never instead of it
-            line["alt_engine"] = alt_engine_line(args, local, world, rank, descs, mine, rows, len(pairs), flush, D)
+        if norm == 0 and m.cols <= 64 and not args.cross_check and not args.no_alt_engine:
+            # same workload, same run, through the other Hamming engine (bit-identical tables): the north-star
+            # XOR+POPC kernel is reported beside the tensor engine AUTO picks, with its own POPC-pipe roofline
+            line["alt_engine"] = alt_engine_line(args, local, world, rank, descs, mine, rows, len(pairs), flush, D,
+                                                 "popc" if engine == "tensor" else "tensor", n_sm, sm_max_mhz, peaks)
         if args.verify:
             line["verified"] = verify_pairs(table, descs, norm, args.verify, args.cross_check, world)
         if world == 1 and not args.no_cpu_baseline:

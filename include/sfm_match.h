@@ -80,8 +80,11 @@ enum {
 
 /* Which pipe evaluates Hamming distances.  Results are bit-identical. */
 enum {
-    SFMM_BINARY_POPC = 0,   /* default, the north-star design: XOR + carry-save + POPC on the integer pipes */
-    SFMM_BINARY_TENSOR = 1  /* opt-in: bits unpacked to bytes, tcgen05 kind::i8 contraction (descriptors <= 512 bit) */
+    SFMM_BINARY_AUTO = 0,   /* default: the tensor engine when the descriptors are <= 512 bit and their unpacked copy
+                               (8x the packed bytes) fits in half of the free device memory, else POPC */
+    SFMM_BINARY_POPC = 1,   /* the north-star design: XOR + carry-save + POPC on the integer pipes, packed descriptors */
+    SFMM_BINARY_TENSOR = 2  /* bits unpacked to {0,1} bytes, popc(a)+popc(b)-2a.b on tcgen05 kind::i8 (~6x the POPC rate);
+                               SFMM_EINVAL for descriptors > 512 bit */
 };
 
 typedef struct SfmmConfig {
@@ -107,7 +110,7 @@ typedef struct SfmmStats {
     int64_t last_knn_launches; /* number of 2-NN kernel launches behind last_knn_ms */
     int64_t float_path;        /* L2: 0 = not decided yet, SFMM_FLOAT_EXACT or SFMM_FLOAT_TENSOR = the kernel in use,
                                   3 = tensor-core TF32 ranking + exact refinement (arbitrary floats);
-                                  Hamming: SFMM_FLOAT_TENSOR when the SFMM_BINARY_TENSOR engine is active, else 0 */
+                                  Hamming: SFMM_FLOAT_TENSOR when the tensor engine is in use, else 0 */
 } SfmmStats;
 
 typedef struct SfmmCtx SfmmCtx;

@@ -4,9 +4,9 @@ Only what the path needs: ``csrc/`` (CUDA kernels + the C ABI of include/sfm_mat
 ``matcher`` (host-side mirror of StructFromMotion::getMatching), ``distributed`` (pair sharding
 across ranks + NCCL broadcast/gather) and ``synth`` (seeded descriptor sets for tests/bench).
 """
-from ._lib import (BINARY_POPC, BINARY_TENSOR, DMATCH_DTYPE, FLOAT_AUTO, FLOAT_EXACT, FLOAT_TENSOR, NORM_HAMMING,  # noqa: F401
+from ._lib import (BINARY_AUTO, BINARY_POPC, BINARY_TENSOR, DMATCH_DTYPE, FLOAT_AUTO, FLOAT_EXACT, FLOAT_TENSOR, NORM_HAMMING,  # noqa: F401
                    NORM_L2, SfmmError)
 from .matcher import Matcher  # noqa: F401
 
 __all__ = ["Matcher", "SfmmError", "DMATCH_DTYPE", "NORM_HAMMING", "NORM_L2", "FLOAT_AUTO", "FLOAT_EXACT",
-           "FLOAT_TENSOR", "BINARY_POPC", "BINARY_TENSOR"]
+           "FLOAT_TENSOR", "BINARY_AUTO", "BINARY_POPC", "BINARY_TENSOR"]

@@ -13,7 +13,7 @@ SFMM_OK, SFMM_EINVAL, SFMM_ENOMEM, SFMM_ECUDA, SFMM_ESTATE, SFMM_ERANGE, SFMM_EN
 NORM_HAMMING, NORM_L2 = 0, 1
 U8, F32 = 0, 1
 FLOAT_AUTO, FLOAT_EXACT, FLOAT_TENSOR = 0, 1, 2
-BINARY_POPC, BINARY_TENSOR = 0, 1
+BINARY_AUTO, BINARY_POPC, BINARY_TENSOR = 0, 1, 2
 
 #: numpy view of SfmDMatch == cv::DMatch
 DMATCH_DTYPE = np.dtype([("queryIdx", "<i4"), ("trainIdx", "<i4"), ("imgIdx", "<i4"), ("distance", "<f4")])

@@ -252,18 +252,38 @@ __global__ void binary_unpack_kernel(const uint32_t* __restrict__ blob, int word
 }
 
 // ------------------------------------------------------------------ the kernel
+// One work item (= one KnnTile), decoded by the prefetch warp for the other roles.
+struct FtItem {
+    uint32_t a_row;     // blob row of the tile's first query row
+    uint32_t b_row0;    // blob row of the first train row of the range
+    uint32_t n_rows;    // train rows in the range
+    uint32_t n_tiles;   // 128-row train tiles
+    uint32_t q0, nq;    // first query row of the tile (image-relative), rows of the query image
+    uint32_t t0;        // first train row of the range (image-relative)
+    uint32_t split;     // which partial list the tile writes
+    uint32_t reverse;   // roles of the two images swapped (cross-check)
+    uint32_t n_splits;
+    uint32_t q_off;     // first row of the pair in the per-launch candidate scratch
+    uint32_t pad;
+    uint64_t knn_off, col_off;
+};
+
 struct FtSmem {  // after the 1024-byte aligned operand area
-    uint64_t a_full;
+    uint64_t a_full, a_empty;
     uint64_t b_full[FT_B_STAGES];
     uint64_t b_empty[FT_B_STAGES];
     uint64_t acc_full[FT_ACC_STAGES];
     uint64_t acc_empty[FT_ACC_STAGES];
     uint64_t nb_full[FT_ACC_STAGES];
     uint64_t nb_empty[FT_ACC_STAGES];
+    uint64_t item_full[2];
+    uint64_t item_empty[2];
     uint32_t tmem_base;
     uint32_t pad;
+    FtItem item[2];
     alignas(16) float nb[FT_ACC_STAGES][FT_N];  // |t|^2 of the train tile, bulk-copied next to the operands
-    uint4 merge[FT_M];                          // (d2_1, i1, d2_2, i2) of the group that took the odd tiles
+    float rowval[2][FT_M];                      // per query row of the item: |q|^2 (+2^23) / popc(q) / collect threshold
+    uint4 merge[2][FT_M];                       // (d2_1, i1, d2_2, i2) of the epilogue group with the odd tiles
 };
 
 static inline size_t float_tensor_smem_bytes(int kblocks) {
@@ -419,51 +439,52 @@ __device__ __forceinline__ void chunk_collect(const uint32_t (&acc)[32], uint32_
     }
 }
 
-// CL = 2: thread-block cluster of two CTAs working on neighbouring query tiles of the same pair.
-// Each CTA fetches HALF of every train tile and TMA-multicasts it into both CTAs' shared memory,
-// halving the L2 -> SM operand traffic that bounds the single-CTA version (9 TB/s measured at
-// 51 % tensor-pipe activity, profiles/ncu_float_tensor_r01d.txt).  A stage is recycled only when
-// BOTH CTAs' MMAs have consumed it (tcgen05.commit multicast onto both b_empty barriers).
-template <int KB /* 128-byte K-blocks per row: 4 for 128-d float / 512-bit binary */, int MODE, int CL>
+// PERSISTENT kernel: one CTA per SM walks the launch's KnnTile list with stride gridDim.x.  The TMA / MMA /
+// epilogue pipeline keeps running across item boundaries (ring indices and mbarrier phases follow a tile counter
+// that never resets), so the epilogue of item k -- draining the 4 TMEM stages, merging the two groups' lists,
+// writing the row results -- overlaps the loads and MMAs of item k+1, and barrier init / TMEM allocation /
+// tensor-map prefetch are paid once per SM instead of once per 128 query rows.  With one CTA per (pair, query
+// tile) the fixed cost was ~4 us against 30 us of tensor work at cfg-2 (40 train tiles per item) and against
+// 6 us for ORB-size images.
+//
+//   warp 0      TMA producer  : query tile per item (as soon as the previous item's MMAs released it), then
+//                               128-row train tiles through a 2-stage smem ring + their norms (4-slot ring)
+//   warp 1      MMA issuer    : whole warp, uniform control flow, elect.sync picks the issuing lane
+//   warp 2      TMEM allocator
+//   warp 3      item prefetch : decodes the next KnnTile/PairDesc and computes the per-row constants
+//                               (|q|^2, popc(q), or the pass-2 threshold) into a 2-slot smem ring, off the critical path
+//   warps 4-11  epilogue      : two groups of four warps on alternate tiles
+template <int KB /* 128-byte K-blocks per row: 4 for 128-d float / 512-bit binary */, int MODE>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ norms /* int32 popcounts when INT8 */,
-                         const KnnTile* __restrict__ tiles, const PairDesc* __restrict__ pairs,
-                         KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */,
-                         uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
+                   const KnnTile* __restrict__ tiles, const uint32_t n_items, const PairDesc* __restrict__ pairs,
+                   KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */,
+                   uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
     constexpr bool INT8 = MODE == TM_I8;
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                   // KB x 16 KB
-    unsigned char* sB = base + (size_t)KB * FT_KBLOCK_BYTES;    // FT_B_STAGES x KB x 8 KB
+    unsigned char* sB = base + (size_t)KB * FT_KBLOCK_BYTES;    // FT_B_STAGES x KB x 16 KB
     FtSmem& sm = *reinterpret_cast<FtSmem*>(base + (size_t)KB * (FT_KBLOCK_BYTES + FT_B_STAGES * FT_B_KBLOCK_BYTES));
 
-    KnnTile tile = tiles[blockIdx.x];
-    PairDesc pd = pairs[tile.pair];
-    // Symmetric cross-check = the same problem with the roles swapped: a "reverse" tile (bit 31 of
-    // split) takes its rows from the train image and streams the query image; its row-wise 1-NN is
-    // the column minimum the filter needs (lowest query index on ties, by the same insertion rule).
-    const bool reverse = (tile.split >> 31) != 0;
-    tile.split &= 0x7FFFFFFFu;
-    if (reverse) {
-        const uint32_t r0 = pd.q_row0, n = pd.nq;
-        pd.q_row0 = pd.t_row0; pd.nq = pd.nt;
-        pd.t_row0 = r0; pd.nt = n;
-    }
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t n_rows = tile.t1 - tile.t0;
-    const uint32_t n_tiles = (n_rows + FT_N - 1) / FT_N;
 
     if (threadIdx.x == 0) {
         mbar_init(&sm.a_full, 1);
+        mbar_init(&sm.a_empty, 1);
         for (int s = 0; s < FT_B_STAGES; ++s) {
             mbar_init(&sm.b_full[s], 1);
-            mbar_init(&sm.b_empty[s], CL);
+            mbar_init(&sm.b_empty[s], 1);
         }
         for (int s = 0; s < FT_ACC_STAGES; ++s) {
             mbar_init(&sm.acc_full[s], 1);
             mbar_init(&sm.acc_empty[s], FT_EPI_WARPS / 2);  // the four warps of the group that owns the tile
             mbar_init(&sm.nb_full[s], 1);
             mbar_init(&sm.nb_empty[s], FT_EPI_WARPS / 2);
+        }
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&sm.item_full[s], 1);
+            mbar_init(&sm.item_empty[s], 2 + FT_EPI_WARPS);  // producer thread, MMA warp, eight epilogue warps
         }
         mbar_fence_init();
     }
@@ -474,46 +495,47 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
     }
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync_all();  // the peer's barriers are initialised before anything is multicast to them
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
-    const uint32_t cta_rank = CL > 1 ? cluster_ctarank() : 0;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
             asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-            mbar_expect_tx(&sm.a_full, KB * FT_KBLOCK_BYTES);
-#pragma unroll
-            for (int kb = 0; kb < KB; ++kb)
-#pragma unroll
-                for (int h = 0; h < 2; ++h)
-                    tma_load_2d(sA + kb * FT_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS),
-                                (int)(pd.q_row0 + tile.q0) + h * FT_BOX_ROWS, &sm.a_full);
-            for (uint32_t j = 0; j < n_tiles; ++j) {
-                const uint32_t s = j % FT_B_STAGES;
-                const uint32_t a = j % FT_ACC_STAGES;
-                mbar_wait(&sm.nb_empty[a], ((j / FT_ACC_STAGES) & 1) ^ 1);
-                mbar_expect_tx(&sm.nb_full[a], FT_N * sizeof(float));
-                // image rows start at multiples of 4 and t0 at multiples of 128: 16-byte aligned source;
-                // the norms array is padded so that the copy may run past the image's last row
-                tma_load_1d(sm.nb[a], norms + pd.t_row0 + tile.t0 + j * FT_N, FT_N * sizeof(float), &sm.nb_full[a]);
-                mbar_wait(&sm.b_empty[s], ((j / FT_B_STAGES) & 1) ^ 1);
-                mbar_expect_tx(&sm.b_full[s], KB * FT_B_KBLOCK_BYTES);
-                unsigned char* dst = sB + (size_t)s * KB * FT_B_KBLOCK_BYTES;
-                const int row = (int)(pd.t_row0 + tile.t0 + j * FT_N);
+            uint32_t g = 0, it = 0;  // tiles / items this CTA has gone through: ring slots and mbarrier phases
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const uint32_t slot = it & 1;
+                mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
+                const uint32_t a_row = sm.item[slot].a_row, b_row0 = sm.item[slot].b_row0, n_tiles = sm.item[slot].n_tiles;
+                mbar_arrive(&sm.item_empty[slot]);
+                mbar_wait(&sm.a_empty, (it & 1) ^ 1);  // the previous item's MMAs have read the query tile
+                mbar_expect_tx(&sm.a_full, KB * FT_KBLOCK_BYTES);
 #pragma unroll
                 for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
-                    for (int h = 0; h < FT_N / FT_BOX_ROWS; ++h) {
-                        unsigned char* d = dst + kb * FT_B_KBLOCK_BYTES + h * FT_BOX_BYTES;
-                        if constexpr (CL > 1) {  // the 64-row boxes are dealt to the two CTAs; each is delivered to both
-                            if (((kb * (FT_N / FT_BOX_ROWS) + h) & 1) == (int)cta_rank)
-                                tma_load_2d_mcast(d, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS), row + h * FT_BOX_ROWS, &sm.b_full[s], (uint16_t)0x3);
-                        } else {
-                            tma_load_2d(d, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS), row + h * FT_BOX_ROWS, &sm.b_full[s]);
-                        }
-                    }
+                    for (int h = 0; h < 2; ++h)
+                        tma_load_2d(sA + kb * FT_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS),
+                                    (int)a_row + h * FT_BOX_ROWS, &sm.a_full);
+#pragma unroll 1
+                for (uint32_t j = 0; j < n_tiles; ++j, ++g) {
+                    const uint32_t s = g % FT_B_STAGES;
+                    const uint32_t a = g % FT_ACC_STAGES;
+                    mbar_wait(&sm.nb_empty[a], ((g / FT_ACC_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&sm.nb_full[a], FT_N * sizeof(float));
+                    // image rows start at multiples of 4 and t0 at multiples of 128: 16-byte aligned source;
+                    // the norms array is padded so that the copy may run past the image's last row
+                    tma_load_1d(sm.nb[a], norms + b_row0 + j * FT_N, FT_N * sizeof(float), &sm.nb_full[a]);
+                    mbar_wait(&sm.b_empty[s], ((g / FT_B_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&sm.b_full[s], KB * FT_B_KBLOCK_BYTES);
+                    unsigned char* dst = sB + (size_t)s * KB * FT_B_KBLOCK_BYTES;
+                    const int row = (int)(b_row0 + j * FT_N);
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                        for (int h = 0; h < FT_N / FT_BOX_ROWS; ++h)
+                            tma_load_2d(dst + kb * FT_B_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS),
+                                        row + h * FT_BOX_ROWS, &sm.b_full[s]);
+                }
             }
         }
     } else if (warp == 1) {
@@ -521,156 +543,223 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
         const uint32_t tb = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
         const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
         const uint32_t idesc = INT8 ? FT_IDESC_I8 : FT_IDESC;
-        mbar_wait(&sm.a_full, 0);
-        for (uint32_t j = 0; j < n_tiles; ++j) {
-            const uint32_t s = j % FT_B_STAGES, a = j % FT_ACC_STAGES;
-            mbar_wait(&sm.b_full[s], (j / FT_B_STAGES) & 1);
-            mbar_wait(&sm.acc_empty[a], ((j / FT_ACC_STAGES) & 1) ^ 1);
-            tc_fence_after();
-            const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB + (size_t)s * KB * FT_B_KBLOCK_BYTES));
-            const uint32_t d_tmem = tb + a * FT_N;
-            // the start-address field counts 16-byte units: stepping inside the tile is an integer add
-            tc_mma<INT8, false>(d_tmem, a_desc0, b_desc0, idesc);
+        uint32_t g = 0, it = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t slot = it & 1;
+            mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
+            const uint32_t n_tiles = __shfl_sync(0xFFFFFFFFu, sm.item[slot].n_tiles, 0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.item_empty[slot]);
+            mbar_wait(&sm.a_full, it & 1);
+#pragma unroll 1
+            for (uint32_t j = 0; j < n_tiles; ++j, ++g) {
+                const uint32_t s = g % FT_B_STAGES, a = g % FT_ACC_STAGES;
+                mbar_wait(&sm.b_full[s], (g / FT_B_STAGES) & 1);
+                mbar_wait(&sm.acc_empty[a], ((g / FT_ACC_STAGES) & 1) ^ 1);
+                tc_fence_after();
+                const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB + (size_t)s * KB * FT_B_KBLOCK_BYTES));
+                const uint32_t d_tmem = tb + a * FT_N;
+                // the start-address field counts 16-byte units: stepping inside the tile is an integer add
+                tc_mma<INT8, false>(d_tmem, a_desc0, b_desc0, idesc);
 #pragma unroll
-            for (int i = 1; i < 4 * KB; ++i) {  // i = kb*4 + k: 4 x (32 bytes of K) inside each 128-byte swizzle row
-                const int kb = i >> 2, k = i & 3;
-                tc_mma<INT8, true>(d_tmem, a_desc0 + ((kb * FT_KBLOCK_BYTES + k * 32) >> 4), b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
+                for (int i = 1; i < 4 * KB; ++i) {  // i = kb*4 + k: 4 x (32 bytes of K) inside each 128-byte swizzle row
+                    const int kb = i >> 2, k = i & 3;
+                    tc_mma<INT8, true>(d_tmem, a_desc0 + ((kb * FT_KBLOCK_BYTES + k * 32) >> 4), b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
+                }
+                tc_commit_elect(&sm.b_empty[s]);   // smem stage reusable once these MMAs have read it
+                tc_commit_elect(&sm.acc_full[a]);  // accumulator ready for the epilogue
             }
-            if constexpr (CL > 1) tc_commit_mcast_elect(&sm.b_empty[s], (uint16_t)0x3);  // both CTAs' producers learn that I am done with it
-            else tc_commit_elect(&sm.b_empty[s]);  // smem stage reusable once these MMAs have read it
-            tc_commit_elect(&sm.acc_full[a]);      // accumulator ready for the epilogue
+            tc_commit_elect(&sm.a_empty);  // every MMA of this item has read the query tile: the producer may replace it
+        }
+    } else if (warp == 3) {
+        // ===================== item prefetch =====================
+        uint32_t it = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t slot = it & 1;
+            mbar_wait(&sm.item_empty[slot], ((it >> 1) & 1) ^ 1);
+            KnnTile tile = tiles[item];
+            PairDesc pd = pairs[tile.pair];
+            // Symmetric cross-check = the same problem with the roles swapped: a "reverse" tile (bit 31 of
+            // split) takes its rows from the train image and streams the query image; its row-wise 1-NN is
+            // the column minimum the filter needs (lowest query index on ties, by the same insertion rule).
+            const bool reverse = (tile.split >> 31) != 0;
+            tile.split &= 0x7FFFFFFFu;
+            if (reverse) {
+                const uint32_t r0 = pd.q_row0, n = pd.nq;
+                pd.q_row0 = pd.t_row0; pd.nq = pd.nt;
+                pd.t_row0 = r0; pd.nt = n;
+            }
+            if (lane == 0) {
+                FtItem& o = sm.item[slot];
+                o.a_row = pd.q_row0 + tile.q0;
+                o.b_row0 = pd.t_row0 + tile.t0;
+                o.n_rows = tile.t1 - tile.t0;
+                o.n_tiles = (tile.t1 - tile.t0 + FT_N - 1) / FT_N;
+                o.q0 = tile.q0; o.nq = pd.nq; o.t0 = tile.t0; o.split = tile.split; o.reverse = reverse ? 1u : 0u;
+                o.n_splits = pd.n_splits; o.q_off = pd.q_off; o.knn_off = pd.knn_off; o.col_off = pd.col_off;
+            }
+#pragma unroll
+            for (int rr = 0; rr < FT_M / 32; ++rr) {
+                const uint32_t row = rr * 32 + lane, qrow = tile.q0 + row;
+                const bool valid = qrow < pd.nq;
+                const float nq2 = valid ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
+                float v;
+                if constexpr (MODE == TM_TF32_EXACT) {
+                    v = nq2 + 8388608.f;  // |q|^2 + 2^23 (exact): see Top2
+                } else if constexpr (MODE == TM_TF32_COLLECT) {
+                    // m2 = approximate second-smallest d^2 of this row from pass 1 (merged over the splits, clamped at 0:
+                    // if two or more approximations were negative, pass 1's signed-integer order may have kept the wrong
+                    // two of them, but then every one of them -- and the true second-smallest -- is <= 0 + eps).
+                    // |approx - exact| <= eps with
+                    // eps = 2^-8 |q| max|t| (both operands truncated to TF32: relative error < 2^-10 each, Cauchy-Schwarz)
+                    // + accumulation / norm rounding slack; every column of the exact top-2 has approx <= m2 + 2 eps.
+                    if (valid) {
+                        unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
+                        for (uint32_t sidx = 0; sidx < pd.n_splits; ++sidx) {
+                            const KnnEntry e = knn[pd.knn_off + (size_t)sidx * pd.nq + qrow];
+                            const unsigned long long hi = max(k1, e.x);
+                            k1 = min(k1, e.x);
+                            k2 = min(min(k2, hi), e.y);
+                        }
+                        const uint32_t m2bits = static_cast<uint32_t>(k2 >> 32);
+                        const float m2 = m2bits >= 0x7f800000u ? __int_as_float(0x7f7fffff) : __uint_as_float(m2bits);  // none / inf / NaN: collect all
+                        const float eps = 0.00390625f * 1.02f * sqrtf(nq2) * sqrtf(pd.t_maxnorm2) + 1e-6f * (nq2 + pd.t_maxnorm2);
+                        v = m2 + 2.f * eps - nq2 + 1e-6f * (m2 + nq2);  // (|q|^2 moved to this side; last term: rounding of that move)
+                    } else {
+                        v = __int_as_float(0xff800000);  // -inf: rows past the image collect nothing (their accumulators are
+                                                         // dot products with some other image's rows and can be anything)
+                    }
+                } else {
+                    v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (rank)
+                }
+                sm.rowval[slot][row] = v;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.item_full[slot]);
         }
     } else if (warp >= 4) {
         // ===================== epilogue: fused top-2 =====================
-        // Two groups of four warps (one warp per TMEM lane quarter) take alternate train tiles, so that on
-        // every SM sub-partition one warp computes while the other waits for its barrier / TMEM load.
+        // Two groups of four warps (one warp per TMEM lane quarter) take alternate tiles (by the running tile
+        // counter, so that odd tile counts do not favour one group), so that on every SM sub-partition one
+        // warp computes while the other waits for its barrier / TMEM load.
         const uint32_t ew = warp - 4;
-        const uint32_t quarter = ew & 3, half = ew >> 2;   // TMEM lanes 32*quarter..; group `half` owns tiles j = half, half+2, ...
+        const uint32_t quarter = ew & 3, half = ew >> 2;   // TMEM lanes 32*quarter..
         const uint32_t row = quarter * 32 + lane;          // row of the query tile == TMEM lane
-        const uint32_t qrow = tile.q0 + row;
-        const float nq2 = qrow < pd.nq ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
-        const float cq = (MODE == TM_TF32_EXACT) ? nq2 + 8388608.f  // |q|^2 + 2^23 (exact): see Top2
-                                                 : nq2;            // popc(q) as integer bits (i8) / |q|^2 (rank, collect)
-        Top2 best;
-        best.init();
-        [[maybe_unused]] float tau = 0.f;
-        [[maybe_unused]] uint32_t* cand_count_row = nullptr;
-        [[maybe_unused]] uint32_t* cand_idx_row = nullptr;
-        [[maybe_unused]] uint32_t fill = 0;
-        [[maybe_unused]] int r1 = 0x7FFFFFFF, r2 = 0x7FFFFFFF;  // TM_TF32_RANK: two smallest approximate d^2 (float bits), over all tiles
-        if constexpr (MODE == TM_TF32_COLLECT) {
-            // m2 = approximate second-smallest d^2 of this row from pass 1 (merged over the splits, clamped at 0:
-            // if two or more approximations were negative, pass 1's signed-integer order may have kept the wrong
-            // two of them, but then every one of them -- and the true second-smallest -- is <= 0 + eps).
-            // |approx - exact| <= eps with
-            // eps = 2^-8 |q| max|t| (both operands truncated to TF32: relative error < 2^-10 each, Cauchy-Schwarz)
-            // + accumulation / norm rounding slack; every column of the exact top-2 has approx <= m2 + 2 eps.
-            if (qrow < pd.nq) {
-                unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
-                for (uint32_t sidx = 0; sidx < pd.n_splits; ++sidx) {
-                    const KnnEntry e = knn[pd.knn_off + (size_t)sidx * pd.nq + qrow];
-                    const unsigned long long hi = max(k1, e.x);
-                    k1 = min(k1, e.x);
-                    k2 = min(min(k2, hi), e.y);
-                }
-                const uint32_t m2bits = static_cast<uint32_t>(k2 >> 32);
-                const float m2 = m2bits >= 0x7f800000u ? __int_as_float(0x7f7fffff) : __uint_as_float(m2bits);  // none / inf / NaN: collect all
-                const float eps = 0.00390625f * 1.02f * sqrtf(nq2) * sqrtf(pd.t_maxnorm2) + 1e-6f * (nq2 + pd.t_maxnorm2);
-                tau = m2 + 2.f * eps - nq2 + 1e-6f * (m2 + nq2);  // (|q|^2 moved to this side; last term: rounding of that move)
-            } else {
-                tau = __int_as_float(0xff800000);  // -inf: rows past the image collect nothing (their accumulators are
-                                                   // dot products with some other image's rows and can be anything)
-            }
-            // each epilogue group owns one counter and half of the row's list
-            cand_count_row = cand_count + 2 * (size_t)(pd.q_off + min(qrow, pd.nq - 1)) + half;
-            cand_idx_row = cand_idx + (size_t)(pd.q_off + min(qrow, pd.nq - 1)) * FT_CAND_CAP + half * (FT_CAND_CAP / 2);
-        }
-        for (uint32_t j = half; j < n_tiles; j += 2) {
-            const uint32_t a = j % FT_ACC_STAGES;
-            mbar_wait(&sm.acc_full[a], (j / FT_ACC_STAGES) & 1);
-            tc_fence_after();
-            uint32_t acc[2][32];  // register double buffer: chunk c+1 streams in from TMEM while chunk c is folded
-            const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + a * FT_N;
-            tc_ld_32x32(taddr, acc[0]);
-            mbar_wait(&sm.nb_full[a], (j / FT_ACC_STAGES) & 1);
-            tc_wait_ld(acc[0]);
-            const uint32_t col0 = j * FT_N;                // first column of the tile, relative to tile.t0
-            const bool partial = col0 + FT_N > n_rows;     // warp-uniform: only the last tile
-            uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;   // two smallest keys of this tile
-            constexpr int NCH = FT_N / 32;  // 32-column chunks per tile
-#pragma unroll
-            for (int c = 0; c < NCH; ++c) {
-                if (c < NCH - 1) tc_ld_32x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
-                const uint32_t nb_saddr = smem_u32(&sm.nb[a][c * 32]);
-                if constexpr (MODE == TM_TF32_COLLECT) {
-                    const uint32_t c0 = col0 + c * 32;  // columns at or past n_rows belong to another image / padding
-                    const uint32_t valid = c0 + 32 <= n_rows ? 0xFFFFFFFFu : (c0 < n_rows ? (1u << (n_rows - c0)) - 1u : 0u);
-                    chunk_collect(acc[c & 1], nb_saddr, tau, valid, tile.t0 + c0, pd.n_splits != 1, fill, cand_count_row, cand_idx_row);
-                } else if constexpr (MODE == TM_TF32_RANK) {
-                    if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
-                    else chunk_rank<true>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
-                } else {
-                    if (!partial) chunk_top2<false, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
-                    else chunk_top2<true, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
-                }
-                if (c < NCH - 1) tc_wait_ld(acc[(c + 1) & 1]);
-                if (c == (NCH > 1 ? NCH - 2 : 0)) {  // the last TMEM read of this tile has landed: the MMA that reuses the stage may start
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
-                }
-            }
+        uint32_t g0 = 0, it = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t slot = it & 1;
+            mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
+            const FtItem& im = sm.item[slot];
+            const uint32_t n_rows = im.n_rows, n_tiles = im.n_tiles, nq = im.nq, t0 = im.t0, split = im.split, n_splits = im.n_splits;
+            const uint32_t qrow = im.q0 + row, q_off = im.q_off;
+            const bool reverse = im.reverse != 0;
+            const unsigned long long knn_off = im.knn_off, col_off = im.col_off;
+            const float cq = sm.rowval[slot][row];  // TM_TF32_COLLECT: the threshold tau
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.nb_empty[a]);
-            // merge the tile's two best into the running pair (ascending tiles = arrival order)
-            if constexpr (MODE != TM_TF32_RANK && MODE != TM_TF32_COLLECT) {
-                const int tbase = (int)(tile.t0 + col0);
-                if (m1 != 0xFFFFFFFFu) best.offer(m1 >> 9, tbase + (int)(m1 & 511u));
-                if (m2 != 0xFFFFFFFFu) best.offer(m2 >> 9, tbase + (int)(m2 & 511u));
+            if (lane == 0) mbar_arrive(&sm.item_empty[slot]);
+
+            Top2 best;
+            best.init();
+            [[maybe_unused]] uint32_t* cand_count_row = nullptr;
+            [[maybe_unused]] uint32_t* cand_idx_row = nullptr;
+            [[maybe_unused]] uint32_t fill = 0;
+            [[maybe_unused]] int r1 = 0x7FFFFFFF, r2 = 0x7FFFFFFF;  // TM_TF32_RANK: two smallest approximate d^2 (float bits), over all tiles
+            if constexpr (MODE == TM_TF32_COLLECT) {
+                // each epilogue group owns one counter and half of the row's list
+                cand_count_row = cand_count + 2 * (size_t)(q_off + min(qrow, nq - 1)) + half;
+                cand_idx_row = cand_idx + (size_t)(q_off + min(qrow, nq - 1)) * FT_CAND_CAP + half * (FT_CAND_CAP / 2);
             }
-        }
-        if constexpr (MODE == TM_TF32_RANK) {  // values only, clamped at 0; the index field is unused
-            if (r1 != 0x7FFFFFFF) { best.d1 = (uint32_t)max(r1, 0); best.i1 = 0; }
-            if (r2 != 0x7FFFFFFF) { best.d2 = (uint32_t)max(r2, 0); best.i2 = 0; }
-        }
-        if constexpr (MODE == TM_TF32_COLLECT)
-            if (pd.n_splits == 1 && qrow < pd.nq) *cand_count_row = fill;
-        // merge the two groups' lists of each row (even / odd tiles): lexicographic (d^2, index), then d = sqrtf(d^2)
-        // (an exact integer under the root: bit-identical to OpenCV's sqrtf(sum (a-b)^2))
-        if (half == 1) sm.merge[row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
-        asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-        if (MODE != TM_TF32_COLLECT && half == 0 && qrow < pd.nq) {
-            bool return_early = false;
-            const uint4 o = sm.merge[row];
-            unsigned long long k1 = best.i1 < 0 ? KEY_NONE : make_key(best.d1, (uint32_t)best.i1);
-            unsigned long long k2 = best.i2 < 0 ? KEY_NONE : make_key(best.d2, (uint32_t)best.i2);
-            const unsigned long long o1 = (int)o.y < 0 ? KEY_NONE : make_key(o.x, o.y);
-            const unsigned long long o2 = (int)o.w < 0 ? KEY_NONE : make_key(o.z, o.w);
-            unsigned long long hi = max(k1, o1);
-            k1 = min(k1, o1);
-            k2 = min(min(k2, hi), o2);
-            if (reverse) {  // column minimum of the forward problem: (d^2, lowest query index); splits merge by atomicMin
-                if (k1 != KEY_NONE) atomicMin(colmin + pd.col_off + qrow, k1);
-                return_early = true;
+#pragma unroll 1
+            for (uint32_t j = (half ^ g0) & 1; j < n_tiles; j += 2) {
+                const uint32_t g = g0 + j;
+                const uint32_t a = g % FT_ACC_STAGES;
+                mbar_wait(&sm.acc_full[a], (g / FT_ACC_STAGES) & 1);
+                tc_fence_after();
+                uint32_t acc[2][32];  // register double buffer: chunk c+1 streams in from TMEM while chunk c is folded
+                const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + a * FT_N;
+                tc_ld_32x32(taddr, acc[0]);
+                mbar_wait(&sm.nb_full[a], (g / FT_ACC_STAGES) & 1);
+                tc_wait_ld(acc[0]);
+                const uint32_t col0 = j * FT_N;                // first column of the tile, relative to t0
+                const bool partial = col0 + FT_N > n_rows;     // warp-uniform: only the last tile
+                uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;   // two smallest keys of this tile
+                constexpr int NCH = FT_N / 32;  // 32-column chunks per tile
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    if (c < NCH - 1) tc_ld_32x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
+                    const uint32_t nb_saddr = smem_u32(&sm.nb[a][c * 32]);
+                    if constexpr (MODE == TM_TF32_COLLECT) {
+                        const uint32_t c0 = col0 + c * 32;  // columns at or past n_rows belong to another image / padding
+                        const uint32_t valid = c0 + 32 <= n_rows ? 0xFFFFFFFFu : (c0 < n_rows ? (1u << (n_rows - c0)) - 1u : 0u);
+                        chunk_collect(acc[c & 1], nb_saddr, cq, valid, t0 + c0, n_splits != 1, fill, cand_count_row, cand_idx_row);
+                    } else if constexpr (MODE == TM_TF32_RANK) {
+                        if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
+                        else chunk_rank<true>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
+                    } else {
+                        if (!partial) chunk_top2<false, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
+                        else chunk_top2<true, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
+                    }
+                    if (c < NCH - 1) tc_wait_ld(acc[(c + 1) & 1]);
+                    if (c == (NCH > 1 ? NCH - 2 : 0)) {  // the last TMEM read of this tile has landed: the MMA that reuses the stage may start
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.nb_empty[a]);
+                // merge the tile's two best into the running pair (ascending tiles = arrival order)
+                if constexpr (MODE != TM_TF32_RANK && MODE != TM_TF32_COLLECT) {
+                    const int tbase = (int)(t0 + col0);
+                    if (m1 != 0xFFFFFFFFu) best.offer(m1 >> 9, tbase + (int)(m1 & 511u));
+                    if (m2 != 0xFFFFFFFFu) best.offer(m2 >> 9, tbase + (int)(m2 & 511u));
+                }
             }
-            KnnEntry e;
-            if constexpr (MODE == TM_I8 || MODE == TM_TF32_RANK) {
-                // i8: the Hamming distance stays an integer in the key (binary_knn.cuh's convention);
-                // rank pass: float bits of the approximate d^2 (only pass 2 reads it)
-                e.x = k1;
-                e.y = k2;
-            } else {  // integer d^2 -> float bits of d
-                e.x = k1 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32))), (uint32_t)k1);
-                e.y = k2 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k2 >> 32))), (uint32_t)k2);
+            g0 += n_tiles;
+            if constexpr (MODE == TM_TF32_RANK) {  // values only, clamped at 0; the index field is unused
+                if (r1 != 0x7FFFFFFF) { best.d1 = (uint32_t)max(r1, 0); best.i1 = 0; }
+                if (r2 != 0x7FFFFFFF) { best.d2 = (uint32_t)max(r2, 0); best.i2 = 0; }
             }
-            if (!return_early) knn[pd.knn_off + (size_t)tile.split * pd.nq + qrow] = e;
+            if constexpr (MODE == TM_TF32_COLLECT) {
+                if (n_splits == 1 && qrow < nq) *cand_count_row = fill;
+            } else {
+                // merge the two groups' lists of each row: lexicographic (d^2, index), then d = sqrtf(d^2)
+                // (an exact integer under the root: bit-identical to OpenCV's sqrtf(sum (a-b)^2)).  The buffer
+                // alternates between items: group 1 may already be an item ahead when group 0 reads.
+                if (half == 1) sm.merge[it & 1][row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
+                asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+                if (half == 0 && qrow < nq) {
+                    const uint4 o = sm.merge[it & 1][row];
+                    unsigned long long k1 = best.i1 < 0 ? KEY_NONE : make_key(best.d1, (uint32_t)best.i1);
+                    unsigned long long k2 = best.i2 < 0 ? KEY_NONE : make_key(best.d2, (uint32_t)best.i2);
+                    const unsigned long long o1 = (int)o.y < 0 ? KEY_NONE : make_key(o.x, o.y);
+                    const unsigned long long o2 = (int)o.w < 0 ? KEY_NONE : make_key(o.z, o.w);
+                    unsigned long long hi = max(k1, o1);
+                    k1 = min(k1, o1);
+                    k2 = min(min(k2, hi), o2);
+                    if (reverse) {  // column minimum of the forward problem: (d^2, lowest query index); splits merge by atomicMin
+                        if (k1 != KEY_NONE) atomicMin(colmin + col_off + qrow, k1);
+                    } else {
+                        KnnEntry e;
+                        if constexpr (MODE == TM_I8 || MODE == TM_TF32_RANK) {
+                            // i8: the Hamming distance stays an integer in the key (binary_knn.cuh's convention);
+                            // rank pass: float bits of the approximate d^2 (only pass 2 reads it)
+                            e.x = k1;
+                            e.y = k2;
+                        } else {  // integer d^2 -> float bits of d
+                            e.x = k1 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32))), (uint32_t)k1);
+                            e.y = k2 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k2 >> 32))), (uint32_t)k2);
+                        }
+                        knn[knn_off + (size_t)split * nq + qrow] = e;
+                    }
+                }
+            }
         }
     }
 
     __syncwarp();
     tc_fence_before();
     __syncthreads();
-    if constexpr (CL > 1) cluster_sync_all();  // nobody exits while the peer may still multicast to it
     if (warp == 2) {
         tc_fence_after();
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");

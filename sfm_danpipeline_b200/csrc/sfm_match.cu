@@ -161,7 +161,7 @@ struct SfmmCtx {
     int tensor_kblocks = 0;    // 128-byte K-blocks per operand row
     bool tensor_refine = false; // arbitrary floats: TF32 ranking pass + candidate collection + exact refinement
     std::vector<float> img_maxnorm2;  // per image max |x|^2 (error bound of the ranking pass)
-    int tensor_cluster = 1;    // CTAs per cluster sharing train tiles by TMA multicast (1 or 2); 2 measured no faster: not L2-bound
+    int tensor_cluster = 1;    // CTAs per cluster sharing train tiles: the 2-CTA TMA-multicast variant measured no faster (not L2-bound) and was removed
     CUtensorMap tmap{};
     DevBuf d_norms, d_flags;
     DevBuf d_unpacked;  // SFMM_BINARY_TENSOR: one byte per descriptor bit
@@ -370,45 +370,30 @@ cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     return cudaGetLastError();
 }
 
-template <int KB, int MODE, int CL>
+template <int KB, int MODE>
 cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     const size_t smem = float_tensor_smem_bytes(KB);
-    auto kern = tensor_knn2_kernel<KB, MODE, CL>;
+    auto kern = tensor_knn2_kernel<KB, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(n_tiles);
-    cfg.blockDim = dim3(FT_THREADS);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = sl.stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = CL;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, ctx->tmap, (const float*)ctx->d_norms.as<float>(), (const KnnTile*)sl.d_tiles.as<KnnTile>(),
-                              (const PairDesc*)sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u,
-                              sl.d_cand_count.as<uint32_t>(), sl.d_cand_idx.as<uint32_t>());
-}
-
-template <int MODE, int CL>
-cudaError_t launch_tensor_c(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks) {
-    switch (kblocks) {
-        case 1: return launch_tensor_t<1, MODE, CL>(ctx, sl, n_tiles);
-        case 2: return launch_tensor_t<2, MODE, CL>(ctx, sl, n_tiles);
-        case 3: return launch_tensor_t<3, MODE, CL>(ctx, sl, n_tiles);
-        case 4: return launch_tensor_t<4, MODE, CL>(ctx, sl, n_tiles);
-    }
-    return cudaErrorInvalidValue;
+    // persistent: one CTA per SM (shared memory allows no more) walks the tile list with stride gridDim.x
+    const uint32_t grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(ctx->sm_count));
+    kern<<<grid, FT_THREADS, smem, sl.stream>>>(ctx->tmap, (const float*)ctx->d_norms.as<float>(), (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles,
+                                                (const PairDesc*)sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
+                                                sl.d_colmin.as<unsigned long long>(), 512u, sl.d_cand_count.as<uint32_t>(),
+                                                sl.d_cand_idx.as<uint32_t>());
+    return cudaGetLastError();
 }
 
 template <int MODE>
 cudaError_t launch_tensor(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks) {
-    if constexpr (MODE == TM_TF32_EXACT || MODE == TM_I8)
-        if (ctx->tensor_cluster == 2) return launch_tensor_c<MODE, 2>(ctx, sl, n_tiles, kblocks);
-    return launch_tensor_c<MODE, 1>(ctx, sl, n_tiles, kblocks);
+    switch (kblocks) {
+        case 1: return launch_tensor_t<1, MODE>(ctx, sl, n_tiles);
+        case 2: return launch_tensor_t<2, MODE>(ctx, sl, n_tiles);
+        case 3: return launch_tensor_t<3, MODE>(ctx, sl, n_tiles);
+        case 4: return launch_tensor_t<4, MODE>(ctx, sl, n_tiles);
+    }
+    return cudaErrorInvalidValue;
 }
 
 // Arbitrary float data: TF32 ranking pass -> candidate collection (same tiles) -> exact refinement.
@@ -460,14 +445,21 @@ int make_tensor_map(SfmmCtx* ctx, void* base, CUtensorMapDataType dtype, size_t 
     return SFMM_OK;
 }
 
-// SFMM_BINARY_TENSOR: unpack the bit rows to bytes once per descriptor set (lazily, like prepare_float).
+// Tensor engine for Hamming (SFMM_BINARY_TENSOR / AUTO): unpack the bit rows to bytes once per descriptor set
+// (lazily, like prepare_float).
 int prepare_binary_tensor(SfmmCtx* ctx) {
     if (ctx->elem_type != SFMM_U8 || ctx->float_prepared) return SFMM_OK;
     ctx->use_tensor = false;
-    if (ctx->cfg.binary_engine == SFMM_BINARY_TENSOR) {
-        const int words = binary_words(ctx->cols);
-        const int kbytes = (words * 32 + 127) / 128 * 128;
-        if (kbytes > 512) return fail(ctx, SFMM_EINVAL, "SFMM_BINARY_TENSOR supports descriptors of at most 512 bits");
+    const int words = binary_words(ctx->cols);
+    const int kbytes = (words * 32 + 127) / 128 * 128;  // unpacked row: one byte per bit, whole 128-byte K-blocks
+    bool want = ctx->cfg.binary_engine == SFMM_BINARY_TENSOR;
+    if (want && kbytes > 512) return fail(ctx, SFMM_EINVAL, "SFMM_BINARY_TENSOR supports descriptors of at most 512 bits");
+    if (ctx->cfg.binary_engine == SFMM_BINARY_AUTO && kbytes <= 512 && ctx->total_rows > 0) {
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
+        want = static_cast<size_t>(ctx->total_rows) * kbytes <= free_b / 2 + ctx->d_unpacked.cap;  // (a buffer we already own counts as free)
+    }
+    if (want) {
         if (ctx->total_rows > 0) {
             cudaStream_t st = ctx->slot[0].stream;
             CU_TRY(ctx, ctx->d_unpacked.ensure(static_cast<size_t>(ctx->total_rows) * kbytes));
@@ -828,7 +820,7 @@ SFMM_API void sfmm_default_config(SfmmConfig* cfg) {
     cfg->cross_check = 0;      // src/Sfm.cpp:593 (crossCheck=false)
     cfg->float_mode = SFMM_FLOAT_AUTO;
     cfg->pair_batch = 0;
-    cfg->binary_engine = SFMM_BINARY_POPC;
+    cfg->binary_engine = SFMM_BINARY_AUTO;
 }
 
 SFMM_API const char* sfmm_last_error(const SfmmCtx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -843,7 +835,7 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     if (!(cfg->ratio >= 0.f)) return fail(nullptr, SFMM_EINVAL, "sfmm_create: ratio must be >= 0");
     if (cfg->float_mode < SFMM_FLOAT_AUTO || cfg->float_mode > SFMM_FLOAT_TENSOR)
         return fail(nullptr, SFMM_EINVAL, "sfmm_create: unknown float_mode");
-    if (cfg->binary_engine != SFMM_BINARY_POPC && cfg->binary_engine != SFMM_BINARY_TENSOR)
+    if (cfg->binary_engine != SFMM_BINARY_AUTO && cfg->binary_engine != SFMM_BINARY_POPC && cfg->binary_engine != SFMM_BINARY_TENSOR)
         return fail(nullptr, SFMM_EINVAL, "sfmm_create: unknown binary_engine");
     int n_dev = 0;
     cudaError_t e = cudaGetDeviceCount(&n_dev);
@@ -864,7 +856,6 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     ctx->cfg = *cfg;
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* s = std::getenv("SFMM_CSA_LEVEL")) ctx->csa_level = std::max(0, std::min(3, std::atoi(s)));
-    if (const char* s = std::getenv("SFMM_TENSOR_CLUSTER")) ctx->tensor_cluster = std::atoi(s) == 2 ? 2 : 1;
     bool ok = (e = cudaSetDevice(cfg->device)) == cudaSuccess;
     for (Slot& sl : ctx->slot) {
         ok = ok && (e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) == cudaSuccess;

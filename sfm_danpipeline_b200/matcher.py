@@ -28,7 +28,7 @@ class Matcher:
     """
 
     def __init__(self, norm: int = NORM_L2, ratio: float = 0.8, cross_check: bool = False, device: int = 0,
-                 float_mode: int = _lib.FLOAT_AUTO, pair_batch: int = 0, binary_engine: int = _lib.BINARY_POPC):
+                 float_mode: int = _lib.FLOAT_AUTO, pair_batch: int = 0, binary_engine: int = _lib.BINARY_AUTO):
         self._L = _lib.load()
         cfg = _lib.SfmmConfig()
         self._L.sfmm_default_config(C.byref(cfg))

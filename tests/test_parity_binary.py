@@ -5,10 +5,27 @@ import numpy as np
 import pytest
 
 import oracle
-from sfm_danpipeline_b200 import Matcher, NORM_HAMMING, SfmmError, synth
+from sfm_danpipeline_b200 import BINARY_AUTO, BINARY_POPC, Matcher, NORM_HAMMING, SfmmError, synth
 from _golden import GoldenSet
 
 pytestmark = pytest.mark.gpu
+
+
+_ENGINE = BINARY_AUTO
+
+
+@pytest.fixture(autouse=True, params=[BINARY_POPC, BINARY_AUTO], ids=["popc", "auto"])
+def engine(request):
+    """Every test of the generic part runs on the XOR+POPC kernel and on the default (AUTO: the tcgen05 i8
+    engine for <= 512-bit descriptors, POPC above)."""
+    global _ENGINE
+    _ENGINE = request.param
+    return request.param
+
+
+def _matcher(*args, **kw):
+    kw.setdefault("binary_engine", _ENGINE)
+    return Matcher(NORM_HAMMING, *args, **kw)
 
 
 def _expect_equal(got, exp):
@@ -20,7 +37,7 @@ def _expect_equal(got, exp):
 @pytest.mark.parametrize("cross", [False, True])
 def test_all_pairs_equal_cv2_golden(name, cross):
     g = GoldenSet(name)
-    with Matcher(NORM_HAMMING, 0.8, cross) as m:
+    with _matcher(0.8, cross) as m:
         m.set_descriptors(g.descs)
         m.match_all_pairs()
         for p, (q, t, *_r) in enumerate(g.pairs):
@@ -33,7 +50,7 @@ def test_all_pairs_equal_cv2_golden(name, cross):
 @pytest.mark.parametrize("name", ["temple_akaze", "temple_orb"])
 def test_raw_knn_equals_cv2_golden(name):
     g = GoldenSet(name)
-    with Matcher(NORM_HAMMING) as m:
+    with _matcher() as m:
         m.set_descriptors(g.descs)
         for q, t, kd, ki, *_r in g.pairs[::5]:
             idx, dist = m.knn_pair(q, t)
@@ -46,7 +63,7 @@ def test_widths_and_ties_vs_oracle(cols):
     # few distinct byte values => many exact distance ties, exercising lowest-index tie-breaking
     descs = [rng.integers(0, 2, (n, cols), dtype=np.uint8) * 255 for n in (700, 513, 1024, 3)]
     for cross in (False, True):
-        with Matcher(NORM_HAMMING, 0.8, cross) as m:
+        with _matcher(0.8, cross) as m:
             m.set_descriptors(descs)
             m.match_all_pairs()
             for (q, t) in synth.all_pairs(len(descs)):
@@ -56,7 +73,7 @@ def test_widths_and_ties_vs_oracle(cols):
 def test_cfg2_shape_sample_vs_oracle():
     # configs[1]: 486-bit AKAZE-shape, 5k rows per image; a few pairs at full size
     descs = synth.binary_images(4, 5000, seed=0)
-    with Matcher(NORM_HAMMING) as m:
+    with _matcher() as m:
         m.set_descriptors(descs)
         m.match_all_pairs()
         for (q, t) in [(0, 1), (1, 3), (2, 3)]:
@@ -74,7 +91,7 @@ def test_ragged_and_degenerate_images():
     rng = np.random.default_rng(1)
     descs = [rng.integers(0, 256, (n, 61), dtype=np.uint8) for n in (0, 1, 2, 130, 1500, 0, 37)]
     for cross in (False, True):
-        with Matcher(NORM_HAMMING, 0.9, cross) as m:
+        with _matcher(0.9, cross) as m:
             m.set_descriptors(descs)
             m.match_all_pairs()
             for (q, t) in synth.all_pairs(len(descs)):
@@ -92,7 +109,7 @@ def test_strided_rows_and_padding_are_neutral():
     rng = np.random.default_rng(2)
     wide = rng.integers(0, 256, (400, 80), dtype=np.uint8)
     a, b = wide[:200, :61], wide[200:, :61]  # row step 80, 61 used bytes
-    with Matcher(NORM_HAMMING) as m:
+    with _matcher() as m:
         m.set_descriptors([a, b])
         got = m.match_pair(0, 1)
     _expect_equal(got, oracle.match_pair(np.ascontiguousarray(a), np.ascontiguousarray(b), 0))
@@ -103,7 +120,7 @@ def test_duplicate_rows_lowest_index_in_both_slots():
     T[7, 0] = 1
     Q = np.zeros((2, 61), np.uint8)
     Q[1, 0] = 1
-    with Matcher(NORM_HAMMING) as m:
+    with _matcher() as m:
         m.set_descriptors([Q, T])
         idx, dist = m.knn_pair(0, 1)
         assert idx.tolist() == [[0, 1], [7, 0]] and dist.tolist() == [[0.0, 0.0], [0.0, 1.0]]
@@ -113,7 +130,7 @@ def test_duplicate_rows_lowest_index_in_both_slots():
 
 def test_batched_launches_give_the_same_table():
     descs = synth.binary_images(7, [300, 650, 1, 512, 513, 90, 1200], seed=3)
-    with Matcher(NORM_HAMMING) as a, Matcher(NORM_HAMMING, pair_batch=4) as b:
+    with _matcher() as a, _matcher(pair_batch=4) as b:
         a.set_descriptors(descs)
         b.set_descriptors(descs)
         a.match_all_pairs()
@@ -128,7 +145,7 @@ def test_batched_launches_give_the_same_table():
 
 
 def test_error_codes():
-    with Matcher(NORM_HAMMING) as m:
+    with _matcher() as m:
         with pytest.raises(SfmmError) as e:
             m.match_all_pairs()
         assert e.value.code == -4  # no descriptors yet
@@ -152,7 +169,7 @@ def test_full_size_properties_cfg2():
     # self-match of an image finds itself at distance 0, permutation equivariance of the train set
     descs = synth.binary_images(3, 5000, seed=9)
     perm = np.random.default_rng(0).permutation(5000)
-    with Matcher(NORM_HAMMING) as m:
+    with _matcher() as m:
         m.set_descriptors([descs[0], descs[1], descs[1][perm]])
         m.match_all_pairs()
         a, b = m.getMatching(0, 1), m.getMatching(0, 2)
@@ -193,7 +210,7 @@ def test_tensor_engine_widths_ties_ragged(cols):
     descs = [rng.integers(0, 2, (n, cols), dtype=np.uint8) * 255 for n in (700, 513, 1024, 3, 0, 129)]
     descs[4] = np.zeros((0, cols), np.uint8)
     for cross in (False, True):
-        with Matcher(NORM_HAMMING, 0.8, cross, binary_engine=BINARY_TENSOR) as m, Matcher(NORM_HAMMING, 0.8, cross) as ref:
+        with Matcher(NORM_HAMMING, 0.8, cross, binary_engine=BINARY_TENSOR) as m, Matcher(NORM_HAMMING, 0.8, cross, binary_engine=BINARY_POPC) as ref:
             m.set_descriptors(descs)
             ref.set_descriptors(descs)
             m.match_all_pairs()
@@ -221,7 +238,7 @@ def test_incremental_match_pairs_like_addmoreviews():
     # addMoreViews / find2D3DMatches (src/Sfm.cpp:964-977, 1020-1042) ask for one new view against the done views:
     # the table grows call by call and earlier pairs stay addressable
     descs = synth.binary_images(5, [400, 380, 512, 90, 700], seed=17)
-    with Matcher(NORM_HAMMING) as m:
+    with _matcher() as m:
         m.set_descriptors(descs)
         m.match_pairs([(0, 1)])
         first = m.getMatching(0, 1)
