@@ -9,7 +9,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libsfmmatch.so")
 SOURCES = ["sfm_match.cu"]
-HEADERS = ["common.cuh", "binary_knn.cuh", "filter.cuh", "float_exact.cuh", "float_tensor.cuh", "../../include/sfm_match.h"]
+HEADERS = sorted(f for f in os.listdir(CSRC) if f.endswith(".cuh")) + ["../../include/sfm_match.h"]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",

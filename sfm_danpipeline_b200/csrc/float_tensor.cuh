@@ -44,6 +44,7 @@ enum TensorMode {
     TM_TF32_EXACT = 0,    // TF32-exact float data: keys carry the exact integer d^2, result is final
     TM_I8 = 1,            // binary descriptors unpacked to bytes (kind::i8), result is final
     TM_TF32_RANK = 2,     // arbitrary floats, pass 1: approximate d^2 (TF32 truncation) -> approximate top-2 per row
+    TM_I8P = 4,           // TM_I8 with two 16-bit keys per register (descriptors < 512 bit): half the min/max work
     TM_TF32_COLLECT = 3   // arbitrary floats, pass 2: every column whose approximate d^2 can still be in the exact
                           // top-2 (<= m2 + 2*eps, a rigorous bound) is appended to the row's candidate list, which
                           // float_refine_kernel then evaluates exactly (fp32 direct difference, float_exact.cuh's arithmetic)
@@ -251,6 +252,48 @@ __global__ void binary_unpack_kernel(const uint32_t* __restrict__ blob, int word
     if (lane == 0) norms[row] = pc;
 }
 
+// Per train row of the binary tensor engine: the part of the top-2 key that does not depend on the query,
+//     nbkey = (popc(t) + I8_BIAS) * 512 + (row inside its image mod 128),
+// so that the epilogue forms its key with ONE IMAD per accumulator element:
+//     key = acc * (-1024) + nbkey = (popc(t) - 2 q.t + I8_BIAS) << 9 | column-in-tile.
+// popc(q) is the same for every column of a row: it does not change the order and is added when the
+// tile's two winners are merged (hamming = (key >> 9) - I8_BIAS + popc(q)).  Train tiles start at multiples
+// of 128 rows of the image, so the column inside the tile is a property of the row.  IMAD runs at 64
+// lanes/clk/SM (profiles/pipe_bench_r01.txt): three of them per element were 768 cycles per 128x128 tile,
+// more than the 512 cycles the MMAs of a 256-bit descriptor need.
+static constexpr uint32_t I8_BIAS = 512;  // popc(t) - 2 q.t >= -popc(q) >= -512
+//
+// packed (TM_I8P, descriptors of fewer than 512 bits, bias = the bit length): the distance part needs 10 bits,
+// so a key fits 16 bits with a 6-bit column code, and ONE register carries the keys of columns c (low half)
+// and c + 16 (high half) of a 32-column chunk: col6 = (c & 15) | (chunk << 4).  The entry of a row with
+// (column & 16) == 0 holds the query-independent parts of BOTH keys,
+//     nbkey = ((popc(t_c) + bias) << 6 | col6) | ((popc(t_c+16) + bias) << 6 | col6) << 16,
+// and the epilogue forms the pair with two IMADs:  hi = acc[c+16] * (-128 << 16) + nbkey;  key2 = acc[c] * -128 + hi.
+// VIMNMX.U16x2 then keeps the two smallest keys of each half: 1.25 ALU ops per column instead of 2.5 --
+// the ALU pipe (64 lanes/clk/SM) was the epilogue's floor at 640 cycles per 128x128 tile.
+__global__ void binary_nbkey_kernel(const int32_t* __restrict__ popc, const uint32_t* __restrict__ row0 /* n_images, ascending */,
+                                    int n_images, uint32_t total_rows, uint32_t* __restrict__ nbkey, uint32_t packed_bias /* 0 = 32-bit keys */) {
+    const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= total_rows) return;
+    int lo = 0, hi = n_images;  // last image whose first row is <= row
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (row0[mid] <= row) lo = mid; else hi = mid;
+    }
+    const uint32_t lc = (row - row0[lo]) & 127u;  // column inside its 128-row train tile
+    if (packed_bias == 0) {
+        nbkey[row] = (static_cast<uint32_t>(popc[row]) + I8_BIAS) * 512u + lc;
+    } else {
+        const uint32_t col6 = (lc & 15u) | ((lc >> 5) << 4);
+        const uint32_t own = (static_cast<uint32_t>(popc[row]) + packed_bias) << 6 | col6;
+        // the partner row may lie past the image (another image's row, or padding): its key is masked in the
+        // kernel (partial tile), it only has to stay inside its 16 bits
+        const uint32_t pc16 = row + 16 < total_rows ? static_cast<uint32_t>(popc[row + 16]) : 0u;
+        const uint32_t partner = (pc16 + packed_bias) << 6 | col6;
+        nbkey[row] = (lc & 16u) ? own : (own | partner << 16);  // (entries with bit 4 set are not read)
+    }
+}
+
 // ------------------------------------------------------------------ the kernel
 // One work item (= one KnnTile), decoded by the prefetch warp for the other roles.
 struct FtItem {
@@ -350,21 +393,63 @@ __device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[32], uint32_t n
         for (int i = 0; i < 4; ++i) {
             [[maybe_unused]] uint32_t bits = 0;
             if constexpr (MODE == TM_I8) {
-                // hamming = (popc(t) + popc(q)) - 2 q.t in s32; the IMADs keep it off the ALU pipe
-                // (cq carries popc(q) as integer bits, nbv popc(t) as integer bits; key_mul - 514 = -2)
-                uint32_t nbq;
-                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(nbq) : "r"(__float_as_uint(nbv[i])), "r"(key_mul - 511u), "r"(__float_as_uint(cq)));
-                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(bits) : "r"(acc[e + i]), "r"(key_mul - 514u), "r"(nbq));
+                // key = acc * (-1024) + nbkey: see binary_nbkey_kernel (key_mul - 1536 = -1024 comes from a kernel
+                // parameter so that the multiply stays one IMAD on the FMA pipe instead of a shift + subtract on the ALU)
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(acc[e + i]), "r"(key_mul - 1536u), "r"(__float_as_uint(nbv[i])));
             } else {
                 bits = __float_as_uint(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i] + cq));
+                const uint32_t lc = lc0 + e + i;  // column inside the 128-wide tile
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(bits), "r"(key_mul), "r"(lc));
             }
-            const uint32_t lc = lc0 + e + i;  // column inside the 128-wide tile
-            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(bits), "r"(key_mul), "r"(lc));
             if (PARTIAL) k[i] = col0 + e + i < n_rows ? k[i] : 0xFFFFFFFFu;
         }
         top2_pair(m1, m2, k[0], k[1]);
         top2_pair(m1, m2, k[2], k[3]);
     }
+}
+
+// TM_I8P: see binary_nbkey_kernel.  16 packed key pairs per 32-column chunk.
+__device__ __forceinline__ void top2_pair_u16x2(uint32_t& m1, uint32_t& m2, uint32_t a, uint32_t b) {
+    const uint32_t lo = __vminu2(a, b), hi = __vmaxu2(a, b);
+    const uint32_t loser = __vmaxu2(m1, lo);
+    m1 = __vminu2(m1, lo);
+    m2 = __vimin3_u16x2(m2, loser, hi);
+}
+
+template <bool PARTIAL>
+__device__ __forceinline__ void chunk_top2_packed(const uint32_t (&acc)[32], uint32_t nb_saddr, uint32_t mul_lo /* -128 */, uint32_t mul_hi /* -128 << 16 */,
+                                                  uint32_t col0 /* first column of the chunk, relative to t0 */, uint32_t n_rows,
+                                                  uint32_t& m1, uint32_t& m2) {
+#pragma unroll
+    for (int e = 0; e < 16; e += 4) {
+        const float4 nb = lds128(nb_saddr + e * 4);  // entries 0..15 of the chunk: the pair constants
+        const uint32_t nbv[4] = {__float_as_uint(nb.x), __float_as_uint(nb.y), __float_as_uint(nb.z), __float_as_uint(nb.w)};
+        uint32_t k[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            uint32_t hi;
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(acc[e + i + 16]), "r"(mul_hi), "r"(nbv[i]));
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(acc[e + i]), "r"(mul_lo), "r"(hi));
+            if (PARTIAL) k[i] |= (col0 + e + i < n_rows ? 0u : 0xFFFFu) | (col0 + e + i + 16 < n_rows ? 0u : 0xFFFF0000u);
+        }
+        top2_pair_u16x2(m1, m2, k[0], k[1]);
+        top2_pair_u16x2(m1, m2, k[2], k[3]);
+    }
+}
+
+// Tile end of TM_I8P: the two smallest 32-bit keys (hamming << 9 | column-in-tile) among the four 16-bit lane winners.
+__device__ __forceinline__ void unpack_top2_u16x2(uint32_t m1, uint32_t m2, uint32_t dadd /* popc(q) - bias */, uint32_t& q1, uint32_t& q2) {
+    uint32_t c[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const uint32_t k16 = ((i & 2) ? m2 : m1) >> (16 * (i & 1)) & 0xFFFFu;
+        const uint32_t col6 = k16 & 63u;
+        const uint32_t col = (col6 & 15u) + 16u * (i & 1) + 32u * (col6 >> 4);
+        c[i] = k16 >= 0xFFC0u ? 0xFFFFFFFFu : (((k16 >> 6) + dadd) << 9 | col);
+    }
+    const uint32_t lo01 = min(c[0], c[1]), hi01 = max(c[0], c[1]), lo23 = min(c[2], c[3]), hi23 = max(c[2], c[3]);
+    q1 = min(lo01, lo23);
+    q2 = min(max(lo01, lo23), min(hi01, hi23));
 }
 
 // TM_TF32_RANK: only the two smallest VALUES of the row matter (pass 2 re-derives the columns), so the key is
@@ -439,6 +524,64 @@ __device__ __forceinline__ void chunk_collect(const uint32_t (&acc)[32], uint32_
     }
 }
 
+// Pass-2 threshold of one query row (TM_TF32_COLLECT), with |q|^2 already moved to the threshold's side.
+// m2 = approximate second-smallest d^2 of this row from pass 1 (merged over the splits, clamped at 0: if two or
+// more approximations were negative, pass 1's signed-integer order may have kept the wrong two of them, but then
+// every one of them -- and the true second-smallest -- is <= 0 + eps).  |approx - exact| <= eps with
+// eps = 2^-8 |q| max|t| (both operands truncated to TF32: relative error < 2^-10 each, Cauchy-Schwarz)
+// + accumulation / norm rounding slack; every column of the exact top-2 has approx <= m2 + 2 eps.
+__device__ __forceinline__ float collect_threshold(bool valid, float nq2, const PairDesc& pd, const KnnEntry* __restrict__ knn, uint32_t qrow) {
+    if (!valid) return __int_as_float(0xff800000);  // -inf: rows past the image collect nothing (their accumulators are
+                                                    // dot products with some other image's rows and can be anything)
+    unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
+    for (uint32_t sidx = 0; sidx < pd.n_splits; ++sidx) {
+        const KnnEntry e = knn[pd.knn_off + (size_t)sidx * pd.nq + qrow];
+        const unsigned long long hi = max(k1, e.x);
+        k1 = min(k1, e.x);
+        k2 = min(min(k2, hi), e.y);
+    }
+    const uint32_t m2bits = static_cast<uint32_t>(k2 >> 32);
+    const float m2 = m2bits >= 0x7f800000u ? __int_as_float(0x7f7fffff) : __uint_as_float(m2bits);  // none / inf / NaN: collect all
+    const float eps = 0.00390625f * 1.02f * sqrtf(nq2) * sqrtf(pd.t_maxnorm2) + 1e-6f * (nq2 + pd.t_maxnorm2);
+    return m2 + 2.f * eps - nq2 + 1e-6f * (m2 + nq2);  // (last term: rounding of moving |q|^2 across)
+}
+
+// End of an item for the eight epilogue warps: merge the two groups' lists of each row -- lexicographic
+// (d^2, index) -- and write the row's entry; d = sqrtf(d^2) of an exact integer is bit-identical to OpenCV's
+// sqrtf(sum (a-b)^2).  `merge` alternates between items: group 1 may already be an item ahead when group 0 reads.
+template <int MODE>
+__device__ __forceinline__ void finish_rows(uint4* merge, const Top2& best, uint32_t half, uint32_t row, uint32_t qrow, uint32_t nq,
+                                            bool reverse, uint32_t split, unsigned long long knn_off, unsigned long long col_off,
+                                            KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin) {
+    if (half == 1) merge[row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
+    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
+    if (half == 0 && qrow < nq) {
+        const uint4 o = merge[row];
+        unsigned long long k1 = best.i1 < 0 ? KEY_NONE : make_key(best.d1, (uint32_t)best.i1);
+        unsigned long long k2 = best.i2 < 0 ? KEY_NONE : make_key(best.d2, (uint32_t)best.i2);
+        const unsigned long long o1 = (int)o.y < 0 ? KEY_NONE : make_key(o.x, o.y);
+        const unsigned long long o2 = (int)o.w < 0 ? KEY_NONE : make_key(o.z, o.w);
+        unsigned long long hi = max(k1, o1);
+        k1 = min(k1, o1);
+        k2 = min(min(k2, hi), o2);
+        if (reverse) {  // column minimum of the forward problem: (d^2, lowest query index); splits merge by atomicMin
+            if (k1 != KEY_NONE) atomicMin(colmin + col_off + qrow, k1);
+        } else {
+            KnnEntry e;
+            if constexpr (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_TF32_RANK) {
+                // i8: the Hamming distance stays an integer in the key (binary_knn.cuh's convention);
+                // rank pass: float bits of the approximate d^2 (only pass 2 reads it)
+                e.x = k1;
+                e.y = k2;
+            } else {  // integer d^2 -> float bits of d
+                e.x = k1 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32))), (uint32_t)k1);
+                e.y = k2 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k2 >> 32))), (uint32_t)k2);
+            }
+            knn[knn_off + (size_t)split * nq + qrow] = e;
+        }
+    }
+}
+
 // PERSISTENT kernel: one CTA per SM walks the launch's KnnTile list with stride gridDim.x.  The TMA / MMA /
 // epilogue pipeline keeps running across item boundaries (ring indices and mbarrier phases follow a tile counter
 // that never resets), so the epilogue of item k -- draining the 4 TMEM stages, merging the two groups' lists,
@@ -457,10 +600,11 @@ __device__ __forceinline__ void chunk_collect(const uint32_t (&acc)[32], uint32_
 template <int KB /* 128-byte K-blocks per row: 4 for 128-d float / 512-bit binary */, int MODE>
 __global__ void __launch_bounds__(FT_THREADS, 1)
 tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ norms /* int32 popcounts when INT8 */,
+                   const float* __restrict__ nb_src /* per train row: |t|^2, or binary_nbkey_kernel's key part when INT8 */,
                    const KnnTile* __restrict__ tiles, const uint32_t n_items, const PairDesc* __restrict__ pairs,
-                   KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */,
+                   KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */, const uint32_t i8_bias /* TM_I8P: the descriptors' bit length */,
                    uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
-    constexpr bool INT8 = MODE == TM_I8;
+    constexpr bool INT8 = MODE == TM_I8 || MODE == TM_I8P;
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                   // KB x 16 KB
@@ -524,7 +668,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                     mbar_expect_tx(&sm.nb_full[a], FT_N * sizeof(float));
                     // image rows start at multiples of 4 and t0 at multiples of 128: 16-byte aligned source;
                     // the norms array is padded so that the copy may run past the image's last row
-                    tma_load_1d(sm.nb[a], norms + b_row0 + j * FT_N, FT_N * sizeof(float), &sm.nb_full[a]);
+                    tma_load_1d(sm.nb[a], nb_src + b_row0 + j * FT_N, FT_N * sizeof(float), &sm.nb_full[a]);
                     mbar_wait(&sm.b_empty[s], ((g / FT_B_STAGES) & 1) ^ 1);
                     mbar_expect_tx(&sm.b_full[s], KB * FT_B_KBLOCK_BYTES);
                     unsigned char* dst = sB + (size_t)s * KB * FT_B_KBLOCK_BYTES;
@@ -607,28 +751,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 if constexpr (MODE == TM_TF32_EXACT) {
                     v = nq2 + 8388608.f;  // |q|^2 + 2^23 (exact): see Top2
                 } else if constexpr (MODE == TM_TF32_COLLECT) {
-                    // m2 = approximate second-smallest d^2 of this row from pass 1 (merged over the splits, clamped at 0:
-                    // if two or more approximations were negative, pass 1's signed-integer order may have kept the wrong
-                    // two of them, but then every one of them -- and the true second-smallest -- is <= 0 + eps).
-                    // |approx - exact| <= eps with
-                    // eps = 2^-8 |q| max|t| (both operands truncated to TF32: relative error < 2^-10 each, Cauchy-Schwarz)
-                    // + accumulation / norm rounding slack; every column of the exact top-2 has approx <= m2 + 2 eps.
-                    if (valid) {
-                        unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
-                        for (uint32_t sidx = 0; sidx < pd.n_splits; ++sidx) {
-                            const KnnEntry e = knn[pd.knn_off + (size_t)sidx * pd.nq + qrow];
-                            const unsigned long long hi = max(k1, e.x);
-                            k1 = min(k1, e.x);
-                            k2 = min(min(k2, hi), e.y);
-                        }
-                        const uint32_t m2bits = static_cast<uint32_t>(k2 >> 32);
-                        const float m2 = m2bits >= 0x7f800000u ? __int_as_float(0x7f7fffff) : __uint_as_float(m2bits);  // none / inf / NaN: collect all
-                        const float eps = 0.00390625f * 1.02f * sqrtf(nq2) * sqrtf(pd.t_maxnorm2) + 1e-6f * (nq2 + pd.t_maxnorm2);
-                        v = m2 + 2.f * eps - nq2 + 1e-6f * (m2 + nq2);  // (|q|^2 moved to this side; last term: rounding of that move)
-                    } else {
-                        v = __int_as_float(0xff800000);  // -inf: rows past the image collect nothing (their accumulators are
-                                                         // dot products with some other image's rows and can be anything)
-                    }
+                    v = collect_threshold(valid, nq2, pd, knn, qrow);
                 } else {
                     v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (rank)
                 }
@@ -695,6 +818,10 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                     } else if constexpr (MODE == TM_TF32_RANK) {
                         if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
                         else chunk_rank<true>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
+                    } else if constexpr (MODE == TM_I8P) {
+                        // (key_mul - 640 = -128 from the kernel parameter: stays an IMAD on the FMA pipe)
+                        if (!partial) chunk_top2_packed<false>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
+                        else chunk_top2_packed<true>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
                     } else {
                         if (!partial) chunk_top2<false, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
                         else chunk_top2<true, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
@@ -711,8 +838,17 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 // merge the tile's two best into the running pair (ascending tiles = arrival order)
                 if constexpr (MODE != TM_TF32_RANK && MODE != TM_TF32_COLLECT) {
                     const int tbase = (int)(t0 + col0);
-                    if (m1 != 0xFFFFFFFFu) best.offer(m1 >> 9, tbase + (int)(m1 & 511u));
-                    if (m2 != 0xFFFFFFFFu) best.offer(m2 >> 9, tbase + (int)(m2 & 511u));
+                    if constexpr (MODE == TM_I8P) {  // four 16-bit lane winners -> the tile's two smallest (hamming, column)
+                        uint32_t q1, q2;
+                        unpack_top2_u16x2(m1, m2, __float_as_uint(cq) - i8_bias, q1, q2);
+                        if (q1 != 0xFFFFFFFFu) best.offer(q1 >> 9, tbase + (int)(q1 & 511u));
+                        if (q2 != 0xFFFFFFFFu) best.offer(q2 >> 9, tbase + (int)(q2 & 511u));
+                    } else {
+                        // i8: the key carries popc(t) - 2 q.t + I8_BIAS; popc(q) (the bits of cq) completes the Hamming distance
+                        const uint32_t dadd = MODE == TM_I8 ? __float_as_uint(cq) - I8_BIAS : 0u;
+                        if (m1 != 0xFFFFFFFFu) best.offer((m1 >> 9) + dadd, tbase + (int)(m1 & 511u));
+                        if (m2 != 0xFFFFFFFFu) best.offer((m2 >> 9) + dadd, tbase + (int)(m2 & 511u));
+                    }
                 }
             }
             g0 += n_tiles;
@@ -723,36 +859,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             if constexpr (MODE == TM_TF32_COLLECT) {
                 if (n_splits == 1 && qrow < nq) *cand_count_row = fill;
             } else {
-                // merge the two groups' lists of each row: lexicographic (d^2, index), then d = sqrtf(d^2)
-                // (an exact integer under the root: bit-identical to OpenCV's sqrtf(sum (a-b)^2)).  The buffer
-                // alternates between items: group 1 may already be an item ahead when group 0 reads.
-                if (half == 1) sm.merge[it & 1][row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
-                asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-                if (half == 0 && qrow < nq) {
-                    const uint4 o = sm.merge[it & 1][row];
-                    unsigned long long k1 = best.i1 < 0 ? KEY_NONE : make_key(best.d1, (uint32_t)best.i1);
-                    unsigned long long k2 = best.i2 < 0 ? KEY_NONE : make_key(best.d2, (uint32_t)best.i2);
-                    const unsigned long long o1 = (int)o.y < 0 ? KEY_NONE : make_key(o.x, o.y);
-                    const unsigned long long o2 = (int)o.w < 0 ? KEY_NONE : make_key(o.z, o.w);
-                    unsigned long long hi = max(k1, o1);
-                    k1 = min(k1, o1);
-                    k2 = min(min(k2, hi), o2);
-                    if (reverse) {  // column minimum of the forward problem: (d^2, lowest query index); splits merge by atomicMin
-                        if (k1 != KEY_NONE) atomicMin(colmin + col_off + qrow, k1);
-                    } else {
-                        KnnEntry e;
-                        if constexpr (MODE == TM_I8 || MODE == TM_TF32_RANK) {
-                            // i8: the Hamming distance stays an integer in the key (binary_knn.cuh's convention);
-                            // rank pass: float bits of the approximate d^2 (only pass 2 reads it)
-                            e.x = k1;
-                            e.y = k2;
-                        } else {  // integer d^2 -> float bits of d
-                            e.x = k1 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k1 >> 32))), (uint32_t)k1);
-                            e.y = k2 == KEY_NONE ? KEY_NONE : make_key(__float_as_uint(sqrtf((float)(uint32_t)(k2 >> 32))), (uint32_t)k2);
-                        }
-                        knn[knn_off + (size_t)split * nq + qrow] = e;
-                    }
-                }
+                finish_rows<MODE>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin);
             }
         }
     }

@@ -1,0 +1,397 @@
+// Tensor-core 2-NN kernel, "TS" form: the QUERY tile lives in tensor memory, only train tiles go through
+// shared memory.  Same maths, same epilogue and the same results as tensor_knn2_kernel (float_tensor.cuh),
+// which it replaces as the default; the shared-memory-A ("SS") kernel stays selectable (SFMM_TENSOR_SS=1)
+// as the measured baseline.
+//
+// Why: with both operands in shared memory every tcgen05.mma (M=128, N=128, 32 bytes of K) reads 4 KB of A
+// and 4 KB of B in its 64-cycle slot = 128 B/clk, which is ALL of the SM's shared-memory bandwidth
+// (128 B/clk/SM, B300_MICROARCH.md), and the TMA engine has to write the next train tile into the same
+// memory (64 KB per 1024-cycle tile = another 64 B/clk).  192 B/clk of demand on a 128 B/clk port predicts
+// 1536 cycles per tile; the SS kernel measured 1430-1575 (tensor pipe 66-76 % active, ncu
+// profiles/ncu_tensor_persist_r01.txt) whatever else was tuned.  Reading A from TMEM removes 64 B/clk.
+// It also frees the 64 KB query-tile buffer: the train ring grows from 2 to 3 stages (more TMA latency
+// hidden), and the query tile of the NEXT item is loaded while the current one computes (two A buffers in
+// TMEM), which removes the pipeline bubble at item boundaries.
+//
+// TMEM map (512 columns): [0,128) query tile A0 | [128,256) A1 | [256,384) accumulator 0 | [384,512) accumulator 1.
+// A row r of the tile is TMEM lane r; its K bytes are packed in order into 32-bit columns (32 bytes = 8
+// columns per MMA), which is exactly what a thread gets when it reads its row from global memory as
+// 32-bit words -- so four loader warps (one per TMEM lane quarter) copy rows global -> registers ->
+// tcgen05.st, no swizzle and no staging buffer.
+//
+//   warp 0       TMA producer  : train tiles (3-stage ring) + their norms (4-slot ring)
+//   warp 1       MMA issuer    : tcgen05.mma [d_tmem], [a_tmem], b_desc  (A from TMEM)
+//   warp 2       TMEM allocator
+//   warp 3       item prefetch : next KnnTile/PairDesc + per-row constants -> 2-slot smem ring
+//   warps 4-11   epilogue      : two groups of four warps on alternate tiles (one accumulator stage each)
+//   warps 12-15  query loaders : global -> registers -> tcgen05.st, one item ahead
+#pragma once
+#include "float_tensor.cuh"
+
+namespace sfmm {
+
+static constexpr int FTS_B_STAGES = 3;
+static constexpr int FTS_ACC_STAGES = 2;
+static constexpr int FTS_NB_STAGES = 4;
+static constexpr int FTS_THREADS = 512;
+static constexpr uint32_t FTS_ACC_COL0 = 256;  // first accumulator column
+
+struct FtsSmem {  // after the 1024-byte aligned operand area
+    uint64_t a_full[2], a_empty[2];
+    uint64_t b_full[FTS_B_STAGES], b_empty[FTS_B_STAGES];
+    uint64_t acc_full[FTS_ACC_STAGES], acc_empty[FTS_ACC_STAGES];
+    uint64_t nb_full[FTS_NB_STAGES], nb_empty[FTS_NB_STAGES];
+    uint64_t item_full[2], item_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+    FtItem item[2];
+    alignas(16) float nb[FTS_NB_STAGES][FT_N];
+    float rowval[2][FT_M];
+    uint4 merge[2][FT_M];
+};
+
+static inline size_t float_tensor_ts_smem_bytes(int kblocks) {
+    return 1024 /*alignment slack*/ + (size_t)kblocks * FTS_B_STAGES * FT_B_KBLOCK_BYTES + sizeof(FtsSmem);
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T; whole warp calls, one elected lane issues (see tc_mma).
+template <bool INT8, bool ACCUMULATE>
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
+    if constexpr (INT8)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pe, p;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::i8 [%0], [%1], %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d),
+            "r"(tmem_a), "l"(desc_b), "r"(idesc), "n"(ACCUMULATE ? 1 : 0)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pe, p;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d),
+            "r"(tmem_a), "l"(desc_b), "r"(idesc), "n"(ACCUMULATE ? 1 : 0)
+            : "memory");
+}
+
+__device__ __forceinline__ void tc_st_32x32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]),
+        "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]),
+        "r"(r[31])
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+template <int KB /* 128-byte K-blocks per row */, int MODE>
+__global__ void __launch_bounds__(FTS_THREADS, 1)
+tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ a_src /* the matrix the tensor map describes: rows of KB*128 bytes */,
+                      const uint32_t total_rows, const float* __restrict__ norms /* int32 popcounts when INT8 */,
+                   const float* __restrict__ nb_src /* per train row: |t|^2, or binary_nbkey_kernel's key part when INT8 */,
+                      const KnnTile* __restrict__ tiles, const uint32_t n_items, const PairDesc* __restrict__ pairs,
+                      KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */, const uint32_t i8_bias /* TM_I8P: the descriptors' bit length */,
+                      uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
+    constexpr bool INT8 = MODE == TM_I8 || MODE == TM_I8P;
+    extern __shared__ unsigned char ft_smem_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
+    unsigned char* sB = base;  // FTS_B_STAGES x KB x 16 KB
+    FtsSmem& sm = *reinterpret_cast<FtsSmem*>(base + (size_t)KB * FTS_B_STAGES * FT_B_KBLOCK_BYTES);
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < 2; ++s) {
+            mbar_init(&sm.a_full[s], 4);   // the four loader warps
+            mbar_init(&sm.a_empty[s], 1);  // tcgen05.commit after the item's last MMA
+            mbar_init(&sm.item_full[s], 1);
+            mbar_init(&sm.item_empty[s], 2 + FT_EPI_WARPS + 4);  // producer thread, MMA warp, eight epilogue warps, four loader warps
+        }
+        for (int s = 0; s < FTS_B_STAGES; ++s) {
+            mbar_init(&sm.b_full[s], 1);
+            mbar_init(&sm.b_empty[s], 1);
+        }
+        for (int s = 0; s < FTS_ACC_STAGES; ++s) {
+            mbar_init(&sm.acc_full[s], 1);
+            mbar_init(&sm.acc_empty[s], FT_EPI_WARPS / 2);  // the four warps of the group that owns the stage
+        }
+        for (int s = 0; s < FTS_NB_STAGES; ++s) {
+            mbar_init(&sm.nb_full[s], 1);
+            mbar_init(&sm.nb_empty[s], FT_EPI_WARPS / 2);
+        }
+        mbar_fence_init();
+    }
+    if (warp == 2) {  // whole warp: allocate all 512 TMEM columns (1 CTA per SM: smem-limited)
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(smem_u32(&sm.tmem_base))
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = sm.tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer: train tiles only =====================
+        if (lane == 0) {
+            asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+            uint32_t g = 0, it = 0;  // tiles / items this CTA has gone through: ring slots and mbarrier phases
+            for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+                const uint32_t slot = it & 1;
+                mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
+                const uint32_t b_row0 = sm.item[slot].b_row0, n_tiles = sm.item[slot].n_tiles;
+                mbar_arrive(&sm.item_empty[slot]);
+#pragma unroll 1
+                for (uint32_t j = 0; j < n_tiles; ++j, ++g) {
+                    const uint32_t s = g % FTS_B_STAGES;
+                    const uint32_t a = g % FTS_NB_STAGES;
+                    mbar_wait(&sm.nb_empty[a], ((g / FTS_NB_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&sm.nb_full[a], FT_N * sizeof(float));
+                    // image rows start at multiples of 4 and t0 at multiples of 128: 16-byte aligned source;
+                    // the norms array is padded so that the copy may run past the image's last row
+                    tma_load_1d(sm.nb[a], nb_src + b_row0 + j * FT_N, FT_N * sizeof(float), &sm.nb_full[a]);
+                    mbar_wait(&sm.b_empty[s], ((g / FTS_B_STAGES) & 1) ^ 1);
+                    mbar_expect_tx(&sm.b_full[s], KB * FT_B_KBLOCK_BYTES);
+                    unsigned char* dst = sB + (size_t)s * KB * FT_B_KBLOCK_BYTES;
+                    const int row = (int)(b_row0 + j * FT_N);
+#pragma unroll
+                    for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+                        for (int h = 0; h < FT_N / FT_BOX_ROWS; ++h)
+                            tma_load_2d(dst + kb * FT_B_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS),
+                                        row + h * FT_BOX_ROWS, &sm.b_full[s]);
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (whole warp, uniform; one elected lane issues) =====================
+        const uint32_t tb = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
+        const uint32_t idesc = INT8 ? FT_IDESC_I8 : FT_IDESC;
+        uint32_t g = 0, it = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t slot = it & 1;
+            mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
+            const uint32_t n_tiles = __shfl_sync(0xFFFFFFFFu, sm.item[slot].n_tiles, 0);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.item_empty[slot]);
+            mbar_wait(&sm.a_full[slot], (it >> 1) & 1);  // the loaders have stored this item's query tile
+            tc_fence_after();
+            const uint32_t a_tmem = tb + slot * FT_M;  // 128 columns per query-tile buffer
+#pragma unroll 1
+            for (uint32_t j = 0; j < n_tiles; ++j, ++g) {
+                const uint32_t s = g % FTS_B_STAGES, a = g % FTS_ACC_STAGES;
+                mbar_wait(&sm.b_full[s], (g / FTS_B_STAGES) & 1);
+                mbar_wait(&sm.acc_empty[a], ((g / FTS_ACC_STAGES) & 1) ^ 1);
+                tc_fence_after();
+                const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB + (size_t)s * KB * FT_B_KBLOCK_BYTES));
+                const uint32_t d_tmem = tb + FTS_ACC_COL0 + a * FT_N;
+                tc_mma_ts<INT8, false>(d_tmem, a_tmem, b_desc0, idesc);
+#pragma unroll
+                for (int i = 1; i < 4 * KB; ++i) {  // i = kb*4 + k: 32 bytes of K = 8 TMEM columns of A, 32 bytes inside B's swizzle row
+                    const int kb = i >> 2, k = i & 3;
+                    tc_mma_ts<INT8, true>(d_tmem, a_tmem + i * 8, b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
+                }
+                tc_commit_elect(&sm.b_empty[s]);   // smem stage reusable once these MMAs have read it
+                tc_commit_elect(&sm.acc_full[a]);  // accumulator ready for the epilogue
+            }
+            tc_commit_elect(&sm.a_empty[slot]);  // every MMA of this item has read the query tile: its TMEM buffer may be refilled
+        }
+    } else if (warp == 3) {
+        // ===================== item prefetch =====================
+        uint32_t it = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t slot = it & 1;
+            mbar_wait(&sm.item_empty[slot], ((it >> 1) & 1) ^ 1);
+            KnnTile tile = tiles[item];
+            PairDesc pd = pairs[tile.pair];
+            // "reverse" tile (bit 31 of split): the symmetric cross-check's column minima, roles swapped
+            const bool reverse = (tile.split >> 31) != 0;
+            tile.split &= 0x7FFFFFFFu;
+            if (reverse) {
+                const uint32_t r0 = pd.q_row0, n = pd.nq;
+                pd.q_row0 = pd.t_row0; pd.nq = pd.nt;
+                pd.t_row0 = r0; pd.nt = n;
+            }
+            if (lane == 0) {
+                FtItem& o = sm.item[slot];
+                o.a_row = pd.q_row0 + tile.q0;
+                o.b_row0 = pd.t_row0 + tile.t0;
+                o.n_rows = tile.t1 - tile.t0;
+                o.n_tiles = (tile.t1 - tile.t0 + FT_N - 1) / FT_N;
+                o.q0 = tile.q0; o.nq = pd.nq; o.t0 = tile.t0; o.split = tile.split; o.reverse = reverse ? 1u : 0u;
+                o.n_splits = pd.n_splits; o.q_off = pd.q_off; o.knn_off = pd.knn_off; o.col_off = pd.col_off;
+            }
+#pragma unroll
+            for (int rr = 0; rr < FT_M / 32; ++rr) {
+                const uint32_t row = rr * 32 + lane, qrow = tile.q0 + row;
+                const bool valid = qrow < pd.nq;
+                const float nq2 = valid ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
+                float v;
+                if constexpr (MODE == TM_TF32_EXACT) {
+                    v = nq2 + 8388608.f;  // |q|^2 + 2^23 (exact): see Top2
+                } else if constexpr (MODE == TM_TF32_COLLECT) {
+                    v = collect_threshold(valid, nq2, pd, knn, qrow);
+                } else {
+                    v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (rank)
+                }
+                sm.rowval[slot][row] = v;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.item_full[slot]);
+        }
+    } else if (warp >= 12) {
+        // ===================== query loaders: global -> registers -> TMEM, one item ahead =====================
+        const uint32_t lw = warp - 12;  // == warp % 4: the TMEM lane quarter this warp may access
+        const uint32_t row = lw * 32 + lane;
+        uint32_t it = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t slot = it & 1;
+            mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
+            const uint32_t grow = sm.item[slot].a_row + row;
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.item_empty[slot]);
+            mbar_wait(&sm.a_empty[slot], ((it >> 1) & 1) ^ 1);  // the MMAs of the item before last are done with this buffer
+            tc_fence_after();
+            const bool ok = grow < total_rows;  // rows past the blob: zeros (rows past the image but inside the blob are
+                                                // another image's: computed on, never read -- as with TMA's box)
+            const uint4* src = a_src + (size_t)(ok ? grow : 0) * (KB * 8);
+            const uint32_t taddr = tmem_base + ((lw * 32) << 16) + slot * FT_M;
+#pragma unroll
+            for (int kb = 0; kb < KB; ++kb) {
+                uint32_t r[32];
+#pragma unroll
+                for (int v = 0; v < 8; ++v) {
+                    const uint4 x = ok ? __ldg(src + kb * 8 + v) : make_uint4(0, 0, 0, 0);
+                    r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                }
+                tc_st_32x32(taddr + kb * 32, r);
+            }
+            tc_wait_st();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.a_full[slot]);
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue: fused top-2 =====================
+        // Two groups of four warps (one warp per TMEM lane quarter); group h owns the tiles whose running
+        // counter is h mod 2 == accumulator stage h.  (Splitting every tile's columns between the groups instead,
+        // so that a stage is released as soon as it has been read, measured 10 % slower: the TMEM loads no
+        // longer overlap the fold inside a warp.)
+        const uint32_t ew = warp - 4;
+        const uint32_t quarter = ew & 3, half = ew >> 2;   // TMEM lanes 32*quarter..
+        const uint32_t row = quarter * 32 + lane;          // row of the query tile == TMEM lane
+        uint32_t g0 = 0, it = 0;
+        for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
+            const uint32_t slot = it & 1;
+            mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
+            const FtItem& im = sm.item[slot];
+            const uint32_t n_rows = im.n_rows, n_tiles = im.n_tiles, nq = im.nq, t0 = im.t0, split = im.split, n_splits = im.n_splits;
+            const uint32_t qrow = im.q0 + row, q_off = im.q_off;
+            const bool reverse = im.reverse != 0;
+            const unsigned long long knn_off = im.knn_off, col_off = im.col_off;
+            const float cq = sm.rowval[slot][row];  // TM_TF32_COLLECT: the threshold tau
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&sm.item_empty[slot]);
+
+            Top2 best;
+            best.init();
+            [[maybe_unused]] uint32_t* cand_count_row = nullptr;
+            [[maybe_unused]] uint32_t* cand_idx_row = nullptr;
+            [[maybe_unused]] uint32_t fill = 0;
+            [[maybe_unused]] int r1 = 0x7FFFFFFF, r2 = 0x7FFFFFFF;  // TM_TF32_RANK: two smallest approximate d^2 (float bits), over all tiles
+            if constexpr (MODE == TM_TF32_COLLECT) {
+                // each epilogue group owns one counter and half of the row's list
+                cand_count_row = cand_count + 2 * (size_t)(q_off + min(qrow, nq - 1)) + half;
+                cand_idx_row = cand_idx + (size_t)(q_off + min(qrow, nq - 1)) * FT_CAND_CAP + half * (FT_CAND_CAP / 2);
+            }
+#pragma unroll 1
+            for (uint32_t j = (half ^ g0) & 1; j < n_tiles; j += 2) {
+                const uint32_t g = g0 + j;
+                const uint32_t a = half;                 // == g % FTS_ACC_STAGES
+                const uint32_t nbs = g % FTS_NB_STAGES;
+                mbar_wait(&sm.acc_full[a], (g / FTS_ACC_STAGES) & 1);
+                tc_fence_after();
+                uint32_t acc[2][32];  // register double buffer: chunk c+1 streams in from TMEM while chunk c is folded
+                const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + FTS_ACC_COL0 + a * FT_N;
+                tc_ld_32x32(taddr, acc[0]);
+                mbar_wait(&sm.nb_full[nbs], (g / FTS_NB_STAGES) & 1);
+                tc_wait_ld(acc[0]);
+                const uint32_t col0 = j * FT_N;                // first column of the tile, relative to t0
+                const bool partial = col0 + FT_N > n_rows;     // warp-uniform: only the last tile
+                uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;   // two smallest keys of this tile
+                constexpr int NCH = FT_N / 32;  // 32-column chunks per tile
+#pragma unroll
+                for (int c = 0; c < NCH; ++c) {
+                    if (c < NCH - 1) tc_ld_32x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
+                    const uint32_t nb_saddr = smem_u32(&sm.nb[nbs][c * 32]);
+                    if constexpr (MODE == TM_TF32_COLLECT) {
+                        const uint32_t c0 = col0 + c * 32;  // columns at or past n_rows belong to another image / padding
+                        const uint32_t valid = c0 + 32 <= n_rows ? 0xFFFFFFFFu : (c0 < n_rows ? (1u << (n_rows - c0)) - 1u : 0u);
+                        chunk_collect(acc[c & 1], nb_saddr, cq, valid, t0 + c0, n_splits != 1, fill, cand_count_row, cand_idx_row);
+                    } else if constexpr (MODE == TM_TF32_RANK) {
+                        if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
+                        else chunk_rank<true>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
+                    } else if constexpr (MODE == TM_I8P) {
+                        // (key_mul - 640 = -128 from the kernel parameter: stays an IMAD on the FMA pipe)
+                        if (!partial) chunk_top2_packed<false>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
+                        else chunk_top2_packed<true>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
+                    } else {
+                        if (!partial) chunk_top2<false, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
+                        else chunk_top2<true, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
+                    }
+                    if (c < NCH - 1) tc_wait_ld(acc[(c + 1) & 1]);
+                    if (c == (NCH > 1 ? NCH - 2 : 0)) {  // the last TMEM read of this tile has landed: the MMA that reuses the stage may start
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
+                    }
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sm.nb_empty[nbs]);
+                // merge the tile's two best into the running pair (ascending tiles = arrival order)
+                if constexpr (MODE != TM_TF32_RANK && MODE != TM_TF32_COLLECT) {
+                    const int tbase = (int)(t0 + col0);
+                    if constexpr (MODE == TM_I8P) {  // four 16-bit lane winners -> the tile's two smallest (hamming, column)
+                        uint32_t q1, q2;
+                        unpack_top2_u16x2(m1, m2, __float_as_uint(cq) - i8_bias, q1, q2);
+                        if (q1 != 0xFFFFFFFFu) best.offer(q1 >> 9, tbase + (int)(q1 & 511u));
+                        if (q2 != 0xFFFFFFFFu) best.offer(q2 >> 9, tbase + (int)(q2 & 511u));
+                    } else {
+                        // i8: the key carries popc(t) - 2 q.t + I8_BIAS; popc(q) (the bits of cq) completes the Hamming distance
+                        const uint32_t dadd = MODE == TM_I8 ? __float_as_uint(cq) - I8_BIAS : 0u;
+                        if (m1 != 0xFFFFFFFFu) best.offer((m1 >> 9) + dadd, tbase + (int)(m1 & 511u));
+                        if (m2 != 0xFFFFFFFFu) best.offer((m2 >> 9) + dadd, tbase + (int)(m2 & 511u));
+                    }
+                }
+            }
+            g0 += n_tiles;
+            if constexpr (MODE == TM_TF32_RANK) {  // values only, clamped at 0; the index field is unused
+                if (r1 != 0x7FFFFFFF) { best.d1 = (uint32_t)max(r1, 0); best.i1 = 0; }
+                if (r2 != 0x7FFFFFFF) { best.d2 = (uint32_t)max(r2, 0); best.i2 = 0; }
+            }
+            if constexpr (MODE == TM_TF32_COLLECT) {
+                if (n_splits == 1 && qrow < nq) *cand_count_row = fill;
+            } else {
+                finish_rows<MODE>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin);
+            }
+        }
+    }
+
+    __syncwarp();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 512;" ::"r"(tmem_base) : "memory");
+    }
+}
+
+}  // namespace sfmm

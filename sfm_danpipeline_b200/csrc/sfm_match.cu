@@ -30,6 +30,7 @@
 #include "filter.cuh"
 #include "float_exact.cuh"
 #include "float_tensor.cuh"
+#include "float_tensor_ts.cuh"
 
 using namespace sfmm;
 
@@ -161,9 +162,12 @@ struct SfmmCtx {
     int tensor_kblocks = 0;    // 128-byte K-blocks per operand row
     bool tensor_refine = false; // arbitrary floats: TF32 ranking pass + candidate collection + exact refinement
     std::vector<float> img_maxnorm2;  // per image max |x|^2 (error bound of the ranking pass)
+    int tensor_ts = -1;        // query tile in tensor memory (float_tensor_ts.cuh): -1 = where it measured faster (binary engine), 0/1 = SFMM_TENSOR_TS
     int tensor_cluster = 1;    // CTAs per cluster sharing train tiles: the 2-CTA TMA-multicast variant measured no faster (not L2-bound) and was removed
     CUtensorMap tmap{};
     DevBuf d_norms, d_flags;
+    uint32_t i8_bias = 0;    // binary tensor engine: descriptor bit length when the packed 16-bit keys apply (< 512 bit), else 0
+    DevBuf d_nbkey, d_row0;  // binary tensor engine: per-row key part (binary_nbkey_kernel) and the images' first rows
     DevBuf d_unpacked;  // SFMM_BINARY_TENSOR: one byte per descriptor bit
 
     // descriptors (imagesDescriptors, include/Sfm.h:29)
@@ -372,16 +376,32 @@ cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
 
 template <int KB, int MODE>
 cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
-    const size_t smem = float_tensor_smem_bytes(KB);
-    auto kern = tensor_knn2_kernel<KB, MODE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     // persistent: one CTA per SM (shared memory allows no more) walks the tile list with stride gridDim.x
     const uint32_t grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(ctx->sm_count));
-    kern<<<grid, FT_THREADS, smem, sl.stream>>>(ctx->tmap, (const float*)ctx->d_norms.as<float>(), (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles,
-                                                (const PairDesc*)sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
-                                                sl.d_colmin.as<unsigned long long>(), 512u, sl.d_cand_count.as<uint32_t>(),
-                                                sl.d_cand_idx.as<uint32_t>());
+    const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P) ? (const float*)ctx->d_nbkey.as<float>() : (const float*)ctx->d_norms.as<float>();
+    // measured (profiles/tensor_variants_r01.txt): TMEM-A wins for the binary engine, shared-memory-A for float
+    const bool ts = ctx->tensor_ts < 0 ? (MODE == TM_I8P || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0;
+    if (!ts) {  // query tile in shared memory (float_tensor.cuh)
+        const size_t smem = float_tensor_smem_bytes(KB);
+        auto kern = tensor_knn2_kernel<KB, MODE>;
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, FT_THREADS, smem, sl.stream>>>(ctx->tmap, (const float*)ctx->d_norms.as<float>(), nb_src, (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles,
+                                                    (const PairDesc*)sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
+                                                    sl.d_colmin.as<unsigned long long>(), 512u, ctx->i8_bias, sl.d_cand_count.as<uint32_t>(),
+                                                    sl.d_cand_idx.as<uint32_t>());
+        return cudaGetLastError();
+    }
+    // query tile in tensor memory (float_tensor_ts.cuh)
+    const size_t smem = float_tensor_ts_smem_bytes(KB);
+    auto kern = tensor_knn2_ts_kernel<KB, MODE>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P) ? ctx->d_unpacked.as<uint4>() : ctx->blob.as<uint4>();
+    kern<<<grid, FTS_THREADS, smem, sl.stream>>>(ctx->tmap, a_src, static_cast<uint32_t>(ctx->total_rows), (const float*)ctx->d_norms.as<float>(), nb_src,
+                                                 (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles, (const PairDesc*)sl.d_pairs.as<PairDesc>(),
+                                                 sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u, ctx->i8_bias,
+                                                 sl.d_cand_count.as<uint32_t>(), sl.d_cand_idx.as<uint32_t>());
     return cudaGetLastError();
 }
 
@@ -468,8 +488,16 @@ int prepare_binary_tensor(SfmmCtx* ctx) {
             binary_unpack_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ctx->blob.as<uint32_t>(), words, rows, kbytes, ctx->d_unpacked.as<uint8_t>(),
                                                                  ctx->d_norms.as<int32_t>());
             CU_TRY(ctx, cudaGetLastError());
+            // query-independent part of the top-2 key per train row (popcount, bias, column inside its 128-row tile)
+            CU_TRY(ctx, ctx->d_nbkey.ensure((static_cast<size_t>(ctx->total_rows) + 2 * FT_N) * sizeof(uint32_t)));
+            CU_TRY(ctx, ctx->d_row0.ensure((static_cast<size_t>(ctx->n_images) + 1) * sizeof(uint32_t)));
+            CU_TRY(ctx, cudaMemcpyAsync(ctx->d_row0.p, ctx->row0.data(), static_cast<size_t>(ctx->n_images) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+            ctx->i8_bias = ctx->cols * 8 < 512 && !std::getenv("SFMM_I8_KEYS32") ? static_cast<uint32_t>(ctx->cols) * 8u : 0u;
+            binary_nbkey_kernel<<<(rows + 255) / 256, 256, 0, st>>>(ctx->d_norms.as<int32_t>(), ctx->d_row0.as<uint32_t>(), ctx->n_images, rows,
+                                                                     ctx->d_nbkey.as<uint32_t>(), ctx->i8_bias);
+            CU_TRY(ctx, cudaGetLastError());
             CU_TRY(ctx, cudaStreamSynchronize(st));
-            ctx->stats.kernel_launches += 1;
+            ctx->stats.kernel_launches += 2;
             int rc = make_tensor_map(ctx, ctx->d_unpacked.p, CU_TENSOR_MAP_DATA_TYPE_UINT8, 1, static_cast<size_t>(kbytes), ctx->total_rows);
             if (rc) return rc;
             ctx->tensor_kblocks = kbytes / 128;
@@ -605,7 +633,7 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
         cudaError_t e;
         if (ctx->elem_type == SFMM_F32 && ctx->use_tensor && ctx->tensor_refine) e = launch_tensor_refine(ctx, sl, nt, ctx->tensor_kblocks);
         else if (ctx->elem_type == SFMM_F32) e = ctx->use_tensor ? launch_tensor<TM_TF32_EXACT>(ctx, sl, nt, ctx->tensor_kblocks) : launch_float_exact(ctx, sl, nt);
-        else if (ctx->use_tensor) e = launch_tensor<TM_I8>(ctx, sl, nt, ctx->tensor_kblocks);
+        else if (ctx->use_tensor) e = ctx->i8_bias ? launch_tensor<TM_I8P>(ctx, sl, nt, ctx->tensor_kblocks) : launch_tensor<TM_I8>(ctx, sl, nt, ctx->tensor_kblocks);
         else e = cross ? launch_binary<true>(ctx, sl, nt) : launch_binary<false>(ctx, sl, nt);
         CU_TRY(ctx, e);
         ctx->stats.kernel_launches += 1;
@@ -855,6 +883,7 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     if (!ctx) return fail(nullptr, SFMM_ENOMEM, "sfmm_create: out of host memory");
     ctx->cfg = *cfg;
     ctx->sm_count = prop.multiProcessorCount;
+    if (const char* s = std::getenv("SFMM_TENSOR_TS")) ctx->tensor_ts = std::atoi(s) != 0 ? 1 : 0;
     if (const char* s = std::getenv("SFMM_CSA_LEVEL")) ctx->csa_level = std::max(0, std::min(3, std::atoi(s)));
     bool ok = (e = cudaSetDevice(cfg->device)) == cudaSuccess;
     for (Slot& sl : ctx->slot) {
@@ -884,7 +913,7 @@ SFMM_API void sfmm_destroy(SfmmCtx* ctx) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
-    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked}) b->release();
+    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked, &ctx->d_nbkey, &ctx->d_row0}) b->release();
     for (PinBuf& p : ctx->pack) p.release();
     for (cudaEvent_t ev : {ctx->ev_begin, ctx->ev_end, ctx->ev_pack[0], ctx->ev_pack[1]})
         if (ev) cudaEventDestroy(ev);
