@@ -32,6 +32,7 @@
 // this one trades 8x the descriptor bytes for the tensor pipe.
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 
 #include "binary_knn.cuh"  // mbarrier / PTX helpers
 #include "common.cuh"
@@ -45,6 +46,8 @@ enum TensorMode {
     TM_I8 = 1,            // binary descriptors unpacked to bytes (kind::i8), result is final
     TM_TF32_RANK = 2,     // arbitrary floats, pass 1: approximate d^2 (TF32 truncation) -> approximate top-2 per row
     TM_I8P = 4,           // TM_I8 with two 16-bit keys per register (descriptors < 512 bit): half the min/max work
+    TM_F16_EXACT = 5,     // TM_TF32_EXACT on an fp16 copy of the descriptors (integers |v| <= 2048 are exact in fp16):
+                          // kind::f16 contracts 16 elements per MMA, half the tensor time and half the operand bytes
     TM_TF32_COLLECT = 3   // arbitrary floats, pass 2: every column whose approximate d^2 can still be in the exact
                           // top-2 (<= m2 + 2*eps, a rigorous bound) is appended to the row's candidate list, which
                           // float_refine_kernel then evaluates exactly (fp32 direct difference, float_exact.cuh's arithmetic)
@@ -107,9 +110,25 @@ __device__ __forceinline__ void tc_commit(uint64_t* bar) {
 // Called by the WHOLE warp with warp-uniform operands; one elected lane issues.  (Issuing from inside
 // an `if (lane == 0)` made ptxas wrap every MMA in a R2UR.BROADCAST / BRA.U.ANY uniformisation loop
 // and recompute the descriptors: ~90 cycles per instruction for 64 cycles of tensor work.)
-template <bool INT8, bool ACCUMULATE>
+enum OperandKind { OK_TF32 = 0, OK_I8 = 1, OK_F16 = 2 };
+template <int MODE>
+struct OperandOf {
+    static constexpr int kind = (MODE == TM_I8 || MODE == TM_I8P) ? OK_I8 : (MODE == TM_F16_EXACT ? OK_F16 : OK_TF32);
+    static constexpr int kb_elems = kind == OK_I8 ? 128 : (kind == OK_F16 ? 64 : 32);  // elements per 128-byte swizzle row
+};
+template <int KIND, bool ACCUMULATE>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
-    if constexpr (INT8)  // u8 x u8 -> s32, K = 32 per instruction
+    if constexpr (KIND == OK_F16)  // f16 x f16 -> f32, K = 16 per instruction
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pe, p;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d),
+            "l"(desc_a), "l"(desc_b), "r"(idesc), "n"(ACCUMULATE ? 1 : 0)
+            : "memory");
+    else if constexpr (KIND == OK_I8)  // u8 x u8 -> s32, K = 32 per instruction
         asm volatile(
             "{\n\t"
             ".reg .pred pe, p;\n\t"
@@ -190,6 +209,8 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
 static constexpr uint32_t FT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((FT_N >> 3) << 17) | ((FT_M >> 4) << 24);
 // kind::i8: D=S32 (bits 4-5 = 2), A=B=UINT8 (format 0), both K-major.
 static constexpr uint32_t FT_IDESC_I8 = (2u << 4) | (0u << 7) | (0u << 10) | ((FT_N >> 3) << 17) | ((FT_M >> 4) << 24);
+// kind::f16: D=F32 (1), A=B=F16 (format 0), both K-major.
+static constexpr uint32_t FT_IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((FT_N >> 3) << 17) | ((FT_M >> 4) << 24);
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
     float r;
@@ -221,6 +242,26 @@ __global__ void float_prepare_kernel(const float* __restrict__ blob, int kq, uin
         if (bad) atomicOr(&flags[0], 1u);
         atomicMax(&flags[1], __float_as_uint(acc));
     }
+}
+
+// TF32-exact sets: the query-independent part of the epilogue's key argument, |t|^2 + 2^23 + 2^20 (an exact
+// integer below 2^24).  x' = fmaf(q.t, -2, nb') = d^2 - |q|^2 + 2^23 + 2^20 lies in [2^23, 2^24): its low mantissa
+// bits are that integer, it orders the columns of a row exactly like d^2, and |q|^2 is added back once per tile
+// winner -- one FADD per accumulator element less than forming d^2 + 2^23 in place.
+static constexpr float FT_NB_OFFSET = 8388608.f + 1048576.f;
+__global__ void float_nbexact_kernel(const float* __restrict__ norms, uint32_t n, float* __restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) out[i] = norms[i] + FT_NB_OFFSET;
+}
+
+// fp16 copy of a TF32-exact set (integers |v| <= 2047: exact in fp16's 11-bit significand), rows of `cols` halves.
+__global__ void float_to_half_kernel(const float* __restrict__ blob, int kq, uint32_t total_rows, int cols, __half* __restrict__ out) {
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // one thread per pair of elements
+    const size_t per_row = static_cast<size_t>(cols) / 2;
+    if (i >= static_cast<size_t>(total_rows) * per_row) return;
+    const size_t row = i / per_row, c = (i % per_row) * 2;
+    const float2 v = *reinterpret_cast<const float2*>(blob + row * kq * 4 + c);
+    *reinterpret_cast<__half2*>(out + row * cols + c) = __floats2half2_rn(v.x, v.y);
 }
 
 // ------------------------------------------------------------------ prepare (binary tensor engine)
@@ -397,7 +438,7 @@ __device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[32], uint32_t n
                 // parameter so that the multiply stays one IMAD on the FMA pipe instead of a shift + subtract on the ALU)
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(acc[e + i]), "r"(key_mul - 1536u), "r"(__float_as_uint(nbv[i])));
             } else {
-                bits = __float_as_uint(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i] + cq));
+                bits = __float_as_uint(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i]));  // see float_nbexact_kernel
                 const uint32_t lc = lc0 + e + i;  // column inside the 128-wide tile
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(bits), "r"(key_mul), "r"(lc));
             }
@@ -604,7 +645,8 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                    const KnnTile* __restrict__ tiles, const uint32_t n_items, const PairDesc* __restrict__ pairs,
                    KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */, const uint32_t i8_bias /* TM_I8P: the descriptors' bit length */,
                    uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
-    constexpr bool INT8 = MODE == TM_I8 || MODE == TM_I8P;
+    constexpr int KIND = OperandOf<MODE>::kind;
+    constexpr int KB_ELEMS = OperandOf<MODE>::kb_elems;
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sA = base;                                   // KB x 16 KB
@@ -658,7 +700,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
                     for (int h = 0; h < 2; ++h)
-                        tma_load_2d(sA + kb * FT_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS),
+                        tma_load_2d(sA + kb * FT_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * KB_ELEMS,
                                     (int)a_row + h * FT_BOX_ROWS, &sm.a_full);
 #pragma unroll 1
                 for (uint32_t j = 0; j < n_tiles; ++j, ++g) {
@@ -677,7 +719,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                     for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
                         for (int h = 0; h < FT_N / FT_BOX_ROWS; ++h)
-                            tma_load_2d(dst + kb * FT_B_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS),
+                            tma_load_2d(dst + kb * FT_B_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * KB_ELEMS,
                                         row + h * FT_BOX_ROWS, &sm.b_full[s]);
                 }
             }
@@ -686,7 +728,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
         // ===================== MMA issuer (whole warp, uniform; one elected lane issues) =====================
         const uint32_t tb = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
         const uint64_t a_desc0 = umma_desc_sw128(smem_u32(sA));
-        const uint32_t idesc = INT8 ? FT_IDESC_I8 : FT_IDESC;
+        const uint32_t idesc = KIND == OK_I8 ? FT_IDESC_I8 : (KIND == OK_F16 ? FT_IDESC_F16 : FT_IDESC);
         uint32_t g = 0, it = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t slot = it & 1;
@@ -704,11 +746,11 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB + (size_t)s * KB * FT_B_KBLOCK_BYTES));
                 const uint32_t d_tmem = tb + a * FT_N;
                 // the start-address field counts 16-byte units: stepping inside the tile is an integer add
-                tc_mma<INT8, false>(d_tmem, a_desc0, b_desc0, idesc);
+                tc_mma<KIND, false>(d_tmem, a_desc0, b_desc0, idesc);
 #pragma unroll
                 for (int i = 1; i < 4 * KB; ++i) {  // i = kb*4 + k: 4 x (32 bytes of K) inside each 128-byte swizzle row
                     const int kb = i >> 2, k = i & 3;
-                    tc_mma<INT8, true>(d_tmem, a_desc0 + ((kb * FT_KBLOCK_BYTES + k * 32) >> 4), b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
+                    tc_mma<KIND, true>(d_tmem, a_desc0 + ((kb * FT_KBLOCK_BYTES + k * 32) >> 4), b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
                 }
                 tc_commit_elect(&sm.b_empty[s]);   // smem stage reusable once these MMAs have read it
                 tc_commit_elect(&sm.acc_full[a]);  // accumulator ready for the epilogue
@@ -748,12 +790,10 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 const bool valid = qrow < pd.nq;
                 const float nq2 = valid ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
                 float v;
-                if constexpr (MODE == TM_TF32_EXACT) {
-                    v = nq2 + 8388608.f;  // |q|^2 + 2^23 (exact): see Top2
-                } else if constexpr (MODE == TM_TF32_COLLECT) {
+                if constexpr (MODE == TM_TF32_COLLECT) {
                     v = collect_threshold(valid, nq2, pd, knn, qrow);
                 } else {
-                    v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (rank)
+                    v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (exact float modes, rank)
                 }
                 sm.rowval[slot][row] = v;
             }
@@ -844,8 +884,9 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                         if (q1 != 0xFFFFFFFFu) best.offer(q1 >> 9, tbase + (int)(q1 & 511u));
                         if (q2 != 0xFFFFFFFFu) best.offer(q2 >> 9, tbase + (int)(q2 & 511u));
                     } else {
-                        // i8: the key carries popc(t) - 2 q.t + I8_BIAS; popc(q) (the bits of cq) completes the Hamming distance
-                        const uint32_t dadd = MODE == TM_I8 ? __float_as_uint(cq) - I8_BIAS : 0u;
+                        // i8: the key carries popc(t) - 2 q.t + I8_BIAS; popc(q) (the bits of cq) completes the Hamming distance.
+                        // exact float modes: the key carries d^2 - |q|^2 + 2^20 (float_nbexact_kernel); |q|^2 is an integer <= 2^20
+                        const uint32_t dadd = MODE == TM_I8 ? __float_as_uint(cq) - I8_BIAS : static_cast<uint32_t>(cq) - 1048576u;
                         if (m1 != 0xFFFFFFFFu) best.offer((m1 >> 9) + dadd, tbase + (int)(m1 & 511u));
                         if (m2 != 0xFFFFFFFFu) best.offer((m2 >> 9) + dadd, tbase + (int)(m2 & 511u));
                     }

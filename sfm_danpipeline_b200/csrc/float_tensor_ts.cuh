@@ -55,9 +55,19 @@ static inline size_t float_tensor_ts_smem_bytes(int kblocks) {
 }
 
 // D[tmem] (+)= A[tmem] * B[smem]^T; whole warp calls, one elected lane issues (see tc_mma).
-template <bool INT8, bool ACCUMULATE>
+template <int KIND, bool ACCUMULATE>
 __device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
-    if constexpr (INT8)
+    if constexpr (KIND == OK_F16)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pe, p;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d),
+            "r"(tmem_a), "l"(desc_b), "r"(idesc), "n"(ACCUMULATE ? 1 : 0)
+            : "memory");
+    else if constexpr (KIND == OK_I8)
         asm volatile(
             "{\n\t"
             ".reg .pred pe, p;\n\t"
@@ -100,7 +110,8 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                       const KnnTile* __restrict__ tiles, const uint32_t n_items, const PairDesc* __restrict__ pairs,
                       KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */, const uint32_t i8_bias /* TM_I8P: the descriptors' bit length */,
                       uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
-    constexpr bool INT8 = MODE == TM_I8 || MODE == TM_I8P;
+    constexpr int KIND = OperandOf<MODE>::kind;
+    constexpr int KB_ELEMS = OperandOf<MODE>::kb_elems;
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sB = base;  // FTS_B_STAGES x KB x 16 KB
@@ -166,7 +177,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                     for (int kb = 0; kb < KB; ++kb)
 #pragma unroll
                         for (int h = 0; h < FT_N / FT_BOX_ROWS; ++h)
-                            tma_load_2d(dst + kb * FT_B_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * (INT8 ? 128 : FT_KB_ELEMS),
+                            tma_load_2d(dst + kb * FT_B_KBLOCK_BYTES + h * FT_BOX_BYTES, &tmap, kb * KB_ELEMS,
                                         row + h * FT_BOX_ROWS, &sm.b_full[s]);
                 }
             }
@@ -174,7 +185,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp, uniform; one elected lane issues) =====================
         const uint32_t tb = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
-        const uint32_t idesc = INT8 ? FT_IDESC_I8 : FT_IDESC;
+        const uint32_t idesc = KIND == OK_I8 ? FT_IDESC_I8 : (KIND == OK_F16 ? FT_IDESC_F16 : FT_IDESC);
         uint32_t g = 0, it = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t slot = it & 1;
@@ -193,11 +204,11 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 tc_fence_after();
                 const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB + (size_t)s * KB * FT_B_KBLOCK_BYTES));
                 const uint32_t d_tmem = tb + FTS_ACC_COL0 + a * FT_N;
-                tc_mma_ts<INT8, false>(d_tmem, a_tmem, b_desc0, idesc);
+                tc_mma_ts<KIND, false>(d_tmem, a_tmem, b_desc0, idesc);
 #pragma unroll
                 for (int i = 1; i < 4 * KB; ++i) {  // i = kb*4 + k: 32 bytes of K = 8 TMEM columns of A, 32 bytes inside B's swizzle row
                     const int kb = i >> 2, k = i & 3;
-                    tc_mma_ts<INT8, true>(d_tmem, a_tmem + i * 8, b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
+                    tc_mma_ts<KIND, true>(d_tmem, a_tmem + i * 8, b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
                 }
                 tc_commit_elect(&sm.b_empty[s]);   // smem stage reusable once these MMAs have read it
                 tc_commit_elect(&sm.acc_full[a]);  // accumulator ready for the epilogue
@@ -235,12 +246,10 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 const bool valid = qrow < pd.nq;
                 const float nq2 = valid ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
                 float v;
-                if constexpr (MODE == TM_TF32_EXACT) {
-                    v = nq2 + 8388608.f;  // |q|^2 + 2^23 (exact): see Top2
-                } else if constexpr (MODE == TM_TF32_COLLECT) {
+                if constexpr (MODE == TM_TF32_COLLECT) {
                     v = collect_threshold(valid, nq2, pd, knn, qrow);
                 } else {
-                    v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (rank)
+                    v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (exact float modes, rank)
                 }
                 sm.rowval[slot][row] = v;
             }
@@ -365,8 +374,9 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                         if (q1 != 0xFFFFFFFFu) best.offer(q1 >> 9, tbase + (int)(q1 & 511u));
                         if (q2 != 0xFFFFFFFFu) best.offer(q2 >> 9, tbase + (int)(q2 & 511u));
                     } else {
-                        // i8: the key carries popc(t) - 2 q.t + I8_BIAS; popc(q) (the bits of cq) completes the Hamming distance
-                        const uint32_t dadd = MODE == TM_I8 ? __float_as_uint(cq) - I8_BIAS : 0u;
+                        // i8: the key carries popc(t) - 2 q.t + I8_BIAS; popc(q) (the bits of cq) completes the Hamming distance.
+                        // exact float modes: the key carries d^2 - |q|^2 + 2^20 (float_nbexact_kernel); |q|^2 is an integer <= 2^20
+                        const uint32_t dadd = MODE == TM_I8 ? __float_as_uint(cq) - I8_BIAS : static_cast<uint32_t>(cq) - 1048576u;
                         if (m1 != 0xFFFFFFFFu) best.offer((m1 >> 9) + dadd, tbase + (int)(m1 & 511u));
                         if (m2 != 0xFFFFFFFFu) best.offer((m2 >> 9) + dadd, tbase + (int)(m2 & 511u));
                     }

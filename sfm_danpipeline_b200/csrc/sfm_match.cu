@@ -166,6 +166,8 @@ struct SfmmCtx {
     int tensor_cluster = 1;    // CTAs per cluster sharing train tiles: the 2-CTA TMA-multicast variant measured no faster (not L2-bound) and was removed
     CUtensorMap tmap{};
     DevBuf d_norms, d_flags;
+    bool tensor_f16 = false;  // float tensor path runs on an fp16 copy (d_half) with kind::f16
+    DevBuf d_half;
     uint32_t i8_bias = 0;    // binary tensor engine: descriptor bit length when the packed 16-bit keys apply (< 512 bit), else 0
     DevBuf d_nbkey, d_row0;  // binary tensor engine: per-row key part (binary_nbkey_kernel) and the images' first rows
     DevBuf d_unpacked;  // SFMM_BINARY_TENSOR: one byte per descriptor bit
@@ -378,9 +380,10 @@ template <int KB, int MODE>
 cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     // persistent: one CTA per SM (shared memory allows no more) walks the tile list with stride gridDim.x
     const uint32_t grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(ctx->sm_count));
-    const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P) ? (const float*)ctx->d_nbkey.as<float>() : (const float*)ctx->d_norms.as<float>();
-    // measured (profiles/tensor_variants_r01.txt): TMEM-A wins for the binary engine, shared-memory-A for float
-    const bool ts = ctx->tensor_ts < 0 ? (MODE == TM_I8P || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0;
+    const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_TF32_EXACT || MODE == TM_F16_EXACT) ? (const float*)ctx->d_nbkey.as<float>()
+                                                                                                              : (const float*)ctx->d_norms.as<float>();
+    // measured (profiles/tensor_variants_r01.txt): TMEM-A wins for the binary engine and the fp16 float path, shared-memory-A for TF32
+    const bool ts = ctx->tensor_ts < 0 ? (MODE == TM_I8P || MODE == TM_F16_EXACT || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0;
     if (!ts) {  // query tile in shared memory (float_tensor.cuh)
         const size_t smem = float_tensor_smem_bytes(KB);
         auto kern = tensor_knn2_kernel<KB, MODE>;
@@ -397,7 +400,7 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     auto kern = tensor_knn2_ts_kernel<KB, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P) ? ctx->d_unpacked.as<uint4>() : ctx->blob.as<uint4>();
+    const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P) ? ctx->d_unpacked.as<uint4>() : (MODE == TM_F16_EXACT ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>());
     kern<<<grid, FTS_THREADS, smem, sl.stream>>>(ctx->tmap, a_src, static_cast<uint32_t>(ctx->total_rows), (const float*)ctx->d_norms.as<float>(), nb_src,
                                                  (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles, (const PairDesc*)sl.d_pairs.as<PairDesc>(),
                                                  sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u, ctx->i8_bias,
@@ -535,7 +538,29 @@ int prepare_float(SfmmCtx* ctx) {
         ctx->tensor_eligible = flags[0] == 0 && max_norm2 <= 1048576.f;  // integers, |v|<=2047, |x|^2 <= 2^20
         ctx->tensor_refine = false;
         const bool finite = std::isfinite(max_norm2);  // NaN / inf rows: leave those sets to the exact kernel
-        if (ctx->tensor_eligible || (finite && !ctx->cfg.cross_check)) {
+        ctx->tensor_f16 = false;
+        if (ctx->tensor_eligible) {  // per train row: |t|^2 + 2^23 + 2^20, the epilogue's key argument (float_nbexact_kernel)
+            const uint32_t n = rows + 2 * FT_N;
+            CU_TRY(ctx, ctx->d_nbkey.ensure(static_cast<size_t>(n) * sizeof(float)));
+            float_nbexact_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_norms.as<float>(), n, ctx->d_nbkey.as<float>());
+            CU_TRY(ctx, cudaGetLastError());
+            ctx->stats.kernel_launches += 1;
+        }
+        if (ctx->tensor_eligible && ctx->cols % 64 == 0 && !std::getenv("SFMM_NO_F16")) {
+            // TF32-exact data is fp16-exact too: contract an fp16 copy with kind::f16 (16 elements per MMA instead of 8)
+            CU_TRY(ctx, ctx->d_half.ensure(static_cast<size_t>(ctx->total_rows) * ctx->cols * sizeof(__half)));
+            const size_t n2 = static_cast<size_t>(ctx->total_rows) * ctx->cols / 2;
+            float_to_half_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), rows, ctx->cols,
+                                                                                       ctx->d_half.as<__half>());
+            CU_TRY(ctx, cudaGetLastError());
+            CU_TRY(ctx, cudaStreamSynchronize(st));
+            ctx->stats.kernel_launches += 1;
+            int rc = make_tensor_map(ctx, ctx->d_half.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<size_t>(ctx->cols) * 2, ctx->total_rows);
+            if (rc) return rc;
+            ctx->tensor_kblocks = ctx->cols * 2 / 128;
+            ctx->use_tensor = true;
+            ctx->tensor_f16 = true;
+        } else if (ctx->tensor_eligible || (finite && !ctx->cfg.cross_check)) {
             int rc = make_tensor_map(ctx, ctx->blob.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ctx->pitch, ctx->total_rows);
             if (rc) return rc;
             ctx->tensor_kblocks = ctx->cols / FT_KB_ELEMS;
@@ -632,6 +657,7 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
         const uint32_t nt = static_cast<uint32_t>(plan.tiles.size());
         cudaError_t e;
         if (ctx->elem_type == SFMM_F32 && ctx->use_tensor && ctx->tensor_refine) e = launch_tensor_refine(ctx, sl, nt, ctx->tensor_kblocks);
+        else if (ctx->elem_type == SFMM_F32 && ctx->use_tensor && ctx->tensor_f16) e = launch_tensor<TM_F16_EXACT>(ctx, sl, nt, ctx->tensor_kblocks);
         else if (ctx->elem_type == SFMM_F32) e = ctx->use_tensor ? launch_tensor<TM_TF32_EXACT>(ctx, sl, nt, ctx->tensor_kblocks) : launch_float_exact(ctx, sl, nt);
         else if (ctx->use_tensor) e = ctx->i8_bias ? launch_tensor<TM_I8P>(ctx, sl, nt, ctx->tensor_kblocks) : launch_tensor<TM_I8>(ctx, sl, nt, ctx->tensor_kblocks);
         else e = cross ? launch_binary<true>(ctx, sl, nt) : launch_binary<false>(ctx, sl, nt);
@@ -913,7 +939,7 @@ SFMM_API void sfmm_destroy(SfmmCtx* ctx) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
-    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked, &ctx->d_nbkey, &ctx->d_row0}) b->release();
+    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked, &ctx->d_nbkey, &ctx->d_row0, &ctx->d_half}) b->release();
     for (PinBuf& p : ctx->pack) p.release();
     for (cudaEvent_t ev : {ctx->ev_begin, ctx->ev_end, ctx->ev_pack[0], ctx->ev_pack[1]})
         if (ev) cudaEventDestroy(ev);
