@@ -216,15 +216,31 @@ def verify_pairs(table, descs, norm, n, cross, world):
         pos = {(int(q), int(t)): i for i, (q, t) in enumerate(pairs)}
         get = lambda q, t: table[3][table[2][pos[(q, t)]]: table[2][pos[(q, t)]] + table[1][pos[(q, t)]]]  # noqa: E731
     ok = 0
+    integer_valued = norm == 0 or all(bool((d == np.floor(d)).all()) for d in descs[:4])
+    worst = 0.0
     for k in rng.choice(len(pairs), min(n, len(pairs)), replace=False):
         q, t = int(pairs[k][0]), int(pairs[k][1])
         exp = oracle.match_pair_cv2(descs[q], descs[t], norm, 0.8, cross) if oracle.have_cv2() else \
             oracle.match_pair(descs[q], descs[t], norm, 0.8, cross, threads=os.cpu_count() or 1)
         got = np.asarray(get(q, t))
-        if norm == 0 or True:
+        if integer_valued:  # Hamming, and L2 on integer-valued (SIFT-like) data: every fp32 partial sum is exact
             assert got.tobytes() == exp.tobytes(), f"pair ({q},{t}) differs from the oracle"
+        else:
+            # arbitrary floats: north_star's bar -- distances within 1e-4 relative; a match may appear or vanish only
+            # where the ratio test is decided inside that tolerance (fp32 summation order differs from OpenCV's)
+            both = np.intersect1d(got["queryIdx"], exp["queryIdx"])
+            g = got[np.isin(got["queryIdx"], both)]
+            e = exp[np.isin(exp["queryIdx"], both)]
+            rel = np.abs(g["distance"] - e["distance"]) / np.maximum(e["distance"], 1e-30)
+            same = g["trainIdx"] == e["trainIdx"]
+            assert (rel[same] <= 1e-4).all(), f"pair ({q},{t}): distance outside 1e-4 relative"
+            flips = (len(got) - len(both)) + (len(exp) - len(both)) + int((~same).sum())
+            assert flips <= max(2, len(exp) // 1000), f"pair ({q},{t}): {flips} decisions differ"
+            worst = max(worst, float(rel[same].max()) if same.any() else 0.0)
         ok += 1
-    return {"pairs_checked": ok, "against": "cv2 BFMatcher path" if oracle.have_cv2() else "C oracle", "result": "bit-identical"}
+    res = {"pairs_checked": ok, "against": "cv2 BFMatcher path" if oracle.have_cv2() else "C oracle",
+           "result": "bit-identical" if integer_valued else f"within 1e-4 relative (worst {worst:.2e})"}
+    return res
 
 
 def alt_engine_line(args, local, world, rank, descs, mine, rows, n_pairs, flush, D, engine, n_sm, sm_max_mhz, peaks):
@@ -416,8 +432,10 @@ def main():
             i8 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))  # int8 dense = twice the measured bf16 cuBLAS rate
             macs = knn_work / 16.0 * 512.0  # 512 u8 MACs per 16 algorithmic POPC32 (one 486-bit distance)
             roof = {"bound": "tensor", "achieved": 2.0 * macs / knn_s / 1e12, "peak": i8, "unit": "TOP/s",
-                    "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops (int8 dense is twice bf16); ops = 2*Nq*Nt*512 per pair, "
+                    "peak_source": "of measured: 2 x MEASURED_PEAKS.json bf16_tflops (int8 dense is nominally twice bf16; the cuBLAS bf16 burst "
+                                   "figure is ~74 % of nominal, so a kernel on {0,1} bytes can read above 1.0); ops = 2*Nq*Nt*512 per pair, "
                                    "tcgen05 kind::i8 on bits unpacked to bytes",
+                    "nominal": {"peak": 4500.0, "frac": 2.0 * macs / knn_s / 1e12 / 4500.0, "note": "B200 dense int8/fp8 nominal 4.5 POP/s"},
                     "popc_equivalent": {"achieved_GPOPC32": knn_work / knn_s / 1e9,
                                         "x_nominal_popc_roofline": knn_work / knn_s / 1e9 / (n_sm * 16 * sm_max_mhz * 1e6 / 1e9)},
                     "traffic": None}
@@ -430,8 +448,10 @@ def main():
         elif m.stats()["float_path"] in (2, 3):
             tf32 = 0.5 * float(peaks.get("bf16_tflops", 1590.0))  # TF32 dense = half the measured bf16 cuBLAS rate
             roof = {"bound": "tensor", "achieved": knn_work / knn_s / 1e12, "peak": tf32, "unit": "TFLOP/s",
-                    "peak_source": "0.5 x MEASURED_PEAKS.json bf16_tflops (TF32 dense is half the bf16 rate); "
-                                   "algorithmic FLOPs = 2*Nq*Nt*128 per pair, tcgen05 kind::tf32",
+                    "peak_source": "of measured: 0.5 x MEASURED_PEAKS.json bf16_tflops = the TF32 rate the float path is specified in "
+                                   "(north_star: fp32-accurate TF32).  Integer-valued (SIFT) data is contracted from an exact fp16 copy "
+                                   "with kind::f16 at twice that rate, so this fraction can exceed 1.0; algorithmic FLOPs = 2*Nq*Nt*128 per pair",
+                    "f16_frac": knn_work / knn_s / 1e12 / float(peaks.get("bf16_tflops", 1590.0)),
                     "traffic": None}
         else:
             peak = n_sm * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # fp32 FMA lanes: exact mode runs on CUDA cores
@@ -441,7 +461,7 @@ def main():
         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
         # `ncu --set full` captures of exactly this workload (profiles/ncu_*_r01*.txt); null when not captured
         ncu_traffic = {("cfg2", "popc", 1): 18.847e6 + 46.489e6,    # profiles/ncu_binary_r01c_tq2.txt
-                       ("cfg2", "tensor", 1): 2413.4e6 + 88.4e6}    # profiles/ncu_tensor_i8_r01.txt
+                       ("cfg2", "tensor", 1): 2276.5e6 + 86.7e6}    # profiles/ncu_tensor_ts_i8p_r01.txt
         if n_images == WORKLOADS[args.workload][1] and not args.cross_check:
             roof["traffic"] = ncu_traffic.get((args.workload, engine, world))
         roof["frac"] = roof["achieved"] / roof["peak"]
