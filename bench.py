@@ -299,7 +299,8 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-steps", type=int, default=0)
-    ap.add_argument("--e2e-warmup", type=int, default=1)
+    ap.add_argument("--e2e-warmup", type=int, default=2,
+                    help="untimed end-to-end steps: the two pipeline slots size their device/pinned buffers over the first two")
     ap.add_argument("--verify", type=int, default=0, help="check this many random pairs of the e2e table against the CPU oracle")
     args = ap.parse_args()
 
@@ -392,10 +393,16 @@ def main():
         if world > 1:
             table, _ = D.match_all_pairs_distributed(m, descs, 0)
         else:
+            ta = time.perf_counter()
             m.set_descriptors(descs)
+            tb = time.perf_counter()
             m.match_all_pairs()
+            tc = time.perf_counter()
             table = m.result_table(copy=False)
             assert int(table[1].sum()) == len(table[3])  # the host table is complete
+            if os.environ.get("SFMM_BENCH_TRACE") == "1":
+                print(f"[e2e] set_descriptors {1e3 * (tb - ta):.2f} ms  match_all_pairs {1e3 * (tc - tb):.2f} ms  "
+                      f"table {1e3 * (time.perf_counter() - tc):.2f} ms  device {m.stats()['last_match_ms']:.2f} ms", file=sys.stderr)
         s1 = m.stats()
         return table, s1["h2d_bytes"] - s0["h2d_bytes"], s1["d2h_bytes"] - s0["d2h_bytes"]
 

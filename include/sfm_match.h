@@ -73,7 +73,8 @@ enum { SFMM_U8 = 0, SFMM_F32 = 1 };
 /* How the L2 path ranks candidates (distances REPORTED are always fp32 direct-difference). */
 enum {
     SFMM_FLOAT_AUTO = 0,   /* tensor cores whenever the shape allows (exact keys for integer-valued data such as SIFT,
-                              TF32 ranking + exact fp32 refinement of the candidates otherwise), else the exact kernel */
+                              contracted from an fp16 copy; TF32 ranking + exact fp32 refinement of the candidates for
+                              arbitrary values), else the exact kernel */
     SFMM_FLOAT_EXACT = 1,  /* fp32 CUDA-core direct difference for every candidate */
     SFMM_FLOAT_TENSOR = 2  /* tcgen05 TF32 |a|^2+|b|^2-2ab ranking + fp32 refinement of the winners */
 };

@@ -1,35 +1,25 @@
-// Tensor-core L2 2-NN kernel for float descriptors (SIFT 128-d / SURF 64-d) on sm_100a -- SFMM_FLOAT_TENSOR.
+// Tensor-core 2-NN kernels for sm_100a (tcgen05 + TMEM + TMA): shared helpers, the prepare kernels, the epilogue
+// pieces, and the kernel that keeps BOTH operands in shared memory (tensor_knn2_kernel, "SS").  The default for
+// the binary engine and the fp16 float path is the TMEM-A kernel of float_tensor_ts.cuh, which shares everything here.
 //
-// Replaces, for CV_32F descriptor sets, matcher->knnMatch(q, t, knn, 2) with
-// cv::BFMatcher(cv::NORM_L2,false) at /root/reference/src/Sfm.cpp:593,599.
+// Replaces matcher->knnMatch(q, t, knn, 2) with cv::BFMatcher at /root/reference/src/Sfm.cpp:593,599.
 //
-// d^2(q,t) = |q|^2 + |t|^2 - 2 q.t : the q.t contraction runs on the 5th-generation tensor cores
-// (tcgen05.mma kind::tf32, operands staged in shared memory by TMA with the 128-byte swizzle,
-// fp32 accumulators in TMEM), the rest is a fused epilogue that never writes the distance matrix:
+//   float : d^2(q,t)     = |q|^2 + |t|^2 - 2 q.t      tcgen05.mma kind::f16 on an exact fp16 copy / kind::tf32
+//   binary: hamming(q,t) = popc(q) + popc(t) - 2 q.t   tcgen05.mma kind::i8 on bits unpacked to {0,1} bytes (u8 x u8 -> s32, exact)
 //
-//   warp 0      TMA producer : query tile once, then 128-row train tiles through a 2-stage smem ring
-//   warp 1      MMA issuer   : one elected lane, 4*KB tcgen05.mma (M=128,N=128,K=8) per train tile
-//                              into a 4-stage TMEM ring (4 x 128 columns = all 512 columns)
-//   warp 2      TMEM allocator
-//   warps 4-11  epilogue     : two groups of four warps on alternate tiles; tcgen05.ld 32x32b.x32 (register
-//                              double buffer) -> d^2 (one FADD + one FFMA) -> packed integer key (one IMAD)
-//                              -> branch-free top-2 (2.5 VIMNMX per column); see Top2
+// The contraction runs on the tensor cores (operands staged by TMA with the 128-byte swizzle, accumulators in
+// TMEM); the rest is a fused epilogue that never writes the distance matrix: per accumulator element one FFMA /
+// IMAD forms a packed integer key (distance << 9 | column), a branch-free network keeps the two smallest keys of
+// the tile, and once per tile they are merged into the row's running (distance, train index) pair with a strict
+// '<' in arrival order -- cv::batchDistance's insertion rule.
 //
-// Exactness contract.  This mode is selected only for descriptor sets the prepare kernel proved
-// "TF32-exact": every value an integer with |v| <= 2047 (11 significant bits: exactly
-// representable in TF32) and every row norm^2 <= 2^20, so every product, every partial sum of the
-// contraction, |t|^2 - 2 q.t and d^2 = |q|^2 + s are integers below 2^22 -- exact in fp32 whatever
-// the summation order, and small enough for sqrtf to keep distinct d^2 distinct.  Real SIFT output is of this kind (OpenCV quantises to 0..255, norm ~512;
-// verified on data/temple).  Then d = sqrtf(d^2) is bit-identical to OpenCV's
-// sqrtf(sum (a-b)^2), and candidates are inserted in ascending train index with a strict '<'
-// -- OpenCV's own insertion rule -- so indices, distances and ties are bit-exact.  Anything else
-// (arbitrary floats) is routed to float_exact.cuh by SFMM_FLOAT_AUTO.
-//
-// INT8 = true instantiates the same pipeline for BINARY descriptors (opt-in engine
-// SFMM_BINARY_TENSOR): bits unpacked to {0,1} bytes, tcgen05.mma kind::i8 (u8 x u8 -> s32, exact),
-// hamming(q,t) = popc(q) + popc(t) - 2 q.t, same key/top-2 epilogue in integer arithmetic.  The
-// default binary engine remains the XOR+POPC kernel of binary_knn.cuh (the north-star design);
-// this one trades 8x the descriptor bytes for the tensor pipe.
+// Exactness contract (float, TM_TF32_EXACT / TM_F16_EXACT).  Selected only for descriptor sets the prepare kernel
+// proved exact: every value an integer with |v| <= 2047 (exactly representable in TF32 and fp16) and every row
+// norm^2 <= 2^20, so every product, every partial sum of the contraction and d^2 are integers below 2^22 -- exact
+// in fp32 whatever the summation order, and small enough for sqrtf to keep distinct d^2 distinct.  Real SIFT
+// output is of this kind (OpenCV quantises to 0..255, norm ~512; verified on data/temple).  Then d = sqrtf(d^2)
+// is bit-identical to OpenCV's sqrtf(sum (a-b)^2) and indices, distances and ties are bit-exact.  Arbitrary floats
+// take the TM_TF32_RANK -> TM_TF32_COLLECT -> float_refine_kernel path below (bit-identical to float_exact.cuh).
 #pragma once
 #include <cuda.h>
 #include <cuda_fp16.h>

@@ -1,7 +1,8 @@
 // Tensor-core 2-NN kernel, "TS" form: the QUERY tile lives in tensor memory, only train tiles go through
-// shared memory.  Same maths, same epilogue and the same results as tensor_knn2_kernel (float_tensor.cuh),
-// which it replaces as the default; the shared-memory-A ("SS") kernel stays selectable (SFMM_TENSOR_SS=1)
-// as the measured baseline.
+// shared memory.  Same maths, same epilogue pieces and the same results as tensor_knn2_kernel (float_tensor.cuh).
+// Default for the binary engine (TM_I8P, and TM_I8 up to 256 bit) and the fp16 float path (TM_F16_EXACT), where it
+// measured faster; TF32 modes default to the shared-memory-A kernel (SFMM_TENSOR_TS=0/1 forces either;
+// profiles/tensor_variants_r01.txt has every A/B).
 //
 // Why: with both operands in shared memory every tcgen05.mma (M=128, N=128, 32 bytes of K) reads 4 KB of A
 // and 4 KB of B in its 64-cycle slot = 128 B/clk, which is ALL of the SM's shared-memory bandwidth
@@ -11,7 +12,10 @@
 // profiles/ncu_tensor_persist_r01.txt) whatever else was tuned.  Reading A from TMEM removes 64 B/clk.
 // It also frees the 64 KB query-tile buffer: the train ring grows from 2 to 3 stages (more TMA latency
 // hidden), and the query tile of the NEXT item is loaded while the current one computes (two A buffers in
-// TMEM), which removes the pipeline bubble at item boundaries.
+// TMEM), which removes the pipeline bubble at item boundaries.  The price is TMEM: two accumulator stages
+// instead of four, so the epilogue must release a stage within one MMA tile time -- which it does only once
+// its per-column work is small (one IMAD + 1.25 VIMNMX.U16x2 for binary; profiles/ncu_tensor_ts_r01.txt shows
+// the first version with the MMA warp 30 % of its time in the acc_empty wait).
 //
 // TMEM map (512 columns): [0,128) query tile A0 | [128,256) A1 | [256,384) accumulator 0 | [384,512) accumulator 1.
 // A row r of the tile is TMEM lane r; its K bytes are packed in order into 32-bit columns (32 bytes = 8

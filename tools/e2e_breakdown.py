@@ -4,10 +4,12 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from sfm_danpipeline_b200 import Matcher, synth
 kind = sys.argv[1] if len(sys.argv) > 1 else "binary"
+n_img = int(sys.argv[2]) if len(sys.argv) > 2 else (50 if kind == "binary" else 60)
+n_desc = int(sys.argv[3]) if len(sys.argv) > 3 else (5000 if kind == "binary" else 8000)
 if kind == "binary":
-    descs, norm = synth.binary_images(50, 5000, seed=0), 0
+    descs, norm = synth.binary_images(n_img, n_desc, seed=0), 0
 else:
-    descs, norm = synth.float_images(60, 8000, seed=0), 1
+    descs, norm = synth.float_images(n_img, n_desc, seed=0), 1
 m = Matcher(norm)
 for it in range(4):
     t0 = time.perf_counter(); m.set_descriptors(descs)
