@@ -659,8 +659,9 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             mbar_init(&sm.nb_empty[s], FT_EPI_WARPS / 2);
         }
         for (int s = 0; s < 2; ++s) {
-            mbar_init(&sm.item_full[s], 1);
-            mbar_init(&sm.item_empty[s], 2 + FT_EPI_WARPS);  // producer thread, MMA warp, eight epilogue warps
+            // every thread that writes / reads an item slot arrives itself (release / acquire pair per thread)
+            mbar_init(&sm.item_full[s], 32);                       // the prefetch warp's lanes
+            mbar_init(&sm.item_empty[s], 1 + 32 + 32 * FT_EPI_WARPS);  // producer thread, MMA warp, epilogue warps
         }
         mbar_fence_init();
     }
@@ -724,8 +725,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             const uint32_t slot = it & 1;
             mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
             const uint32_t n_tiles = __shfl_sync(0xFFFFFFFFu, sm.item[slot].n_tiles, 0);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.item_empty[slot]);
+            mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
             mbar_wait(&sm.a_full, it & 1);
 #pragma unroll 1
             for (uint32_t j = 0; j < n_tiles; ++j, ++g) {
@@ -787,8 +787,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 }
                 sm.rowval[slot][row] = v;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.item_full[slot]);
+            mbar_arrive(&sm.item_full[slot]);  // every lane, after its own writes
         }
     } else if (warp >= 4) {
         // ===================== epilogue: fused top-2 =====================
@@ -808,8 +807,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             const bool reverse = im.reverse != 0;
             const unsigned long long knn_off = im.knn_off, col_off = im.col_off;
             const float cq = sm.rowval[slot][row];  // TM_TF32_COLLECT: the threshold tau
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.item_empty[slot]);
+            mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
 
             Top2 best;
             best.init();

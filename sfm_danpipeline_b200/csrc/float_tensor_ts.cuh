@@ -127,8 +127,9 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
         for (int s = 0; s < 2; ++s) {
             mbar_init(&sm.a_full[s], 4);   // the four loader warps
             mbar_init(&sm.a_empty[s], 1);  // tcgen05.commit after the item's last MMA
-            mbar_init(&sm.item_full[s], 1);
-            mbar_init(&sm.item_empty[s], 2 + FT_EPI_WARPS + 4);  // producer thread, MMA warp, eight epilogue warps, four loader warps
+            // every thread that writes / reads an item slot arrives itself (release / acquire pair per thread)
+            mbar_init(&sm.item_full[s], 32);                             // the prefetch warp's lanes
+            mbar_init(&sm.item_empty[s], 1 + 32 + 32 * FT_EPI_WARPS + 128);  // producer thread, MMA warp, epilogue warps, loader warps
         }
         for (int s = 0; s < FTS_B_STAGES; ++s) {
             mbar_init(&sm.b_full[s], 1);
@@ -195,8 +196,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             const uint32_t slot = it & 1;
             mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
             const uint32_t n_tiles = __shfl_sync(0xFFFFFFFFu, sm.item[slot].n_tiles, 0);
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.item_empty[slot]);
+            mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
             mbar_wait(&sm.a_full[slot], (it >> 1) & 1);  // the loaders have stored this item's query tile
             tc_fence_after();
             const uint32_t a_tmem = tb + slot * FT_M;  // 128 columns per query-tile buffer
@@ -257,8 +257,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 }
                 sm.rowval[slot][row] = v;
             }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.item_full[slot]);
+            mbar_arrive(&sm.item_full[slot]);  // every lane, after its own writes
         }
     } else if (warp >= 12) {
         // ===================== query loaders: global -> registers -> TMEM, one item ahead =====================
@@ -269,8 +268,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             const uint32_t slot = it & 1;
             mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
             const uint32_t grow = sm.item[slot].a_row + row;
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.item_empty[slot]);
+            mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
             mbar_wait(&sm.a_empty[slot], ((it >> 1) & 1) ^ 1);  // the MMAs of the item before last are done with this buffer
             tc_fence_after();
             const bool ok = grow < total_rows;  // rows past the blob: zeros (rows past the image but inside the blob are
@@ -311,8 +309,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             const bool reverse = im.reverse != 0;
             const unsigned long long knn_off = im.knn_off, col_off = im.col_off;
             const float cq = sm.rowval[slot][row];  // TM_TF32_COLLECT: the threshold tau
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.item_empty[slot]);
+            mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
 
             Top2 best;
             best.init();

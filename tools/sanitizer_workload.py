@@ -3,7 +3,8 @@
     compute-sanitizer --tool memcheck  python tools/sanitizer_workload.py
     compute-sanitizer --tool racecheck python tools/sanitizer_workload.py
 
-Covers the POPC kernel, the i8 and TF32 tensor kernels, the exact fp32 kernel, cross-check on and off,
+Covers the POPC kernel, the tensor kernels (i8 packed / i8 / fp16 / TF32 exact / TF32 rank+collect+refine, TMEM-A and
+shared-memory-A forms), the exact fp32 kernel, cross-check on and off,
 empty / tiny / ragged images, single-pair and raw-knn calls; every result is compared with the oracle."""
 import os
 import sys
@@ -12,12 +13,12 @@ import numpy as np
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import oracle  # noqa: E402
-from sfm_danpipeline_b200 import BINARY_TENSOR, FLOAT_EXACT, FLOAT_TENSOR, Matcher, synth  # noqa: E402
+from sfm_danpipeline_b200 import BINARY_POPC, BINARY_TENSOR, FLOAT_AUTO, FLOAT_EXACT, FLOAT_TENSOR, Matcher, synth  # noqa: E402
 
 d = synth.binary_images(4, [300, 130, 0, 257], seed=3)
 d[2] = np.zeros((0, 61), np.uint8)
 for cross in (False, True):
-    for eng in (0, BINARY_TENSOR):
+    for eng in (BINARY_POPC, BINARY_TENSOR):
         with Matcher(0, 0.8, cross, binary_engine=eng) as m:
             m.set_descriptors(d)
             m.match_all_pairs()
@@ -33,4 +34,27 @@ for mode in (FLOAT_TENSOR, FLOAT_EXACT):
             m.match_all_pairs()
             for (q, t) in synth.all_pairs(3):
                 assert m.getMatching(q, t).tobytes() == oracle.match_pair(f[q], f[t], 1, 0.8, cross).tobytes()
+# 512-bit descriptors: the tensor engine's 32-bit-key path (TM_I8); 256-bit: packed keys with two K-blocks
+rng = np.random.default_rng(5)
+for cols in (64, 32):
+    w = [rng.integers(0, 256, (n, cols), dtype=np.uint8) for n in (150, 129, 40)]
+    with Matcher(0, 0.8, False, binary_engine=BINARY_TENSOR) as m:
+        m.set_descriptors(w)
+        m.match_all_pairs()
+        for (q, t) in synth.all_pairs(3):
+            assert m.getMatching(q, t).tobytes() == oracle.match_pair(w[q], w[t], 0, 0.8, False).tobytes()
+# arbitrary floats: TF32 rank + collect + refine (float_path 3) equals the exact kernel bit for bit; 96-d: the TF32 exact path
+x = synth.float_images(3, [200, 129, 70], seed=6, integer=False)
+with Matcher(1, 0.8, False, float_mode=FLOAT_AUTO) as m, Matcher(1, 0.8, False, float_mode=FLOAT_EXACT) as mx:
+    for mm in (m, mx):
+        mm.set_descriptors(x)
+        mm.match_all_pairs()
+    assert m.stats()["float_path"] == 3
+    for (q, t) in synth.all_pairs(3):
+        assert m.getMatching(q, t).tobytes() == mx.getMatching(q, t).tobytes()
+g = [np.floor(rng.random((n, 96), dtype=np.float32) * 100).astype(np.float32) for n in (140, 129)]
+with Matcher(1, 0.8, False, float_mode=FLOAT_TENSOR) as m:
+    m.set_descriptors(g)
+    m.match_all_pairs()
+    assert m.getMatching(0, 1).tobytes() == oracle.match_pair(g[0], g[1], 1, 0.8, False).tobytes()
 print("sanitizer workload ok")
