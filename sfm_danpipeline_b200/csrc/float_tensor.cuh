@@ -752,7 +752,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
         uint32_t it = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t slot = it & 1;
-            mbar_wait(&sm.item_empty[slot], ((it >> 1) & 1) ^ 1);
+            mbar_wait_relaxed(&sm.item_empty[slot], ((it >> 1) & 1) ^ 1);
             KnnTile tile = tiles[item];
             PairDesc pd = pairs[tile.pair];
             // Symmetric cross-check = the same problem with the roles swapped: a "reverse" tile (bit 31 of

@@ -224,7 +224,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
         uint32_t it = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t slot = it & 1;
-            mbar_wait(&sm.item_empty[slot], ((it >> 1) & 1) ^ 1);
+            mbar_wait_relaxed(&sm.item_empty[slot], ((it >> 1) & 1) ^ 1);
             KnnTile tile = tiles[item];
             PairDesc pd = pairs[tile.pair];
             // "reverse" tile (bit 31 of split): the symmetric cross-check's column minima, roles swapped
@@ -266,10 +266,10 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
         uint32_t it = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t slot = it & 1;
-            mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
+            mbar_wait_relaxed(&sm.item_full[slot], (it >> 1) & 1);
             const uint32_t grow = sm.item[slot].a_row + row;
             mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
-            mbar_wait(&sm.a_empty[slot], ((it >> 1) & 1) ^ 1);  // the MMAs of the item before last are done with this buffer
+            mbar_wait_relaxed(&sm.a_empty[slot], ((it >> 1) & 1) ^ 1);  // the MMAs of the item before last are done with this buffer
             tc_fence_after();
             const bool ok = grow < total_rows;  // rows past the blob: zeros (rows past the image but inside the blob are
                                                 // another image's: computed on, never read -- as with TMA's box)
