@@ -64,48 +64,22 @@ __device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* m
         "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
         : "memory");
 }
-// Same, delivered to the same shared-memory offsets (data and mbarrier) of every CTA in cta_mask.
-__device__ __forceinline__ void tma_load_2d_mcast(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar, uint16_t cta_mask) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
-            smem_u32(smem_dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(cta_mask)
-        : "memory");
-}
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-    uint32_t r;
-    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-    return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-// commit that arrives on the barrier at this offset in every CTA of cta_mask
-__device__ __forceinline__ void tc_commit_mcast(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)),
-                 "h"(cta_mask)
-                 : "memory");
-}
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-                 : "memory");
-}
-// D[tmem] (+)= A[smem] * B[smem]^T, TF32 inputs, fp32 accumulate; M=128, N=128, K=8 per instruction.
-// Called by the WHOLE warp with warp-uniform operands; one elected lane issues.  (Issuing from inside
-// an `if (lane == 0)` made ptxas wrap every MMA in a R2UR.BROADCAST / BRA.U.ANY uniformisation loop
-// and recompute the descriptors: ~90 cycles per instruction for 64 cycles of tensor work.)
+// Operand type of a mode: what the tensor map describes and which tcgen05.mma kind contracts it.
 enum OperandKind { OK_TF32 = 0, OK_I8 = 1, OK_F16 = 2 };
 template <int MODE>
 struct OperandOf {
     static constexpr int kind = (MODE == TM_I8 || MODE == TM_I8P) ? OK_I8 : (MODE == TM_F16_EXACT ? OK_F16 : OK_TF32);
     static constexpr int kb_elems = kind == OK_I8 ? 128 : (kind == OK_F16 ? 64 : 32);  // elements per 128-byte swizzle row
 };
+// D[tmem] (+)= A[smem] * B[smem]^T; M=128, N=128, 32 bytes of K per instruction (8 tf32 / 16 f16 / 32 u8), fp32 or s32
+// accumulate.  Called by the WHOLE warp with warp-uniform operands; one elected lane issues.  (Issuing from inside
+// an `if (lane == 0)` made ptxas wrap every MMA in a R2UR.BROADCAST / BRA.U.ANY uniformisation loop
+// and recompute the descriptors: ~90 cycles per instruction for 64 cycles of tensor work.)
 template <int KIND, bool ACCUMULATE>
 __device__ __forceinline__ void tc_mma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc) {
     if constexpr (KIND == OK_F16)  // f16 x f16 -> f32, K = 16 per instruction
@@ -146,16 +120,6 @@ __device__ __forceinline__ void tc_commit_elect(uint64_t* bar) {
         "elect.sync _|pe, 0xffffffff;\n\t"
         "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
         "}" ::"r"(smem_u32(bar))
-        : "memory");
-}
-__device__ __forceinline__ void tc_commit_mcast_elect(uint64_t* bar, uint16_t cta_mask) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred pe;\n\t"
-        "elect.sync _|pe, 0xffffffff;\n\t"
-        "@pe tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;\n\t"
-        "}" ::"r"(smem_u32(bar)),
-        "h"(cta_mask)
         : "memory");
 }
 __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {

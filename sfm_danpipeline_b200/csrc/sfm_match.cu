@@ -163,7 +163,6 @@ struct SfmmCtx {
     bool tensor_refine = false; // arbitrary floats: TF32 ranking pass + candidate collection + exact refinement
     std::vector<float> img_maxnorm2;  // per image max |x|^2 (error bound of the ranking pass)
     int tensor_ts = -1;        // query tile in tensor memory (float_tensor_ts.cuh): -1 = where it measured faster (binary engine), 0/1 = SFMM_TENSOR_TS
-    int tensor_cluster = 1;    // CTAs per cluster sharing train tiles: the 2-CTA TMA-multicast variant measured no faster (not L2-bound) and was removed
     CUtensorMap tmap{};
     DevBuf d_norms, d_flags;
     bool tensor_f16 = false;  // float tensor path runs on an fp16 copy (d_half) with kind::f16
@@ -293,31 +292,25 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
         const uint32_t per = ((pd.nt + splits - 1) / splits + t_gran - 1) / t_gran * t_gran;
         splits = (pd.nt + per - 1) / per;
         pd.n_splits = splits;
-        // tensor kernels run as clusters of `cl` CTAs that share train tiles: consecutive tiles of the list
-        // must differ in q0 only; a row count that is not a multiple of cl*128 gets a tile past the image
-        // (it computes on rows nobody reads and writes nothing)
-        const uint32_t cl = ctx->use_tensor ? static_cast<uint32_t>(ctx->tensor_cluster) : 1;
-        for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile * cl)
-            for (uint32_t s = 0; s < splits; ++s)
-                for (uint32_t c = 0; c < cl; ++c) {
-                    KnnTile kt;
-                    kt.pair = static_cast<uint32_t>(i);
-                    kt.q0 = q0 + c * q_tile;
-                    kt.t0 = s * per;
-                    kt.t1 = std::min(pd.nt, (s + 1) * per);
-                    kt.split = s;
-                    plan.tiles.push_back(kt);
-                }
+        for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile)
+            for (uint32_t s = 0; s < splits; ++s) {
+                KnnTile kt;
+                kt.pair = static_cast<uint32_t>(i);
+                kt.q0 = q0;
+                kt.t0 = s * per;
+                kt.t1 = std::min(pd.nt, (s + 1) * per);
+                kt.split = s;
+                plan.tiles.push_back(kt);
+            }
         if (ctx->use_tensor && ctx->cfg.cross_check) {
             // tensor kernels: the cross-check's column minima come from "reverse" tiles (roles swapped,
             // bit 31 of split), see float_tensor.cuh; rows = train rows, streamed = query rows
             uint32_t rsplits = std::min<uint32_t>(splits_wanted, std::max<uint32_t>(1, pd.nq / (2 * t_gran)));
             const uint32_t rper = ((pd.nq + rsplits - 1) / rsplits + t_gran - 1) / t_gran * t_gran;
             rsplits = (pd.nq + rper - 1) / rper;
-            for (uint32_t r0 = 0; r0 < pd.nt; r0 += q_tile * cl)
+            for (uint32_t r0 = 0; r0 < pd.nt; r0 += q_tile)
                 for (uint32_t s2 = 0; s2 < rsplits; ++s2)
-                    for (uint32_t c = 0; c < cl; ++c)
-                        plan.tiles.push_back(KnnTile{static_cast<uint32_t>(i), r0 + c * q_tile, s2 * rper, std::min(pd.nq, (s2 + 1) * rper), s2 | 0x80000000u});
+                    plan.tiles.push_back(KnnTile{static_cast<uint32_t>(i), r0, s2 * rper, std::min(pd.nq, (s2 + 1) * rper), s2 | 0x80000000u});
         }
         pd.n_ftiles = (pd.nq + FILTER_TILE - 1) / FILTER_TILE;
         for (uint32_t f = 0; f < pd.n_ftiles; ++f) plan.ftiles.push_back(FilterTile{static_cast<uint32_t>(i), f * FILTER_TILE});
@@ -615,9 +608,7 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
         PairDesc& pd = plan.pairs[0];  // nt == 1: planned as "no matches"; the raw list still has one neighbour
         pd.n_splits = 1;
         const uint32_t q_tile = query_tile_rows(ctx);
-        const uint32_t cl = ctx->use_tensor ? static_cast<uint32_t>(ctx->tensor_cluster) : 1;
-        for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile * cl)
-            for (uint32_t c = 0; c < cl; ++c) plan.tiles.push_back(KnnTile{0, q0 + c * q_tile, 0, pd.nt, 0});
+        for (uint32_t q0 = 0; q0 < pd.nq; q0 += q_tile) plan.tiles.push_back(KnnTile{0, q0, 0, pd.nt, 0});
         plan.knn_entries = pd.nq;
         plan.col_entries = pd.nt;
         if (ctx->tensor_refine) {
