@@ -36,6 +36,8 @@ enum TensorMode {
     TM_I8 = 1,            // binary descriptors unpacked to bytes (kind::i8), result is final
     TM_TF32_RANK = 2,     // arbitrary floats, pass 1: approximate d^2 (TF32 truncation) -> approximate top-2 per row
     TM_I8P = 4,           // TM_I8 with two 16-bit keys per register (descriptors < 512 bit): half the min/max work
+    TM_F16_RANK = 6,      // TM_TF32_RANK / TM_TF32_COLLECT on an fp16 (round-to-nearest) copy: same 10-bit significand as TF32,
+    TM_F16_COLLECT = 7,   // half the MMA time and far less power (the TF32 passes run into the power cap on dense mantissas)
     TM_F16_EXACT = 5,     // TM_TF32_EXACT on an fp16 copy of the descriptors (integers |v| <= 2048 are exact in fp16):
                           // kind::f16 contracts 16 elements per MMA, half the tensor time and half the operand bytes
     TM_TF32_COLLECT = 3   // arbitrary floats, pass 2: every column whose approximate d^2 can still be in the exact
@@ -69,11 +71,13 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__host__ __device__ constexpr bool tm_is_rank(int mode) { return mode == TM_TF32_RANK || mode == TM_F16_RANK; }
+__host__ __device__ constexpr bool tm_is_collect(int mode) { return mode == TM_TF32_COLLECT || mode == TM_F16_COLLECT; }
 // Operand type of a mode: what the tensor map describes and which tcgen05.mma kind contracts it.
 enum OperandKind { OK_TF32 = 0, OK_I8 = 1, OK_F16 = 2 };
 template <int MODE>
 struct OperandOf {
-    static constexpr int kind = (MODE == TM_I8 || MODE == TM_I8P) ? OK_I8 : (MODE == TM_F16_EXACT ? OK_F16 : OK_TF32);
+    static constexpr int kind = (MODE == TM_I8 || MODE == TM_I8P) ? OK_I8 : ((MODE == TM_F16_EXACT || MODE == TM_F16_RANK || MODE == TM_F16_COLLECT) ? OK_F16 : OK_TF32);
     static constexpr int kb_elems = kind == OK_I8 ? 128 : (kind == OK_F16 ? 64 : 32);  // elements per 128-byte swizzle row
 };
 // D[tmem] (+)= A[smem] * B[smem]^T; M=128, N=128, 32 bytes of K per instruction (8 tf32 / 16 f16 / 32 u8), fp32 or s32
@@ -525,6 +529,7 @@ __device__ __forceinline__ void chunk_collect(const uint32_t (&acc)[32], uint32_
 // every one of them -- and the true second-smallest -- is <= 0 + eps).  |approx - exact| <= eps with
 // eps = 2^-8 |q| max|t| (both operands truncated to TF32: relative error < 2^-10 each, Cauchy-Schwarz)
 // + accumulation / norm rounding slack; every column of the exact top-2 has approx <= m2 + 2 eps.
+template <bool F16>
 __device__ __forceinline__ float collect_threshold(bool valid, float nq2, const PairDesc& pd, const KnnEntry* __restrict__ knn, uint32_t qrow) {
     if (!valid) return __int_as_float(0xff800000);  // -inf: rows past the image collect nothing (their accumulators are
                                                     // dot products with some other image's rows and can be anything)
@@ -537,7 +542,11 @@ __device__ __forceinline__ float collect_threshold(bool valid, float nq2, const 
     }
     const uint32_t m2bits = static_cast<uint32_t>(k2 >> 32);
     const float m2 = m2bits >= 0x7f800000u ? __int_as_float(0x7f7fffff) : __uint_as_float(m2bits);  // none / inf / NaN: collect all
-    const float eps = 0.00390625f * 1.02f * sqrtf(nq2) * sqrtf(pd.t_maxnorm2) + 1e-6f * (nq2 + pd.t_maxnorm2);
+    // TF32 operands are truncated (relative error < 2^-10 each): |2 q~.t~ - 2 q.t| <= 2^-8 |q||t|.
+    // fp16 operands are rounded to nearest (relative error <= 2^-11 each, plus <= 2^-25 absolute in the subnormal range):
+    // <= 2^-9 |q||t| + 2^-24 sqrt(d) (|q| + |t|).  The 2 % on top covers the fp32 accumulation of the tensor core.
+    const float rel = F16 ? 0.001953125f : 0.00390625f;
+    const float eps = rel * 1.02f * sqrtf(nq2) * sqrtf(pd.t_maxnorm2) + (F16 ? 2e-6f : 1e-6f) * (nq2 + pd.t_maxnorm2) + (F16 ? 2e-6f : 0.f);
     return m2 + 2.f * eps - nq2 + 1e-6f * (m2 + nq2);  // (last term: rounding of moving |q|^2 across)
 }
 
@@ -563,7 +572,7 @@ __device__ __forceinline__ void finish_rows(uint4* merge, const Top2& best, uint
             if (k1 != KEY_NONE) atomicMin(colmin + col_off + qrow, k1);
         } else {
             KnnEntry e;
-            if constexpr (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_TF32_RANK) {
+            if constexpr (MODE == TM_I8 || MODE == TM_I8P || tm_is_rank(MODE)) {
                 // i8: the Hamming distance stays an integer in the key (binary_knn.cuh's convention);
                 // rank pass: float bits of the approximate d^2 (only pass 2 reads it)
                 e.x = k1;
@@ -744,8 +753,8 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 const bool valid = qrow < pd.nq;
                 const float nq2 = valid ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
                 float v;
-                if constexpr (MODE == TM_TF32_COLLECT) {
-                    v = collect_threshold(valid, nq2, pd, knn, qrow);
+                if constexpr (tm_is_collect(MODE)) {
+                    v = collect_threshold<MODE == TM_F16_COLLECT>(valid, nq2, pd, knn, qrow);
                 } else {
                     v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (exact float modes, rank)
                 }
@@ -779,7 +788,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             [[maybe_unused]] uint32_t* cand_idx_row = nullptr;
             [[maybe_unused]] uint32_t fill = 0;
             [[maybe_unused]] int r1 = 0x7FFFFFFF, r2 = 0x7FFFFFFF;  // TM_TF32_RANK: two smallest approximate d^2 (float bits), over all tiles
-            if constexpr (MODE == TM_TF32_COLLECT) {
+            if constexpr (tm_is_collect(MODE)) {
                 // each epilogue group owns one counter and half of the row's list
                 cand_count_row = cand_count + 2 * (size_t)(q_off + min(qrow, nq - 1)) + half;
                 cand_idx_row = cand_idx + (size_t)(q_off + min(qrow, nq - 1)) * FT_CAND_CAP + half * (FT_CAND_CAP / 2);
@@ -803,11 +812,11 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 for (int c = 0; c < NCH; ++c) {
                     if (c < NCH - 1) tc_ld_32x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
                     const uint32_t nb_saddr = smem_u32(&sm.nb[a][c * 32]);
-                    if constexpr (MODE == TM_TF32_COLLECT) {
+                    if constexpr (tm_is_collect(MODE)) {
                         const uint32_t c0 = col0 + c * 32;  // columns at or past n_rows belong to another image / padding
                         const uint32_t valid = c0 + 32 <= n_rows ? 0xFFFFFFFFu : (c0 < n_rows ? (1u << (n_rows - c0)) - 1u : 0u);
                         chunk_collect(acc[c & 1], nb_saddr, cq, valid, t0 + c0, n_splits != 1, fill, cand_count_row, cand_idx_row);
-                    } else if constexpr (MODE == TM_TF32_RANK) {
+                    } else if constexpr (tm_is_rank(MODE)) {
                         if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
                         else chunk_rank<true>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
                     } else if constexpr (MODE == TM_I8P) {
@@ -828,7 +837,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.nb_empty[a]);
                 // merge the tile's two best into the running pair (ascending tiles = arrival order)
-                if constexpr (MODE != TM_TF32_RANK && MODE != TM_TF32_COLLECT) {
+                if constexpr (!tm_is_rank(MODE) && !tm_is_collect(MODE)) {
                     const int tbase = (int)(t0 + col0);
                     if constexpr (MODE == TM_I8P) {  // four 16-bit lane winners -> the tile's two smallest (hamming, column)
                         uint32_t q1, q2;
@@ -845,11 +854,11 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 }
             }
             g0 += n_tiles;
-            if constexpr (MODE == TM_TF32_RANK) {  // values only, clamped at 0; the index field is unused
+            if constexpr (tm_is_rank(MODE)) {  // values only, clamped at 0; the index field is unused
                 if (r1 != 0x7FFFFFFF) { best.d1 = (uint32_t)max(r1, 0); best.i1 = 0; }
                 if (r2 != 0x7FFFFFFF) { best.d2 = (uint32_t)max(r2, 0); best.i2 = 0; }
             }
-            if constexpr (MODE == TM_TF32_COLLECT) {
+            if constexpr (tm_is_collect(MODE)) {
                 if (n_splits == 1 && qrow < nq) *cand_count_row = fill;
             } else {
                 finish_rows<MODE>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin);

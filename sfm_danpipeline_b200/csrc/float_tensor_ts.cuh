@@ -250,8 +250,8 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 const bool valid = qrow < pd.nq;
                 const float nq2 = valid ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
                 float v;
-                if constexpr (MODE == TM_TF32_COLLECT) {
-                    v = collect_threshold(valid, nq2, pd, knn, qrow);
+                if constexpr (tm_is_collect(MODE)) {
+                    v = collect_threshold<MODE == TM_F16_COLLECT>(valid, nq2, pd, knn, qrow);
                 } else {
                     v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (exact float modes, rank)
                 }
@@ -317,7 +317,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             [[maybe_unused]] uint32_t* cand_idx_row = nullptr;
             [[maybe_unused]] uint32_t fill = 0;
             [[maybe_unused]] int r1 = 0x7FFFFFFF, r2 = 0x7FFFFFFF;  // TM_TF32_RANK: two smallest approximate d^2 (float bits), over all tiles
-            if constexpr (MODE == TM_TF32_COLLECT) {
+            if constexpr (tm_is_collect(MODE)) {
                 // each epilogue group owns one counter and half of the row's list
                 cand_count_row = cand_count + 2 * (size_t)(q_off + min(qrow, nq - 1)) + half;
                 cand_idx_row = cand_idx + (size_t)(q_off + min(qrow, nq - 1)) * FT_CAND_CAP + half * (FT_CAND_CAP / 2);
@@ -342,11 +342,11 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 for (int c = 0; c < NCH; ++c) {
                     if (c < NCH - 1) tc_ld_32x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
                     const uint32_t nb_saddr = smem_u32(&sm.nb[nbs][c * 32]);
-                    if constexpr (MODE == TM_TF32_COLLECT) {
+                    if constexpr (tm_is_collect(MODE)) {
                         const uint32_t c0 = col0 + c * 32;  // columns at or past n_rows belong to another image / padding
                         const uint32_t valid = c0 + 32 <= n_rows ? 0xFFFFFFFFu : (c0 < n_rows ? (1u << (n_rows - c0)) - 1u : 0u);
                         chunk_collect(acc[c & 1], nb_saddr, cq, valid, t0 + c0, n_splits != 1, fill, cand_count_row, cand_idx_row);
-                    } else if constexpr (MODE == TM_TF32_RANK) {
+                    } else if constexpr (tm_is_rank(MODE)) {
                         if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
                         else chunk_rank<true>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
                     } else if constexpr (MODE == TM_I8P) {
@@ -367,7 +367,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sm.nb_empty[nbs]);
                 // merge the tile's two best into the running pair (ascending tiles = arrival order)
-                if constexpr (MODE != TM_TF32_RANK && MODE != TM_TF32_COLLECT) {
+                if constexpr (!tm_is_rank(MODE) && !tm_is_collect(MODE)) {
                     const int tbase = (int)(t0 + col0);
                     if constexpr (MODE == TM_I8P) {  // four 16-bit lane winners -> the tile's two smallest (hamming, column)
                         uint32_t q1, q2;
@@ -384,11 +384,11 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 }
             }
             g0 += n_tiles;
-            if constexpr (MODE == TM_TF32_RANK) {  // values only, clamped at 0; the index field is unused
+            if constexpr (tm_is_rank(MODE)) {  // values only, clamped at 0; the index field is unused
                 if (r1 != 0x7FFFFFFF) { best.d1 = (uint32_t)max(r1, 0); best.i1 = 0; }
                 if (r2 != 0x7FFFFFFF) { best.d2 = (uint32_t)max(r2, 0); best.i2 = 0; }
             }
-            if constexpr (MODE == TM_TF32_COLLECT) {
+            if constexpr (tm_is_collect(MODE)) {
                 if (n_splits == 1 && qrow < nq) *cand_count_row = fill;
             } else {
                 finish_rows<MODE>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin);

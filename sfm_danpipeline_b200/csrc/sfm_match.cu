@@ -376,7 +376,7 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_TF32_EXACT || MODE == TM_F16_EXACT) ? (const float*)ctx->d_nbkey.as<float>()
                                                                                                               : (const float*)ctx->d_norms.as<float>();
     // measured (profiles/tensor_variants_r01.txt): TMEM-A wins for the binary engine and the fp16 float path, shared-memory-A for TF32
-    const bool ts = ctx->tensor_ts < 0 ? (MODE == TM_I8P || MODE == TM_F16_EXACT || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0;
+    const bool ts = ctx->tensor_ts < 0 ? (MODE == TM_I8P || OperandOf<MODE>::kind == OK_F16 || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0;
     if (!ts) {  // query tile in shared memory (float_tensor.cuh)
         const size_t smem = float_tensor_smem_bytes(KB);
         auto kern = tensor_knn2_kernel<KB, MODE>;
@@ -393,7 +393,7 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     auto kern = tensor_knn2_ts_kernel<KB, MODE>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P) ? ctx->d_unpacked.as<uint4>() : (MODE == TM_F16_EXACT ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>());
+    const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P) ? ctx->d_unpacked.as<uint4>() : (OperandOf<MODE>::kind == OK_F16 ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>());
     kern<<<grid, FTS_THREADS, smem, sl.stream>>>(ctx->tmap, a_src, static_cast<uint32_t>(ctx->total_rows), (const float*)ctx->d_norms.as<float>(), nb_src,
                                                  (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles, (const PairDesc*)sl.d_pairs.as<PairDesc>(),
                                                  sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u, ctx->i8_bias,
@@ -417,8 +417,13 @@ cudaError_t launch_tensor_refine(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int k
     const uint32_t rows = static_cast<uint32_t>(sl.plan.pair_of_row.size());
     cudaError_t e = cudaMemsetAsync(sl.d_cand_count.p, 0, std::max<size_t>(1, rows) * 2 * sizeof(uint32_t), sl.stream);
     if (e != cudaSuccess) return e;
-    if ((e = launch_tensor<TM_TF32_RANK>(ctx, sl, n_tiles, kblocks)) != cudaSuccess) return e;
-    if ((e = launch_tensor<TM_TF32_COLLECT>(ctx, sl, n_tiles, kblocks)) != cudaSuccess) return e;
+    if (ctx->tensor_f16) {
+        if ((e = launch_tensor<TM_F16_RANK>(ctx, sl, n_tiles, kblocks)) != cudaSuccess) return e;
+        if ((e = launch_tensor<TM_F16_COLLECT>(ctx, sl, n_tiles, kblocks)) != cudaSuccess) return e;
+    } else {
+        if ((e = launch_tensor<TM_TF32_RANK>(ctx, sl, n_tiles, kblocks)) != cudaSuccess) return e;
+        if ((e = launch_tensor<TM_TF32_COLLECT>(ctx, sl, n_tiles, kblocks)) != cudaSuccess) return e;
+    }
     if (rows)
         float_refine_kernel<<<(rows + 63) / 64, 256, 0, sl.stream>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), sl.d_pairs.as<PairDesc>(),
                                                                   static_cast<uint32_t>(sl.plan.pairs.size()), sl.d_pair_of_row.as<uint32_t>(),
@@ -554,9 +559,26 @@ int prepare_float(SfmmCtx* ctx) {
             ctx->use_tensor = true;
             ctx->tensor_f16 = true;
         } else if (ctx->tensor_eligible || (finite && !ctx->cfg.cross_check)) {
-            int rc = make_tensor_map(ctx, ctx->blob.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ctx->pitch, ctx->total_rows);
+            // arbitrary floats whose magnitudes fit fp16 (|v| <= sqrt(max |x|^2) < 65504): the ranking and collection passes
+            // contract an fp16 round-to-nearest copy (same 10-bit significand as TF32, half the MMA time, no power cap);
+            // the refinement reads the fp32 blob either way
+            const bool f16_rank = !ctx->tensor_eligible && ctx->cols % 64 == 0 && max_norm2 < 4.0e9f && !std::getenv("SFMM_NO_F16");
+            int rc;
+            if (f16_rank) {
+                CU_TRY(ctx, ctx->d_half.ensure(static_cast<size_t>(ctx->total_rows) * ctx->cols * sizeof(__half)));
+                const size_t n2 = static_cast<size_t>(ctx->total_rows) * ctx->cols / 2;
+                float_to_half_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), rows,
+                                                                                           ctx->cols, ctx->d_half.as<__half>());
+                CU_TRY(ctx, cudaGetLastError());
+                ctx->stats.kernel_launches += 1;
+                rc = make_tensor_map(ctx, ctx->d_half.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<size_t>(ctx->cols) * 2, ctx->total_rows);
+                ctx->tensor_kblocks = ctx->cols * 2 / 128;
+                ctx->tensor_f16 = true;
+            } else {
+                rc = make_tensor_map(ctx, ctx->blob.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, ctx->pitch, ctx->total_rows);
+                ctx->tensor_kblocks = ctx->cols / FT_KB_ELEMS;
+            }
             if (rc) return rc;
-            ctx->tensor_kblocks = ctx->cols / FT_KB_ELEMS;
             ctx->use_tensor = true;
             if (!ctx->tensor_eligible) {
                 // arbitrary floats: the TF32 pass only ranks; per-image max |x|^2 feeds its error bound
