@@ -110,7 +110,7 @@ typedef struct SfmmStats {
     double last_knn_work;      /* algorithmic work of those launches: POPC32 ops (Hamming) or FLOPs (L2) */
     int64_t last_knn_launches; /* number of 2-NN kernel launches behind last_knn_ms */
     int64_t float_path;        /* L2: 0 = not decided yet, SFMM_FLOAT_EXACT or SFMM_FLOAT_TENSOR = the kernel in use,
-                                  3 = tensor-core TF32 ranking + exact refinement (arbitrary floats);
+                                  3 = tensor-core fp16/TF32 ranking + exact refinement (arbitrary floats);
                                   Hamming: SFMM_FLOAT_TENSOR when the tensor engine is in use, else 0 */
 } SfmmStats;
 

@@ -206,10 +206,13 @@ __global__ void float_prepare_kernel(const float* __restrict__ blob, int kq, uin
 // integer below 2^24).  x' = fmaf(q.t, -2, nb') = d^2 - |q|^2 + 2^23 + 2^20 lies in [2^23, 2^24): its low mantissa
 // bits are that integer, it orders the columns of a row exactly like d^2, and |q|^2 is added back once per tile
 // winner -- one FADD per accumulator element less than forming d^2 + 2^23 in place.
+// The ranking pass of arbitrary floats uses the same table with offset C = max |x|^2 over the set: x' = |t|^2 - 2 q.t + C
+// is >= 0 (up to the approximation error), so its float bits still order as signed integers, and d~^2 = x' - C + |q|^2
+// is formed once per row at the end of the item.
 static constexpr float FT_NB_OFFSET = 8388608.f + 1048576.f;
-__global__ void float_nbexact_kernel(const float* __restrict__ norms, uint32_t n, float* __restrict__ out) {
+__global__ void float_nbexact_kernel(const float* __restrict__ norms, uint32_t n, float offset, float* __restrict__ out) {
     const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = norms[i] + FT_NB_OFFSET;
+    if (i < n) out[i] = norms[i] + offset;
 }
 
 // fp16 copy of a TF32-exact set (integers |v| <= 2047: exact in fp16's 11-bit significand), rows of `cols` halves.
@@ -454,7 +457,7 @@ __device__ __forceinline__ void unpack_top2_u16x2(uint32_t m1, uint32_t m2, uint
 // TM_TF32_RANK: only the two smallest VALUES of the row matter (pass 2 re-derives the columns), so the key is
 // the raw float, ordered as a signed integer: the float order for values >= 0.  Slightly negative values (only
 // possible within the error bound of 0) sort first in scrambled order; the caller clamps the result at 0, which
-// keeps the threshold an upper bound (see the COLLECT prologue).  FADD + FFMA + 2.5 VIMNMX per column.
+// keeps the threshold an upper bound (see collect_threshold).  FFMA + 2.5 VIMNMX per column.
 __device__ __forceinline__ void top2_pair_s32(int& m1, int& m2, int a, int b) {
     const int lo = min(a, b), hi = max(a, b);
     const int loser = max(m1, lo);
@@ -463,7 +466,7 @@ __device__ __forceinline__ void top2_pair_s32(int& m1, int& m2, int a, int b) {
 }
 
 template <bool PARTIAL>
-__device__ __forceinline__ void chunk_rank(const uint32_t (&acc)[32], uint32_t nb_saddr, float cq, uint32_t col0,
+__device__ __forceinline__ void chunk_rank(const uint32_t (&acc)[32], uint32_t nb_saddr, uint32_t col0,
                                            uint32_t n_rows, int& m1, int& m2) {
 #pragma unroll
     for (int e = 0; e < 32; e += 4) {
@@ -472,7 +475,7 @@ __device__ __forceinline__ void chunk_rank(const uint32_t (&acc)[32], uint32_t n
         int k[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            k[i] = __float_as_int(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i] + cq));
+            k[i] = __float_as_int(fmaf(__uint_as_float(acc[e + i]), -2.f, nbv[i]));  // nbv = |t|^2 + C (float_nbexact_kernel)
             if (PARTIAL) k[i] = col0 + e + i < n_rows ? k[i] : 0x7FFFFFFF;
         }
         top2_pair_s32(m1, m2, k[0], k[1]);
@@ -530,7 +533,8 @@ __device__ __forceinline__ void chunk_collect(const uint32_t (&acc)[32], uint32_
 // eps = 2^-8 |q| max|t| (both operands truncated to TF32: relative error < 2^-10 each, Cauchy-Schwarz)
 // + accumulation / norm rounding slack; every column of the exact top-2 has approx <= m2 + 2 eps.
 template <bool F16>
-__device__ __forceinline__ float collect_threshold(bool valid, float nq2, const PairDesc& pd, const KnnEntry* __restrict__ knn, uint32_t qrow) {
+__device__ __forceinline__ float collect_threshold(bool valid, float nq2, const PairDesc& pd, const KnnEntry* __restrict__ knn, uint32_t qrow,
+                                                   float rank_offset /* C of the ranking pass's key table */) {
     if (!valid) return __int_as_float(0xff800000);  // -inf: rows past the image collect nothing (their accumulators are
                                                     // dot products with some other image's rows and can be anything)
     unsigned long long k1 = KEY_NONE, k2 = KEY_NONE;
@@ -546,7 +550,10 @@ __device__ __forceinline__ float collect_threshold(bool valid, float nq2, const 
     // fp16 operands are rounded to nearest (relative error <= 2^-11 each, plus <= 2^-25 absolute in the subnormal range):
     // <= 2^-9 |q||t| + 2^-24 sqrt(d) (|q| + |t|).  The 2 % on top covers the fp32 accumulation of the tensor core.
     const float rel = F16 ? 0.001953125f : 0.00390625f;
-    const float eps = rel * 1.02f * sqrtf(nq2) * sqrtf(pd.t_maxnorm2) + (F16 ? 2e-6f : 1e-6f) * (nq2 + pd.t_maxnorm2) + (F16 ? 2e-6f : 0.f);
+    // The ranking pass formed x' = |t|^2 - 2 q.t + C and d~^2 = x' - C + |q|^2 in fp32 at magnitudes up to 4C: two roundings
+    // of at most 2^-24 * 4C each, covered by 1e-6 * C (negligible unless one row of the set dwarfs this pair's norms).
+    const float eps = rel * 1.02f * sqrtf(nq2) * sqrtf(pd.t_maxnorm2) + (F16 ? 2e-6f : 1e-6f) * (nq2 + pd.t_maxnorm2) + (F16 ? 2e-6f : 0.f) +
+                      1e-6f * rank_offset;
     return m2 + 2.f * eps - nq2 + 1e-6f * (m2 + nq2);  // (last term: rounding of moving |q|^2 across)
 }
 
@@ -606,7 +613,7 @@ __global__ void __launch_bounds__(FT_THREADS, 1)
 tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __restrict__ norms /* int32 popcounts when INT8 */,
                    const float* __restrict__ nb_src /* per train row: |t|^2, or binary_nbkey_kernel's key part when INT8 */,
                    const KnnTile* __restrict__ tiles, const uint32_t n_items, const PairDesc* __restrict__ pairs,
-                   KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */, const uint32_t i8_bias /* TM_I8P: the descriptors' bit length */,
+                   KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */, const uint32_t i8_bias /* TM_I8P: the descriptors' bit length; rank / collect modes: float bits of the key-table offset C */,
                    uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
     constexpr int KIND = OperandOf<MODE>::kind;
     constexpr int KB_ELEMS = OperandOf<MODE>::kb_elems;
@@ -754,7 +761,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                 const float nq2 = valid ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
                 float v;
                 if constexpr (tm_is_collect(MODE)) {
-                    v = collect_threshold<MODE == TM_F16_COLLECT>(valid, nq2, pd, knn, qrow);
+                    v = collect_threshold<MODE == TM_F16_COLLECT>(valid, nq2, pd, knn, qrow, __uint_as_float(i8_bias));
                 } else {
                     v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (exact float modes, rank)
                 }
@@ -817,8 +824,8 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
                         const uint32_t valid = c0 + 32 <= n_rows ? 0xFFFFFFFFu : (c0 < n_rows ? (1u << (n_rows - c0)) - 1u : 0u);
                         chunk_collect(acc[c & 1], nb_saddr, cq, valid, t0 + c0, n_splits != 1, fill, cand_count_row, cand_idx_row);
                     } else if constexpr (tm_is_rank(MODE)) {
-                        if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
-                        else chunk_rank<true>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
+                        if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, col0 + c * 32, n_rows, r1, r2);
+                        else chunk_rank<true>(acc[c & 1], nb_saddr, col0 + c * 32, n_rows, r1, r2);
                     } else if constexpr (MODE == TM_I8P) {
                         // (key_mul - 640 = -128 from the kernel parameter: stays an IMAD on the FMA pipe)
                         if (!partial) chunk_top2_packed<false>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
@@ -855,8 +862,10 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             }
             g0 += n_tiles;
             if constexpr (tm_is_rank(MODE)) {  // values only, clamped at 0; the index field is unused
-                if (r1 != 0x7FFFFFFF) { best.d1 = (uint32_t)max(r1, 0); best.i1 = 0; }
-                if (r2 != 0x7FFFFFFF) { best.d2 = (uint32_t)max(r2, 0); best.i2 = 0; }
+                // x' = d~^2 - |q|^2 + C (C = the set's max |x|^2, passed in i8_bias as float bits): back to d~^2, clamped at 0
+                const float back = cq - __uint_as_float(i8_bias);
+                if (r1 != 0x7FFFFFFF) { best.d1 = __float_as_uint(fmaxf(__int_as_float(max(r1, 0)) + back, 0.f)); best.i1 = 0; }
+                if (r2 != 0x7FFFFFFF) { best.d2 = __float_as_uint(fmaxf(__int_as_float(max(r2, 0)) + back, 0.f)); best.i2 = 0; }
             }
             if constexpr (tm_is_collect(MODE)) {
                 if (n_splits == 1 && qrow < nq) *cand_count_row = fill;

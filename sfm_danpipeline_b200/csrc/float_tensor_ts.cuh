@@ -112,7 +112,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                       const uint32_t total_rows, const float* __restrict__ norms /* int32 popcounts when INT8 */,
                    const float* __restrict__ nb_src /* per train row: |t|^2, or binary_nbkey_kernel's key part when INT8 */,
                       const KnnTile* __restrict__ tiles, const uint32_t n_items, const PairDesc* __restrict__ pairs,
-                      KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */, const uint32_t i8_bias /* TM_I8P: the descriptors' bit length */,
+                      KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */, const uint32_t i8_bias /* TM_I8P: the descriptors' bit length; rank / collect modes: float bits of the key-table offset C */,
                       uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
     constexpr int KIND = OperandOf<MODE>::kind;
     constexpr int KB_ELEMS = OperandOf<MODE>::kb_elems;
@@ -251,7 +251,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 const float nq2 = valid ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
                 float v;
                 if constexpr (tm_is_collect(MODE)) {
-                    v = collect_threshold<MODE == TM_F16_COLLECT>(valid, nq2, pd, knn, qrow);
+                    v = collect_threshold<MODE == TM_F16_COLLECT>(valid, nq2, pd, knn, qrow, __uint_as_float(i8_bias));
                 } else {
                     v = nq2;  // popc(q) as integer bits (i8) / |q|^2 (exact float modes, rank)
                 }
@@ -347,8 +347,8 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                         const uint32_t valid = c0 + 32 <= n_rows ? 0xFFFFFFFFu : (c0 < n_rows ? (1u << (n_rows - c0)) - 1u : 0u);
                         chunk_collect(acc[c & 1], nb_saddr, cq, valid, t0 + c0, n_splits != 1, fill, cand_count_row, cand_idx_row);
                     } else if constexpr (tm_is_rank(MODE)) {
-                        if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
-                        else chunk_rank<true>(acc[c & 1], nb_saddr, cq, col0 + c * 32, n_rows, r1, r2);
+                        if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, col0 + c * 32, n_rows, r1, r2);
+                        else chunk_rank<true>(acc[c & 1], nb_saddr, col0 + c * 32, n_rows, r1, r2);
                     } else if constexpr (MODE == TM_I8P) {
                         // (key_mul - 640 = -128 from the kernel parameter: stays an IMAD on the FMA pipe)
                         if (!partial) chunk_top2_packed<false>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
@@ -385,8 +385,10 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             }
             g0 += n_tiles;
             if constexpr (tm_is_rank(MODE)) {  // values only, clamped at 0; the index field is unused
-                if (r1 != 0x7FFFFFFF) { best.d1 = (uint32_t)max(r1, 0); best.i1 = 0; }
-                if (r2 != 0x7FFFFFFF) { best.d2 = (uint32_t)max(r2, 0); best.i2 = 0; }
+                // x' = d~^2 - |q|^2 + C (C = the set's max |x|^2, passed in i8_bias as float bits): back to d~^2, clamped at 0
+                const float back = cq - __uint_as_float(i8_bias);
+                if (r1 != 0x7FFFFFFF) { best.d1 = __float_as_uint(fmaxf(__int_as_float(max(r1, 0)) + back, 0.f)); best.i1 = 0; }
+                if (r2 != 0x7FFFFFFF) { best.d2 = __float_as_uint(fmaxf(__int_as_float(max(r2, 0)) + back, 0.f)); best.i2 = 0; }
             }
             if constexpr (tm_is_collect(MODE)) {
                 if (n_splits == 1 && qrow < nq) *cand_count_row = fill;

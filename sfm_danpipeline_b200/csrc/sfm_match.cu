@@ -165,6 +165,7 @@ struct SfmmCtx {
     int tensor_ts = -1;        // query tile in tensor memory (float_tensor_ts.cuh): -1 = where it measured faster (binary engine), 0/1 = SFMM_TENSOR_TS
     CUtensorMap tmap{};
     DevBuf d_norms, d_flags;
+    float rank_offset = 0.f;  // C of the ranking pass's key table (float_nbexact_kernel)
     bool tensor_f16 = false;  // float tensor path runs on an fp16 copy (d_half) with kind::f16
     DevBuf d_half;
     uint32_t i8_bias = 0;    // binary tensor engine: descriptor bit length when the packed 16-bit keys apply (< 512 bit), else 0
@@ -373,9 +374,11 @@ template <int KB, int MODE>
 cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     // persistent: one CTA per SM (shared memory allows no more) walks the tile list with stride gridDim.x
     const uint32_t grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(ctx->sm_count));
-    const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_TF32_EXACT || MODE == TM_F16_EXACT) ? (const float*)ctx->d_nbkey.as<float>()
+    const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_TF32_EXACT || MODE == TM_F16_EXACT || tm_is_rank(MODE)) ? (const float*)ctx->d_nbkey.as<float>()
                                                                                                               : (const float*)ctx->d_norms.as<float>();
     // measured (profiles/tensor_variants_r01.txt): TMEM-A wins for the binary engine and the fp16 float path, shared-memory-A for TF32
+    uint32_t aux = ctx->i8_bias;  // TM_I8P: descriptor bit length; rank modes: float bits of the key-table offset
+    if (tm_is_rank(MODE) || tm_is_collect(MODE)) std::memcpy(&aux, &ctx->rank_offset, sizeof(aux));
     const bool ts = ctx->tensor_ts < 0 ? (MODE == TM_I8P || OperandOf<MODE>::kind == OK_F16 || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0;
     if (!ts) {  // query tile in shared memory (float_tensor.cuh)
         const size_t smem = float_tensor_smem_bytes(KB);
@@ -384,7 +387,7 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
         if (e != cudaSuccess) return e;
         kern<<<grid, FT_THREADS, smem, sl.stream>>>(ctx->tmap, (const float*)ctx->d_norms.as<float>(), nb_src, (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles,
                                                     (const PairDesc*)sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
-                                                    sl.d_colmin.as<unsigned long long>(), 512u, ctx->i8_bias, sl.d_cand_count.as<uint32_t>(),
+                                                    sl.d_colmin.as<unsigned long long>(), 512u, aux, sl.d_cand_count.as<uint32_t>(),
                                                     sl.d_cand_idx.as<uint32_t>());
         return cudaGetLastError();
     }
@@ -396,7 +399,7 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P) ? ctx->d_unpacked.as<uint4>() : (OperandOf<MODE>::kind == OK_F16 ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>());
     kern<<<grid, FTS_THREADS, smem, sl.stream>>>(ctx->tmap, a_src, static_cast<uint32_t>(ctx->total_rows), (const float*)ctx->d_norms.as<float>(), nb_src,
                                                  (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles, (const PairDesc*)sl.d_pairs.as<PairDesc>(),
-                                                 sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u, ctx->i8_bias,
+                                                 sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u, aux,
                                                  sl.d_cand_count.as<uint32_t>(), sl.d_cand_idx.as<uint32_t>());
     return cudaGetLastError();
 }
@@ -540,7 +543,7 @@ int prepare_float(SfmmCtx* ctx) {
         if (ctx->tensor_eligible) {  // per train row: |t|^2 + 2^23 + 2^20, the epilogue's key argument (float_nbexact_kernel)
             const uint32_t n = rows + 2 * FT_N;
             CU_TRY(ctx, ctx->d_nbkey.ensure(static_cast<size_t>(n) * sizeof(float)));
-            float_nbexact_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_norms.as<float>(), n, ctx->d_nbkey.as<float>());
+            float_nbexact_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_norms.as<float>(), n, FT_NB_OFFSET, ctx->d_nbkey.as<float>());
             CU_TRY(ctx, cudaGetLastError());
             ctx->stats.kernel_launches += 1;
         }
@@ -581,8 +584,17 @@ int prepare_float(SfmmCtx* ctx) {
             if (rc) return rc;
             ctx->use_tensor = true;
             if (!ctx->tensor_eligible) {
-                // arbitrary floats: the TF32 pass only ranks; per-image max |x|^2 feeds its error bound
+                // arbitrary floats: the tensor passes only rank; per-image max |x|^2 feeds the error bound, and the
+                // ranking pass reads |t|^2 + C (C = the set's max |x|^2) from the key table
                 ctx->tensor_refine = true;
+                ctx->rank_offset = max_norm2;
+                {
+                    const uint32_t n = rows + 2 * FT_N;
+                    CU_TRY(ctx, ctx->d_nbkey.ensure(static_cast<size_t>(n) * sizeof(float)));
+                    float_nbexact_kernel<<<(n + 255) / 256, 256, 0, st>>>(ctx->d_norms.as<float>(), n, max_norm2, ctx->d_nbkey.as<float>());
+                    CU_TRY(ctx, cudaGetLastError());
+                    ctx->stats.kernel_launches += 1;
+                }
                 std::vector<float> h(static_cast<size_t>(ctx->total_rows));
                 CU_TRY(ctx, cudaMemcpyAsync(h.data(), ctx->d_norms.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost, st));
                 CU_TRY(ctx, cudaStreamSynchronize(st));

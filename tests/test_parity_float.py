@@ -211,6 +211,24 @@ def test_rank_and_refine_small_scale_values_and_negative_entries():
         _tables_equal(m, mx)
 
 
+@pytest.mark.parametrize("scale", [1e3, 1e5])
+def test_rank_and_refine_with_one_dominant_row(scale):
+    """One row of the set dwarfs every other norm: the ranking pass's key-table offset (the set's max |x|^2) then sits far
+    above the pair's own distances, and its fp32 rounding has to be part of the error bound.  scale 1e5 also leaves
+    fp16's range, so the passes run on TF32 operands.  Result: still the exact kernel's table, bit for bit."""
+    rng = np.random.default_rng(11)
+    descs = [(rng.random((n, 128), dtype=np.float32) * 3).astype(np.float32) for n in (400, 390, 260)]
+    descs[2][7] *= scale  # |x|^2 ~ 4e8 (fp16 range) / 4e12 (beyond it)
+    descs[0][:50] = descs[1][:50] + rng.normal(0, 0.01, (50, 128)).astype(np.float32)  # near duplicates: tiny distances
+    with Matcher(NORM_L2, 0.8, float_mode=FLOAT_AUTO) as m, Matcher(NORM_L2, 0.8, float_mode=FLOAT_EXACT) as mx:
+        m.set_descriptors(descs)
+        mx.set_descriptors(descs)
+        m.match_all_pairs()
+        mx.match_all_pairs()
+        assert m.stats()["float_path"] == 3
+        _tables_equal(m, mx)
+
+
 def test_tensor_mode_cross_check_temple_and_ragged():
     g = GoldenSet("temple_sift")
     with Matcher(NORM_L2, 0.8, True, float_mode=FLOAT_TENSOR) as m:
