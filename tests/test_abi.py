@@ -84,3 +84,25 @@ def test_product_package_never_imports_the_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, re.M), f
                 assert "liboracle" not in src and "bf_oracle" not in src, f
+
+
+def test_every_kernel_header_is_tracked_by_the_build():
+    """A .cuh missing from build.HEADERS lets a stale libsfmmatch.so travel to the GPU box unnoticed."""
+    import glob
+    import re
+    from sfm_danpipeline_b200 import build
+    csrc = build.CSRC
+    included = set()
+    for f in glob.glob(os.path.join(csrc, "*.cu")) + glob.glob(os.path.join(csrc, "*.cuh")):
+        included |= set(re.findall(r'#include "([\w.]+\.cuh)"', open(f).read()))
+    assert included and included <= set(build.HEADERS), included - set(build.HEADERS)
+    assert not build.stale(), "libsfmmatch.so is older than its sources: run python -m sfm_danpipeline_b200.build"
+
+
+def test_default_engines_are_auto():
+    """AUTO = 0 for both selectors, so a zero-initialised SfmmConfig means "let the library pick"."""
+    from sfm_danpipeline_b200 import _lib
+    assert _lib.BINARY_AUTO == 0 and _lib.FLOAT_AUTO == 0
+    cfg = _lib.SfmmConfig()
+    _lib.load().sfmm_default_config(C.byref(cfg))
+    assert cfg.binary_engine == _lib.BINARY_AUTO and cfg.float_mode == _lib.FLOAT_AUTO
