@@ -255,3 +255,24 @@ def test_incremental_match_pairs_like_addmoreviews():
         m.clear_results()
         with pytest.raises(SfmmError):
             m.getMatching(0, 1)
+
+
+# --------------------------------------------------------------------------- randomised differential
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=20, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.sampled_from([32, 61, 64]), st.lists(st.integers(0, 300), min_size=2, max_size=4), st.integers(0, 2**31 - 1), st.booleans(),
+       st.sampled_from([2, 256]))
+def test_randomised_differential_vs_oracle(cols, rows, seed, cross, levels):
+    rng = np.random.default_rng(seed)
+    descs = [(rng.integers(0, levels, (n, cols)) * (255 // (levels - 1))).astype(np.uint8) for n in rows]
+    if rows[0] >= 1 and rows[1] >= 3:  # duplicates in a train set and an exact copy of a query row
+        descs[1][-1] = descs[1][0]
+        descs[1][1] = descs[0][0]
+    with _matcher(0.8, cross) as m:
+        m.set_descriptors(descs)
+        m.match_all_pairs()
+        for q, t in synth.all_pairs(len(descs)):
+            _expect_equal(m.getMatching(q, t), oracle.match_pair(descs[q], descs[t], 0, 0.8, cross))

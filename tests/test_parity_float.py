@@ -261,3 +261,26 @@ def test_tensor_mode_cross_check_cfg4_shape_equals_exact_kernel():
         mx.match_all_pairs()
         for a, b in zip(mt.result_table(), mx.result_table()):
             assert a.tobytes() == b.tobytes()
+
+
+# --------------------------------------------------------------------------- randomised differential
+from hypothesis import HealthCheck, given, settings  # noqa: E402
+from hypothesis import strategies as st  # noqa: E402
+
+
+@settings(max_examples=15, deadline=None, suppress_health_check=list(HealthCheck))
+@given(st.sampled_from([64, 96, 128]), st.lists(st.integers(0, 300), min_size=2, max_size=3), st.integers(0, 2**31 - 1), st.booleans(),
+       st.sampled_from([FLOAT_AUTO, FLOAT_EXACT]))
+def test_randomised_differential_integer_valued_vs_oracle(cols, rows, seed, cross, mode):
+    """Integer-valued data (the SIFT regime): every kernel -- fp16 tensor (64, 128), TF32 tensor (96), exact fp32 -- is bit-exact."""
+    rng = np.random.default_rng(seed)
+    descs = [np.floor(rng.random((n, cols), dtype=np.float32) * 9).astype(np.float32) for n in rows]
+    if rows[0] >= 1 and rows[1] >= 3:
+        descs[1][-1] = descs[1][0]
+        descs[1][1] = descs[0][0]
+    with Matcher(NORM_L2, 0.8, cross, float_mode=mode) as m:
+        m.set_descriptors(descs)
+        m.match_all_pairs()
+        for q, t in synth.all_pairs(len(descs)):
+            got, exp = m.getMatching(q, t), oracle.match_pair(descs[q], descs[t], 1, 0.8, cross)
+            assert got.tobytes() == exp.tobytes(), (cols, rows, q, t)
