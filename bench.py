@@ -468,7 +468,8 @@ def main():
         # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
         # `ncu --set full` captures of exactly this workload (profiles/ncu_*_r01*.txt); null when not captured
         ncu_traffic = {("cfg2", "popc", 1): 18.847e6 + 46.489e6,    # profiles/ncu_binary_r01c_tq2.txt
-                       ("cfg2", "tensor", 1): 2276.5e6 + 86.7e6}    # profiles/ncu_tensor_ts_i8p_r01.txt
+                       ("cfg2", "tensor", 1): 2276.5e6 + 86.7e6,    # profiles/ncu_tensor_ts_i8p_r01.txt
+                       ("cfg5s", "tensor", 1): 4100.7e6 + 117.8e6}  # profiles/ncu_tensor_ts_i8p_cfg5s_r01.txt (one of the step's two launches)
         if n_images == WORKLOADS[args.workload][1] and not args.cross_check:
             roof["traffic"] = ncu_traffic.get((args.workload, engine, world))
         roof["frac"] = roof["achieved"] / roof["peak"]
