@@ -1249,15 +1249,18 @@ SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) 
     ctx->call_pairs = n_pairs;
     ctx->call_base = ctx->table.size();
     CU_TRY(ctx, cudaEventRecord(ctx->ev_begin, ctx->slot[0].stream));
-    // Chunk size: about an eighth of the job (so that copies and bookkeeping overlap kernels),
+    // Chunk size: about an eighth of the job (so that copies and bookkeeping overlap kernels; 4 chunks measured the
+    // same end-to-end time at cfg-2, 2 chunks 10 % more),
     // never more than the scratch budget, never so small that a launch cannot fill the GPU.
     uint64_t q_rows = 0;
     for (int64_t i = 0; i < n_pairs; ++i) {
         const int32_t q = qt[2 * i];
         if (q >= 0 && q < ctx->n_images) q_rows += static_cast<uint64_t>(ctx->rows[q]);
     }
+    const char* env_c = std::getenv("SFMM_CHUNKS");  // experiments: chunks per job
+    const uint64_t env_chunks = env_c ? std::max(1, std::atoi(env_c)) : 0;
     const uint64_t min_rows = static_cast<uint64_t>(query_tile_rows(ctx)) * ctx->sm_count * 8;
-    const uint64_t budget = std::min<uint64_t>(ctx->tensor_refine ? MAX_CHUNK_ROWS / 4 : MAX_CHUNK_ROWS, std::max<uint64_t>(min_rows, q_rows / 8 + 1));
+    const uint64_t budget = std::min<uint64_t>(ctx->tensor_refine ? MAX_CHUNK_ROWS / 4 : MAX_CHUNK_ROWS, std::max<uint64_t>(min_rows, q_rows / (env_chunks ? env_chunks : 8) + 1));
     int64_t next = 0;
     int k = 0;
     int pending[2] = {-1, -1};  // slot indices in launch order
