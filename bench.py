@@ -13,7 +13,9 @@ synthetic descriptor set (findBestPair's loop, /root/reference/src/Sfm.cpp:511-5
            (sfmm_match_pairs_device), device-timed with CUDA events, max over ranks.
   e2e    : the same metric through the public API with HOST buffers: H2D of the descriptors,
            (NCCL broadcast), matching, (NCCL gather to rank 0), D2H of the match table.
-  roofline: the 2-NN kernel against the POPC-pipe (binary) or FP32/tensor (float) peak.
+  roofline: the 2-NN kernel that actually ran against its bound: the tensor pipe (default engines, `of measured` =
+           MEASURED_PEAKS.json bf16 scaled to the operand type) or the POPC pipe / FP32 lanes (--binary-engine popc,
+           --float-mode exact).  alt_engine: the other Hamming engine on the same shard in the same run.
   cpu_baseline: the reference's own CPU path (OpenCV BFMatcher via cv2, else the C oracle) on a
            bounded sample of the same pairs, timed on this box's host cores (N=1, rank 0).
 
