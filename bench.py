@@ -7,20 +7,28 @@
 
 A "step" is one pass of the hot path over the whole workload: every image pair q<t of the
 synthetic descriptor set (findBestPair's loop, /root/reference/src/Sfm.cpp:511-515) goes through
-2-NN + ratio test (getMatching, src/Sfm.cpp:590-608).  One "pair-match" = one such pair.
+2-NN + ratio test (getMatching, src/Sfm.cpp:590-608).  One "pair-match" = one such pair, its match
+list delivered to rank 0's HOST memory.
 
-  value  : pair-matches/s with descriptors already resident in HBM, results left in HBM
-           (sfmm_match_pairs_device), device-timed with CUDA events, max over ranks.
-  e2e    : the same metric through the public API with HOST buffers: H2D of the descriptors,
-           (NCCL broadcast), matching, (NCCL gather to rank 0), D2H of the match table.
-  roofline: the 2-NN kernel that actually ran against its bound: the tensor pipe (default engines, `of measured` =
-           MEASURED_PEAKS.json bf16 scaled to the operand type) or the POPC pipe / FP32 lanes (--binary-engine popc,
-           --float-mode exact).  alt_engine: the other Hamming engine on the same shard in the same run.
-  cpu_baseline: the reference's own CPU path (OpenCV BFMatcher via cv2, else the C oracle) on a
-           bounded sample of the same pairs, timed on this box's host cores (N=1, rank 0).
+Default workload at every N: BASELINE.json configs[2] -- 200 images x 10 000 x 486-bit (AKAZE-shape)
+descriptors, all 19 900 pairs, STRONG scaling: the same job on 1, 2, 4, 8 GPUs (it fits one GPU, and it is
+the configuration the metric "at 1/2/4/8 B200" is quoted on).  configs[1] (cfg2, 50 x 5 000) and the float
+shape (cfg4s) ride along in the N=1 line as `configs1_cfg2` and `float` blocks.
 
-Default workload at N GPUs: AKAZE-shape 486-bit descriptors, 5000 per image (BASELINE.json
-configs[1]); the image count grows with N so that every GPU keeps ~1225 pairs (weak scaling).
+  value  : pair-matches/s with the descriptors already resident in HBM on every rank when the timed region
+           starts; the region covers matching on all ranks AND the gather of every match list to rank 0's host
+           memory (N=1: the library's pipelined device->host path; N>1: per-chunk NCCL gather to rank 0 +
+           device->host there).  Timed on the device (CUDA events around each step), max over ranks.
+  e2e    : the same metric through the public API with HOST buffers in: H2D of the descriptors, (NCCL
+           broadcast), matching, (NCCL gather to rank 0), D2H of the match table.  Wall clock, max over ranks.
+  resident_device_only: the round-1 definition of `value` (match lists left in HBM), for continuity.
+  roofline: the 2-NN kernel that actually ran against its bound: the tensor pipe (default engines) or the POPC
+           pipe / FP32 lanes (--binary-engine popc, --float-mode exact).  Peaks: measured tcgen05 issue rates
+           (profiles/tcgen05_peaks_r02.json, tools/pipe_bench) when present, else MEASURED_PEAKS.json scaled.
+  alt_engine: the other Hamming engine on the same shard in the same run.
+  verified: `--verify` (default 2) random pairs of the end-to-end table, byte-compared with the CPU oracle.
+  cpu_baseline: the reference's own CPU path (OpenCV BFMatcher via cv2, else the C oracle) on a bounded sample
+           of the same pairs, timed on this box's host cores (N=1, rank 0).
 """
 from __future__ import annotations
 
@@ -39,19 +47,21 @@ sys.path.insert(0, ROOT)
 
 WORKLOADS = {
     # name: (kind, images at N=1, descriptors per image, weak-scale images with N?)
-    "cfg2": ("binary", 50, 5000, True),     # configs[1]: 50 x 5k x 486 bit, 1 GPU
-    "cfg3": ("binary", 200, 10000, False),  # configs[2]: 200 x 10k, sharded over 2/4/8
+    "cfg2": ("binary", 50, 5000, False),    # configs[1]: 50 x 5k x 486 bit, 1 GPU
+    "cfg2w": ("binary", 50, 5000, True),    # the same per-GPU work at every N (round 1's default)
+    "cfg3": ("binary", 200, 10000, False),  # configs[2]: 200 x 10k, sharded over 2/4/8 -- the default
     "cfg4": ("float", 300, 8000, False),    # configs[3]: 300 x 8k x 128 f32
     "cfg5": ("binary", 1000, 20000, False), # configs[4]: headline, ~500k pairs
     "cfg5s": ("binary", 40, 20000, True),   # cfg5's pair shape (20k x 20k) on a 40-image subset
     "orb": ("orb", 100, 2000, True),        # ORB shape: 256 bit
     "float2": ("float", 40, 4000, True),
     "cfg4s": ("float", 60, 8000, True),     # cfg4's pair shape (8k x 8k x 128 f32) on a 60-image subset
-    "cfg4x": ("floatx", 60, 8000, True),    # same shape, NON-integer values: TF32 ranking + exact refinement path
+    "cfg4x": ("floatx", 60, 8000, True),    # same shape, NON-integer values: fp16/TF32 ranking + exact refinement path
     # configs[0]: the reference's own fixture (data/temple, 10 images, 45 pairs) through the committed cv2 descriptors
     "temple_sift": ("golden:temple_sift", 10, 850, False),
     "temple_akaze": ("golden:temple_akaze", 10, 700, False),
 }
+DEFAULT_WORKLOAD = "cfg3"
 
 
 def images_for(n1: int, gpus: int, weak: bool) -> int:
@@ -72,7 +82,7 @@ def make_descriptors(kind: str, n_images: int, n_desc: int, seed: int = 0):
         is_f = "sift" in kind
         d = z["desc"].astype(np.float32 if is_f else np.uint8)
         return [np.ascontiguousarray(d[offs[i]:offs[i + 1]]) for i in range(len(z["rows"]))], (1 if is_f else 0)
-    if kind in ("binary", "orb") and n_images * n_desc >= 4_000_000:
+    if kind in ("binary", "orb") and n_images * n_desc >= 1_000_000:
         # large sets (cfg3, cfg5): same generator, same seeds, images dealt to worker processes
         import multiprocessing as mp
         from concurrent.futures import ProcessPoolExecutor
@@ -84,6 +94,13 @@ def make_descriptors(kind: str, n_images: int, n_desc: int, seed: int = 0):
     if kind == "orb":
         return synth.binary_images(n_images, n_desc, synth.ORB_BITS, seed), 0
     return synth.float_images(n_images, n_desc, 128, seed, integer=(kind != "floatx")), 1
+
+
+def workload_string(name, kind, n_images, n_desc, cross):
+    shape = ("486-bit AKAZE" if kind in ("binary", "golden:temple_akaze") else ("256-bit ORB" if kind == "orb" else "128-d f32 SIFT")) \
+        + ("-shape" if not kind.startswith("golden:") else " (real, about that many rows per image)")
+    n_pairs = n_images * (n_images - 1) // 2
+    return f"{name}: {n_images} images x {n_desc} x {shape} descriptors, all {n_pairs} pairs q<t, ratio 0.8, cross_check={bool(cross)}"
 
 
 # ------------------------------------------------------------------------------ clocks
@@ -181,42 +198,43 @@ def time_cpu_sample(descs, norm, budget_s: float, max_pairs: int, seed: int = 0)
         run(descs[q], descs[t])
         done += 1
     dt = time.perf_counter() - t0
-    return done / dt, kind, cores, f"{done} of {len(pairs)} pairs ({how}), {dt:.1f} s"
+    return done / dt, kind, cores, f"{done} of {len(pairs)} pairs ({how}), {dt:.1f} s", dt
 
 
-def run_reference_arm(args, kind, n_images, n_desc):
+def run_reference_arm(args, name, kind, n_images, n_desc):
+    """The reference's own CPU implementation of the path on this box's host cores, same workload string as our arm.
+    Under torchrun rank 0 alone runs it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # the pairs of the workload all have the same shape: a subset of the images is enough to draw the bounded sample from
     descs, norm = make_descriptors(kind, min(n_images, 24), n_desc, args.seed)
-    per_step = []
+    per_step, step_s = [], []
     how = cores = kind_s = None
     for s in range(args.warmup + args.steps):
-        v, kind_s, cores, how = time_cpu_sample(descs, norm, args.cpu_seconds / max(args.steps, 1), 100000, seed=s)
+        v, kind_s, cores, how, dt = time_cpu_sample(descs, norm, args.cpu_seconds / max(args.steps, 1), 100000, seed=s)
         if s >= args.warmup:
             per_step.append(v)
+            step_s.append(dt)
     value = float(np.mean(per_step))
+    n_pairs = n_images * (n_images - 1) // 2
     line = {"impl": "reference", "metric": "image-pair matches/sec (all-pairs 2-NN + ratio test)", "value": value,
             "unit": "pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 / value, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": 1e3 * float(np.mean(step_s)), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "u8" if norm == 0 else "f32", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {kind} {n_desc} descriptors/image; each step = a bounded random sample of the pairs"},
+            "config": {"workload": workload_string(name, kind, n_images, n_desc, False),
+                       "sample": "each step = a bounded random sample of the workload's pairs (all pairs have the same shape), "
+                                 f"drawn from the first {min(n_images, 24)} images; the whole workload would take {n_pairs / value:.0f} s"},
             "cpu_baseline": {"value": value, "unit": "pairs/s", "cores": cores, "kind": kind_s, "sample": how},
             "e2e": {"value": value, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
-def verify_pairs(table, descs, norm, n, cross, world):
+def verify_pairs(get, pairs, descs, norm, n, cross):
     """Bit-exactness spot check of the end-to-end table at full size: n random pairs vs the CPU oracle."""
     import oracle
     rng = np.random.default_rng(123)
-    if world > 1:
-        pairs, get = table.pairs, table.getMatching
-    else:
-        pairs = table[0]
-        pos = {(int(q), int(t)): i for i, (q, t) in enumerate(pairs)}
-        get = lambda q, t: table[3][table[2][pos[(q, t)]]: table[2][pos[(q, t)]] + table[1][pos[(q, t)]]]  # noqa: E731
     ok = 0
     integer_valued = norm == 0 or all(bool((d == np.floor(d)).all()) for d in descs[:4])
     worst = 0.0
@@ -240,108 +258,98 @@ def verify_pairs(table, descs, norm, n, cross, world):
             assert flips <= max(2, len(exp) // 1000), f"pair ({q},{t}): {flips} decisions differ"
             worst = max(worst, float(rel[same].max()) if same.any() else 0.0)
         ok += 1
-    res = {"pairs_checked": ok, "against": "cv2 BFMatcher path" if oracle.have_cv2() else "C oracle",
-           "result": "bit-identical" if integer_valued else f"within 1e-4 relative (worst {worst:.2e})"}
-    return res
+    return {"pairs_checked": ok, "against": "cv2 BFMatcher path" if oracle.have_cv2() else "C oracle",
+            "result": "bit-identical" if integer_valued else f"within 1e-4 relative (worst {worst:.2e})"}
 
 
-def alt_engine_line(args, local, world, rank, descs, mine, rows, n_pairs, flush, D, engine, n_sm, sm_max_mhz, peaks):
-    """Resident throughput of the OTHER Hamming engine on the same shard (rank 0's shard at N>1), with its own roofline."""
-    import torch
-    from sfm_danpipeline_b200 import BINARY_POPC, BINARY_TENSOR, Matcher
-    m2 = Matcher(0, 0.8, False, device=local, binary_engine=BINARY_TENSOR if engine == "tensor" else BINARY_POPC)
+# ------------------------------------------------------------------------------ peaks
+def load_peaks():
+    peaks = {}
     try:
-        m2.set_descriptors(descs)
-        ms, knn, work = [], 0.0, 0.0
-        for it in range(2 + 3):
-            flush.zero_()
-            torch.cuda.synchronize()
-            _c, _m, n = D.match_shard(m2, mine, rows)
-            if it >= 2:
-                st = m2.stats()
-                ms.append(st["last_match_ms"])
-                knn += st["last_knn_ms"]
-                work += st["last_knn_work"]
-        per = float(np.mean(ms))
-        out = {"binary_engine": "tensor (tcgen05 kind::i8 on unpacked bits)" if engine == "tensor" else "popc (XOR + carry-save + POPC, packed bits)",
-               "pairs_per_s_per_gpu": len(mine) / (per * 1e-3), "ms_per_step": per, "matches_per_step_this_rank": int(n),
-               "note": "same workload, same run, identical match tables; selectable with SfmmConfig.binary_engine"}
-        if engine == "popc":
-            peak = n_sm * 16 * sm_max_mhz * 1e6 / 1e9
-            out["roofline"] = {"bound": "popc", "achieved": work / (knn * 1e-3) / 1e9, "peak": peak, "unit": "GPOPC32/s",
-                               "frac": work / (knn * 1e-3) / 1e9 / peak,
-                               "peak_source": f"nominal 16 POPC/clk/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz"}
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    tc = {}
+    try:  # measured tcgen05.mma issue rates of this pool (tools/pipe_bench tcgen05 -> profiles/tcgen05_peaks_r02.json)
+        tc = json.load(open(os.path.join(ROOT, "profiles", "tcgen05_peaks_r02.json")))
+    except Exception:
+        pass
+    traffic = {}
+    try:  # dram__bytes_read.sum + dram__bytes_write.sum per launch of the dominant kernel, from the committed ncu captures
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic_r02.json")))
+    except Exception:
+        pass
+    return peaks, tc, traffic
+
+
+def roofline_block(stats_path, norm, engine, knn_ms, knn_work, knn_launches, step_ms_sum, n_sm, peaks, tc):
+    """The dominant kernel against the pipe that bounds it.  knn_work = algorithmic POPC32 ops (Hamming) / FLOPs (L2)."""
+    sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
+    bf16 = float(peaks.get("bf16_tflops", 1590.0))
+    bf16_src = "MEASURED_PEAKS.json bf16_tflops (cuBLAS burst)" if "bf16_tflops" in peaks else "fallback 1590 TFLOP/s (B200_PROFILING.md)"
+    knn_s = max(knn_ms, 1e-9) * 1e-3
+    if engine == "tensor":
+        macs = knn_work / 16.0 * 512.0  # 512 u8 MACs per 16 algorithmic POPC32 (one 486-bit distance)
+        ach = 2.0 * macs / knn_s / 1e12
+        if "i8_tops" in tc:
+            peak, src = float(tc["i8_tops"]), "of measured: tcgen05.mma kind::i8 issue-only microbenchmark on this pool (profiles/tcgen05_peaks_r02.json)"
         else:
-            i8 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))
-            ach = 2.0 * (work / 16.0 * 512.0) / (knn * 1e-3) / 1e12
-            out["roofline"] = {"bound": "tensor", "achieved": ach, "peak": i8, "unit": "TOP/s", "frac": ach / i8,
-                               "peak_source": "2 x MEASURED_PEAKS.json bf16_tflops"}
-        return out
-    finally:
-        m2.close()
+            peak, src = 2.0 * bf16, f"of measured (inferred): 2 x {bf16_src}; int8 dense is nominally twice bf16"
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TOP/s",
+                "peak_source": src + "; ops = 2*Nq*Nt*512 per pair, tcgen05 kind::i8 on bits unpacked to bytes",
+                "nominal": {"peak": 4500.0, "frac": ach / 4500.0, "note": "B200 dense int8/fp8 nominal 4.5 POP/s"},
+                "popc_equivalent": {"achieved_GPOPC32": knn_work / knn_s / 1e9,
+                                    "x_nominal_popc_roofline": knn_work / knn_s / 1e9 / (n_sm * 16 * sm_max_mhz * 1e6 / 1e9)}}
+    elif norm == 0:
+        peak = n_sm * 16 * sm_max_mhz * 1e6 / 1e9  # GPOPC32/s: 16 POPC/clk/SM x SMs x max SM clock
+        ach = knn_work / knn_s / 1e9
+        roof = {"bound": "popc", "achieved": ach, "peak": peak, "unit": "GPOPC32/s",
+                "peak_source": f"nominal 16 POPC/clk/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz (measured 16.0/clk/SM, profiles/pipe_bench_r01.txt)",
+                "executed_popc_frac": ach * 9.0 / 16.0 / peak,
+                "note": "carry-save compression executes 9 POPC per 16 algorithmic ones (486-bit rows): `frac` counts algorithmic work and can "
+                        "exceed 1, `executed_popc_frac` is the share of the XU pipe's issue slots actually used"}
+    elif stats_path in (2, 3):
+        ach = knn_work / knn_s / 1e12
+        if "f16_tflops" in tc:
+            peak, src = float(tc["f16_tflops"]), "of measured: tcgen05.mma kind::f16 issue-only microbenchmark on this pool (profiles/tcgen05_peaks_r02.json)"
+        else:
+            peak, src = bf16, f"of measured: {bf16_src}"
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s",
+                "peak_source": src + "; the float path contracts an fp16 copy with kind::f16 (integer-valued SIFT data: exact; arbitrary values: two "
+                                     "ranking passes + exact refinement, counted once); algorithmic FLOPs = 2*Nq*Nt*128 per pair"}
+    else:
+        peak = n_sm * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # fp32 FMA lanes: exact mode runs on CUDA cores
+        roof = {"bound": "fp32", "achieved": knn_work / knn_s / 1e12, "peak": peak, "unit": "TFLOP/s",
+                "peak_source": f"128 FFMA lanes/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz; algorithmic FLOPs = 2*Nq*Nt*128"}
+    roof["frac"] = roof["achieved"] / roof["peak"]
+    roof["kernel_ms_per_launch"] = knn_ms / max(knn_launches, 1)
+    roof["kernel_share_of_step"] = knn_ms / max(step_ms_sum, 1e-9)
+    roof["traffic"] = None
+    return roof
 
 
-# ------------------------------------------------------------------------------ GPU arm
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
-    ap.add_argument("--images", type=int, default=0)
-    ap.add_argument("--desc", type=int, default=0)
-    ap.add_argument("--seed", type=int, default=0)
-    ap.add_argument("--cross-check", action="store_true")
-    ap.add_argument("--float-mode", default="auto", choices=["auto", "exact", "tensor"])
-    ap.add_argument("--binary-engine", default="auto", choices=["auto", "popc", "tensor"],
-                    help="auto = the library default (tensor engine for <= 512-bit descriptors); popc = XOR+CSA+POPC kernel "
-                         "(the north-star design); tensor = tcgen05 kind::i8 engine.  The other engine is reported as alt_engine")
-    ap.add_argument("--no-alt-engine", action="store_true")
-    ap.add_argument("--cpu-seconds", type=float, default=12.0)
-    ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--e2e-steps", type=int, default=0)
-    ap.add_argument("--e2e-warmup", type=int, default=2,
-                    help="untimed end-to-end steps: the two pipeline slots size their device/pinned buffers over the first two")
-    ap.add_argument("--verify", type=int, default=0, help="check this many random pairs of the e2e table against the CPU oracle")
-    args = ap.parse_args()
+# ------------------------------------------------------------------------------ one workload
+class Env:
+    pass
 
-    kind, n1, n_desc, weak = WORKLOADS[args.workload]
-    n_desc = args.desc or n_desc
-    n_images = args.images or images_for(n1, args.gpus, weak)
-    if args.impl == "reference":
-        return run_reference_arm(args, kind, n_images, n_desc)
 
+def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps, e2e_warmup, cross=False, float_mode=0, binary_engine=0,
+            alt=False, verify=0, clocks=False, device_only_iters=3):
+    """Runs one workload on env.world ranks; returns the measurements on rank 0 (None elsewhere)."""
     import torch
     import torch.distributed as dist
-    from sfm_danpipeline_b200 import FLOAT_AUTO, Matcher
+    from sfm_danpipeline_b200 import Matcher
     from sfm_danpipeline_b200 import distributed as D
-
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if world != args.gpus:
-        if world == 1 and args.gpus > 1:
-            raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
-    torch.cuda.set_device(local)
-    if world > 1:
-        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    world, rank, local, dev = env.world, env.rank, env.local, env.dev
+    norm = 0 if kind in ("binary", "orb", "golden:temple_akaze") else 1
+    descs = make_descriptors(kind, n_images, n_desc, args.seed)[0] if rank == 0 else None
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # synthetic descriptors exist on rank 0 only; the other ranks receive them by NCCL broadcast
-    norm = 0 if kind in ("binary", "orb", "golden:temple_akaze") else 1
-    descs = make_descriptors(kind, n_images, n_desc, args.seed)[0] if rank == 0 else None
-    dev = torch.device("cuda", local)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    m = Matcher(norm, 0.8, args.cross_check, device=local, float_mode={"auto": 0, "exact": 1, "tensor": 2}[args.float_mode],
-                binary_engine={"auto": 0, "popc": 1, "tensor": 2}[args.binary_engine])
-    # ---- resident arm: descriptors in HBM before the timed region -------------------------
+    m = Matcher(norm, 0.8, cross, device=local, float_mode=float_mode, binary_engine=binary_engine)
     if world > 1:
         D.broadcast_descriptors(m, descs, 0)
     else:
@@ -351,45 +359,86 @@ def main():
     shards = D.shard_pairs(pairs, rows, world)
     mine = pairs[shards[rank]]
     torch.cuda.synchronize()
+    acc = {"knn_ms": 0.0, "knn_work": 0.0, "knn_launches": 0, "matches": 0}
+
+    def note_stats():
+        st = m.stats()
+        acc["knn_ms"] += st["last_knn_ms"]
+        acc["knn_work"] += st["last_knn_work"]
+        acc["knn_launches"] += st["last_knn_launches"]
+
+    def match_fn(chunk, slot):
+        c, mm, k = D.match_shard(m, chunk, rows, slot=slot)
+        note_stats()
+        acc["matches"] += k
+        return c, mm
 
     def resident_step():
-        flush.zero_()
-        torch.cuda.synchronize()
-        _c, _m, n = D.match_shard(m, mine, rows)
-        return n, m.stats()
+        """Descriptors resident -> every match list in rank 0's host memory."""
+        if world > 1:
+            return D.match_and_gather(match_fn, pairs, shards, rows, 0)
+        m.match_all_pairs()
+        note_stats()
+        t = m.result_table(copy=False)
+        acc["matches"] += len(t[3])
+        return t
 
-    for _ in range(args.warmup):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed_steps(k, fn):
+        total = 0.0
+        for _ in range(k):
+            env.flush.zero_()
+            barrier()
+            e0.record()
+            fn()
+            e1.record()
+            e1.synchronize()
+            total += e0.elapsed_time(e1)
+        return total
+
+    for _ in range(warmup):
         resident_step()
     barrier()
+    for k in acc:
+        acc[k] = 0
     launches0 = m.stats()["kernel_launches"]
-    dev_ms = knn_ms = knn_work = 0.0
-    knn_launches = 0
-    n_matches = 0
-    with ClockSampler(local) as clk:
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            n_matches, st = resident_step()
-            dev_ms += st["last_match_ms"]
-            knn_ms += st["last_knn_ms"]
-            knn_work += st["last_knn_work"]
-            knn_launches += st["last_knn_launches"]
-        barrier()
-        wall_ms = (time.perf_counter() - t0) * 1e3
+    sampler = ClockSampler(local) if clocks else None
+    if sampler:
+        sampler.__enter__()
+    t0 = time.perf_counter()
+    step_ms_sum = timed_steps(steps, resident_step)
+    barrier()
+    wall_ms = (time.perf_counter() - t0) * 1e3
+    if sampler:
+        sampler.__exit__()
     launches = m.stats()["kernel_launches"] - launches0
-    stat = torch.tensor([dev_ms, float(launches), knn_ms, knn_work, float(knn_launches), float(n_matches)],
-                        dtype=torch.float64, device=dev)
+    res_acc = dict(acc)
+
+    # ---- round-1 definition (match lists left in HBM): continuity + the kernel's share of a pure device step
+    dev_ms = []
+    for it in range(1 + device_only_iters):
+        env.flush.zero_()
+        barrier()
+        D.match_shard(m, mine, rows)
+        if it:
+            dev_ms.append(m.stats()["last_match_ms"])
+    dev_only = float(np.mean(dev_ms)) if dev_ms else 0.0
+
+    stat = torch.tensor([step_ms_sum, float(launches), res_acc["knn_ms"], res_acc["knn_work"], float(res_acc["knn_launches"]),
+                         float(res_acc["matches"]), dev_only], dtype=torch.float64, device=dev)
     if world > 1:
         mx = stat.clone()
         dist.all_reduce(mx, op=dist.ReduceOp.MAX)
         sm = stat.clone()
         dist.all_reduce(sm, op=dist.ReduceOp.SUM)
-        dev_ms_max, launches_sum, total_matches = mx[0].item(), int(sm[1].item()), int(sm[5].item())
+        step_ms_max, launches_sum, dev_only_max = mx[0].item(), int(sm[1].item()), mx[6].item()
+        total_matches = int(sm[5].item())
     else:
-        dev_ms_max, launches_sum, total_matches = dev_ms, int(launches), int(n_matches)
-    ms_per_step = dev_ms_max / args.steps
-    value = len(pairs) / (ms_per_step * 1e-3)
+        step_ms_max, launches_sum, dev_only_max, total_matches = step_ms_sum, int(launches), dev_only, int(res_acc["matches"])
+    ms_per_step = step_ms_max / steps
 
-    # ---- end-to-end arm: host buffers in, host table out ----------------------------------
+    # ---- end to end: host buffers in, host table out
     def e2e_step():
         s0 = m.stats()
         if world > 1:
@@ -399,121 +448,196 @@ def main():
             m.set_descriptors(descs)
             tb = time.perf_counter()
             m.match_all_pairs()
-            tc = time.perf_counter()
+            tc_ = time.perf_counter()
             table = m.result_table(copy=False)
             assert int(table[1].sum()) == len(table[3])  # the host table is complete
             if os.environ.get("SFMM_BENCH_TRACE") == "1":
-                print(f"[e2e] set_descriptors {1e3 * (tb - ta):.2f} ms  match_all_pairs {1e3 * (tc - tb):.2f} ms  "
-                      f"table {1e3 * (time.perf_counter() - tc):.2f} ms  device {m.stats()['last_match_ms']:.2f} ms", file=sys.stderr)
+                print(f"[e2e] set_descriptors {1e3 * (tb - ta):.2f} ms  match_all_pairs {1e3 * (tc_ - tb):.2f} ms  "
+                      f"table {1e3 * (time.perf_counter() - tc_):.2f} ms  device {m.stats()['last_match_ms']:.2f} ms", file=sys.stderr)
         s1 = m.stats()
         return table, s1["h2d_bytes"] - s0["h2d_bytes"], s1["d2h_bytes"] - s0["d2h_bytes"]
 
-    for _ in range(args.e2e_warmup):
-        e2e_step()
-    barrier()
-    t0 = time.perf_counter()
-    e2e_steps = args.e2e_steps or max(2, min(args.steps, 3))
+    table = None
+    for _ in range(e2e_warmup):
+        table = None
+        table, _a, _b = e2e_step()
+    e2e_total = 0.0
+    h2d = d2h = 0
     for _ in range(e2e_steps):
-        flush.zero_()
+        table = None
+        env.flush.zero_()
+        barrier()
+        t0 = time.perf_counter()
         table, h2d, d2h = e2e_step()
-    barrier()
-    e2e_ms = (time.perf_counter() - t0) * 1e3 / e2e_steps
+        torch.cuda.synchronize()
+        e2e_total += (time.perf_counter() - t0) * 1e3
+    e2e_ms = e2e_total / max(e2e_steps, 1)
     if world > 1:
         tmax = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_ms = tmax.item()
         if rank == 0:
             d2h = int(table.matches.nbytes + table.counts.nbytes)
-    e2e_value = len(pairs) / (e2e_ms * 1e-3)
 
+    out = None
     if rank == 0:
-        peaks = {}
-        try:
-            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-        except Exception:
-            pass
-        sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
-        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-        knn_s = knn_ms * 1e-3
-        # the engine the library actually ran (AUTO resolves to the tensor engine for <= 512-bit descriptors)
         engine = ("tensor" if m.stats()["float_path"] == 2 else "popc") if norm == 0 else "float"
-        if engine == "tensor":
-            i8 = 2.0 * float(peaks.get("bf16_tflops", 1590.0))  # int8 dense = twice the measured bf16 cuBLAS rate
-            macs = knn_work / 16.0 * 512.0  # 512 u8 MACs per 16 algorithmic POPC32 (one 486-bit distance)
-            roof = {"bound": "tensor", "achieved": 2.0 * macs / knn_s / 1e12, "peak": i8, "unit": "TOP/s",
-                    "peak_source": "of measured: 2 x MEASURED_PEAKS.json bf16_tflops (int8 dense is nominally twice bf16; the cuBLAS bf16 burst "
-                                   "figure is ~74 % of nominal, so a kernel on {0,1} bytes can read above 1.0); ops = 2*Nq*Nt*512 per pair, "
-                                   "tcgen05 kind::i8 on bits unpacked to bytes",
-                    "nominal": {"peak": 4500.0, "frac": 2.0 * macs / knn_s / 1e12 / 4500.0, "note": "B200 dense int8/fp8 nominal 4.5 POP/s"},
-                    "popc_equivalent": {"achieved_GPOPC32": knn_work / knn_s / 1e9,
-                                        "x_nominal_popc_roofline": knn_work / knn_s / 1e9 / (n_sm * 16 * sm_max_mhz * 1e6 / 1e9)},
-                    "traffic": None}
-        elif norm == 0:
-            peak = n_sm * 16 * sm_max_mhz * 1e6 / 1e9  # GPOPC32/s: 16 POPC/clk/SM x SMs x max SM clock
-            roof = {"bound": "popc", "achieved": knn_work / knn_s / 1e9, "peak": peak, "unit": "GPOPC32/s",
-                    "peak_source": f"nominal 16 POPC/clk/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz (MEASURED_PEAKS.json sm_max_mhz); "
-                                   "measured issue rates in profiles/pipe_bench_r01.txt",
-                    "traffic": None}
-        elif m.stats()["float_path"] in (2, 3):
-            tf32 = 0.5 * float(peaks.get("bf16_tflops", 1590.0))  # TF32 dense = half the measured bf16 cuBLAS rate
-            roof = {"bound": "tensor", "achieved": knn_work / knn_s / 1e12, "peak": tf32, "unit": "TFLOP/s",
-                    "peak_source": "of measured: 0.5 x MEASURED_PEAKS.json bf16_tflops = the TF32 rate the float path is specified in "
-                                   "(north_star: fp32-accurate TF32).  Integer-valued (SIFT) data is contracted from an exact fp16 copy "
-                                   "with kind::f16 at twice that rate, so this fraction can exceed 1.0; algorithmic FLOPs = 2*Nq*Nt*128 per pair",
-                    "f16_frac": knn_work / knn_s / 1e12 / float(peaks.get("bf16_tflops", 1590.0)),
-                    "traffic": None}
+        n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+        roof = roofline_block(m.stats()["float_path"], norm, engine, res_acc["knn_ms"], res_acc["knn_work"], res_acc["knn_launches"],
+                              step_ms_sum, n_sm, env.peaks, env.tc)
+        key = f"{name}/{engine}/{'cross' if cross else 'plain'}"
+        if key in env.traffic and n_images == WORKLOADS[name][1]:
+            roof["traffic"] = env.traffic[key]["bytes_per_launch"]
+            roof["traffic_source"] = env.traffic[key]["source"]
         else:
-            peak = n_sm * 128 * 2 * sm_max_mhz * 1e6 / 1e12  # fp32 FMA lanes: exact mode runs on CUDA cores
-            roof = {"bound": "fp32", "achieved": knn_work / knn_s / 1e12, "peak": peak, "unit": "TFLOP/s",
-                    "peak_source": f"128 FFMA lanes/SM x {n_sm} SMs x {sm_max_mhz:.0f} MHz; algorithmic FLOPs = 2*Nq*Nt*128",
-                    "traffic": None}
-        # dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed
-        # `ncu --set full` captures of exactly this workload (profiles/ncu_*_r01*.txt); null when not captured
-        ncu_traffic = {("cfg2", "popc", 1): 18.847e6 + 46.489e6,    # profiles/ncu_binary_r01c_tq2.txt
-                       ("cfg2", "tensor", 1): 2276.5e6 + 86.7e6,    # profiles/ncu_tensor_ts_i8p_r01.txt
-                       ("cfg5s", "tensor", 1): 4100.7e6 + 117.8e6}  # profiles/ncu_tensor_ts_i8p_cfg5s_r01.txt (one of the step's two launches)
-        if n_images == WORKLOADS[args.workload][1] and not args.cross_check:
-            roof["traffic"] = ncu_traffic.get((args.workload, engine, world))
-        roof["frac"] = roof["achieved"] / roof["peak"]
-        roof["kernel_ms_per_launch"] = knn_ms / max(knn_launches, 1)
-        roof["kernel_share_of_step"] = knn_ms / max(dev_ms, 1e-9)
+            roof["traffic_source"] = "no ncu --set full capture of this exact workload is committed: null"
         row_bytes = m.cols * (1 if norm == 0 else 4)
-        alg_bytes = float(sum((rows[q] + rows[t]) * row_bytes for q, t in mine)) * args.steps + 16.0 * n_matches * args.steps
-        roof["hbm"] = {"algorithmic_GBps": alg_bytes / knn_s / 1e9, "peak_GBps": peaks.get("hbm_gbs"),
+        alg_bytes = float(sum((rows[q] + rows[t]) * row_bytes for q, t in mine)) * steps + 16.0 * res_acc["matches"]
+        roof["hbm"] = {"algorithmic_GBps": alg_bytes / max(res_acc["knn_ms"] * 1e-3, 1e-12) / 1e9, "peak_GBps": env.peaks.get("hbm_gbs"),
                        "note": "compute-bound path: HBM is reported, not the binding roof"}
-        desc_shape = ("486-bit AKAZE" if kind in ("binary", "golden:temple_akaze") else ("256-bit ORB" if kind == "orb" else "128-d f32 SIFT")) \
-            + ("-shape" if not kind.startswith("golden:") else " (real, about that many rows per image)")
+        out = {"value": len(pairs) / (ms_per_step * 1e-3), "ms_per_step": ms_per_step, "wall_ms_per_step": wall_ms / steps,
+               "pairs": int(len(pairs)), "pairs_per_gpu": int(len(mine)), "matches_per_step": total_matches // max(steps, 1),
+               "engine": engine, "norm": norm, "workload": workload_string(name, kind, n_images, n_desc, cross) +
+               (f", binary_engine={engine}" if norm == 0 else ""),
+               "e2e": {"value": len(pairs) / (e2e_ms * 1e-3), "unit": "pairs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
+                       "d2h_bytes_per_step": int(d2h)},
+               "resident_device_only": {"value": len(pairs) / (dev_only_max * 1e-3) if dev_only_max else None, "ms_per_step": dev_only_max,
+                                        "note": "round-1 definition of `value`: match lists left in HBM (sfmm_match_pairs_device), library CUDA events"},
+               "gpu_launches": launches_sum, "roofline": roof, "clocks": sampler.summary() if sampler else None,
+               "gather_chunks": D.gather_chunks(pairs, shards, rows) if world > 1 else None}
+        if verify:
+            get = table.getMatching if world > 1 else (lambda q, t: m.getMatching(q, t))
+            out["verified"] = verify_pairs(get, pairs, descs, norm, verify, cross)
+    if alt and norm == 0 and m.cols <= 64 and not cross:
+        # same workload, same run, through the other Hamming engine (bit-identical tables): the north-star XOR+POPC kernel
+        # is reported beside the tensor engine AUTO picks, with its own POPC-pipe roofline (rank 0's shard at N>1)
+        eng_now = "tensor" if m.stats()["float_path"] == 2 else "popc"
+        other = "popc" if eng_now == "tensor" else "tensor"
+        table = None
+        m.close()
+        m = None
+        if rank == 0:
+            m2 = Matcher(0, 0.8, False, device=local, binary_engine=1 if other == "popc" else 2)
+            try:
+                m2.set_descriptors(descs)
+                ms, knn, work, nl = [], 0.0, 0.0, 0
+                for it in range(1 + 2):
+                    env.flush.zero_()
+                    torch.cuda.synchronize()
+                    _c, _m, n = D.match_shard(m2, mine, rows)
+                    if it >= 1:
+                        st = m2.stats()
+                        ms.append(st["last_match_ms"])
+                        knn += st["last_knn_ms"]
+                        work += st["last_knn_work"]
+                        nl += st["last_knn_launches"]
+                per = float(np.mean(ms))
+                n_sm = torch.cuda.get_device_properties(local).multi_processor_count
+                r2 = roofline_block(m2.stats()["float_path"], 0, other, knn, work, nl, per * len(ms), n_sm, env.peaks, env.tc)
+                out["alt_engine"] = {"binary_engine": "tensor (tcgen05 kind::i8 on unpacked bits)" if other == "tensor" else "popc (XOR + carry-save + POPC, packed bits)",
+                                     "pairs_per_s_per_gpu": len(mine) / (per * 1e-3), "ms_per_step": per, "matches_per_step_this_rank": int(n),
+                                     "definition": "resident_device_only (match lists left in HBM)", "roofline": r2,
+                                     "note": "same workload, same run, identical match tables; selectable with SfmmConfig.binary_engine"}
+            finally:
+                m2.close()
+        if world > 1:
+            dist.barrier()
+    if m is not None:
+        table = None
+        m.close()
+    return out, descs, norm
+
+
+# ------------------------------------------------------------------------------ GPU arm
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
+    ap.add_argument("--images", type=int, default=0)
+    ap.add_argument("--desc", type=int, default=0)
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--cross-check", action="store_true")
+    ap.add_argument("--float-mode", default="auto", choices=["auto", "exact", "tensor"])
+    ap.add_argument("--binary-engine", default="auto", choices=["auto", "popc", "tensor"],
+                    help="auto = the library default (tensor engine for <= 512-bit descriptors); popc = XOR+CSA+POPC kernel "
+                         "(the north-star design); tensor = tcgen05 kind::i8 engine.  The other engine is reported as alt_engine")
+    ap.add_argument("--no-alt-engine", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs1_cfg2 and float blocks of the N=1 line")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-steps", type=int, default=0)
+    ap.add_argument("--e2e-warmup", type=int, default=2,
+                    help="untimed end-to-end steps: the pipeline slots size their device/pinned buffers over the first two")
+    ap.add_argument("--verify", type=int, default=2, help="check this many random pairs of the e2e table against the CPU oracle (0 = off)")
+    args = ap.parse_args()
+
+    kind, n1, n_desc, weak = WORKLOADS[args.workload]
+    n_desc = args.desc or n_desc
+    n_images = args.images or images_for(n1, args.gpus, weak)
+    if args.impl == "reference":
+        return run_reference_arm(args, args.workload, kind, n_images, n_desc)
+
+    import torch
+    import torch.distributed as dist
+
+    env = Env()
+    env.world = int(os.environ.get("WORLD_SIZE", "1"))
+    env.rank = int(os.environ.get("RANK", "0"))
+    env.local = int(os.environ.get("LOCAL_RANK", "0"))
+    if env.world != args.gpus and env.world == 1 and args.gpus > 1:
+        raise SystemExit("--gpus N>1 must be launched with torch.distributed.run --nproc-per-node N")
+    torch.cuda.set_device(env.local)
+    if env.world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", env.local))
+    env.dev = torch.device("cuda", env.local)
+    env.flush = torch.empty(256 << 20, dtype=torch.uint8, device=env.dev)  # > 126 MB L2
+    env.peaks, env.tc, env.traffic = load_peaks()
+
+    fm = {"auto": 0, "exact": 1, "tensor": 2}[args.float_mode]
+    be = {"auto": 0, "popc": 1, "tensor": 2}[args.binary_engine]
+    e2e_steps = args.e2e_steps or max(2, min(args.steps, 3))
+    res, descs, norm = measure(env, args, args.workload, kind, n_images, n_desc, steps=args.steps, warmup=args.warmup, e2e_steps=e2e_steps,
+                               e2e_warmup=args.e2e_warmup, cross=args.cross_check, float_mode=fm, binary_engine=be,
+                               alt=not args.no_alt_engine, verify=args.verify, clocks=True)
+    if env.rank == 0:
         line = {
-            "metric": "image-pair matches/sec (all-pairs 2-NN + ratio test)", "value": value, "unit": "pairs/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+            "metric": "image-pair matches/sec (all-pairs 2-NN + ratio test)", "value": res["value"], "unit": "pairs/s",
+            "n_gpus": env.world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": res["ms_per_step"],
             "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
             "dtype": "u8" if norm == 0 else "f32", "data": "synthetic" if not kind.startswith("golden:") else "cv2 descriptors of the reference's data/temple fixture",
-            "config": {"workload": f"{args.workload}: {n_images} images x {n_desc} x " + desc_shape +
-                                   f" descriptors, all {len(pairs)} pairs q<t, ratio 0.8, cross_check={bool(args.cross_check)}"
-                                   + (f", binary_engine={engine}" if norm == 0 else ""),
-                       "pairs": int(len(pairs)), "pairs_per_gpu": int(len(mine)), "matches_per_step": total_matches,
-                       "l2": "flushed between steps (256 MiB memset outside the timed events)",
-                       "parallelism": f"pairs sharded over {world} rank(s); NCCL broadcast + gather only in e2e"},
-            "wall_ms_per_step": wall_ms / args.steps,
-            "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": e2e_ms, "h2d_bytes_per_step": int(h2d),
-                    "d2h_bytes_per_step": int(d2h)},
-            "gpu_launches": launches_sum,
-            "roofline": roof,
-            "clocks": clk.summary(),
+            "config": {"workload": res["workload"], "pairs": res["pairs"], "pairs_per_gpu": res["pairs_per_gpu"],
+                       "matches_per_step": res["matches_per_step"],
+                       "timed_region": "descriptors resident in HBM on every rank -> all match lists in rank 0's host memory "
+                                       "(matching + gather + device->host), CUDA events per step, max over ranks",
+                       "l2": "flushed between steps (256 MiB memset outside the timed events); the operand set is also larger than L2",
+                       "parallelism": f"pairs sharded over {env.world} rank(s) by cost-sorted snake deal"
+                                      + (f"; NCCL broadcast (e2e only) + pipelined NCCL gather to rank 0 in {res['gather_chunks']} chunks" if env.world > 1 else "")},
+            "wall_ms_per_step": res["wall_ms_per_step"],
+            "e2e": res["e2e"], "resident_device_only": res["resident_device_only"],
+            "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "clocks": res["clocks"],
         }
-        if norm == 0 and m.cols <= 64 and not args.cross_check and not args.no_alt_engine:
-            # same workload, same run, through the other Hamming engine (bit-identical tables): the north-star
-            # XOR+POPC kernel is reported beside the tensor engine AUTO picks, with its own POPC-pipe roofline
-            line["alt_engine"] = alt_engine_line(args, local, world, rank, descs, mine, rows, len(pairs), flush, D,
-                                                 "popc" if engine == "tensor" else "tensor", n_sm, sm_max_mhz, peaks)
-        if args.verify:
-            line["verified"] = verify_pairs(table, descs, norm, args.verify, args.cross_check, world)
-        if world == 1 and not args.no_cpu_baseline:
-            v, kind_s, cores, how = time_cpu_sample(descs, norm, args.cpu_seconds, 100000)
+        for k in ("alt_engine", "verified"):
+            if k in res:
+                line[k] = res[k]
+        if env.world == 1 and not args.no_cpu_baseline:
+            v, kind_s, cores, how, _dt = time_cpu_sample(descs, norm, args.cpu_seconds, 100000)
             line["cpu_baseline"] = {"value": v, "unit": "pairs/s", "cores": cores, "kind": kind_s, "sample": how}
+    descs = None
+    if env.world == 1 and not args.no_extra and args.workload == DEFAULT_WORKLOAD and not args.cross_check:
+        # BASELINE.json configs[1] and the float (SIFT) shape, measured the same way in the same run
+        k2, n2, d2, _w = WORKLOADS["cfg2"]
+        r2, _d, _n = measure(env, args, "cfg2", k2, n2, d2, steps=max(3, min(args.steps, 10)), warmup=3, e2e_steps=3, e2e_warmup=2, verify=1)
+        line["configs1_cfg2"] = {k: r2[k] for k in ("workload", "value", "ms_per_step", "e2e", "resident_device_only", "roofline", "verified")}
+        k4, n4, d4, _w = WORKLOADS["cfg4s"]
+        r4, _d, _n = measure(env, args, "cfg4s", k4, n4, d4, steps=3, warmup=3, e2e_steps=2, e2e_warmup=2, verify=1)
+        line["float"] = {k: r4[k] for k in ("workload", "value", "ms_per_step", "e2e", "resident_device_only", "roofline", "verified")}
+    if env.rank == 0:
         print(json.dumps(line), flush=True)
-    m.close()
-    if world > 1:
+    if env.world > 1:
         dist.barrier()
         dist.destroy_process_group()
 

@@ -14,11 +14,15 @@
  *                                                                   src/Sfm.cpp:426,977,1031
  *
  * Conventions
- *   - plain C types only: pointers, sizes, POD structs.  Nothing throws across the ABI.
+ *   - plain C types only: pointers, sizes, POD structs.  Nothing throws across the ABI (every entry
+ *     point that allocates maps C++ exceptions to SFMM_ENOMEM / SFMM_EINVAL).
  *   - every call returns SFMM_OK (0) or a negative SFMM_E* code; sfmm_last_error() gives text.
  *   - a context is bound to ONE CUDA device and is not thread-safe (the reference calls
- *     getMatching from a single thread); sfmm_get_pair is read-only and may be called
- *     concurrently once sfmm_match_all_pairs / sfmm_match_pairs has returned.
+ *     getMatching from a single thread); the look-ups sfmm_get_pair / sfmm_get_pair_points /
+ *     sfmm_result_table / sfmm_image_rows are read-only, do not touch the error text (their codes are
+ *     self-explanatory: SFMM_ESTATE = not computed) and may be called concurrently once
+ *     sfmm_match_all_pairs / sfmm_match_pairs has returned.  A failing sfmm_match_pairs leaves no chunk
+ *     in flight and rolls the table back to where the call started.
  *   - there is NO CPU fallback: without a usable CUDA device sfmm_create fails with
  *     SFMM_ENODEVICE.
  *   - match lists are in ascending queryIdx, at most one entry per query row, imgIdx == 0,
@@ -66,7 +70,11 @@ enum {
 };
 
 /* cv::NORM_HAMMING / cv::NORM_L2 of the BFMatcher constructor (src/Sfm.cpp:593).  The reference
- * hard-wires NORM_L2; HAMMING is the right norm for its AKAZE/ORB detectors (src/Sfm.cpp:331-384). */
+ * hard-wires NORM_L2 for all three detectors; HAMMING is the right norm for its AKAZE/ORB detectors
+ * (src/Sfm.cpp:331-384).  Both pairings the reference can produce are supported: NORM_L2 over CV_32F rows
+ * (SIFT) and NORM_L2 over CV_8U rows (AKAZE / ORB through the literal src/Sfm.cpp:593 call: OpenCV's
+ * batchDistL2_8u32f, sqrtf of the exact integer sum -- the bytes are widened to fp32 on upload and the float
+ * kernels take over, bit-exact).  NORM_HAMMING needs CV_8U rows, as cv::BFMatcher asserts. */
 enum { SFMM_NORM_HAMMING = 0, SFMM_NORM_L2 = 1 };
 /* cv::Mat depth of imagesDescriptors (include/Sfm.h:29): CV_8U (AKAZE, ORB) or CV_32F (SIFT). */
 enum { SFMM_U8 = 0, SFMM_F32 = 1 };
@@ -139,6 +147,9 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
                                   const int32_t* rows, int32_t cols, const size_t* step_bytes,
                                   int32_t elem_type);
 
+/* rows[image] of the current descriptor set (cv::Mat::rows of imagesDescriptors[image]). */
+SFMM_API int sfmm_image_rows(const SfmmCtx* ctx, int32_t image, int32_t* rows);
+
 /* Device address and size of the packed descriptor blob (all images back to back, row pitch
  * sfmm_row_pitch(cols, elem_type)).  A multi-GPU host broadcasts rank 0's blob into the other
  * ranks' blobs (NCCL) instead of re-uploading from the host. */
@@ -203,10 +214,43 @@ SFMM_API int sfmm_get_pair_points(const SfmmCtx* ctx, int32_t q, int32_t t, cons
 /* Persisted all-pairs match table (the reference has no checkpointing): a flat
  * little-endian file -- 64-byte header, rows[n_images], qt[2*n_pairs], counts[n_pairs],
  * offsets[n_pairs], SfmDMatch[n_matches] -- so that later runs / downstream stages skip matching.
- * sfmm_load_table needs the same image count and row counts as the current descriptor set and
- * replaces the table; afterwards sfmm_get_pair serves the stored lists. */
+ * sfmm_load_table needs the same image count, row counts, norm, ratio and cross_check setting as the
+ * current context (a table is only valid for the filter it was computed with; SFMM_EINVAL otherwise) and a
+ * file whose size agrees with its header; it replaces the table, afterwards sfmm_get_pair serves the stored
+ * lists.  Aligned points are not part of the file: sfmm_get_pair_points answers SFMM_ESTATE after a load. */
 SFMM_API int sfmm_save_table(const SfmmCtx* ctx, const char* path);
 SFMM_API int sfmm_load_table(SfmmCtx* ctx, const char* path);
+
+/* ---- all GPUs of one box from ONE host process ----------------------------
+ * The reference is a single C++ program (main.cpp:18): a group gives it every B200 of the box without
+ * becoming multi-process.  One context per device plus one NCCL communicator per device created with
+ * ncclCommInitAll (NCCL is dlopen'ed at the first sfmm_group_create: "libnccl.so.2"; SFMM_ENODEVICE
+ * if it cannot be loaded -- single-device contexts never need it).
+ *   sfmm_group_set_descriptors : imagesDescriptors re-pitched and copied host->device ONCE (device 0's
+ *       PCIe link), then ncclBroadcast of the packed blob to the other devices over NVLink;
+ *   sfmm_group_match_all_pairs / _match_pairs : findBestPair's q<t pairs (src/Sfm.cpp:511-515) dealt to
+ *       the devices by descending cost rows_q*rows_t in snake order (deterministic, balanced), one host
+ *       thread per device drives its shard through the pipelined chunk scheduler; every device copies
+ *       its records to host memory over its own PCIe link as chunks finish (no rank-0 funnel);
+ *   sfmm_group_get_pair : getMatching(q,t) (src/Sfm.cpp:590-608) as a look-up in the owning device's
+ *       host table.  Same ownership / lifetime rules as sfmm_get_pair. */
+typedef struct SfmmGroup SfmmGroup;
+SFMM_API int sfmm_group_create(const SfmmConfig* cfg /* .device ignored */, int32_t n_devices,
+                               const int32_t* devices /* NULL = 0..n_devices-1 */, SfmmGroup** out);
+SFMM_API void sfmm_group_destroy(SfmmGroup* g);
+SFMM_API const char* sfmm_group_last_error(const SfmmGroup* g);
+SFMM_API int32_t sfmm_group_size(const SfmmGroup* g);
+/* The context of member i (statistics, on-demand sfmm_match_pair, ...); owned by the group. */
+SFMM_API SfmmCtx* sfmm_group_context(SfmmGroup* g, int32_t i);
+SFMM_API int sfmm_group_set_descriptors(SfmmGroup* g, int32_t n_images, const void* const* data,
+                                        const int32_t* rows, int32_t cols, const size_t* step_bytes,
+                                        int32_t elem_type);
+SFMM_API int sfmm_group_match_all_pairs(SfmmGroup* g);
+SFMM_API int sfmm_group_match_pairs(SfmmGroup* g, const int32_t* qt, int64_t n_pairs);
+SFMM_API int sfmm_group_get_pair(const SfmmGroup* g, int32_t q, int32_t t, const SfmDMatch** matches,
+                                 int32_t* count);
+/* Bytes moved by the last sfmm_group_set_descriptors: host->device (once) and device->device (NCCL). */
+SFMM_API int sfmm_group_transfer_stats(const SfmmGroup* g, int64_t* h2d_bytes, int64_t* nccl_bytes);
 
 SFMM_API int sfmm_clear_results(SfmmCtx* ctx);
 SFMM_API int sfmm_get_stats(const SfmmCtx* ctx, SfmmStats* out);

@@ -34,6 +34,38 @@ struct Error : std::runtime_error {
     Error(int c, const std::string& what) : std::runtime_error(what), code(c) {}
 };
 
+// std::vector<cv::Mat> imagesDescriptors (include/Sfm.h:29) -> the pointer / rows / step arrays of sfmm_set_descriptors.
+// One BFMatcher, one descriptor type: every non-empty Mat must have the same width and depth.
+inline void describe(const std::vector<cv::Mat>& imagesDescriptors, std::vector<const void*>& data, std::vector<int32_t>& rows,
+                     std::vector<size_t>& steps, int& cols, int& type) {
+    const int n = static_cast<int>(imagesDescriptors.size());
+    data.assign(n, nullptr);
+    rows.assign(n, 0);
+    steps.assign(n, 0);
+    cols = 0;
+    type = SFMM_F32;
+    for (int i = 0; i < n; ++i) {
+        const cv::Mat& m = imagesDescriptors[i];
+        if (m.empty()) {  // an image without keypoints: cv::Mat() -- zero rows
+            data[i] = nullptr; rows[i] = 0; steps[i] = 0;
+            continue;
+        }
+        if (m.dims != 2 || m.channels() != 1 || (m.depth() != CV_8U && m.depth() != CV_32F))
+            throw Error(SFMM_EINVAL, "descriptors must be single-channel 2-D CV_8U or CV_32F");
+        const int t = (m.depth() == CV_8U) ? SFMM_U8 : SFMM_F32;
+        if (cols == 0) {
+            cols = m.cols;
+            type = t;
+        } else if (m.cols != cols || t != type) {  // one BFMatcher, one descriptor type: every image must agree
+            throw Error(SFMM_EINVAL, "all descriptor sets must have the same width and depth");
+        }
+        if (static_cast<size_t>(m.step) < static_cast<size_t>(m.cols) * m.elemSize())
+            throw Error(SFMM_EINVAL, "descriptor row step smaller than a row");
+        data[i] = m.data; rows[i] = m.rows; steps[i] = m.step;
+    }
+    if (cols == 0) cols = 1;  // no image has descriptors: an empty table
+}
+
 class AllPairsMatcher {
   public:
     // normType: cv::NORM_L2 (what src/Sfm.cpp:593 passes) or cv::NORM_HAMMING / NORM_HAMMING2-free
@@ -64,23 +96,12 @@ class AllPairsMatcher {
     // list of ordered pairs (q0,t0,q1,t1,...) -- the unit that is sharded across devices.
     void matchPairs(const std::vector<int32_t>& qt) { check(sfmm_match_pairs(ctx_, qt.data(), static_cast<int64_t>(qt.size() / 2))); }
     void upload(const std::vector<cv::Mat>& imagesDescriptors) {
-        const int n = static_cast<int>(imagesDescriptors.size());
-        std::vector<const void*> data(n);
-        std::vector<int32_t> rows(n);
-        std::vector<size_t> steps(n);
-        int cols = 1, type = SFMM_F32;
-        for (int i = 0; i < n; ++i) {
-            const cv::Mat& m = imagesDescriptors[i];
-            if (m.empty()) {  // an image without keypoints: cv::Mat() -- zero rows
-                data[i] = nullptr; rows[i] = 0; steps[i] = 0;
-                continue;
-            }
-            if (m.depth() != CV_8U && m.depth() != CV_32F) throw Error(SFMM_EINVAL, "descriptors must be CV_8U or CV_32F");
-            cols = m.cols;
-            type = (m.depth() == CV_8U) ? SFMM_U8 : SFMM_F32;
-            data[i] = m.data; rows[i] = m.rows; steps[i] = m.step;
-        }
-        check(sfmm_set_descriptors(ctx_, n, data.data(), rows.data(), cols, steps.data(), type));
+        std::vector<const void*> data;
+        std::vector<int32_t> rows;
+        std::vector<size_t> steps;
+        int cols = 0, type = SFMM_F32;
+        describe(imagesDescriptors, data, rows, steps, cols, type);
+        check(sfmm_set_descriptors(ctx_, static_cast<int32_t>(rows.size()), data.data(), rows.data(), cols, steps.data(), type));
     }
 
   public:
@@ -91,16 +112,15 @@ class AllPairsMatcher {
         const SfmDMatch* m = nullptr;
         int32_t n = 0;
         int rc = sfmm_get_pair(ctx_, idx_query, idx_train, &m, &n);
-        if (rc == SFMM_ESTATE) {  // a pair outside the q<t table (never requested by the reference): on demand
-            std::vector<SfmDMatch> tmp(1);
-            rc = sfmm_match_pair(ctx_, idx_query, idx_train, tmp.data(), 0, &n);
-            if (rc != SFMM_ERANGE && rc != SFMM_OK) check(rc);
-            tmp.resize(n > 0 ? n : 1);
+        if (rc == SFMM_ESTATE) {  // a pair outside the q<t table (never requested by the reference): on demand, one call
+            int32_t nq = 0;
+            if (sfmm_image_rows(ctx_, idx_query, &nq) != SFMM_OK) throw Error(SFMM_ERANGE, "getMatching: image index out of range");
+            std::vector<SfmDMatch> tmp(static_cast<size_t>(nq > 0 ? nq : 1));  // at most one match per query row
             check(sfmm_match_pair(ctx_, idx_query, idx_train, tmp.data(), static_cast<int32_t>(tmp.size()), &n));
             append(tmp.data(), n, goodMatches);
             return;
         }
-        check(rc);
+        if (rc != SFMM_OK) throw Error(rc, rc == SFMM_ERANGE ? "getMatching: image index out of range" : "getMatching: no descriptors uploaded");
         append(m, n, goodMatches);
     }
 
@@ -123,7 +143,8 @@ class AllPairsMatcher {
     void getAlignedPoints(int idx_query, int idx_train, std::vector<cv::Point2d>& alignedL, std::vector<cv::Point2d>& alignedR) {
         const double *l = nullptr, *r = nullptr;
         int32_t n = 0;
-        check(sfmm_get_pair_points(ctx_, idx_query, idx_train, &l, &r, &n));
+        const int rc = sfmm_get_pair_points(ctx_, idx_query, idx_train, &l, &r, &n);  // (look-ups do not set the error text)
+        if (rc != SFMM_OK) throw Error(rc, "getAlignedPoints: pair not matched with points (compute(desc, pts) first; not restored by loadTable)");
         const size_t ol = alignedL.size(), orr = alignedR.size();
         alignedL.resize(ol + n);
         alignedR.resize(orr + n);
@@ -155,83 +176,74 @@ class AllPairsMatcher {
     SfmmCtx* ctx_;
 };
 
-// All GPUs of the box from ONE host process -- the shape of the reference (a single C++ program).
-// Every device gets the descriptors (its own H2D over its own PCIe link, in parallel host threads),
-// the q<t pairs are dealt by descending cost rows_q*rows_t in a snake order (the same rule as
-// sfm_danpipeline_b200/distributed.py, so shards are balanced and deterministic), each device
-// matches its shard into its own host table, and getMatching() looks the pair up in the owning
-// context.  No inter-GPU traffic is needed: results are wanted in host memory anyway.  (The
-// multi-PROCESS variant -- NCCL broadcast + gather to rank 0 -- lives in distributed.py.)
+// All GPUs of the box from ONE host process -- the shape of the reference (a single C++ program, main.cpp:18).
+// Thin wrapper over the library's device group (sfmm_group_*, sfm_match.h): the descriptors are re-pitched and
+// copied host->device once, broadcast to the other devices with NCCL over NVLink (single-process
+// ncclCommInitAll inside the library), the q<t pairs are dealt by descending cost rows_q*rows_t in snake order,
+// every device matches its shard and copies its records to host memory over its own PCIe link, and
+// getMatching() is a look-up in the owning device's table.  (The multi-PROCESS variant -- one rank per GPU,
+// torch.distributed -- lives in sfm_danpipeline_b200/distributed.py.)
 class MultiGpuMatcher {
   public:
-    explicit MultiGpuMatcher(int nDevices, int normType = cv::NORM_L2, float ratio = 0.8f, bool crossCheck = false) {
+    explicit MultiGpuMatcher(int nDevices, int normType = cv::NORM_L2, float ratio = 0.8f, bool crossCheck = false) : g_(nullptr) {
         if (nDevices < 1) throw Error(SFMM_EINVAL, "MultiGpuMatcher: need at least one device");
-        for (int d = 0; d < nDevices; ++d) dev_.emplace_back(new AllPairsMatcher(normType, ratio, crossCheck, d));
+        SfmmConfig cfg;
+        sfmm_default_config(&cfg);
+        cfg.norm = (normType == cv::NORM_HAMMING) ? SFMM_NORM_HAMMING : SFMM_NORM_L2;
+        cfg.ratio = ratio;
+        cfg.cross_check = crossCheck ? 1 : 0;
+        const int rc = sfmm_group_create(&cfg, nDevices, nullptr, &g_);
+        if (rc != SFMM_OK) throw Error(rc, sfmm_group_last_error(nullptr));
     }
+    ~MultiGpuMatcher() { sfmm_group_destroy(g_); }
+    MultiGpuMatcher(const MultiGpuMatcher&) = delete;
+    MultiGpuMatcher& operator=(const MultiGpuMatcher&) = delete;
 
+    // Call once after extractFeature() (src/Sfm.cpp:21), like AllPairsMatcher::compute.
     void compute(const std::vector<cv::Mat>& imagesDescriptors) {
-        const int n = static_cast<int>(imagesDescriptors.size()), nd = static_cast<int>(dev_.size());
-        // findBestPair's enumeration (src/Sfm.cpp:511-512), then the cost-sorted snake deal
-        std::vector<std::pair<int, int> > pairs;
-        for (int q = 0; q + 1 < n; ++q)
-            for (int t = q + 1; t < n; ++t) pairs.push_back(std::make_pair(q, t));
-        std::vector<size_t> order(pairs.size());
-        std::iota(order.begin(), order.end(), size_t(0));
-        std::stable_sort(order.begin(), order.end(), [&](size_t a, size_t b) {
-            const long long ca = 1LL * imagesDescriptors[pairs[a].first].rows * imagesDescriptors[pairs[a].second].rows;
-            const long long cb = 1LL * imagesDescriptors[pairs[b].first].rows * imagesDescriptors[pairs[b].second].rows;
-            return ca > cb;
-        });
-        owner_.assign(static_cast<size_t>(n) * n, -1);
-        std::vector<std::vector<int32_t> > shard(nd);
-        std::vector<std::vector<size_t> > members(nd);
-        for (size_t pos = 0; pos < order.size(); ++pos) {
-            const size_t lap = pos / nd, off = pos % nd;
-            members[(lap % 2 == 0) ? off : nd - 1 - off].push_back(order[pos]);
-        }
-        for (int d = 0; d < nd; ++d) {
-            std::sort(members[d].begin(), members[d].end());  // ascending pair order inside a device
-            for (size_t k : members[d]) {
-                shard[d].push_back(pairs[k].first);
-                shard[d].push_back(pairs[k].second);
-                owner_[static_cast<size_t>(pairs[k].first) * n + pairs[k].second] = d;
-            }
-        }
-        n_images_ = n;
-        std::vector<std::string> errors(nd);
-        std::vector<int> codes(nd, SFMM_OK);
-        std::vector<std::thread> pool;
-        for (int d = 0; d < nd; ++d)
-            pool.emplace_back([&, d]() {
-                try {
-                    dev_[d]->upload(imagesDescriptors);
-                    dev_[d]->matchPairs(shard[d]);
-                } catch (const Error& e) {
-                    codes[d] = e.code;
-                    errors[d] = e.what();
-                }
-            });
-        for (auto& t : pool) t.join();
-        for (int d = 0; d < nd; ++d)
-            if (codes[d] != SFMM_OK) throw Error(codes[d], "device " + std::to_string(d) + ": " + errors[d]);
+        std::vector<const void*> data;
+        std::vector<int32_t> rows;
+        std::vector<size_t> steps;
+        int cols = 0, type = SFMM_F32;
+        describe(imagesDescriptors, data, rows, steps, cols, type);
+        check(sfmm_group_set_descriptors(g_, static_cast<int32_t>(rows.size()), data.data(), rows.data(), cols, steps.data(), type));
+        check(sfmm_group_match_all_pairs(g_));
     }
 
-    // Drop-in body of StructFromMotion::getMatching (appends).
+    // Drop-in body of StructFromMotion::getMatching (appends).  Pairs outside the q<t table are computed on demand by member 0.
     void getMatching(const int& idx_query, const int& idx_train, std::vector<cv::DMatch>* goodMatches) {
-        int d = 0;
-        if (idx_query >= 0 && idx_train >= 0 && idx_query < n_images_ && idx_train < n_images_) {
-            const int o = owner_[static_cast<size_t>(idx_query) * n_images_ + idx_train];
-            if (o >= 0) d = o;  // pairs outside the table are computed on demand by device 0
+        const SfmDMatch* m = nullptr;
+        int32_t n = 0;
+        const int rc = sfmm_group_get_pair(g_, idx_query, idx_train, &m, &n);
+        if (rc == SFMM_ESTATE) {
+            SfmmCtx* c0 = sfmm_group_context(g_, 0);
+            int32_t nq = 0;
+            if (sfmm_image_rows(c0, idx_query, &nq) != SFMM_OK) throw Error(SFMM_ERANGE, "getMatching: image index out of range");
+            std::vector<SfmDMatch> tmp(static_cast<size_t>(nq > 0 ? nq : 1));
+            const int rc2 = sfmm_match_pair(c0, idx_query, idx_train, tmp.data(), static_cast<int32_t>(tmp.size()), &n);
+            if (rc2 != SFMM_OK) throw Error(rc2, sfmm_last_error(c0));
+            m = tmp.data();
+            appendTo(m, n, goodMatches);
+            return;
         }
-        dev_[d]->getMatching(idx_query, idx_train, goodMatches);
+        if (rc != SFMM_OK) throw Error(rc, "getMatching: image index out of range");
+        appendTo(m, n, goodMatches);
     }
 
-    int devices() const { return static_cast<int>(dev_.size()); }
+    int devices() const { return static_cast<int>(sfmm_group_size(g_)); }
+    SfmmGroup* handle() { return g_; }
 
   private:
-    std::vector<std::unique_ptr<AllPairsMatcher> > dev_;
-    std::vector<int> owner_;
-    int n_images_ = 0;
+    static void appendTo(const SfmDMatch* m, int32_t n, std::vector<cv::DMatch>* out) {
+        if (n <= 0) return;
+        const size_t old = out->size();
+        out->resize(old + static_cast<size_t>(n));
+        std::memcpy(static_cast<void*>(out->data() + old), m, static_cast<size_t>(n) * sizeof(SfmDMatch));
+    }
+    void check(int rc) {
+        if (rc != SFMM_OK) throw Error(rc, sfmm_group_last_error(g_));
+    }
+    SfmmGroup* g_;
 };
 
 }  // namespace sfmm

@@ -66,7 +66,8 @@ def lib() -> ctypes.CDLL:
 
 def _check(Q: np.ndarray, T: np.ndarray, norm: int):
     want = np.uint8 if norm == NORM_HAMMING else np.float32
-    if Q.dtype != want or T.dtype != want:
+    l2_on_bytes = norm == NORM_L2 and Q.dtype == np.uint8 and T.dtype == np.uint8  # see _widen
+    if not l2_on_bytes and (Q.dtype != want or T.dtype != want):
         raise TypeError(f"norm {norm} needs {want} rows, got {Q.dtype}/{T.dtype}")
     if Q.ndim != 2 or T.ndim != 2 or Q.shape[1] != T.shape[1]:
         raise ValueError("descriptor sets must be 2-D with equal width")
@@ -74,10 +75,22 @@ def _check(Q: np.ndarray, T: np.ndarray, norm: int):
         raise ValueError("rows must be contiguous")
 
 
+def _widen(Q, T, norm):
+    """NORM_L2 on CV_8U rows -- what the reference's cv::BFMatcher(cv::NORM_L2) (src/Sfm.cpp:593) computes for its
+    AKAZE / ORB detectors (src/Sfm.cpp:331-384).  OpenCV's batchDistL2_8u32f is sqrtf of the sum of squared byte
+    differences; that sum is an integer below 2^24 for rows of up to 258 bytes, so accumulating the same integers
+    in fp32 is exact in any order: widening to float32 and taking the L2 restatement is bit-identical
+    (tests/test_oracle.py checks it against cv2)."""
+    if norm == NORM_L2 and Q.dtype == np.uint8:
+        return Q.astype(np.float32), T.astype(np.float32)
+    return Q, T
+
+
 # ----------------------------------------------------------------------------- C oracle
 def knn2_c(Q: np.ndarray, T: np.ndarray, norm: int, threads: int = 1):
     """batchDistance(K=2): returns (dist[nq,2], idx[nq,2]); dist is int32 (Hamming) or float32."""
     _check(Q, T, norm)
+    Q, T = _widen(Q, T, norm)
     L = lib()
     nq, nt, cols = Q.shape[0], T.shape[0], Q.shape[1]
     idx = np.empty((nq, 2), np.int32)
@@ -101,6 +114,7 @@ def knn2_c(Q: np.ndarray, T: np.ndarray, norm: int, threads: int = 1):
 def colmin_c(Q: np.ndarray, T: np.ndarray, norm: int, threads: int = 1) -> np.ndarray:
     """For each train row the lowest-index nearest query row (cross-check half)."""
     _check(Q, T, norm)
+    Q, T = _widen(Q, T, norm)
     L = lib()
     nq, nt, cols = Q.shape[0], T.shape[0], Q.shape[1]
     best = np.empty(nt, np.int32)
@@ -148,6 +162,7 @@ def match_pair(Q, T, norm, ratio=0.8, cross_check=False, threads: int = 1) -> np
 def match_pair_c_single(Q, T, norm, ratio=0.8, cross_check=False) -> np.ndarray:
     """The single C function oracle_match_pair (no Python in the arithmetic)."""
     _check(Q, T, norm)
+    Q, T = _widen(Q, T, norm)
     out = np.zeros(max(Q.shape[0], 1), DMATCH_DTYPE)
     n = lib().oracle_match_pair(Q.ctypes.data, Q.shape[0], Q.strides[0] if Q.shape[0] else 0,
                                 T.ctypes.data, T.shape[0], T.strides[0] if T.shape[0] else 0,
@@ -169,6 +184,7 @@ _POP8 = np.array([bin(i).count("1") for i in range(256)], np.int32)
 def knn2_np(Q, T, norm):
     """numpy restatement of batchDistance(K=2) with strict-'<' insertion (small cases)."""
     _check(Q, T, norm)
+    Q, T = _widen(Q, T, norm)
     nq, nt = Q.shape[0], T.shape[0]
     if norm == NORM_HAMMING:
         D = _POP8[Q[:, None, :] ^ T[None, :, :]].sum(-1, dtype=np.int32) if nt else np.zeros((nq, 0), np.int32)

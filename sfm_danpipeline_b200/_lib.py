@@ -24,7 +24,10 @@ EXPORTS = (
     "sfmm_set_descriptors", "sfmm_descriptor_blob", "sfmm_row_pitch", "sfmm_match_all_pairs",
     "sfmm_match_pairs", "sfmm_get_pair", "sfmm_match_pair", "sfmm_knn_pair", "sfmm_result_table",
     "sfmm_match_pairs_device", "sfmm_clear_results", "sfmm_get_stats",
-    "sfmm_set_points", "sfmm_get_pair_points", "sfmm_save_table", "sfmm_load_table",
+    "sfmm_set_points", "sfmm_get_pair_points", "sfmm_save_table", "sfmm_load_table", "sfmm_image_rows",
+    "sfmm_group_create", "sfmm_group_destroy", "sfmm_group_last_error", "sfmm_group_size", "sfmm_group_context",
+    "sfmm_group_set_descriptors", "sfmm_group_match_all_pairs", "sfmm_group_match_pairs", "sfmm_group_get_pair",
+    "sfmm_group_transfer_stats",
 )
 
 
@@ -87,6 +90,21 @@ def load() -> C.CDLL:
     L.sfmm_save_table.argtypes = [vp, C.c_char_p]
     L.sfmm_load_table.argtypes = [vp, C.c_char_p]
     L.sfmm_get_stats.argtypes = [vp, P(SfmmStats)]
+    L.sfmm_image_rows.argtypes = [vp, i32, P(i32)]
+    L.sfmm_group_create.argtypes = [P(SfmmConfig), i32, P(i32), P(vp)]
+    L.sfmm_group_destroy.restype = None
+    L.sfmm_group_destroy.argtypes = [vp]
+    L.sfmm_group_last_error.restype = C.c_char_p
+    L.sfmm_group_last_error.argtypes = [vp]
+    L.sfmm_group_size.restype = i32
+    L.sfmm_group_size.argtypes = [vp]
+    L.sfmm_group_context.restype = vp
+    L.sfmm_group_context.argtypes = [vp, i32]
+    L.sfmm_group_set_descriptors.argtypes = [vp, i32, P(vp), P(i32), i32, P(sz), i32]
+    L.sfmm_group_match_all_pairs.argtypes = [vp]
+    L.sfmm_group_match_pairs.argtypes = [vp, vp, i64]
+    L.sfmm_group_get_pair.argtypes = [vp, i32, i32, P(vp), P(i32)]
+    L.sfmm_group_transfer_stats.argtypes = [vp, P(i64), P(i64)]
     for name in EXPORTS:
         fn = getattr(L, name)
         if fn.restype is C.c_int:  # default

@@ -23,6 +23,8 @@
 #include <vector>
 
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nccl.h>  // types and prototypes only: the library is dlopen'ed by sfmm_group_create, never linked
 
 #include "../../include/sfm_match.h"
 #include "binary_knn.cuh"
@@ -176,8 +178,11 @@ struct SfmmCtx {
     int32_t n_images = 0;
     std::vector<int32_t> rows;
     std::vector<uint32_t> row0;
-    int32_t cols = 0;
-    int32_t elem_type = -1;
+    int32_t cols = 0;       // elements per blob row as the kernels see them
+    int32_t elem_type = -1; // element type of the blob (SFMM_F32 for widened CV_8U rows under NORM_L2)
+    int32_t src_cols = 0;   // what the caller passed to sfmm_set_descriptors
+    int32_t src_elem_type = -1;
+    int32_t elem_type_pending = -1;  // blob element type while sfmm_set_descriptors is still filling it
     size_t pitch = 0;
     uint64_t total_rows = 0;  // blob rows, including the zero rows that align every image to 4 rows
     DevBuf blob;
@@ -209,6 +214,20 @@ int fail(const SfmmCtx* ctx, int code, const std::string& msg) {
     if (ctx) ctx->err = msg;
     else g_create_error = msg;
     return code;
+}
+
+// Nothing may throw across the C ABI: entry points that allocate on the host run their body through this.
+template <class F>
+int guarded(const SfmmCtx* ctx, F&& body) {
+    try {
+        return body();
+    } catch (const std::bad_alloc&) {
+        return fail(ctx, SFMM_ENOMEM, "out of host memory");
+    } catch (const std::exception& e) {
+        return fail(ctx, SFMM_EINVAL, std::string("unexpected C++ exception: ") + e.what());
+    } catch (...) {
+        return fail(ctx, SFMM_EINVAL, "unexpected C++ exception");
+    }
 }
 
 #define CU_TRY(ctx, expr)                                                                         \
@@ -271,7 +290,7 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
     if (base_tiles > 0 && base_tiles < want_tiles)
         splits_wanted = static_cast<uint32_t>(std::min<uint64_t>(32, (want_tiles + base_tiles - 1) / base_tiles));
 
-    const double work_per_eval = is_float ? 2.0 * ctx->cols : static_cast<double>((ctx->cols * 8 + 31) / 32);
+    const double work_per_eval = is_float ? 2.0 * ctx->src_cols : static_cast<double>((ctx->cols * 8 + 31) / 32);
     for (int64_t i = 0; i < n; ++i) {
         const int32_t q = qt[2 * i], t = qt[2 * i + 1];
         PairDesc& pd = plan.pairs[i];
@@ -867,6 +886,7 @@ void begin_stats(SfmmCtx* ctx) {
 void pack_rows(const SfmmCtx* ctx, const void* const* data, const size_t* step_bytes, size_t row_bytes, uint64_t r0, uint64_t r1,
                unsigned char* dst) {
     const size_t pitch = ctx->pitch;
+    const bool widen = ctx->src_elem_type == SFMM_U8 && ctx->elem_type_pending == SFMM_F32;  // NORM_L2 on CV_8U rows
     // image holding blob row r0
     int32_t img = static_cast<int32_t>(std::upper_bound(ctx->row0.begin(), ctx->row0.end(), static_cast<uint32_t>(r0)) - ctx->row0.begin()) - 1;
     for (uint64_t r = r0; r < r1; ++r, dst += pitch) {
@@ -874,8 +894,16 @@ void pack_rows(const SfmmCtx* ctx, const void* const* data, const size_t* step_b
         const uint64_t local = r - ctx->row0[img];
         if (local < static_cast<uint64_t>(ctx->rows[img])) {
             const size_t step = step_bytes ? step_bytes[img] : row_bytes;
-            std::memcpy(dst, static_cast<const unsigned char*>(data[img]) + local * step, row_bytes);
-            if (pitch > row_bytes) std::memset(dst + row_bytes, 0, pitch - row_bytes);
+            const unsigned char* src = static_cast<const unsigned char*>(data[img]) + local * step;
+            if (widen) {  // bytes -> the same integers as fp32 (exact), zero padding up to the pitch
+                float* f = reinterpret_cast<float*>(dst);
+                const size_t n = pitch / sizeof(float);
+                for (size_t c = 0; c < row_bytes; ++c) f[c] = static_cast<float>(src[c]);
+                for (size_t c = row_bytes; c < n; ++c) f[c] = 0.f;
+            } else {
+                std::memcpy(dst, src, row_bytes);
+                if (pitch > row_bytes) std::memset(dst + row_bytes, 0, pitch - row_bytes);
+            }
         } else {
             std::memset(dst, 0, pitch);  // alignment rows between images
         }
@@ -978,17 +1006,23 @@ SFMM_API size_t sfmm_row_pitch(int32_t cols, int32_t elem_type) {
     return 0;
 }
 
-SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* const* data, const int32_t* rows,
+static int impl_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* const* data, const int32_t* rows,
                                   int32_t cols, const size_t* step_bytes, int32_t elem_type) {
     if (!ctx) return SFMM_EINVAL;
     if (n_images < 0 || (n_images > 0 && !rows) || cols <= 0) return fail(ctx, SFMM_EINVAL, "set_descriptors: bad sizes");
     if (elem_type != SFMM_U8 && elem_type != SFMM_F32) return fail(ctx, SFMM_EINVAL, "set_descriptors: unknown elem_type");
-    // cv::BFMatcher asserts the same pairing: NORM_HAMMING needs CV_8U, the L2 path here takes CV_32F
-    if ((ctx->cfg.norm == SFMM_NORM_HAMMING) != (elem_type == SFMM_U8))
-        return fail(ctx, SFMM_EINVAL, "set_descriptors: NORM_HAMMING needs SFMM_U8 rows and NORM_L2 needs SFMM_F32 rows");
-    const size_t pitch = sfmm_row_pitch(cols, elem_type);
+    // cv::BFMatcher asserts NORM_HAMMING <-> CV_8U.  NORM_L2 takes both depths: on CV_8U rows it is what the reference
+    // literally does for its AKAZE / ORB detectors (cv::BFMatcher(cv::NORM_L2) at src/Sfm.cpp:593 whatever the
+    // detector; OpenCV's batchDistL2_8u32f = sqrtf of the exact integer sum).  Those rows are widened to fp32 on
+    // upload (exact, zero-padded to a multiple of 32 columns) and take the float kernels.
+    if (ctx->cfg.norm == SFMM_NORM_HAMMING && elem_type != SFMM_U8)
+        return fail(ctx, SFMM_EINVAL, "set_descriptors: NORM_HAMMING needs SFMM_U8 rows");
+    const bool widen = ctx->cfg.norm == SFMM_NORM_L2 && elem_type == SFMM_U8;
+    const int32_t blob_type = widen ? SFMM_F32 : elem_type;
+    const int32_t blob_cols = widen ? (cols + 31) / 32 * 32 : cols;
+    const size_t pitch = sfmm_row_pitch(blob_cols, blob_type);
     if (pitch == 0) return fail(ctx, SFMM_EINVAL, "set_descriptors: unsupported descriptor width (binary <= 128 bytes)");
-    if (elem_type == SFMM_F32 && cols > 256) return fail(ctx, SFMM_EINVAL, "set_descriptors: float descriptors wider than 256 are not supported");
+    if (blob_type == SFMM_F32 && blob_cols > 256) return fail(ctx, SFMM_EINVAL, "set_descriptors: float descriptors wider than 256 are not supported");
     const size_t elem = elem_type == SFMM_U8 ? 1 : 4;
     // every image starts at a blob row that is a multiple of 4 (16-byte aligned slices of the
     // per-row norm array for the TMA bulk copies of the tensor path); the rows in between are zero
@@ -1007,6 +1041,8 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
     if ((rc = sync_all(ctx))) return rc;
     clear_results(ctx);
     ctx->elem_type = -1;
+    ctx->src_elem_type = elem_type;
+    ctx->elem_type_pending = blob_type;
     ctx->float_prepared = false;
     ctx->use_tensor = false;
     ctx->tensor_refine = false;
@@ -1022,7 +1058,8 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
         r0 += (static_cast<uint64_t>(rows[i]) + 3) & ~3ull;
     }
     ctx->n_images = n_images;
-    ctx->cols = cols;
+    ctx->cols = blob_cols;
+    ctx->src_cols = cols;
     ctx->pitch = pitch;
     ctx->total_rows = total;
     ctx->blob_bytes = bytes;
@@ -1061,7 +1098,15 @@ SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* co
         }
         CU_TRY(ctx, cudaStreamSynchronize(st));
     }
-    ctx->elem_type = elem_type;
+    ctx->elem_type = blob_type;
+    return SFMM_OK;
+}
+
+SFMM_API int sfmm_image_rows(const SfmmCtx* ctx, int32_t image, int32_t* rows) {
+    if (!ctx || !rows) return SFMM_EINVAL;
+    if (ctx->elem_type < 0) return SFMM_ESTATE;
+    if (image < 0 || image >= ctx->n_images) return SFMM_ERANGE;
+    *rows = ctx->rows[static_cast<size_t>(image)];
     return SFMM_OK;
 }
 
@@ -1075,7 +1120,7 @@ SFMM_API int sfmm_descriptor_blob(SfmmCtx* ctx, void** device_ptr, size_t* bytes
     return SFMM_OK;
 }
 
-SFMM_API int sfmm_set_points(SfmmCtx* ctx, int32_t n_images, const double* const* xy) {
+static int impl_set_points(SfmmCtx* ctx, int32_t n_images, const double* const* xy) {
     int rc = require_descriptors(ctx);
     if (rc) return rc;
     if (n_images != ctx->n_images || (n_images > 0 && !xy)) return fail(ctx, SFMM_EINVAL, "set_points: image count differs from the descriptor set");
@@ -1098,13 +1143,13 @@ SFMM_API int sfmm_set_points(SfmmCtx* ctx, int32_t n_images, const double* const
 }
 
 SFMM_API int sfmm_get_pair_points(const SfmmCtx* ctx, int32_t q, int32_t t, const double** left_xy, const double** right_xy, int32_t* count) {
-    int rc = require_descriptors(ctx);
-    if (rc) return rc;
-    if (!left_xy || !right_xy || !count) return fail(ctx, SFMM_EINVAL, "get_pair_points: NULL argument");
-    if (q < 0 || q >= ctx->n_images || t < 0 || t >= ctx->n_images) return fail(ctx, SFMM_ERANGE, "get_pair_points: image index out of range");
+    if (!ctx) return SFMM_EINVAL;
+    if (ctx->elem_type < 0) return SFMM_ESTATE;
+    if (!left_xy || !right_xy || !count) return SFMM_EINVAL;
+    if (q < 0 || q >= ctx->n_images || t < 0 || t >= ctx->n_images) return SFMM_ERANGE;
     auto it = ctx->index.find(pair_key(q, t));
-    if (it == ctx->index.end()) return fail(ctx, SFMM_ESTATE, "get_pair_points: pair has not been matched");
-    if (ctx->pts_left.size() != ctx->table.size()) return fail(ctx, SFMM_ESTATE, "get_pair_points: sfmm_set_points was not called before matching");
+    if (it == ctx->index.end()) return SFMM_ESTATE;
+    if (ctx->pts_left.size() != ctx->table.size()) return SFMM_ESTATE;
     const PairSlot& s = ctx->res_slots[static_cast<size_t>(it->second)];
     *left_xy = reinterpret_cast<const double*>(ctx->pts_left.data() + s.offset);
     *right_xy = reinterpret_cast<const double*>(ctx->pts_right.data() + s.offset);
@@ -1132,8 +1177,8 @@ SFMM_API int sfmm_save_table(const SfmmCtx* ctx, const char* path) {
     if (!f) return fail(ctx, SFMM_EINVAL, std::string("save_table: cannot open ") + path);
     TableHeader h{};
     std::memcpy(h.magic, "SFMMTBL1", 8);
-    h.n_images = ctx->n_images; h.norm = ctx->cfg.norm; h.cross_check = ctx->cfg.cross_check; h.elem_type = ctx->elem_type;
-    h.ratio = ctx->cfg.ratio; h.cols = ctx->cols;
+    h.n_images = ctx->n_images; h.norm = ctx->cfg.norm; h.cross_check = ctx->cfg.cross_check; h.elem_type = ctx->src_elem_type;
+    h.ratio = ctx->cfg.ratio; h.cols = ctx->src_cols;
     h.n_pairs = static_cast<int64_t>(ctx->res_counts.size()); h.n_matches = ctx->n_matches;
     bool ok = std::fwrite(&h, sizeof h, 1, f) == 1;
     auto put = [&](const void* p, size_t bytes) { ok = ok && (bytes == 0 || std::fwrite(p, 1, bytes, f) == bytes); };
@@ -1150,53 +1195,59 @@ SFMM_API int sfmm_load_table(SfmmCtx* ctx, const char* path) {
     int rc = require_descriptors(ctx);
     if (rc) return rc;
     if (!path) return fail(ctx, SFMM_EINVAL, "load_table: NULL path");
-    FILE* f = std::fopen(path, "rb");
-    if (!f) return fail(ctx, SFMM_EINVAL, std::string("load_table: cannot open ") + path);
-    TableHeader h{};
-    bool ok = std::fread(&h, sizeof h, 1, f) == 1 && std::memcmp(h.magic, "SFMMTBL1", 8) == 0;
-    if (ok && (h.n_images != ctx->n_images || h.norm != ctx->cfg.norm || h.elem_type != ctx->elem_type || h.cols != ctx->cols ||
-               h.n_pairs < 0 || h.n_matches < 0)) {
-        std::fclose(f);
-        return fail(ctx, SFMM_EINVAL, "load_table: the file belongs to a different descriptor set / norm");
-    }
-    std::vector<int32_t> rows(ok ? h.n_images : 0), qt, counts;
-    std::vector<int64_t> offsets;
-    std::vector<SfmDMatch> table;
-    auto get = [&](void* p, size_t bytes) { ok = ok && (bytes == 0 || std::fread(p, 1, bytes, f) == bytes); };
-    if (ok) {
-        try {
-            qt.resize(2 * static_cast<size_t>(h.n_pairs)); counts.resize(h.n_pairs); offsets.resize(h.n_pairs); table.resize(h.n_matches);
-        } catch (const std::bad_alloc&) {
-            std::fclose(f);
-            return fail(ctx, SFMM_ENOMEM, "load_table: out of host memory");
-        }
+    return guarded(ctx, [&]() -> int {
+        FILE* f = std::fopen(path, "rb");
+        if (!f) return fail(ctx, SFMM_EINVAL, std::string("load_table: cannot open ") + path);
+        struct Closer { FILE* f; ~Closer() { std::fclose(f); } } closer{f};
+        TableHeader h{};
+        if (std::fread(&h, sizeof h, 1, f) != 1 || std::memcmp(h.magic, "SFMMTBL1", 8) != 0)
+            return fail(ctx, SFMM_EINVAL, std::string("load_table: not a match table: ") + path);
+        if (h.n_images != ctx->n_images || h.norm != ctx->cfg.norm || h.elem_type != ctx->src_elem_type || h.cols != ctx->src_cols)
+            return fail(ctx, SFMM_EINVAL, "load_table: the file belongs to a different descriptor set / norm");
+        // a table is only valid for the filter settings it was computed with
+        if (std::memcmp(&h.ratio, &ctx->cfg.ratio, sizeof(float)) != 0 || (h.cross_check != 0) != (ctx->cfg.cross_check != 0))
+            return fail(ctx, SFMM_EINVAL, "load_table: the file was computed with a different ratio / cross_check setting");
+        // the directory sizes come from the file: bound them by the file itself before allocating anything
+        if (std::fseek(f, 0, SEEK_END) != 0) return fail(ctx, SFMM_EINVAL, "load_table: cannot seek");
+        const long long file_bytes = std::ftell(f);
+        if (std::fseek(f, static_cast<long>(sizeof h), SEEK_SET) != 0) return fail(ctx, SFMM_EINVAL, "load_table: cannot seek");
+        const long long per_pair = 2 * sizeof(int32_t) + sizeof(int32_t) + sizeof(int64_t);
+        const long long fixed = static_cast<long long>(sizeof h) + static_cast<long long>(h.n_images) * sizeof(int32_t);
+        if (h.n_pairs < 0 || h.n_matches < 0 || file_bytes < fixed || h.n_pairs > (file_bytes - fixed) / per_pair ||
+            h.n_matches > (file_bytes - fixed - h.n_pairs * per_pair) / static_cast<long long>(sizeof(SfmDMatch)) ||
+            fixed + h.n_pairs * per_pair + h.n_matches * static_cast<long long>(sizeof(SfmDMatch)) != file_bytes)
+            return fail(ctx, SFMM_EINVAL, std::string("load_table: header does not match the file size (truncated or corrupt): ") + path);
+        std::vector<int32_t> rows(static_cast<size_t>(h.n_images)), qt(2 * static_cast<size_t>(h.n_pairs)), counts(static_cast<size_t>(h.n_pairs));
+        std::vector<int64_t> offsets(static_cast<size_t>(h.n_pairs));
+        std::vector<SfmDMatch> table(static_cast<size_t>(h.n_matches));
+        bool ok = true;
+        auto get = [&](void* p, size_t bytes) { ok = ok && (bytes == 0 || std::fread(p, 1, bytes, f) == bytes); };
         get(rows.data(), rows.size() * sizeof(int32_t));
         get(qt.data(), qt.size() * sizeof(int32_t));
         get(counts.data(), counts.size() * sizeof(int32_t));
         get(offsets.data(), offsets.size() * sizeof(int64_t));
         get(table.data(), table.size() * sizeof(SfmDMatch));
-    }
-    std::fclose(f);
-    if (!ok) return fail(ctx, SFMM_EINVAL, std::string("load_table: not a match table or truncated: ") + path);
-    if (rows != ctx->rows) return fail(ctx, SFMM_EINVAL, "load_table: per-image row counts differ from the current descriptor set");
-    for (int64_t i = 0; i < h.n_pairs; ++i) {
-        const int32_t q = qt[2 * i], t = qt[2 * i + 1];
-        if (q < 0 || q >= ctx->n_images || t < 0 || t >= ctx->n_images || counts[i] < 0 || offsets[i] < 0 ||
-            offsets[i] + counts[i] > h.n_matches)
-            return fail(ctx, SFMM_EINVAL, "load_table: corrupt pair directory");
-    }
-    clear_results(ctx);
-    ctx->res_qt = std::move(qt);
-    ctx->res_counts = std::move(counts);
-    ctx->res_offsets = std::move(offsets);
-    ctx->table = std::move(table);
-    ctx->n_matches = h.n_matches;
-    ctx->res_slots.reserve(static_cast<size_t>(h.n_pairs));
-    for (int64_t i = 0; i < h.n_pairs; ++i) {
-        ctx->index[pair_key(ctx->res_qt[2 * i], ctx->res_qt[2 * i + 1])] = i;
-        ctx->res_slots.push_back(PairSlot{ctx->res_offsets[i], ctx->res_counts[i]});
-    }
-    return SFMM_OK;
+        if (!ok) return fail(ctx, SFMM_EINVAL, std::string("load_table: short read: ") + path);
+        if (rows != ctx->rows) return fail(ctx, SFMM_EINVAL, "load_table: per-image row counts differ from the current descriptor set");
+        for (int64_t i = 0; i < h.n_pairs; ++i) {
+            const int32_t q = qt[2 * i], t = qt[2 * i + 1];
+            if (q < 0 || q >= ctx->n_images || t < 0 || t >= ctx->n_images || counts[i] < 0 || offsets[i] < 0 ||
+                offsets[i] > h.n_matches - counts[i])
+                return fail(ctx, SFMM_EINVAL, "load_table: corrupt pair directory");
+        }
+        clear_results(ctx);
+        ctx->res_qt = std::move(qt);
+        ctx->res_counts = std::move(counts);
+        ctx->res_offsets = std::move(offsets);
+        ctx->table = std::move(table);
+        ctx->n_matches = h.n_matches;
+        ctx->res_slots.reserve(static_cast<size_t>(h.n_pairs));
+        for (int64_t i = 0; i < h.n_pairs; ++i) {
+            ctx->index[pair_key(ctx->res_qt[2 * i], ctx->res_qt[2 * i + 1])] = i;
+            ctx->res_slots.push_back(PairSlot{ctx->res_offsets[i], ctx->res_counts[i]});
+        }
+        return SFMM_OK;
+    });
 }
 
 SFMM_API int sfmm_clear_results(SfmmCtx* ctx) {
@@ -1205,7 +1256,7 @@ SFMM_API int sfmm_clear_results(SfmmCtx* ctx) {
     return SFMM_OK;
 }
 
-SFMM_API int sfmm_match_pairs_device(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs, int32_t* d_counts,
+static int impl_match_pairs_device(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs, int32_t* d_counts,
                                      SfmDMatch* d_matches, int64_t match_capacity, int64_t* n_matches) {
     int rc = require_descriptors(ctx);
     if (rc) return rc;
@@ -1239,7 +1290,7 @@ SFMM_API int sfmm_match_pairs_device(SfmmCtx* ctx, const int32_t* qt, int64_t n_
     return SFMM_OK;
 }
 
-SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) {
+static int impl_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) {
     int rc = require_descriptors(ctx);
     if (rc) return rc;
     if (n_pairs < 0 || (n_pairs > 0 && !qt)) return fail(ctx, SFMM_EINVAL, "match_pairs: bad argument");
@@ -1264,23 +1315,50 @@ SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) 
     int64_t next = 0;
     int k = 0;
     int pending[2] = {-1, -1};  // slot indices in launch order
+    // A failure in the middle of the call must not leave a chunk in flight or a half-indexed table behind:
+    // drain both slots and roll the table back to where this call started.
+    const size_t base_pairs = ctx->res_counts.size(), base_pts = ctx->pts_left.size();
+    const int64_t base_matches = ctx->n_matches;
+    auto abort_call = [&](int code) -> int {
+        for (Slot& sl : ctx->slot) {
+            if (sl.stream) cudaStreamSynchronize(sl.stream);
+            sl.busy = false;
+        }
+        cudaStreamSynchronize(ctx->copy_stream);
+        (void)cudaGetLastError();
+        for (size_t i = base_pairs; i < ctx->res_counts.size(); ++i) ctx->index.erase(pair_key(ctx->res_qt[2 * i], ctx->res_qt[2 * i + 1]));
+        ctx->res_qt.resize(2 * base_pairs);
+        ctx->res_counts.resize(base_pairs);
+        ctx->res_offsets.resize(base_pairs);
+        ctx->res_slots.resize(base_pairs);
+        ctx->table.resize(ctx->call_base);
+        ctx->pts_left.resize(base_pts);
+        ctx->pts_right.resize(base_pts);
+        ctx->n_matches = base_matches;
+        return code;
+    };
     auto collect_oldest = [&]() -> int {
         const int s = pending[0];
         pending[0] = pending[1];
         pending[1] = -1;
         return collect_chunk(ctx, ctx->slot[s], qt);
     };
-    while (next < n_pairs) {
-        if (pending[1] >= 0 && (rc = collect_oldest())) return rc;  // both slots busy: free the older one
-        const int s = k & 1;
-        const int64_t n = chunk_extent(ctx, qt, next, n_pairs, budget);
-        if ((rc = launch_chunk(ctx, ctx->slot[s], qt, next, n, nullptr, nullptr, 0))) return rc;
-        (pending[0] < 0 ? pending[0] : pending[1]) = s;
-        next += n;
-        ++k;
+    try {
+        while (next < n_pairs) {
+            if (pending[1] >= 0 && (rc = collect_oldest())) return abort_call(rc);  // both slots busy: free the older one
+            const int s = k & 1;
+            const int64_t n = chunk_extent(ctx, qt, next, n_pairs, budget);
+            if ((rc = launch_chunk(ctx, ctx->slot[s], qt, next, n, nullptr, nullptr, 0))) return abort_call(rc);
+            (pending[0] < 0 ? pending[0] : pending[1]) = s;
+            next += n;
+            ++k;
+        }
+        while (pending[0] >= 0)
+            if ((rc = collect_oldest())) return abort_call(rc);
+    } catch (...) {
+        abort_call(0);
+        throw;  // mapped to an error code by the entry point's guard
     }
-    while (pending[0] >= 0)
-        if ((rc = collect_oldest())) return rc;
     // device time of the whole call: from the first launch to the later of the two streams
     CU_TRY(ctx, cudaEventRecord(ctx->ev_end, ctx->slot[0].stream));
     if ((rc = sync_all(ctx))) return rc;
@@ -1291,7 +1369,7 @@ SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) 
     return SFMM_OK;
 }
 
-SFMM_API int sfmm_match_all_pairs(SfmmCtx* ctx) {
+static int impl_match_all_pairs(SfmmCtx* ctx) {
     int rc = require_descriptors(ctx);
     if (rc) return rc;
     clear_results(ctx);
@@ -1304,16 +1382,16 @@ SFMM_API int sfmm_match_all_pairs(SfmmCtx* ctx) {
             qt.push_back(q);
             qt.push_back(t);
         }
-    return sfmm_match_pairs(ctx, qt.data(), static_cast<int64_t>(qt.size() / 2));
+    return impl_match_pairs(ctx, qt.data(), static_cast<int64_t>(qt.size() / 2));
 }
 
 SFMM_API int sfmm_get_pair(const SfmmCtx* ctx, int32_t q, int32_t t, const SfmDMatch** matches, int32_t* count) {
-    int rc = require_descriptors(ctx);
-    if (rc) return rc;
-    if (!matches || !count) return fail(ctx, SFMM_EINVAL, "get_pair: NULL argument");
-    if (q < 0 || q >= ctx->n_images || t < 0 || t >= ctx->n_images) return fail(ctx, SFMM_ERANGE, "get_pair: image index out of range");
+    if (!ctx) return SFMM_EINVAL;
+    if (ctx->elem_type < 0) return SFMM_ESTATE;
+    if (!matches || !count) return SFMM_EINVAL;
+    if (q < 0 || q >= ctx->n_images || t < 0 || t >= ctx->n_images) return SFMM_ERANGE;
     auto it = ctx->index.find(pair_key(q, t));
-    if (it == ctx->index.end()) return fail(ctx, SFMM_ESTATE, "get_pair: pair has not been matched (call sfmm_match_all_pairs / sfmm_match_pairs)");
+    if (it == ctx->index.end()) return SFMM_ESTATE;
     const PairSlot& s = ctx->res_slots[static_cast<size_t>(it->second)];
     *matches = ctx->table.data() + s.offset;
     *count = s.count;
@@ -1322,9 +1400,9 @@ SFMM_API int sfmm_get_pair(const SfmmCtx* ctx, int32_t q, int32_t t, const SfmDM
 
 SFMM_API int sfmm_result_table(const SfmmCtx* ctx, int64_t* n_pairs, const int32_t** qt, const int32_t** counts,
                                const int64_t** offsets, const SfmDMatch** matches, int64_t* n_matches) {
-    int rc = require_descriptors(ctx);
-    if (rc) return rc;
-    if (!n_pairs || !qt || !counts || !offsets || !matches || !n_matches) return fail(ctx, SFMM_EINVAL, "result_table: NULL argument");
+    if (!ctx) return SFMM_EINVAL;
+    if (ctx->elem_type < 0) return SFMM_ESTATE;
+    if (!n_pairs || !qt || !counts || !offsets || !matches || !n_matches) return SFMM_EINVAL;
     *n_pairs = static_cast<int64_t>(ctx->res_counts.size());
     *qt = ctx->res_qt.data();
     *counts = ctx->res_counts.data();
@@ -1334,7 +1412,7 @@ SFMM_API int sfmm_result_table(const SfmmCtx* ctx, int64_t* n_pairs, const int32
     return SFMM_OK;
 }
 
-SFMM_API int sfmm_match_pair(SfmmCtx* ctx, int32_t q, int32_t t, SfmDMatch* out, int32_t cap, int32_t* count) {
+static int impl_match_pair(SfmmCtx* ctx, int32_t q, int32_t t, SfmDMatch* out, int32_t cap, int32_t* count) {
     int rc = require_descriptors(ctx);
     if (rc) return rc;
     if (!count || cap < 0 || (cap > 0 && !out)) return fail(ctx, SFMM_EINVAL, "match_pair: bad argument");
@@ -1361,7 +1439,7 @@ SFMM_API int sfmm_match_pair(SfmmCtx* ctx, int32_t q, int32_t t, SfmDMatch* out,
     return SFMM_OK;
 }
 
-SFMM_API int sfmm_knn_pair(SfmmCtx* ctx, int32_t q, int32_t t, int32_t* train_idx, float* distance) {
+static int impl_knn_pair(SfmmCtx* ctx, int32_t q, int32_t t, int32_t* train_idx, float* distance) {
     int rc = require_descriptors(ctx);
     if (rc) return rc;
     if (q < 0 || q >= ctx->n_images || t < 0 || t >= ctx->n_images) return fail(ctx, SFMM_ERANGE, "knn_pair: image index out of range");
@@ -1400,6 +1478,272 @@ SFMM_API int sfmm_knn_pair(SfmmCtx* ctx, int32_t q, int32_t t, int32_t* train_id
 SFMM_API int sfmm_get_stats(const SfmmCtx* ctx, SfmmStats* out) {
     if (!ctx || !out) return SFMM_EINVAL;
     *out = ctx->stats;
+    return SFMM_OK;
+}
+
+SFMM_API int sfmm_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* const* data, const int32_t* rows,
+                                  int32_t cols, const size_t* step_bytes, int32_t elem_type) {
+    return guarded(ctx, [&]() -> int { return impl_set_descriptors(ctx, n_images, data, rows, cols, step_bytes, elem_type); });
+}
+
+SFMM_API int sfmm_set_points(SfmmCtx* ctx, int32_t n_images, const double* const* xy) {
+    return guarded(ctx, [&]() -> int { return impl_set_points(ctx, n_images, xy); });
+}
+
+SFMM_API int sfmm_match_pairs_device(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs, int32_t* d_counts,
+                                     SfmDMatch* d_matches, int64_t match_capacity, int64_t* n_matches) {
+    return guarded(ctx, [&]() -> int { return impl_match_pairs_device(ctx, qt, n_pairs, d_counts, d_matches, match_capacity, n_matches); });
+}
+
+SFMM_API int sfmm_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) {
+    return guarded(ctx, [&]() -> int { return impl_match_pairs(ctx, qt, n_pairs); });
+}
+
+SFMM_API int sfmm_match_pair(SfmmCtx* ctx, int32_t q, int32_t t, SfmDMatch* out, int32_t cap, int32_t* count) {
+    return guarded(ctx, [&]() -> int { return impl_match_pair(ctx, q, t, out, cap, count); });
+}
+
+SFMM_API int sfmm_knn_pair(SfmmCtx* ctx, int32_t q, int32_t t, int32_t* train_idx, float* distance) {
+    return guarded(ctx, [&]() -> int { return impl_knn_pair(ctx, q, t, train_idx, distance); });
+}
+
+SFMM_API int sfmm_match_all_pairs(SfmmCtx* ctx) {
+    return guarded(ctx, [&]() -> int { return impl_match_all_pairs(ctx); });
+}
+
+}  // extern "C"
+
+// =============================================================================== device groups (single process, NCCL)
+namespace {
+
+// The handful of NCCL entry points the group needs, resolved at run time so that libsfmmatch.so has no link-time
+// dependency on NCCL (a process that already loaded an NCCL -- e.g. torch's -- gets that one: same SONAME).
+struct NcclApi {
+    void* handle = nullptr;
+    decltype(&ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&ncclBroadcast) Broadcast = nullptr;
+    decltype(&ncclGroupStart) GroupStart = nullptr;
+    decltype(&ncclGroupEnd) GroupEnd = nullptr;
+    decltype(&ncclGetErrorString) GetErrorString = nullptr;
+    std::string error;
+    bool load() {
+        if (handle) return true;
+        const char* env = std::getenv("SFMM_NCCL_LIB");
+        const char* names[] = {env, "libnccl.so.2", "libnccl.so"};
+        for (const char* n : names) {
+            if (!n || !*n) continue;
+            handle = dlopen(n, RTLD_NOW | RTLD_GLOBAL);
+            if (handle) break;
+            error = dlerror();
+        }
+        if (!handle) return false;
+        bool ok = true;
+        auto sym = [&](const char* name) -> void* {
+            void* p = dlsym(handle, name);
+            if (!p) { ok = false; error = std::string("missing NCCL symbol ") + name; }
+            return p;
+        };
+        CommInitAll = reinterpret_cast<decltype(CommInitAll)>(sym("ncclCommInitAll"));
+        CommDestroy = reinterpret_cast<decltype(CommDestroy)>(sym("ncclCommDestroy"));
+        Broadcast = reinterpret_cast<decltype(Broadcast)>(sym("ncclBroadcast"));
+        GroupStart = reinterpret_cast<decltype(GroupStart)>(sym("ncclGroupStart"));
+        GroupEnd = reinterpret_cast<decltype(GroupEnd)>(sym("ncclGroupEnd"));
+        GetErrorString = reinterpret_cast<decltype(GetErrorString)>(sym("ncclGetErrorString"));
+        if (!ok) { dlclose(handle); handle = nullptr; }
+        return ok;
+    }
+};
+NcclApi g_nccl;
+
+}  // namespace
+
+struct SfmmGroup {
+    std::vector<SfmmCtx*> ctx;
+    std::vector<int> devices;
+    std::vector<ncclComm_t> comms;
+    std::vector<int8_t> owner;  // n_images x n_images: member that matched (q,t), -1 = nobody
+    int32_t n_images = 0;
+    int64_t h2d_bytes = 0, nccl_bytes = 0;
+    mutable std::string err;
+};
+
+namespace {
+thread_local std::string g_group_create_error;
+int gfail(const SfmmGroup* g, int code, const std::string& msg) {
+    if (g) g->err = msg;
+    else g_group_create_error = msg;
+    return code;
+}
+}  // namespace
+
+extern "C" {
+
+SFMM_API const char* sfmm_group_last_error(const SfmmGroup* g) { return g ? g->err.c_str() : g_group_create_error.c_str(); }
+SFMM_API int32_t sfmm_group_size(const SfmmGroup* g) { return g ? static_cast<int32_t>(g->ctx.size()) : 0; }
+SFMM_API SfmmCtx* sfmm_group_context(SfmmGroup* g, int32_t i) {
+    return (g && i >= 0 && i < static_cast<int32_t>(g->ctx.size())) ? g->ctx[static_cast<size_t>(i)] : nullptr;
+}
+
+SFMM_API void sfmm_group_destroy(SfmmGroup* g) {
+    if (!g) return;
+    for (size_t i = 0; i < g->comms.size(); ++i)
+        if (g->comms[i]) {
+            cudaSetDevice(g->devices[i]);
+            g_nccl.CommDestroy(g->comms[i]);
+        }
+    for (SfmmCtx* c : g->ctx) sfmm_destroy(c);
+    delete g;
+}
+
+SFMM_API int sfmm_group_create(const SfmmConfig* cfg, int32_t n_devices, const int32_t* devices, SfmmGroup** out) {
+    if (!cfg || !out || n_devices < 1 || n_devices > 64) return gfail(nullptr, SFMM_EINVAL, "group_create: bad argument");
+    *out = nullptr;
+    try {
+        std::unique_ptr<SfmmGroup, void (*)(SfmmGroup*)> g(new SfmmGroup(), sfmm_group_destroy);
+        for (int32_t i = 0; i < n_devices; ++i) {
+            const int dev = devices ? devices[i] : i;
+            for (int d : g->devices)
+                if (d == dev) return gfail(nullptr, SFMM_EINVAL, "group_create: a device is listed twice");
+            SfmmConfig c = *cfg;
+            c.device = dev;
+            SfmmCtx* ctx = nullptr;
+            const int rc = sfmm_create(&c, &ctx);
+            if (rc) return gfail(nullptr, rc, std::string("group_create: device ") + std::to_string(dev) + ": " + sfmm_last_error(nullptr));
+            g->ctx.push_back(ctx);
+            g->devices.push_back(dev);
+        }
+        if (n_devices > 1) {  // one communicator per device, single process
+            if (!g_nccl.load()) return gfail(nullptr, SFMM_ENODEVICE, "group_create: NCCL could not be loaded (" + g_nccl.error + ")");
+            g->comms.assign(static_cast<size_t>(n_devices), nullptr);
+            const ncclResult_t r = g_nccl.CommInitAll(g->comms.data(), n_devices, g->devices.data());
+            if (r != ncclSuccess) {
+                g->comms.clear();
+                return gfail(nullptr, SFMM_ECUDA, std::string("ncclCommInitAll: ") + g_nccl.GetErrorString(r));
+            }
+        }
+        *out = g.release();
+        return SFMM_OK;
+    } catch (const std::exception& e) {
+        return gfail(nullptr, SFMM_ENOMEM, std::string("group_create: ") + e.what());
+    }
+}
+
+SFMM_API int sfmm_group_set_descriptors(SfmmGroup* g, int32_t n_images, const void* const* data, const int32_t* rows, int32_t cols,
+                                        const size_t* step_bytes, int32_t elem_type) {
+    if (!g) return SFMM_EINVAL;
+    g->owner.clear();
+    g->n_images = 0;
+    g->h2d_bytes = g->nccl_bytes = 0;
+    // member 0 packs and uploads (the only host->device copy of the descriptors); the others reserve the same layout
+    const int64_t h2d0 = g->ctx[0]->stats.h2d_bytes;
+    int rc = sfmm_set_descriptors(g->ctx[0], n_images, data, rows, cols, step_bytes, elem_type);
+    if (rc) return gfail(g, rc, std::string("member 0: ") + sfmm_last_error(g->ctx[0]));
+    g->h2d_bytes = g->ctx[0]->stats.h2d_bytes - h2d0;
+    for (size_t i = 1; i < g->ctx.size(); ++i)
+        if ((rc = sfmm_set_descriptors(g->ctx[i], n_images, nullptr, rows, cols, nullptr, elem_type)))
+            return gfail(g, rc, "member " + std::to_string(i) + ": " + sfmm_last_error(g->ctx[i]));
+    const size_t bytes = g->ctx[0]->blob_bytes;
+    if (g->ctx.size() > 1 && bytes) {
+        ncclResult_t r = g_nccl.GroupStart();
+        for (size_t i = 0; i < g->ctx.size() && r == ncclSuccess; ++i) {
+            cudaSetDevice(g->devices[i]);
+            r = g_nccl.Broadcast(g->ctx[i]->blob.p /* in place: only the root's is read */, g->ctx[i]->blob.p, bytes, ncclUint8, 0, g->comms[i],
+                                 g->ctx[i]->slot[0].stream);
+        }
+        const ncclResult_t r2 = g_nccl.GroupEnd();
+        if (r != ncclSuccess || r2 != ncclSuccess)
+            return gfail(g, SFMM_ECUDA, std::string("ncclBroadcast: ") + g_nccl.GetErrorString(r != ncclSuccess ? r : r2));
+        for (size_t i = 0; i < g->ctx.size(); ++i) {
+            cudaSetDevice(g->devices[i]);
+            const cudaError_t e = cudaStreamSynchronize(g->ctx[i]->slot[0].stream);
+            if (e != cudaSuccess) return gfail(g, SFMM_ECUDA, std::string("broadcast sync: ") + cudaGetErrorString(e));
+            g->ctx[i]->float_prepared = false;  // the blob was filled behind the context's back: re-derive norms / operand copies
+        }
+        g->nccl_bytes = static_cast<int64_t>(bytes) * static_cast<int64_t>(g->ctx.size() - 1);
+    }
+    g->n_images = n_images;
+    return SFMM_OK;
+}
+
+SFMM_API int sfmm_group_match_pairs(SfmmGroup* g, const int32_t* qt, int64_t n_pairs) {
+    if (!g || n_pairs < 0 || (n_pairs > 0 && !qt)) return SFMM_EINVAL;
+    if (g->ctx[0]->elem_type < 0) return gfail(g, SFMM_ESTATE, "group_match_pairs: sfmm_group_set_descriptors has not been called");
+    try {
+        const size_t nd = g->ctx.size();
+        const int64_t n = g->n_images;
+        const std::vector<int32_t>& rows = g->ctx[0]->rows;
+        for (int64_t i = 0; i < n_pairs; ++i)
+            if (qt[2 * i] < 0 || qt[2 * i] >= n || qt[2 * i + 1] < 0 || qt[2 * i + 1] >= n)
+                return gfail(g, SFMM_ERANGE, "group_match_pairs: image index out of range in pair list");
+        // cost-sorted snake deal (the rule of sfm_danpipeline_b200/distributed.py: shard_pairs), then ascending pair order per member
+        std::vector<int64_t> order(static_cast<size_t>(n_pairs));
+        for (int64_t i = 0; i < n_pairs; ++i) order[static_cast<size_t>(i)] = i;
+        std::stable_sort(order.begin(), order.end(), [&](int64_t a, int64_t b) {
+            return static_cast<int64_t>(rows[qt[2 * a]]) * rows[qt[2 * a + 1]] > static_cast<int64_t>(rows[qt[2 * b]]) * rows[qt[2 * b + 1]];
+        });
+        std::vector<std::vector<int64_t>> members(nd);
+        for (size_t pos = 0; pos < order.size(); ++pos) {
+            const size_t lap = pos / nd, off = pos % nd;
+            members[(lap % 2 == 0) ? off : nd - 1 - off].push_back(order[pos]);
+        }
+        if (g->owner.size() != static_cast<size_t>(n * n)) g->owner.assign(static_cast<size_t>(n * n), -1);
+        std::vector<std::vector<int32_t>> shard(nd);
+        for (size_t d = 0; d < nd; ++d) {
+            std::sort(members[d].begin(), members[d].end());
+            shard[d].reserve(2 * members[d].size());
+            for (int64_t k : members[d]) {
+                shard[d].push_back(qt[2 * k]);
+                shard[d].push_back(qt[2 * k + 1]);
+                g->owner[static_cast<size_t>(qt[2 * k]) * n + qt[2 * k + 1]] = static_cast<int8_t>(d);
+            }
+        }
+        std::vector<int> codes(nd, SFMM_OK);
+        std::vector<std::thread> pool;
+        for (size_t d = 1; d < nd; ++d)
+            pool.emplace_back([&, d]() { codes[d] = sfmm_match_pairs(g->ctx[d], shard[d].data(), static_cast<int64_t>(shard[d].size() / 2)); });
+        codes[0] = sfmm_match_pairs(g->ctx[0], shard[0].data(), static_cast<int64_t>(shard[0].size() / 2));
+        for (auto& t : pool) t.join();
+        for (size_t d = 0; d < nd; ++d)
+            if (codes[d]) return gfail(g, codes[d], "member " + std::to_string(d) + ": " + sfmm_last_error(g->ctx[d]));
+        return SFMM_OK;
+    } catch (const std::exception& e) {
+        return gfail(g, SFMM_ENOMEM, std::string("group_match_pairs: ") + e.what());
+    }
+}
+
+SFMM_API int sfmm_group_match_all_pairs(SfmmGroup* g) {
+    if (!g) return SFMM_EINVAL;
+    try {
+        for (SfmmCtx* c : g->ctx) clear_results(c);
+        std::fill(g->owner.begin(), g->owner.end(), static_cast<int8_t>(-1));
+        std::vector<int32_t> qt;  // findBestPair's enumeration, src/Sfm.cpp:511-512
+        const int64_t n = g->n_images;
+        qt.reserve(static_cast<size_t>(n > 1 ? n * (n - 1) : 0));
+        for (int32_t q = 0; q + 1 < n; ++q)
+            for (int32_t t = q + 1; t < n; ++t) {
+                qt.push_back(q);
+                qt.push_back(t);
+            }
+        return sfmm_group_match_pairs(g, qt.data(), static_cast<int64_t>(qt.size() / 2));
+    } catch (const std::exception& e) {
+        return gfail(g, SFMM_ENOMEM, std::string("group_match_all_pairs: ") + e.what());
+    }
+}
+
+SFMM_API int sfmm_group_get_pair(const SfmmGroup* g, int32_t q, int32_t t, const SfmDMatch** matches, int32_t* count) {
+    if (!g || !matches || !count) return SFMM_EINVAL;
+    if (q < 0 || q >= g->n_images || t < 0 || t >= g->n_images) return SFMM_ERANGE;
+    if (g->owner.empty()) return SFMM_ESTATE;
+    const int8_t o = g->owner[static_cast<size_t>(q) * g->n_images + t];
+    if (o < 0) return SFMM_ESTATE;
+    return sfmm_get_pair(g->ctx[static_cast<size_t>(o)], q, t, matches, count);
+}
+
+SFMM_API int sfmm_group_transfer_stats(const SfmmGroup* g, int64_t* h2d_bytes, int64_t* nccl_bytes) {
+    if (!g || !h2d_bytes || !nccl_bytes) return SFMM_EINVAL;
+    *h2d_bytes = g->h2d_bytes;
+    *nccl_bytes = g->nccl_bytes;
     return SFMM_OK;
 }
 

@@ -7,9 +7,11 @@ The reference is a single-threaded CPU loop over image pairs (findBestPair,
      to every other rank's blob (NCCL over NVLink) -- every rank holds all descriptors;
   2. the N(N-1)/2 pairs are dealt to ranks by a deterministic cost-balanced rule
      (cost = rows_q * rows_t) that every rank evaluates identically -- no scheduling traffic;
-  3. every rank matches its shard with the CUDA library (results stay on its device);
+  3. every rank matches its shard with the CUDA library, chunk by chunk (results stay on its device);
   4. per-pair counts and the packed cv::DMatch records are GATHERED to rank 0 (send/recv of
-     ragged segments), which copies them to host memory once and indexes them per pair.
+     ragged segments) as every chunk finishes; rank 0 copies chunk k to host memory on a side
+     stream while chunk k+1 is being matched (``match_and_gather``), and indexes the records per
+     pair.  (``gather_results`` is the one-shot form of the same step.)
 
 There is no collective inside the matching itself.  The same functions run on CPU tensors with
 the gloo backend (tests/test_distributed_cpu.py drives them with the oracle standing in for
@@ -66,11 +68,11 @@ def broadcast_descriptors(matcher, descriptors, src: int = 0, group=None):
     meta = [None]
     if rank == src:
         matcher.set_descriptors(descriptors)
-        meta[0] = (list(matcher.rows), int(matcher.cols))
+        meta[0] = (list(matcher.rows), int(matcher.cols), bool(matcher.elem_u8))
     dist.broadcast_object_list(meta, src=src, group=group)
-    rows, cols = meta[0]
+    rows, cols, elem_u8 = meta[0]
     if rank != src:
-        matcher.reserve_descriptors(rows, cols)
+        matcher.reserve_descriptors(rows, cols, elem_u8)
     ptr, nbytes = matcher.descriptor_blob()
     if nbytes:
         blob = device_bytes_as_tensor(ptr, nbytes, matcher.device)
@@ -80,23 +82,31 @@ def broadcast_descriptors(matcher, descriptors, src: int = 0, group=None):
 
 
 # --------------------------------------------------------------------------- gather
-_PINNED: dict = {}
+class _PinnedPool:
+    """Page-locked int32 buffers for the gathered records.  A fresh pinned allocation costs more than the copy
+    it serves, so buffers are recycled -- but never while a PairTable still views one: a table OWNS its buffer
+    (``PairTable._keep``) and a finalizer hands it back when the table is garbage collected."""
+
+    def __init__(self):
+        self.free: list[torch.Tensor] = []
+
+    def take(self, n_int32: int, pinned: bool) -> torch.Tensor:
+        best = None
+        for i, b in enumerate(self.free):
+            if b.numel() >= n_int32 and b.is_pinned() == pinned and (best is None or b.numel() < self.free[best].numel()):
+                best = i
+        if best is not None:
+            return self.free.pop(best)
+        n = max(n_int32 + n_int32 // 4, 1 << 16)
+        return torch.empty(n, dtype=torch.int32, pin_memory=pinned)
+
+    def give(self, buf: torch.Tensor):
+        self.free.append(buf)
+        self.free.sort(key=lambda b: b.numel())
+        del self.free[:-4]  # keep the four largest
 
 
-def _to_host(t: torch.Tensor) -> np.ndarray:
-    """Device -> host through a cached page-locked buffer (a fresh pinned allocation per call
-    would cost more than the copy)."""
-    if t.device.type != "cuda":
-        return t.numpy()
-    n = t.numel()
-    buf = _PINNED.get(t.dtype)
-    if buf is None or buf.numel() < n:
-        buf = torch.empty(max(n + n // 4, 1 << 16), dtype=t.dtype, pin_memory=True)
-        _PINNED[t.dtype] = buf
-    view = buf[:n].view(t.shape)
-    view.copy_(t, non_blocking=True)
-    torch.cuda.current_stream(t.device).synchronize()
-    return view.numpy()
+_POOL = _PinnedPool()
 
 
 @dataclass
@@ -105,7 +115,8 @@ class PairTable:
     pairs: np.ndarray    # (n,2) int32
     counts: np.ndarray   # (n,) int32
     offsets: np.ndarray  # (n,) int64
-    matches: np.ndarray  # (total,) DMATCH_DTYPE
+    matches: np.ndarray  # (total,) DMATCH_DTYPE -- a view of the buffer this table owns (valid as long as the table)
+    _keep: object = None
 
     def getMatching(self, idx_query: int, idx_train: int) -> np.ndarray:
         if not hasattr(self, "_index"):
@@ -163,27 +174,203 @@ def gather_results(pairs: np.ndarray, shards: list[np.ndarray], local_counts: to
         if len(c_h):
             counts[shards[r]] = c_h
             offsets[shards[r]] = base[r] + np.concatenate([[0], np.cumsum(c_h[:-1], dtype=np.int64)])
-    host = _to_host(all_matches).view(DMATCH_DTYPE).reshape(-1)  # the one device->host read (view of a reused pinned buffer)
-    return PairTable(pairs, counts, offsets, host)
+    # the one device->host read, into a buffer the table owns
+    buf = _POOL.take(all_matches.numel(), dev.type == "cuda")
+    view = buf[: all_matches.numel()].view(all_matches.shape)
+    view.copy_(all_matches, non_blocking=True)
+    if dev.type == "cuda":
+        torch.cuda.current_stream(dev).synchronize()
+    return _own(PairTable(pairs, counts, offsets, view.numpy().view(DMATCH_DTYPE).reshape(-1)), buf)
+
+
+def _own(table: "PairTable", buf: torch.Tensor) -> "PairTable":
+    import weakref
+    table._keep = buf
+    weakref.finalize(table, _POOL.give, buf)
+    return table
+
+
+# --------------------------------------------------------------------------- pipelined match + gather
+def chunk_bounds(shard_rows_q: np.ndarray, n_chunks: int) -> list[tuple[int, int]]:
+    """Cut one rank's pair list (query-row count per pair, in shard order) into `n_chunks` contiguous ranges of
+    about equal query rows (~ equal work).  Deterministic: every rank computes every other rank's cuts."""
+    n = len(shard_rows_q)
+    if n == 0:
+        return [(0, 0)] * n_chunks
+    csum = np.cumsum(shard_rows_q, dtype=np.int64)
+    cuts = [0]
+    for k in range(1, n_chunks):
+        cuts.append(max(cuts[-1], int(np.searchsorted(csum, csum[-1] * k / n_chunks, side="left"))))
+    cuts.append(n)
+    return [(cuts[k], cuts[k + 1]) for k in range(n_chunks)]
+
+
+def gather_chunks(pairs: np.ndarray, shards: list[np.ndarray], rows) -> int:
+    """How many chunks the pipelined gather uses: one per ~4 Mi query rows of the busiest rank (a few ms of
+    matching each on a B200 -- long enough to hide a chunk's transfer, short enough that the last, unhidden
+    chunk is a small fraction), between 1 and 16.  The same on every rank."""
+    rows = np.asarray(rows, np.int64)
+    busiest = max((int(rows[pairs[sh, 0]].sum()) for sh in shards if len(sh)), default=0)
+    return int(min(16, max(1, -(-busiest // (4 << 20)))))
+
+
+def match_and_gather(match_fn, pairs: np.ndarray, shards: list[np.ndarray], rows, dst: int = 0, group=None,
+                     n_chunks: int | None = None):
+    """Steps 3 + 4, pipelined: every rank matches its shard in `n_chunks` pieces; as soon as a piece is done its
+    counts and records travel to `dst` (two point-to-point messages per rank: counts first, so that `dst` can size
+    the second), and `dst` copies piece k to host memory on a side stream while piece k+1 is being matched.  What
+    stays exposed at the end is the last piece only.
+
+    match_fn(pairs_chunk, slot) -> (counts int32[n], records int32[m, 4]) on this rank's device (or CPU tensors under
+    gloo); `slot` (0..2) names the output buffer set it may reuse -- a set is only reused three pieces later, when its
+    sends / copies have long finished.  Returns a PairTable on `dst`, None elsewhere."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    rows = np.asarray(rows, np.int64)
+    K = n_chunks or gather_chunks(pairs, shards, rows)
+    bounds = [chunk_bounds(rows[pairs[sh, 0]] if len(sh) else np.zeros(0, np.int64), K) for sh in shards]
+    mine = pairs[shards[rank]]
+
+    if rank != dst:
+        inflight: list[list] = [[], [], []]
+        for k in range(K):
+            lo, hi = bounds[rank][k]
+            slot = k % 3
+            for w in inflight[slot]:
+                w.wait()
+            inflight[slot] = []
+            if hi == lo:
+                continue
+            counts, recs = match_fn(mine[lo:hi], slot)
+            inflight[slot].append(dist.isend(counts, dst, group=group))
+            if recs.shape[0]:
+                inflight[slot].append(dist.isend(recs, dst, group=group))
+        for ws in inflight:
+            for w in ws:
+                w.wait()
+        return None
+
+    # ---- destination rank
+    dev = None
+    counts = np.zeros(len(pairs), np.int32)
+    offsets = np.zeros(len(pairs), np.int64)
+    worst = int(rows[pairs[:, 0]].sum()) if len(pairs) else 0
+    cap = min(worst, max(worst // 4, 1 << 16))  # records; synthetic and real data keep ~1/8 of the query rows
+    buf = None
+    host = None  # int32 [cap, 4] view of buf
+    used = 0
+    side = None
+    staging = [None, None, None]   # device buffers the other ranks' records land in, per slot
+    events = [None, None, None]
+
+    def ensure_host(n_records: int, pinned: bool):
+        nonlocal buf, host, cap
+        if host is not None and n_records <= cap:
+            return
+        if host is not None:  # grow: rare (more than a quarter of all query rows matched)
+            if side is not None:
+                side.synchronize()
+            cap = max(n_records, min(worst, 2 * cap))
+            nbuf = _POOL.take(cap * 4, pinned)
+            nbuf[: used * 4].copy_(buf[: used * 4])
+            _POOL.give(buf)
+            buf = nbuf
+        else:
+            cap = max(cap, n_records)
+            buf = _POOL.take(cap * 4, pinned)
+        cap = buf.numel() // 4
+        host = buf[: cap * 4].view(cap, 4)
+
+    for k in range(K):
+        slot = k % 3
+        lo, hi = bounds[rank][k]
+        own_counts = own_recs = None
+        if events[slot] is not None:
+            events[slot].synchronize()  # this slot's previous copies to the host (three pieces ago) have finished
+        if hi > lo:
+            own_counts, own_recs = match_fn(mine[lo:hi], slot)
+            dev = own_counts.device
+        if dev is None:
+            dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+        is_cuda = dev.type == "cuda"
+        if is_cuda and side is None:
+            side = torch.cuda.Stream(dev)
+        # phase 1: the other ranks' counts of piece k
+        peers = [r for r in range(world) if r != rank and bounds[r][k][1] > bounds[r][k][0]]
+        sizes = [bounds[r][k][1] - bounds[r][k][0] for r in peers]
+        cbuf = torch.empty(sum(sizes), dtype=torch.int32, device=dev)
+        cparts = list(cbuf.split(sizes)) if peers else []
+        ops = [dist.P2POp(dist.irecv, cparts[i], r, group) for i, r in enumerate(peers)]
+        for w in (dist.batch_isend_irecv(ops) if ops else []):
+            w.wait()
+        c_h = cbuf.cpu().numpy() if peers else np.zeros(0, np.int32)  # (synchronises: the sizes of phase 2)
+        own_c_h = own_counts.cpu().numpy() if own_counts is not None else np.zeros(0, np.int32)
+        totals = [int(x.sum()) for x in np.split(c_h, np.cumsum(sizes)[:-1])] if peers else []
+        own_total = int(own_c_h.sum())
+        ensure_host(used + own_total + sum(totals), is_cuda)
+        # phase 2: their records, into this slot's staging buffer
+        need = sum(totals)
+        if staging[slot] is None or staging[slot].shape[0] < need:
+            staging[slot] = torch.empty((max(need + need // 4, 1), 4), dtype=torch.int32, device=dev)
+        sparts, o = [], 0
+        for t in totals:
+            sparts.append(staging[slot][o: o + t])
+            o += t
+        ops = [dist.P2POp(dist.irecv, sparts[i], r, group) for i, r in enumerate(peers) if totals[i]]
+        works = dist.batch_isend_irecv(ops) if ops else []
+        for w in works:
+            w.wait()  # NCCL: the current stream waits, the host does not
+        # directory of piece k: records are laid out in arrival order (own, then peers in rank order)
+        def place(r, lo_r, c_arr, start):
+            idx = shards[r][lo_r: lo_r + len(c_arr)]
+            counts[idx] = c_arr
+            offsets[idx] = start + np.concatenate([[0], np.cumsum(c_arr[:-1], dtype=np.int64)]) if len(c_arr) else start
+        own_at = used
+        if own_counts is not None:
+            place(rank, lo, own_c_h, used)
+        used += own_total
+        peers_at = used
+        for i, r in enumerate(peers):
+            place(r, bounds[r][k][0], c_h[sum(sizes[:i]): sum(sizes[:i + 1])], used)
+            used += totals[i]
+        # device -> host of piece k on the side stream: overlaps the matching of piece k+1
+        if is_cuda:
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                if own_total:
+                    host[own_at: own_at + own_total].copy_(own_recs[:own_total], non_blocking=True)
+                if need:
+                    host[peers_at: peers_at + need].copy_(staging[slot][:need], non_blocking=True)
+                events[slot] = torch.cuda.Event()
+                events[slot].record(side)
+        else:
+            if own_total:
+                host[own_at: own_at + own_total].copy_(own_recs[:own_total])
+            if need:
+                host[peers_at: peers_at + need].copy_(staging[slot][:need])
+    if side is not None:
+        side.synchronize()
+    ensure_host(used, dev is not None and dev.type == "cuda")
+    return _own(PairTable(pairs, counts, offsets, host[:used].numpy().view(DMATCH_DTYPE).reshape(-1)), buf)
 
 
 # --------------------------------------------------------------------------- one rank's shard
 _SHARD_BUF: dict = {}
 
 
-def match_shard(matcher, mine: np.ndarray, rows, fraction: float = 0.25):
+def match_shard(matcher, mine: np.ndarray, rows, fraction: float = 0.25, slot: int = 0):
     """Step 3: match this rank's pairs, results left in torch-owned device buffers.
 
     The worst case is one record per query row (16 B each: 20 GB per rank at cfg-5), so the buffer
     is first sized for `fraction` of that (synthetic and real data keep ~1/8) and the call is
-    repeated with the full size if the library reports SFMM_ERANGE.  Buffers are cached per device.
+    repeated with the full size if the library reports SFMM_ERANGE.  Buffers are cached per (device, slot)
+    and REUSED by the next call with the same slot: what is returned are views of them, valid until then.
     Returns (counts int32[len(mine)], matches int32[n,4], n)."""
     from ._lib import SFMM_ERANGE, SfmmError
     dev = torch.device("cuda", matcher.device)
     worst = int(np.asarray(rows, np.int64)[mine[:, 0]].sum()) if len(mine) else 0
     cap = min(worst, max(int(worst * fraction), 1 << 20))
     while True:
-        key = (matcher.device,)
+        key = (matcher.device, slot)
         buf = _SHARD_BUF.get(key)
         if buf is None or buf[0].numel() < max(len(mine), 1) or buf[1].shape[0] < max(cap, 1):
             buf = (torch.empty(max(len(mine), 1), dtype=torch.int32, device=dev),
@@ -201,10 +388,10 @@ def match_shard(matcher, mine: np.ndarray, rows, fraction: float = 0.25):
 
 
 # --------------------------------------------------------------------------- the whole job
-def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, resident: bool = False):
+def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, resident: bool = False, pipelined: bool = True):
     """Steps 1-4 on every rank of the default (NCCL) group.  `descriptors` is read on rank `dst`
-    only; `resident=True` skips step 1 (descriptors already broadcast).  Returns
-    (PairTable on dst | None, info dict)."""
+    only; `resident=True` skips step 1 (descriptors already broadcast); `pipelined=False` matches the whole
+    shard first and gathers once at the end (gather_results).  Returns (PairTable on dst | None, info dict)."""
     import os
     import time
     trace = os.environ.get("SFMM_TRACE") == "1"
@@ -218,10 +405,20 @@ def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, 
     shards = shard_pairs(pairs, rows, world)
     mine = pairs[shards[rank]]
     t2 = time.perf_counter()
-    d_counts, d_matches, n = match_shard(matcher, mine, rows)
-    t3 = time.perf_counter()
-    table = gather_results(pairs, shards, d_counts, d_matches, dst, group)
-    t4 = time.perf_counter()
+    n = 0
+    if pipelined:
+        def match_fn(chunk, slot):
+            nonlocal n
+            c, m, k = match_shard(matcher, chunk, rows, slot=slot)
+            n += k
+            return c, m
+        table = match_and_gather(match_fn, pairs, shards, rows, dst, group)
+        t3 = t4 = time.perf_counter()
+    else:
+        d_counts, d_matches, n = match_shard(matcher, mine, rows)
+        t3 = time.perf_counter()
+        table = gather_results(pairs, shards, d_counts, d_matches, dst, group)
+        t4 = time.perf_counter()
     info = {"pairs_local": len(mine), "matches_local": n,
             "ms": {"broadcast": 1e3 * (t1 - t0), "shard": 1e3 * (t2 - t1), "match": 1e3 * (t3 - t2), "gather": 1e3 * (t4 - t3)}}
     if trace and rank == dst:

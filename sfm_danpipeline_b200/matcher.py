@@ -42,6 +42,7 @@ class Matcher:
         self.norm, self.device = int(norm), int(device)
         self.rows: list[int] = []
         self.cols = 0
+        self.elem_u8 = self.norm == NORM_HAMMING
 
     # -- lifetime -------------------------------------------------------------------------
     def close(self):
@@ -68,30 +69,18 @@ class Matcher:
     # -- descriptors ----------------------------------------------------------------------
     def set_descriptors(self, descriptors: Sequence[np.ndarray]):
         """imagesDescriptors: one (rows_i, cols) uint8 / float32 array per image (rows may be strided)."""
-        n = len(descriptors)
-        want = np.uint8 if self.norm == NORM_HAMMING else np.float32
-        cols = descriptors[0].shape[1] if n else 1
-        keep = []
-        for d in descriptors:
-            if d.ndim != 2 or d.dtype != want or d.shape[1] != cols:
-                raise SfmmError(_lib.SFMM_EINVAL, f"every descriptor set must be (rows, {cols}) {want.__name__}")
-            if d.shape[0] and d.strides[1] != d.itemsize:
-                d = np.ascontiguousarray(d)
-            keep.append(d)
-        ptrs = (C.c_void_p * max(n, 1))(*[d.ctypes.data if d.shape[0] else None for d in keep])
-        rows = (C.c_int32 * max(n, 1))(*[d.shape[0] for d in keep])
-        steps = (C.c_size_t * max(n, 1))(*[d.strides[0] if d.shape[0] > 1 else d.shape[1] * d.itemsize for d in keep])
-        self._check(self._L.sfmm_set_descriptors(self._ctx, n, ptrs, rows, cols, steps,
-                                                 _lib.U8 if want is np.uint8 else _lib.F32))
-        self.rows, self.cols = [d.shape[0] for d in keep], cols
+        ptrs, rows, steps, cols, elem, keep = _marshal_descriptors(descriptors, self.norm)
+        self._check(self._L.sfmm_set_descriptors(self._ctx, len(keep), ptrs, rows, cols, steps, elem))
+        self.rows, self.cols, self.elem_u8 = [d.shape[0] for d in keep], cols, elem == _lib.U8
 
-    def reserve_descriptors(self, rows: Sequence[int], cols: int):
+    def reserve_descriptors(self, rows: Sequence[int], cols: int, elem_u8: bool | None = None):
         """Allocate the device layout only (non-root ranks, before the blob broadcast)."""
         n = len(rows)
         r = (C.c_int32 * max(n, 1))(*[int(x) for x in rows])
-        self._check(self._L.sfmm_set_descriptors(self._ctx, n, None, r, int(cols), None,
-                                                 _lib.U8 if self.norm == NORM_HAMMING else _lib.F32))
-        self.rows, self.cols = [int(x) for x in rows], int(cols)
+        if elem_u8 is None:
+            elem_u8 = self.norm == NORM_HAMMING
+        self._check(self._L.sfmm_set_descriptors(self._ctx, n, None, r, int(cols), None, _lib.U8 if elem_u8 else _lib.F32))
+        self.rows, self.cols, self.elem_u8 = [int(x) for x in rows], int(cols), bool(elem_u8)
 
     def descriptor_blob(self) -> tuple[int, int]:
         """(device pointer, bytes) of the packed descriptor blob."""
@@ -119,7 +108,10 @@ class Matcher:
     def getMatching(self, idx_query: int, idx_train: int) -> np.ndarray:
         """The reference's entry point: the ratio-filtered 1-NN list of (idx_query, idx_train)."""
         p, n = C.c_void_p(), C.c_int32()
-        self._check(self._L.sfmm_get_pair(self._ctx, int(idx_query), int(idx_train), C.byref(p), C.byref(n)))
+        rc = self._L.sfmm_get_pair(self._ctx, int(idx_query), int(idx_train), C.byref(p), C.byref(n))
+        if rc != 0:  # look-ups do not set the library's error text
+            raise SfmmError(rc, {_lib.SFMM_ESTATE: "pair has not been matched (match_all_pairs / match_pairs first)",
+                                 _lib.SFMM_ERANGE: "image index out of range"}.get(rc, "getMatching failed"))
         if n.value == 0:
             return np.zeros(0, DMATCH_DTYPE)
         buf = (C.c_char * (n.value * DMATCH_DTYPE.itemsize)).from_address(p.value)
@@ -179,7 +171,9 @@ class Matcher:
     def aligned_points(self, idx_query: int, idx_train: int):
         """(alignedL, alignedR): (count, 2) float64 arrays in match order (src/Sfm.cpp:694-711)."""
         l, r, n = C.c_void_p(), C.c_void_p(), C.c_int32()
-        self._check(self._L.sfmm_get_pair_points(self._ctx, int(idx_query), int(idx_train), C.byref(l), C.byref(r), C.byref(n)))
+        rc = self._L.sfmm_get_pair_points(self._ctx, int(idx_query), int(idx_train), C.byref(l), C.byref(r), C.byref(n))
+        if rc != 0:
+            raise SfmmError(rc, "pair not matched with points (set_points before matching; not restored by load_table)")
         if n.value == 0:
             return np.zeros((0, 2)), np.zeros((0, 2))
 
@@ -201,4 +195,99 @@ class Matcher:
     def stats(self) -> dict:
         s = _lib.SfmmStats()
         self._check(self._L.sfmm_get_stats(self._ctx, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in s._fields_}
+
+
+def _marshal_descriptors(descriptors, norm):
+    """(ptrs, rows, steps, cols, elem) ctypes arguments of sfmm_set_descriptors + the arrays that must stay alive."""
+    n = len(descriptors)
+    want = np.uint8 if norm == NORM_HAMMING else (np.uint8 if n and descriptors[0].dtype == np.uint8 else np.float32)
+    cols = descriptors[0].shape[1] if n else 1
+    keep = []
+    for d in descriptors:
+        if d.ndim != 2 or d.dtype != want or d.shape[1] != cols:
+            raise SfmmError(_lib.SFMM_EINVAL, f"every descriptor set must be (rows, {cols}) {want.__name__}")
+        if d.shape[0] and d.strides[1] != d.itemsize:
+            d = np.ascontiguousarray(d)
+        keep.append(d)
+    ptrs = (C.c_void_p * max(n, 1))(*[d.ctypes.data if d.shape[0] else None for d in keep])
+    rows = (C.c_int32 * max(n, 1))(*[d.shape[0] for d in keep])
+    steps = (C.c_size_t * max(n, 1))(*[d.strides[0] if d.shape[0] > 1 else d.shape[1] * d.itemsize for d in keep])
+    return ptrs, rows, steps, cols, (_lib.U8 if want is np.uint8 else _lib.F32), keep
+
+
+class GroupMatcher:
+    """Every B200 of the box from ONE process (sfmm_group_*): descriptors uploaded once and broadcast with NCCL
+    (single-process ncclCommInitAll inside the library), pairs dealt to the devices, getMatching as a look-up.
+    The shape a patched single-process iTree3DMap would use; torch is not involved."""
+
+    def __init__(self, n_devices: int, norm: int = NORM_L2, ratio: float = 0.8, cross_check: bool = False,
+                 devices: Sequence[int] | None = None, float_mode: int = _lib.FLOAT_AUTO, binary_engine: int = _lib.BINARY_AUTO):
+        self._L = _lib.load()
+        cfg = _lib.SfmmConfig()
+        self._L.sfmm_default_config(C.byref(cfg))
+        cfg.norm, cfg.ratio, cfg.cross_check = int(norm), float(ratio), int(bool(cross_check))
+        cfg.float_mode, cfg.binary_engine = int(float_mode), int(binary_engine)
+        devs = (C.c_int32 * n_devices)(*[int(d) for d in devices]) if devices is not None else None
+        self._g = C.c_void_p()
+        rc = self._L.sfmm_group_create(C.byref(cfg), int(n_devices), devs, C.byref(self._g))
+        if rc != 0:
+            raise SfmmError(rc, self._L.sfmm_group_last_error(None).decode())
+        self.norm = int(norm)
+        self.rows: list[int] = []
+
+    def close(self):
+        if getattr(self, "_g", None) and self._g.value:
+            self._L.sfmm_group_destroy(self._g)
+            self._g = C.c_void_p()
+
+    __del__ = close
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def _check(self, rc: int):
+        if rc != 0:
+            raise SfmmError(rc, self._L.sfmm_group_last_error(self._g).decode())
+
+    @property
+    def size(self) -> int:
+        return int(self._L.sfmm_group_size(self._g))
+
+    def set_descriptors(self, descriptors: Sequence[np.ndarray]):
+        ptrs, rows, steps, cols, elem, keep = _marshal_descriptors(descriptors, self.norm)
+        self._check(self._L.sfmm_group_set_descriptors(self._g, len(keep), ptrs, rows, cols, steps, elem))
+        self.rows = [d.shape[0] for d in keep]
+
+    def match_all_pairs(self):
+        self._check(self._L.sfmm_group_match_all_pairs(self._g))
+
+    def match_pairs(self, pairs):
+        qt = np.ascontiguousarray(np.asarray(pairs, np.int32).reshape(-1, 2))
+        self._check(self._L.sfmm_group_match_pairs(self._g, qt.ctypes.data, len(qt)))
+
+    def getMatching(self, idx_query: int, idx_train: int) -> np.ndarray:
+        p, n = C.c_void_p(), C.c_int32()
+        rc = self._L.sfmm_group_get_pair(self._g, int(idx_query), int(idx_train), C.byref(p), C.byref(n))
+        if rc != 0:
+            raise SfmmError(rc, "pair has not been matched" if rc == _lib.SFMM_ESTATE else "image index out of range")
+        if n.value == 0:
+            return np.zeros(0, DMATCH_DTYPE)
+        buf = (C.c_char * (n.value * DMATCH_DTYPE.itemsize)).from_address(p.value)
+        return np.frombuffer(buf, DMATCH_DTYPE).copy()
+
+    def transfer_stats(self) -> dict:
+        a, b = C.c_int64(), C.c_int64()
+        self._check(self._L.sfmm_group_transfer_stats(self._g, C.byref(a), C.byref(b)))
+        return {"h2d_bytes": a.value, "nccl_bytes": b.value}
+
+    def member_stats(self, i: int) -> dict:
+        s = _lib.SfmmStats()
+        ctx = self._L.sfmm_group_context(self._g, int(i))
+        rc = self._L.sfmm_get_stats(ctx, C.byref(s))
+        if rc != 0:
+            raise SfmmError(rc, "no such member")
         return {k: getattr(s, k) for k, _ in s._fields_}

@@ -11,6 +11,9 @@ SETS = {  # name -> (norm, descriptor dtype)
     "synth_binary": (0, np.uint8),
     "temple_sift": (1, np.float32),
     "synth_float": (1, np.float32),
+    # the reference's literal call for detectors 2 and 3: NORM_L2 over CV_8U rows (src/Sfm.cpp:593)
+    "temple_orb_l2": (1, np.uint8),
+    "temple_akaze_l2": (1, np.uint8),
 }
 
 

@@ -14,7 +14,7 @@ int main(int argc, char** argv) {
     if (argc < 2) return 2;
     FILE* f = fopen(argv[1], "rb");
     if (!f) return 2;
-    int32_t hdr[4];  // n_images, cols, depth(0=u8,1=f32), cross
+    int32_t hdr[5];  // n_images, cols, depth(0=u8,1=f32), cross, norm(0=HAMMING,1=L2; L2 over CV_8U rows = the reference's literal call)
     if (!rd(f, hdr, sizeof hdr)) return 2;
     const int n = hdr[0], cols = hdr[1], depth = hdr[2] ? CV_32F : CV_8U, esz = hdr[2] ? 4 : 1;
     std::vector<int32_t> rows(n);
@@ -27,7 +27,7 @@ int main(int argc, char** argv) {
         if (rows[i]) imagesDescriptors[i] = cv::Mat(rows[i], cols, depth, store[i].data());
     }
     try {
-        sfmm::AllPairsMatcher matcher(hdr[2] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
+        sfmm::AllPairsMatcher matcher(hdr[4] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
         matcher.compute(imagesDescriptors);
         for (int q = 0; q < n - 1; ++q)
             for (int t = q + 1; t < n; ++t) {
@@ -44,7 +44,7 @@ int main(int argc, char** argv) {
             std::vector<std::vector<cv::Point2d> > pts(n);
             for (int i = 0; i < n; ++i)
                 for (int r = 0; r < rows[i]; ++r) pts[i].push_back(cv::Point2d(i * 1000.0 + r, -0.5 * r));
-            sfmm::AllPairsMatcher m2(hdr[2] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
+            sfmm::AllPairsMatcher m2(hdr[4] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
             m2.compute(imagesDescriptors, pts);
             for (int q = 0; q < n - 1; ++q)
                 for (int t = q + 1; t < n; ++t) {
@@ -59,7 +59,7 @@ int main(int argc, char** argv) {
                 }
             const std::string path = std::string(argv[1]) + ".tbl";
             m2.saveTable(path);
-            sfmm::AllPairsMatcher m3(hdr[2] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
+            sfmm::AllPairsMatcher m3(hdr[4] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
             m3.loadTable(imagesDescriptors, path);
             for (int q = 0; q < n - 1; ++q)
                 for (int t = q + 1; t < n; ++t) {
@@ -72,9 +72,9 @@ int main(int argc, char** argv) {
         {   // single process, several devices (as many as the box has, at most 2 here): same lists
             int n_dev = 1;
             if (argc > 2) n_dev = atoi(argv[2]);
-            sfmm::MultiGpuMatcher multi(n_dev, hdr[2] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0);
+            sfmm::MultiGpuMatcher multi(n_dev, hdr[4] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0);
             multi.compute(imagesDescriptors);
-            sfmm::AllPairsMatcher single(hdr[2] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
+            sfmm::AllPairsMatcher single(hdr[4] ? cv::NORM_L2 : cv::NORM_HAMMING, 0.8f, hdr[3] != 0, 0);
             single.compute(imagesDescriptors);
             for (int q = 0; q < n - 1; ++q)
                 for (int t = q + 1; t < n; ++t) {
@@ -84,6 +84,15 @@ int main(int argc, char** argv) {
                     if (a.size() != b.size() || (a.size() && memcmp(static_cast<const void*>(a.data()), b.data(), a.size() * sizeof(cv::DMatch)))) { printf("multi-gpu mismatch %d,%d\n", q, t); return 1; }
                 }
             printf("multi-gpu ok on %d device(s)\n", multi.devices());
+        }
+        {   // a mixed set (different widths) must be refused, not read out of bounds
+            std::vector<cv::Mat> bad = imagesDescriptors;
+            std::vector<unsigned char> narrow(64, 0);
+            bad.push_back(cv::Mat(2, cols > 8 ? cols - 8 : cols + 8, depth, narrow.data()));
+            bool refused = false;
+            try { matcher.upload(bad); } catch (const sfmm::Error& e) { refused = e.code == SFMM_EINVAL; }
+            if (!refused) { printf("mixed descriptor widths were accepted\n"); return 1; }
+            matcher.compute(imagesDescriptors);
         }
         std::vector<cv::DMatch> rev;  // q>t is never asked by the reference; the adapter computes it on demand
         matcher.getMatching(1, 0, &rev);

@@ -21,12 +21,14 @@ struct Point2d {
     double x, y;
 };
 struct Mat {  // continuous row-major matrix header over caller memory
-    Mat() : rows(0), cols(0), data(nullptr), step(0), depth_(CV_8U) {}
+    Mat() : dims(2), rows(0), cols(0), data(nullptr), step(0), depth_(CV_8U) {}
     Mat(int r, int c, int depth, void* d, size_t s = 0)
-        : rows(r), cols(c), data(static_cast<unsigned char*>(d)), step(s ? s : static_cast<size_t>(c) * (depth == CV_32F ? 4 : 1)), depth_(depth) {}
+        : dims(2), rows(r), cols(c), data(static_cast<unsigned char*>(d)), step(s ? s : static_cast<size_t>(c) * (depth == CV_32F ? 4 : 1)), depth_(depth) {}
     bool empty() const { return rows == 0 || cols == 0 || data == nullptr; }
     int depth() const { return depth_; }
-    int rows, cols;
+    int channels() const { return 1; }
+    size_t elemSize() const { return depth_ == CV_32F ? 4 : 1; }
+    int dims, rows, cols;
     unsigned char* data;
     size_t step;
     int depth_;

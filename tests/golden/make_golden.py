@@ -75,8 +75,27 @@ def temple_gray():
     return [cv2.cvtColor(cv2.imread(f), cv2.COLOR_BGR2GRAY) for f in files]
 
 
+def main_l2_on_bytes(imgs):
+    """The reference's LITERAL call for its binary detectors: cv::BFMatcher(cv::NORM_L2) is hard-wired at
+    src/Sfm.cpp:593 whatever `detector` is, so AKAZE (detector 2) and ORB (detector 3) rows are matched with L2
+    over the bytes (OpenCV's batchDistL2_8u32f)."""
+    orb = cv2.ORB_create(500, 1.2, 8, 31, 0, 2, cv2.ORB_HARRIS_SCORE, 31, 20)
+    d = [orb.detectAndCompute(g, None)[1] for g in imgs]
+    rec = build_set(d, cv2.NORM_L2)
+    np.savez_compressed(os.path.join(HERE, "temple_orb_l2.npz"), **rec)
+    print("orb/L2 matches", int(rec["match_count"].sum()), "cross", int(rec["match_cross"].sum()))
+    akaze = cv2.AKAZE_create(cv2.AKAZE_DESCRIPTOR_MLDB, 0, 3, 0.001, 4, 4, cv2.KAZE_DIFF_PM_G2)
+    d = [akaze.detectAndCompute(g, None)[1] for g in imgs[:4]]  # four images, six pairs: keeps the file small
+    rec = build_set(d, cv2.NORM_L2)
+    np.savez_compressed(os.path.join(HERE, "temple_akaze_l2.npz"), **rec)
+    print("akaze/L2 (4 images) matches", int(rec["match_count"].sum()), "cross", int(rec["match_cross"].sum()))
+
+
 def main():
     imgs = temple_gray()
+    if "--only-l2-on-bytes" in sys.argv:
+        return main_l2_on_bytes(imgs)
+    main_l2_on_bytes(imgs)
 
     akaze = cv2.AKAZE_create(cv2.AKAZE_DESCRIPTOR_MLDB, 0, 3, 0.001, 4, 4, cv2.KAZE_DIFF_PM_G2)
     d = [akaze.detectAndCompute(g, None)[1] for g in imgs]

@@ -106,3 +106,18 @@ def test_default_engines_are_auto():
     cfg = _lib.SfmmConfig()
     _lib.load().sfmm_default_config(C.byref(cfg))
     assert cfg.binary_engine == _lib.BINARY_AUTO and cfg.float_mode == _lib.FLOAT_AUTO
+
+
+@pytest.mark.skipif(_has_gpu(), reason="only meaningful without a CUDA device")
+def test_group_without_gpu_is_an_error_too():
+    from sfm_danpipeline_b200 import GroupMatcher
+    with pytest.raises(SfmmError) as e:
+        GroupMatcher(2, _lib.NORM_HAMMING)
+    assert e.value.code == _lib.SFMM_ENODEVICE
+
+
+def test_nccl_is_not_a_link_time_dependency():
+    """The group API dlopens NCCL on first use: a single-GPU user never needs it installed."""
+    import subprocess
+    out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nccl" not in out.lower()

@@ -31,7 +31,7 @@ def test_adapter_compiles_as_cxx11_against_the_abi():
 
 def _write_case(path, descs, norm, cross):
     with open(path, "wb") as f:
-        f.write(np.array([len(descs), descs[0].shape[1], norm, int(cross)], np.int32).tobytes())
+        f.write(np.array([len(descs), descs[0].shape[1], int(descs[0].dtype == np.float32), int(cross), norm], np.int32).tobytes())
         f.write(np.array([d.shape[0] for d in descs], np.int32).tobytes())
         for d in descs:
             f.write(np.ascontiguousarray(d).tobytes())
@@ -42,18 +42,19 @@ def _write_case(path, descs, norm, cross):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("kind,cross", [("binary", False), ("binary", True), ("float", False)])
+@pytest.mark.parametrize("kind,cross", [("binary", False), ("binary", True), ("float", False), ("binary_l2", False)])
 def test_patched_getmatching_equals_oracle(tmp_path, kind, cross):
+    """binary_l2 = the default-constructed adapter (cv::NORM_L2, like src/Sfm.cpp:593) over CV_8U Mats."""
     exe = _build()
-    if kind == "binary":
-        descs, norm = synth.binary_images(4, [600, 0, 333, 1030], seed=21), 0
+    if kind.startswith("binary"):
+        descs, norm = synth.binary_images(4, [600, 0, 333, 1030], seed=21), (1 if kind == "binary_l2" else 0)
         descs[1] = np.zeros((0, 61), np.uint8)
     else:
         descs, norm = synth.float_images(3, [300, 200, 150], seed=22), 1
     case = str(tmp_path / "case.bin")
     _write_case(case, descs, norm, cross)
     import torch
-    n_dev = min(torch.cuda.device_count(), 2)
+    n_dev = torch.cuda.device_count()  # every visible GPU: the group broadcasts with NCCL when there is more than one
     r = subprocess.run([exe, case, str(n_dev)], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
     assert "adapter ok" in r.stdout and f"multi-gpu ok on {n_dev} device(s)" in r.stdout

@@ -44,7 +44,17 @@ def _free_port():
     return p
 
 
-def _worker(rank, world, port, rows_list, out_path):
+def _oracle_match_fn(descs):
+    """Stands in for the CUDA matcher: (pairs chunk, slot) -> (counts, records) as CPU tensors."""
+    def fn(chunk, slot):
+        res = [oracle.match_pair(descs[q], descs[t], 0) for q, t in chunk]
+        counts = torch.tensor([len(r) for r in res], dtype=torch.int32)
+        cat = np.concatenate(res) if res else np.zeros(0, oracle.DMATCH_DTYPE)
+        return counts, torch.from_numpy(cat.view(np.int32).reshape(-1, 4).copy())
+    return fn
+
+
+def _worker(rank, world, port, rows_list, out_path, n_chunks=0):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
@@ -53,11 +63,11 @@ def _worker(rank, world, port, rows_list, out_path):
         pairs = D.all_pairs(len(descs))
         shards = D.shard_pairs(pairs, rows_list, world)
         mine = pairs[shards[rank]]
-        res = [oracle.match_pair(descs[q], descs[t], 0) for q, t in mine]
-        counts = torch.tensor([len(r) for r in res], dtype=torch.int32)
-        cat = np.concatenate(res) if res else np.zeros(0, oracle.DMATCH_DTYPE)
-        matches = torch.from_numpy(cat.view(np.int32).reshape(-1, 4).copy())
-        table = D.gather_results(pairs, shards, counts, matches, dst=0)
+        if n_chunks:  # the pipelined form: matched and gathered piece by piece
+            table = D.match_and_gather(_oracle_match_fn(descs), pairs, shards, rows_list, dst=0, n_chunks=n_chunks)
+        else:
+            counts, matches = _oracle_match_fn(descs)(mine, 0)
+            table = D.gather_results(pairs, shards, counts, matches, dst=0)
         if rank == 0:
             ok = True
             for i, (q, t) in enumerate(pairs):
@@ -77,3 +87,38 @@ def test_gather_to_rank0_over_gloo(tmp_path, world, rows):
     out = str(tmp_path / "result.txt")
     mp.spawn(_worker, args=(world, _free_port(), rows, out), nprocs=world, join=True)
     assert open(out).read() == "ok"
+
+
+@pytest.mark.parametrize("world,rows,chunks", [(2, [120, 0, 300, 64, 1, 200], 3), (3, [50, 60], 2), (3, [90, 70, 0, 33, 150], 5),
+                                               (8, [60, 0, 90, 33, 1, 120, 75, 48, 80], 4)])
+def test_pipelined_match_and_gather_over_gloo(tmp_path, world, rows, chunks):
+    """match_and_gather: pieces with no pairs on some ranks, ranks without any pair, empty images -- world size up to 8."""
+    out = str(tmp_path / "result.txt")
+    mp.spawn(_worker, args=(world, _free_port(), rows, out, chunks), nprocs=world, join=True)
+    assert open(out).read() == "ok"
+
+
+def test_chunk_bounds_cover_the_shard_on_every_rank():
+    rng = np.random.default_rng(0)
+    for n, k in [(0, 3), (1, 4), (7, 7), (100, 8), (5, 16)]:
+        r = rng.integers(0, 5000, n)
+        b = D.chunk_bounds(r, k)
+        assert len(b) == k and b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] and b[i][0] <= b[i][1] for i in range(k - 1))
+    rows = rng.integers(1, 20000, 30)
+    pairs = D.all_pairs(30)
+    shards = D.shard_pairs(pairs, rows, 4)
+    assert 1 <= D.gather_chunks(pairs, shards, rows) <= 16
+
+
+def test_returned_tables_do_not_alias_each_other():
+    """A PairTable owns its (pooled) buffer: a later gather must not overwrite an earlier table."""
+    a = D._POOL.take(1000, False)
+    ta = D._own(D.PairTable(np.zeros((0, 2), np.int32), np.zeros(0, np.int32), np.zeros(0, np.int64),
+                            a[:8].numpy().view(oracle.DMATCH_DTYPE)), a)
+    b = D._POOL.take(1000, False)
+    assert b.data_ptr() != a.data_ptr()
+    del ta
+    import gc
+    gc.collect()
+    assert any(x.data_ptr() == a.data_ptr() for x in D._POOL.free)  # handed back only once the table is gone

@@ -73,3 +73,67 @@ def test_persisted_table_round_trip(tmp_path):
         with pytest.raises(SfmmError) as e:
             m3.load_table(path)
         assert e.value.code == -1
+
+
+def test_persisted_table_is_bound_to_its_filter_settings_and_survives_corrupt_headers(tmp_path):
+    """a table computed with another ratio / cross-check must not be served, and a header with absurd
+    sizes must come back as an error code (nothing may throw across the C ABI)."""
+    import struct
+    descs = synth.binary_images(3, [300, 280, 150], seed=34)
+    path = str(tmp_path / "t.sfmm")
+    with Matcher(NORM_HAMMING, 0.8, False) as m:
+        m.set_descriptors(descs)
+        m.match_all_pairs()
+        m.save_table(path)
+    for ratio, cross in [(0.7, False), (0.8, True)]:
+        with Matcher(NORM_HAMMING, ratio, cross) as m:
+            m.set_descriptors(descs)
+            with pytest.raises(SfmmError) as e:
+                m.load_table(path)
+            assert e.value.code == -1 and "ratio" in str(e.value)
+    raw = bytearray(open(path, "rb").read())
+    with Matcher(NORM_HAMMING, 0.8, False) as m:
+        m.set_descriptors(descs)
+        m.load_table(path)
+        with pytest.raises(SfmmError) as e:  # the file holds no aligned points
+            m.aligned_points(0, 1)
+        assert e.value.code == -4
+        for n_pairs, n_matches in [(2 ** 62, 0), (3, 2 ** 61), (-1, 0), (3, 7)]:
+            bad = bytearray(raw)
+            bad[32:48] = struct.pack("<qq", n_pairs, n_matches)  # header: magic[8] 4xi32 f32 i32 | n_pairs n_matches
+            open(path, "wb").write(bad)
+            with pytest.raises(SfmmError) as e:
+                m.load_table(path)
+            assert e.value.code == -1
+        assert len(m.getMatching(0, 1)) == len(oracle.match_pair(descs[0], descs[1], 0))  # the loaded table is still served
+
+
+def test_group_matcher_single_process_all_gpus():
+    """sfmm_group_*: every visible GPU from one process -- one H2D, NCCL broadcast inside the library, sharded pairs."""
+    import torch
+    from sfm_danpipeline_b200 import GroupMatcher
+    n_dev = torch.cuda.device_count()
+    rows = [900, 0, 1300, 257, 64, 2100, 31]
+    descs = synth.binary_images(len(rows), rows, seed=51)
+    descs[1] = np.zeros((0, 61), np.uint8)
+    for cross in (False, True):
+        with GroupMatcher(n_dev, NORM_HAMMING, 0.8, cross) as g:
+            assert g.size == n_dev
+            for _ in range(2):  # twice: buffers reused, re-broadcast
+                g.set_descriptors(descs)
+                g.match_all_pairs()
+            ts = g.transfer_stats()
+            blob = sum((r + 3) // 4 * 4 for r in rows) * 64
+            assert ts["h2d_bytes"] == blob and ts["nccl_bytes"] == blob * (n_dev - 1)  # uploaded once, broadcast to the rest
+            for (q, t) in synth.all_pairs(len(rows)):
+                assert g.getMatching(q, t).tobytes() == oracle.match_pair(descs[q], descs[t], 0, 0.8, cross).tobytes(), (q, t, cross)
+            with pytest.raises(SfmmError) as e:
+                g.getMatching(3, 1)  # q>t: not in findBestPair's table
+            assert e.value.code == -4
+            assert sum(g.member_stats(i)["pairs_matched"] for i in range(n_dev)) == 2 * len(synth.all_pairs(len(rows)))
+    fd = synth.float_images(4, [300, 200, 150, 90], seed=52)
+    with GroupMatcher(n_dev) as g:  # the reference's constants: NORM_L2, 0.8, no cross-check
+        g.set_descriptors(fd)
+        g.match_pairs([(0, 1), (2, 3), (1, 3)])
+        for (q, t) in [(0, 1), (2, 3), (1, 3)]:
+            assert g.getMatching(q, t).tobytes() == oracle.match_pair(fd[q], fd[t], 1).tobytes()

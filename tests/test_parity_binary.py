@@ -87,6 +87,28 @@ def test_cfg2_shape_sample_vs_oracle():
         assert ties > 0.02  # the data really exercises tie-breaking
 
 
+@pytest.mark.parametrize("rows", [10000, 20000])
+def test_cfg3_cfg5_row_counts_vs_oracle(rows):
+    """One full-size pair at configs[2] (10 000 rows) and configs[4] (20 000 rows) per engine, byte-compared with the
+    oracle, raw 2-NN lists included; plus a ragged partner so that the last query tile and the last train tile are partial."""
+    import os
+    threads = os.cpu_count() or 8
+    descs = synth.binary_images(3, [rows, rows, rows - 4321], seed=rows)
+    with _matcher() as m:
+        m.set_descriptors(descs)
+        m.match_all_pairs()
+        for (q, t) in [(0, 1), (1, 2)]:
+            exp = oracle.match_pair(descs[q], descs[t], 0, 0.8, False, threads=threads)
+            _expect_equal(m.getMatching(q, t), exp)
+            assert rows // 16 < len(exp) < rows // 4
+        idx, dist = m.knn_pair(2, 0)   # never in the q<t table: on demand, reverse direction
+        d, i = oracle.knn2_c(descs[2], descs[0], 0, threads=threads)
+        assert (idx == i).all() and (dist == d.astype(np.float32)).all()
+    with _matcher(0.8, True) as m:     # cross-check at full size
+        m.set_descriptors(descs[:2])
+        _expect_equal(m.match_pair(0, 1), oracle.match_pair(descs[0], descs[1], 0, 0.8, True, threads=threads))
+
+
 def test_ragged_and_degenerate_images():
     rng = np.random.default_rng(1)
     descs = [rng.integers(0, 256, (n, 61), dtype=np.uint8) for n in (0, 1, 2, 130, 1500, 0, 37)]

@@ -284,3 +284,44 @@ def test_randomised_differential_integer_valued_vs_oracle(cols, rows, seed, cros
         for q, t in synth.all_pairs(len(descs)):
             got, exp = m.getMatching(q, t), oracle.match_pair(descs[q], descs[t], 1, 0.8, cross)
             assert got.tobytes() == exp.tobytes(), (cols, rows, q, t)
+
+
+# ----------------------------------------------------------------- NORM_L2 over CV_8U rows: the reference's literal call
+# cv::BFMatcher(cv::NORM_L2) is hard-wired at src/Sfm.cpp:593, so its AKAZE (detector 2) and ORB (detector 3)
+# descriptors are matched with L2 over the bytes.  The library widens the bytes to fp32 on upload (exact) and the
+# float kernels take over; distances are sqrtf of exact integers, so the bar is bit-exact.
+@pytest.mark.parametrize("name", ["temple_orb_l2", "temple_akaze_l2"])
+@pytest.mark.parametrize("cross", [False, True])
+@pytest.mark.parametrize("mode", [FLOAT_AUTO, FLOAT_EXACT])
+def test_l2_over_bytes_equals_cv2_golden(name, cross, mode):
+    g = GoldenSet(name)
+    assert g.descs[0].dtype == np.uint8
+    with Matcher(NORM_L2, 0.8, cross, float_mode=mode) as m:
+        m.set_descriptors(g.descs)
+        m.match_all_pairs()
+        for p, (q, t, kd, ki, *_r) in enumerate(g.pairs):
+            got = m.getMatching(q, t)
+            eq, et, ed = g.expected(p, cross)
+            assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all(), (name, q, t)
+            assert (got["distance"] == ed).all() and (got["imgIdx"] == 0).all()
+        for q, t, kd, ki, *_r in g.pairs[::7]:
+            idx, dist = m.knn_pair(q, t)
+            assert (idx == ki).all() and (dist == kd).all()
+
+
+def test_l2_over_bytes_random_widths_vs_oracle():
+    rng = np.random.default_rng(77)
+    for cols in (16, 32, 61, 64, 100):
+        descs = [rng.integers(0, 256, (n, cols), dtype=np.uint8) for n in (300, 0, 129, 2, 700)]
+        descs[4][5] = descs[4][9]          # duplicate train rows: lowest index first in both slots
+        descs[0][3] = descs[4][5]
+        with Matcher(NORM_L2, 0.9, False) as m:
+            m.set_descriptors(descs)
+            m.match_all_pairs()
+            for (q, t) in synth.all_pairs(len(descs)):
+                exp = oracle.match_pair(descs[q], descs[t], 1, 0.9, False)
+                assert m.getMatching(q, t).tobytes() == exp.tobytes(), (cols, q, t)
+    with Matcher(0) as m:  # NORM_HAMMING still refuses float rows, like cv::BFMatcher
+        with pytest.raises(SfmmError) as e:
+            m.set_descriptors([np.zeros((4, 128), np.float32)])
+        assert e.value.code == -1
