@@ -138,6 +138,22 @@ __device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+__device__ __forceinline__ void tc_ld_32x32(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld(uint32_t (&r)[16]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]), "+r"(r[9]),
+                   "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+}
 // Waits for this thread's outstanding tcgen05.ld; the registers are listed as in/out operands so that
 // the compiler cannot schedule a use of them above the wait (the loads complete asynchronously).
 __device__ __forceinline__ void tc_wait_ld(uint32_t (&r)[32]) {
@@ -382,12 +398,12 @@ __device__ __forceinline__ float4 lds128(uint32_t saddr) {
     return v;
 }
 
-template <bool PARTIAL, int MODE>
-__device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[32], uint32_t nb_saddr, float cq, uint32_t key_mul,
+template <bool PARTIAL, int MODE, int W = 32>
+__device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[W], uint32_t nb_saddr, float cq, uint32_t key_mul,
                                            uint32_t lc0 /* first column of the chunk inside the tile */, uint32_t col0 /* same, relative to t0 */,
                                            uint32_t n_rows, uint32_t& m1, uint32_t& m2) {
 #pragma unroll
-    for (int e = 0; e < 32; e += 4) {
+    for (int e = 0; e < W; e += 4) {
         const float4 nb = lds128(nb_saddr + e * 4);  // same address in every lane: broadcast
         const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
         uint32_t k[4];
@@ -560,21 +576,26 @@ __device__ __forceinline__ float collect_threshold(bool valid, float nq2, const 
 // End of an item for the eight epilogue warps: merge the two groups' lists of each row -- lexicographic
 // (d^2, index) -- and write the row's entry; d = sqrtf(d^2) of an exact integer is bit-identical to OpenCV's
 // sqrtf(sum (a-b)^2).  `merge` alternates between items: group 1 may already be an item ahead when group 0 reads.
-template <int MODE>
-__device__ __forceinline__ void finish_rows(uint4* merge, const Top2& best, uint32_t half, uint32_t row, uint32_t qrow, uint32_t nq,
+template <int MODE, int GROUPS = 2>
+__device__ __forceinline__ void finish_rows(uint4* merge /* [GROUPS-1][FT_M] */, const Top2& best, uint32_t grp, uint32_t row, uint32_t qrow, uint32_t nq,
                                             bool reverse, uint32_t split, unsigned long long knn_off, unsigned long long col_off,
                                             KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin) {
-    if (half == 1) merge[row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
-    asm volatile("bar.sync 1, 256;" ::: "memory");  // the 8 epilogue warps only
-    if (half == 0 && qrow < nq) {
-        const uint4 o = merge[row];
+    if (grp != 0) merge[(grp - 1) * FT_M + row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
+    if constexpr (GROUPS == 2) asm volatile("bar.sync 1, 256;" ::: "memory");  // the epilogue warps only
+    else asm volatile("bar.sync 1, 512;" ::: "memory");
+    static_assert(GROUPS == 2 || GROUPS == 4, "named-barrier thread counts above");
+    if (grp == 0 && qrow < nq) {
         unsigned long long k1 = best.i1 < 0 ? KEY_NONE : make_key(best.d1, (uint32_t)best.i1);
         unsigned long long k2 = best.i2 < 0 ? KEY_NONE : make_key(best.d2, (uint32_t)best.i2);
-        const unsigned long long o1 = (int)o.y < 0 ? KEY_NONE : make_key(o.x, o.y);
-        const unsigned long long o2 = (int)o.w < 0 ? KEY_NONE : make_key(o.z, o.w);
-        unsigned long long hi = max(k1, o1);
-        k1 = min(k1, o1);
-        k2 = min(min(k2, hi), o2);
+#pragma unroll
+        for (int g = 0; g < GROUPS - 1; ++g) {
+            const uint4 o = merge[g * FT_M + row];
+            const unsigned long long o1 = (int)o.y < 0 ? KEY_NONE : make_key(o.x, o.y);
+            const unsigned long long o2 = (int)o.w < 0 ? KEY_NONE : make_key(o.z, o.w);
+            const unsigned long long hi = max(k1, o1);
+            k1 = min(k1, o1);
+            k2 = min(min(k2, hi), o2);
+        }
         if (reverse) {  // column minimum of the forward problem: (d^2, lowest query index); splits merge by atomicMin
             if (k1 != KEY_NONE) atomicMin(colmin + col_off + qrow, k1);
         } else {
@@ -870,7 +891,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             if constexpr (tm_is_collect(MODE)) {
                 if (n_splits == 1 && qrow < nq) *cand_count_row = fill;
             } else {
-                finish_rows<MODE>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin);
+                finish_rows<MODE, 2>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin);
             }
         }
     }

@@ -17,7 +17,7 @@
 // its per-column work is small (one IMAD + 1.25 VIMNMX.U16x2 for binary; profiles/ncu_tensor_ts_r01.txt shows
 // the first version with the MMA warp 30 % of its time in the acc_empty wait).
 //
-// TMEM map (512 columns): [0,128) query tile A0 | [128,256) A1 | [256,384) accumulator 0 | [384,512) accumulator 1.
+// TMEM map (512 columns): query tile A0 | A1 (KB*32 columns each) | 128-column accumulators, two (KB = 3, 4) or three (KB <= 2).
 // A row r of the tile is TMEM lane r; its K bytes are packed in order into 32-bit columns (32 bytes = 8
 // columns per MMA), which is exactly what a thread gets when it reads its row from global memory as
 // 32-bit words -- so four loader warps (one per TMEM lane quarter) copy rows global -> registers ->
@@ -27,23 +27,33 @@
 //   warp 1       MMA issuer    : tcgen05.mma [d_tmem], [a_tmem], b_desc  (A from TMEM)
 //   warp 2       TMEM allocator
 //   warp 3       item prefetch : next KnnTile/PairDesc + per-row constants -> 2-slot smem ring
-//   warps 4-11   epilogue      : two groups of four warps on alternate tiles (one accumulator stage each)
-//   warps 12-15  query loaders : global -> registers -> tcgen05.st, one item ahead
+//   warps 4..    epilogue      : GROUPS (2 or 4) groups of four warps taking tiles round robin
+//   last 4 warps query loaders : global -> registers -> tcgen05.st, one item ahead
 #pragma once
 #include "float_tensor.cuh"
 
 namespace sfmm {
 
 static constexpr int FTS_B_STAGES = 3;
-static constexpr int FTS_ACC_STAGES = 2;
+static constexpr int FTS_MAX_ACC_STAGES = 3;
 static constexpr int FTS_NB_STAGES = 4;
-static constexpr int FTS_THREADS = 512;
-static constexpr uint32_t FTS_ACC_COL0 = 256;  // first accumulator column
+static constexpr int FTS_MAX_GROUPS = 4;
+// TMEM budget (512 columns): two query-tile buffers of KB*32 columns + as many 128-column accumulators as fit, at most three.
+// KB = 4 (486-bit binary): 256 + 2 x 128; KB <= 2 (fp16 128-d float, 256-bit ORB): 128 + 3 x 128 -- the third stage lets the
+// MMA warp run two tiles ahead of the slowest epilogue group.
+__host__ __device__ constexpr int fts_acc_stages(int kb) { return (512 - 2 * kb * 32) / 128 >= 3 ? 3 : 2; }
+// Epilogue groups (four warps each, one per TMEM lane quarter) take tiles round robin.  Two groups are enough where the
+// per-column work is one IMAD + 1.25 VIMNMX.U16x2 (packed binary keys); the 32-bit keys of the float path cost 2.5 VIMNMX per
+// column and each warp runs a dependent min/max chain, so with two warps per SM sub-partition the ALU pipe idles a third of
+// the time (ncu r01: alu 64 %, issue 65 %, tensor 42 %, MMA warp 36 % in the acc_empty wait): four groups put four
+// epilogue warps on every sub-partition.  The register file then holds 768 threads x 80 registers: the epilogue streams
+// 16-column chunks instead of 32.
+__host__ __device__ constexpr int fts_threads(int groups) { return 32 * (4 + 4 * groups + 4); }
 
 struct FtsSmem {  // after the 1024-byte aligned operand area
     uint64_t a_full[2], a_empty[2];
     uint64_t b_full[FTS_B_STAGES], b_empty[FTS_B_STAGES];
-    uint64_t acc_full[FTS_ACC_STAGES], acc_empty[FTS_ACC_STAGES];
+    uint64_t acc_full[FTS_MAX_ACC_STAGES], acc_empty[FTS_MAX_ACC_STAGES];
     uint64_t nb_full[FTS_NB_STAGES], nb_empty[FTS_NB_STAGES];
     uint64_t item_full[2], item_empty[2];
     uint32_t tmem_base;
@@ -51,7 +61,7 @@ struct FtsSmem {  // after the 1024-byte aligned operand area
     FtItem item[2];
     alignas(16) float nb[FTS_NB_STAGES][FT_N];
     float rowval[2][FT_M];
-    uint4 merge[2][FT_M];
+    uint4 merge[2][(FTS_MAX_GROUPS - 1) * FT_M];
 };
 
 static inline size_t float_tensor_ts_smem_bytes(int kblocks) {
@@ -106,8 +116,8 @@ __device__ __forceinline__ void tc_st_32x32(uint32_t taddr, const uint32_t (&r)[
 }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int KB /* 128-byte K-blocks per row */, int MODE>
-__global__ void __launch_bounds__(FTS_THREADS, 1)
+template <int KB /* 128-byte K-blocks per row */, int MODE, int GROUPS = 2 /* epilogue groups of four warps: 2 or 4 */>
+__global__ void __launch_bounds__(fts_threads(GROUPS), 1)
 tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ a_src /* the matrix the tensor map describes: rows of KB*128 bytes */,
                       const uint32_t total_rows, const float* __restrict__ norms /* int32 popcounts when INT8 */,
                    const float* __restrict__ nb_src /* per train row: |t|^2, or binary_nbkey_kernel's key part when INT8 */,
@@ -116,6 +126,13 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                       uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
     constexpr int KIND = OperandOf<MODE>::kind;
     constexpr int KB_ELEMS = OperandOf<MODE>::kb_elems;
+    constexpr int ACC_STAGES = fts_acc_stages(KB);
+    constexpr uint32_t A_COLS = KB * 32;            // TMEM columns of one query-tile buffer
+    constexpr uint32_t ACC_COL0 = 2 * A_COLS;       // first accumulator column
+    constexpr int EPI_WARPS = 4 * GROUPS;
+    constexpr uint32_t LOADER_WARP0 = 4 + EPI_WARPS;  // a multiple of 4: warp % 4 is the TMEM lane quarter it may access
+    static_assert(GROUPS == 2 || GROUPS == 4, "two or four epilogue groups");
+    static_assert(!(GROUPS == 4 && (MODE == TM_I8P || tm_is_collect(MODE) || tm_is_rank(MODE))), "four groups: 32-bit-key top-2 modes only");
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sB = base;  // FTS_B_STAGES x KB x 16 KB
@@ -129,19 +146,19 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             mbar_init(&sm.a_empty[s], 1);  // tcgen05.commit after the item's last MMA
             // every thread that writes / reads an item slot arrives itself (release / acquire pair per thread)
             mbar_init(&sm.item_full[s], 32);                             // the prefetch warp's lanes
-            mbar_init(&sm.item_empty[s], 1 + 32 + 32 * FT_EPI_WARPS + 128);  // producer thread, MMA warp, epilogue warps, loader warps
+            mbar_init(&sm.item_empty[s], 1 + 32 + 32 * EPI_WARPS + 128);  // producer thread, MMA warp, epilogue warps, loader warps
         }
         for (int s = 0; s < FTS_B_STAGES; ++s) {
             mbar_init(&sm.b_full[s], 1);
             mbar_init(&sm.b_empty[s], 1);
         }
-        for (int s = 0; s < FTS_ACC_STAGES; ++s) {
+        for (int s = 0; s < ACC_STAGES; ++s) {
             mbar_init(&sm.acc_full[s], 1);
-            mbar_init(&sm.acc_empty[s], FT_EPI_WARPS / 2);  // the four warps of the group that owns the stage
+            mbar_init(&sm.acc_empty[s], 4);  // the four warps of the group that took the tile
         }
         for (int s = 0; s < FTS_NB_STAGES; ++s) {
             mbar_init(&sm.nb_full[s], 1);
-            mbar_init(&sm.nb_empty[s], FT_EPI_WARPS / 2);
+            mbar_init(&sm.nb_empty[s], 4);
         }
         mbar_fence_init();
     }
@@ -199,15 +216,15 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
             mbar_wait(&sm.a_full[slot], (it >> 1) & 1);  // the loaders have stored this item's query tile
             tc_fence_after();
-            const uint32_t a_tmem = tb + slot * FT_M;  // 128 columns per query-tile buffer
+            const uint32_t a_tmem = tb + slot * A_COLS;
 #pragma unroll 1
             for (uint32_t j = 0; j < n_tiles; ++j, ++g) {
-                const uint32_t s = g % FTS_B_STAGES, a = g % FTS_ACC_STAGES;
+                const uint32_t s = g % FTS_B_STAGES, a = g % ACC_STAGES;
                 mbar_wait(&sm.b_full[s], (g / FTS_B_STAGES) & 1);
-                mbar_wait(&sm.acc_empty[a], ((g / FTS_ACC_STAGES) & 1) ^ 1);
+                mbar_wait(&sm.acc_empty[a], ((g / ACC_STAGES) & 1) ^ 1);
                 tc_fence_after();
                 const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB + (size_t)s * KB * FT_B_KBLOCK_BYTES));
-                const uint32_t d_tmem = tb + FTS_ACC_COL0 + a * FT_N;
+                const uint32_t d_tmem = tb + ACC_COL0 + a * FT_N;
                 tc_mma_ts<KIND, false>(d_tmem, a_tmem, b_desc0, idesc);
 #pragma unroll
                 for (int i = 1; i < 4 * KB; ++i) {  // i = kb*4 + k: 32 bytes of K = 8 TMEM columns of A, 32 bytes inside B's swizzle row
@@ -259,9 +276,9 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             }
             mbar_arrive(&sm.item_full[slot]);  // every lane, after its own writes
         }
-    } else if (warp >= 12) {
+    } else if (warp >= LOADER_WARP0) {
         // ===================== query loaders: global -> registers -> TMEM, one item ahead =====================
-        const uint32_t lw = warp - 12;  // == warp % 4: the TMEM lane quarter this warp may access
+        const uint32_t lw = warp - LOADER_WARP0;  // == warp % 4: the TMEM lane quarter this warp may access
         const uint32_t row = lw * 32 + lane;
         uint32_t it = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
@@ -274,7 +291,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             const bool ok = grow < total_rows;  // rows past the blob: zeros (rows past the image but inside the blob are
                                                 // another image's: computed on, never read -- as with TMA's box)
             const uint4* src = a_src + (size_t)(ok ? grow : 0) * (KB * 8);
-            const uint32_t taddr = tmem_base + ((lw * 32) << 16) + slot * FT_M;
+            const uint32_t taddr = tmem_base + ((lw * 32) << 16) + slot * A_COLS;
 #pragma unroll
             for (int kb = 0; kb < KB; ++kb) {
                 uint32_t r[32];
@@ -292,13 +309,13 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
         }
     } else if (warp >= 4) {
         // ===================== epilogue: fused top-2 =====================
-        // Two groups of four warps (one warp per TMEM lane quarter); group h owns the tiles whose running
-        // counter is h mod 2 == accumulator stage h.  (Splitting every tile's columns between the groups instead,
-        // so that a stage is released as soon as it has been read, measured 10 % slower: the TMEM loads no
-        // longer overlap the fold inside a warp.)
+        // GROUPS groups of four warps (one warp per TMEM lane quarter); group h takes the tiles whose running counter is
+        // h mod GROUPS.  (Splitting every tile's columns between the groups instead, so that a stage is released as soon as
+        // it has been read, measured 10 % slower: the TMEM loads no longer overlap the fold inside a warp.)
         const uint32_t ew = warp - 4;
-        const uint32_t quarter = ew & 3, half = ew >> 2;   // TMEM lanes 32*quarter..
+        const uint32_t quarter = ew & 3, half = ew >> 2;   // TMEM lanes 32*quarter.. ; `half` = the group index
         const uint32_t row = quarter * 32 + lane;          // row of the query tile == TMEM lane
+        constexpr int CW = GROUPS == 4 ? 16 : 32;          // columns per chunk streamed from TMEM (register budget: 80 per thread with four groups)
         uint32_t g0 = 0, it = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t slot = it & 1;
@@ -323,25 +340,25 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 cand_idx_row = cand_idx + (size_t)(q_off + min(qrow, nq - 1)) * FT_CAND_CAP + half * (FT_CAND_CAP / 2);
             }
 #pragma unroll 1
-            for (uint32_t j = (half ^ g0) & 1; j < n_tiles; j += 2) {
-                const uint32_t g = g0 + j;
-                const uint32_t a = half;                 // == g % FTS_ACC_STAGES
+            for (uint32_t j = (half - g0) & (GROUPS - 1); j < n_tiles; j += GROUPS) {
+                const uint32_t g = g0 + j;               // g % GROUPS == half
+                const uint32_t a = g % ACC_STAGES;
                 const uint32_t nbs = g % FTS_NB_STAGES;
-                mbar_wait(&sm.acc_full[a], (g / FTS_ACC_STAGES) & 1);
+                mbar_wait(&sm.acc_full[a], (g / ACC_STAGES) & 1);
                 tc_fence_after();
-                uint32_t acc[2][32];  // register double buffer: chunk c+1 streams in from TMEM while chunk c is folded
-                const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + FTS_ACC_COL0 + a * FT_N;
+                uint32_t acc[2][CW];  // register double buffer: chunk c+1 streams in from TMEM while chunk c is folded
+                const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + ACC_COL0 + a * FT_N;
                 tc_ld_32x32(taddr, acc[0]);
                 mbar_wait(&sm.nb_full[nbs], (g / FTS_NB_STAGES) & 1);
                 tc_wait_ld(acc[0]);
                 const uint32_t col0 = j * FT_N;                // first column of the tile, relative to t0
                 const bool partial = col0 + FT_N > n_rows;     // warp-uniform: only the last tile
                 uint32_t m1 = 0xFFFFFFFFu, m2 = 0xFFFFFFFFu;   // two smallest keys of this tile
-                constexpr int NCH = FT_N / 32;  // 32-column chunks per tile
+                constexpr int NCH = FT_N / CW;  // chunks per tile
 #pragma unroll
                 for (int c = 0; c < NCH; ++c) {
-                    if (c < NCH - 1) tc_ld_32x32(taddr + (c + 1) * 32, acc[(c + 1) & 1]);
-                    const uint32_t nb_saddr = smem_u32(&sm.nb[nbs][c * 32]);
+                    if (c < NCH - 1) tc_ld_32x32(taddr + (c + 1) * CW, acc[(c + 1) & 1]);
+                    const uint32_t nb_saddr = smem_u32(&sm.nb[nbs][c * CW]);
                     if constexpr (tm_is_collect(MODE)) {
                         const uint32_t c0 = col0 + c * 32;  // columns at or past n_rows belong to another image / padding
                         const uint32_t valid = c0 + 32 <= n_rows ? 0xFFFFFFFFu : (c0 < n_rows ? (1u << (n_rows - c0)) - 1u : 0u);
@@ -354,8 +371,8 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                         if (!partial) chunk_top2_packed<false>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
                         else chunk_top2_packed<true>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
                     } else {
-                        if (!partial) chunk_top2<false, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
-                        else chunk_top2<true, MODE>(acc[c & 1], nb_saddr, cq, key_mul, c * 32, col0 + c * 32, n_rows, m1, m2);
+                        if (!partial) chunk_top2<false, MODE, CW>(acc[c & 1], nb_saddr, cq, key_mul, c * CW, col0 + c * CW, n_rows, m1, m2);
+                        else chunk_top2<true, MODE, CW>(acc[c & 1], nb_saddr, cq, key_mul, c * CW, col0 + c * CW, n_rows, m1, m2);
                     }
                     if (c < NCH - 1) tc_wait_ld(acc[(c + 1) & 1]);
                     if (c == (NCH > 1 ? NCH - 2 : 0)) {  // the last TMEM read of this tile has landed: the MMA that reuses the stage may start
@@ -393,7 +410,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             if constexpr (tm_is_collect(MODE)) {
                 if (n_splits == 1 && qrow < nq) *cand_count_row = fill;
             } else {
-                finish_rows<MODE>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin);
+                finish_rows<MODE, GROUPS>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin);
             }
         }
     }

@@ -155,6 +155,7 @@ struct SfmmCtx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_pack[2] = {nullptr, nullptr};
     mutable std::string err;
     int csa_level = 2;
+    int epi_groups = 4;  // epilogue groups of the TMEM-A float kernels (SFMM_EPI_GROUPS)
     size_t fx_attr_smem = 0;
 
     // float path state (norms + TF32-exactness proof, see float_tensor.cuh)
@@ -411,16 +412,22 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
         return cudaGetLastError();
     }
     // query tile in tensor memory (float_tensor_ts.cuh)
-    const size_t smem = float_tensor_ts_smem_bytes(KB);
-    auto kern = tensor_knn2_ts_kernel<KB, MODE>;
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
     const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P) ? ctx->d_unpacked.as<uint4>() : (OperandOf<MODE>::kind == OK_F16 ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>());
-    kern<<<grid, FTS_THREADS, smem, sl.stream>>>(ctx->tmap, a_src, static_cast<uint32_t>(ctx->total_rows), (const float*)ctx->d_norms.as<float>(), nb_src,
+    const size_t smem = float_tensor_ts_smem_bytes(KB);
+    auto go = [&](auto kern, int threads) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        kern<<<grid, threads, smem, sl.stream>>>(ctx->tmap, a_src, static_cast<uint32_t>(ctx->total_rows), (const float*)ctx->d_norms.as<float>(), nb_src,
                                                  (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles, (const PairDesc*)sl.d_pairs.as<PairDesc>(),
                                                  sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u, aux,
                                                  sl.d_cand_count.as<uint32_t>(), sl.d_cand_idx.as<uint32_t>());
-    return cudaGetLastError();
+        return cudaGetLastError();
+    };
+    // four epilogue groups for the 32-bit-key float modes (measured: profiles/tensor_variants_r02.txt); SFMM_EPI_GROUPS=2 forces two
+    if constexpr (MODE == TM_F16_EXACT || MODE == TM_TF32_EXACT) {
+        if (ctx->epi_groups != 2) return go(tensor_knn2_ts_kernel<KB, MODE, 4>, fts_threads(4));
+    }
+    return go(tensor_knn2_ts_kernel<KB, MODE, 2>, fts_threads(2));
 }
 
 template <int MODE>
@@ -964,6 +971,7 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* s = std::getenv("SFMM_TENSOR_TS")) ctx->tensor_ts = std::atoi(s) != 0 ? 1 : 0;
     if (const char* s = std::getenv("SFMM_CSA_LEVEL")) ctx->csa_level = std::max(0, std::min(3, std::atoi(s)));
+    if (const char* s = std::getenv("SFMM_EPI_GROUPS")) ctx->epi_groups = std::atoi(s) == 2 ? 2 : 4;
     bool ok = (e = cudaSetDevice(cfg->device)) == cudaSuccess;
     for (Slot& sl : ctx->slot) {
         ok = ok && (e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) == cudaSuccess;

@@ -325,3 +325,26 @@ def test_l2_over_bytes_random_widths_vs_oracle():
         with pytest.raises(SfmmError) as e:
             m.set_descriptors([np.zeros((4, 128), np.float32)])
         assert e.value.code == -1
+
+
+@pytest.mark.parametrize("groups", ["2", "4"])
+def test_tensor_kernel_epilogue_group_variants_agree(groups, monkeypatch):
+    """The TMEM-A float kernel runs two or four epilogue groups (SFMM_EPI_GROUPS, read when the context is created; four is
+    the default): both must reproduce the cv2 goldens and the oracle at the cfg-4 row count, ragged tails included."""
+    monkeypatch.setenv("SFMM_EPI_GROUPS", groups)
+    g = GoldenSet("temple_sift")
+    with Matcher(NORM_L2, 0.8, False) as m:
+        m.set_descriptors(g.descs)
+        m.match_all_pairs()
+        assert m.stats()["float_path"] == FLOAT_TENSOR
+        for p, (q, t, *_r) in enumerate(g.pairs):
+            got = m.getMatching(q, t)
+            eq, et, ed = g.expected(p)
+            assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all() and (got["distance"] == ed).all(), (q, t)
+    descs = synth.float_images(3, [8000, 7777, 130], seed=5)
+    for cross in (False, True):
+        with Matcher(NORM_L2, 0.8, cross) as m:
+            m.set_descriptors(descs)
+            m.match_all_pairs()
+            for (q, t) in synth.all_pairs(3):
+                assert m.getMatching(q, t).tobytes() == oracle.match_pair(descs[q], descs[t], 1, 0.8, cross, threads=8).tobytes(), (q, t, cross)
