@@ -42,18 +42,21 @@ static constexpr int FTS_MAX_GROUPS = 4;
 // KB = 4 (486-bit binary): 256 + 2 x 128; KB <= 2 (fp16 128-d float, 256-bit ORB): 128 + 3 x 128 -- the third stage lets the
 // MMA warp run two tiles ahead of the slowest epilogue group.
 __host__ __device__ constexpr int fts_acc_stages(int kb) { return (512 - 2 * kb * 32) / 128 >= 3 ? 3 : 2; }
-// Epilogue groups (four warps each, one per TMEM lane quarter) take tiles round robin.  Two groups are enough where the
-// per-column work is one IMAD + 1.25 VIMNMX.U16x2 (packed binary keys); the 32-bit keys of the float path cost 2.5 VIMNMX per
-// column and each warp runs a dependent min/max chain, so with two warps per SM sub-partition the ALU pipe idles a third of
-// the time (ncu r01: alu 64 %, issue 65 %, tensor 42 %, MMA warp 36 % in the acc_empty wait): four groups put four
-// epilogue warps on every sub-partition.  The register file then holds 768 threads x 80 registers: the epilogue streams
-// 16-column chunks instead of 32.
+// Epilogue groups (four warps each, one per TMEM lane quarter) take tiles round robin.  Two groups are the default everywhere.
+// Four groups (GROUPS = 4: 768 threads x 80 registers, 16-column chunks) were tried for the float path, whose 32-bit keys cost
+// 2.5 VIMNMX per column, on the theory that its epilogue warps were latency bound (ncu r01: alu 64 %, issue 65 %, tensor 42 %).
+// Measured (cfg4s, same box): 54.5 k pairs/s with two groups, 51.8 k with four -- the epilogue is bound by issue slots and the
+// ALU pipe, not by latency: per 128x128 tile and SM sub-partition it executes ~730 instructions (322 VIMNMX/VIMNMX3 at one per
+// two clocks = 644 ALU cycles, 128 FFMA, 146 IMAD, 32 LDS, ~100 others; ncu source page of r01) next to ~290 mbarrier-poll
+// instructions of the other warps, against 512 cycles of kind::f16 MMAs.  The ALU pipe's 2.5 VIMNMX per column is the floor of an
+// exact 32-bit-key top-2 (~740 cycles per tile = 69 % tensor-pipe activity at best); the packed 16-bit keys that halve it for the
+// binary engine need distances below 2^10.  The four-group variant stays selectable (SFMM_EPI_GROUPS=4) and tested.
 __host__ __device__ constexpr int fts_threads(int groups) { return 32 * (4 + 4 * groups + 4); }
 
 struct FtsSmem {  // after the 1024-byte aligned operand area
     uint64_t a_full[2], a_empty[2];
     uint64_t b_full[FTS_B_STAGES], b_empty[FTS_B_STAGES];
-    uint64_t acc_full[FTS_MAX_ACC_STAGES], acc_empty[FTS_MAX_ACC_STAGES];
+    uint64_t acc_full[FTS_MAX_GROUPS], acc_empty[FTS_MAX_ACC_STAGES];  // full: ring of max(GROUPS, stages) (see the kernel), empty: one per TMEM stage
     uint64_t nb_full[FTS_NB_STAGES], nb_empty[FTS_NB_STAGES];
     uint64_t item_full[2], item_empty[2];
     uint32_t tmem_base;
@@ -127,6 +130,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
     constexpr int KIND = OperandOf<MODE>::kind;
     constexpr int KB_ELEMS = OperandOf<MODE>::kb_elems;
     constexpr int ACC_STAGES = fts_acc_stages(KB);
+    constexpr int FULL_RING = GROUPS > ACC_STAGES ? GROUPS : ACC_STAGES;  // "accumulator ready" barriers, see their initialisation
     constexpr uint32_t A_COLS = KB * 32;            // TMEM columns of one query-tile buffer
     constexpr uint32_t ACC_COL0 = 2 * A_COLS;       // first accumulator column
     constexpr int EPI_WARPS = 4 * GROUPS;
@@ -152,10 +156,17 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             mbar_init(&sm.b_full[s], 1);
             mbar_init(&sm.b_empty[s], 1);
         }
-        for (int s = 0; s < ACC_STAGES; ++s) {
-            mbar_init(&sm.acc_full[s], 1);
-            mbar_init(&sm.acc_empty[s], 4);  // the four warps of the group that took the tile
-        }
+        // "accumulator of tile g is ready" is signalled on barrier g % FULL_RING, FULL_RING = max(GROUPS, ACC_STAGES).  try_wait.parity
+        // cannot tell "phase k done" from "phase k-2 done", so a barrier must never be two phases away from its waiter, either way:
+        //  - the waiter (group g % GROUPS) has seen its previous tile g - GROUPS complete, and tiles complete in order, so tile
+        //    g - FULL_RING (the barrier's previous phase) is complete because FULL_RING >= GROUPS;
+        //  - the barrier's next phase (tile g + FULL_RING) cannot be signalled before tile g has been consumed, because the MMA warp
+        //    stops at tile g + ACC_STAGES <= g + FULL_RING until tile g's TMEM stage is released.
+        // (One barrier per TMEM stage is wrong with four groups on three stages: a fast group waits for a stage's NEXT use before its
+        // current one has completed and reads the wrong tile.  One barrier per group is wrong with two groups on three stages: tile
+        // g + 2 is signalled before tile g has been consumed.  Both were measured the hard way.)
+        for (int s = 0; s < FULL_RING; ++s) mbar_init(&sm.acc_full[s], 1);
+        for (int s = 0; s < ACC_STAGES; ++s) mbar_init(&sm.acc_empty[s], 4);  // the four warps of the group that took the tile
         for (int s = 0; s < FTS_NB_STAGES; ++s) {
             mbar_init(&sm.nb_full[s], 1);
             mbar_init(&sm.nb_empty[s], 4);
@@ -232,7 +243,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                     tc_mma_ts<KIND, true>(d_tmem, a_tmem + i * 8, b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
                 }
                 tc_commit_elect(&sm.b_empty[s]);   // smem stage reusable once these MMAs have read it
-                tc_commit_elect(&sm.acc_full[a]);  // accumulator ready for the epilogue
+                tc_commit_elect(&sm.acc_full[g % FULL_RING]);  // accumulator ready for the group that takes this tile
             }
             tc_commit_elect(&sm.a_empty[slot]);  // every MMA of this item has read the query tile: its TMEM buffer may be refilled
         }
@@ -344,7 +355,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 const uint32_t g = g0 + j;               // g % GROUPS == half
                 const uint32_t a = g % ACC_STAGES;
                 const uint32_t nbs = g % FTS_NB_STAGES;
-                mbar_wait(&sm.acc_full[a], (g / ACC_STAGES) & 1);
+                mbar_wait(&sm.acc_full[g % FULL_RING], (g / FULL_RING) & 1);
                 tc_fence_after();
                 uint32_t acc[2][CW];  // register double buffer: chunk c+1 streams in from TMEM while chunk c is folded
                 const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + ACC_COL0 + a * FT_N;

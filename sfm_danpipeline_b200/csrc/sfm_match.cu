@@ -155,7 +155,7 @@ struct SfmmCtx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_pack[2] = {nullptr, nullptr};
     mutable std::string err;
     int csa_level = 2;
-    int epi_groups = 4;  // epilogue groups of the TMEM-A float kernels (SFMM_EPI_GROUPS)
+    int epi_groups = 2;  // epilogue groups of the TMEM-A float kernels (SFMM_EPI_GROUPS=4: measured slower, see float_tensor_ts.cuh)
     size_t fx_attr_smem = 0;
 
     // float path state (norms + TF32-exactness proof, see float_tensor.cuh)
@@ -423,9 +423,10 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
                                                  sl.d_cand_count.as<uint32_t>(), sl.d_cand_idx.as<uint32_t>());
         return cudaGetLastError();
     };
-    // four epilogue groups for the 32-bit-key float modes (measured: profiles/tensor_variants_r02.txt); SFMM_EPI_GROUPS=2 forces two
+    // SFMM_EPI_GROUPS=4: four epilogue groups for the 32-bit-key float modes (an experiment that measured 5 % slower than two,
+    // profiles/tensor_variants_r02.txt; kept selectable and covered by the parity tests)
     if constexpr (MODE == TM_F16_EXACT || MODE == TM_TF32_EXACT) {
-        if (ctx->epi_groups != 2) return go(tensor_knn2_ts_kernel<KB, MODE, 4>, fts_threads(4));
+        if (ctx->epi_groups == 4) return go(tensor_knn2_ts_kernel<KB, MODE, 4>, fts_threads(4));
     }
     return go(tensor_knn2_ts_kernel<KB, MODE, 2>, fts_threads(2));
 }
@@ -971,7 +972,7 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* s = std::getenv("SFMM_TENSOR_TS")) ctx->tensor_ts = std::atoi(s) != 0 ? 1 : 0;
     if (const char* s = std::getenv("SFMM_CSA_LEVEL")) ctx->csa_level = std::max(0, std::min(3, std::atoi(s)));
-    if (const char* s = std::getenv("SFMM_EPI_GROUPS")) ctx->epi_groups = std::atoi(s) == 2 ? 2 : 4;
+    if (const char* s = std::getenv("SFMM_EPI_GROUPS")) ctx->epi_groups = std::atoi(s) == 4 ? 4 : 2;
     bool ok = (e = cudaSetDevice(cfg->device)) == cudaSuccess;
     for (Slot& sl : ctx->slot) {
         ok = ok && (e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) == cudaSuccess;
