@@ -89,6 +89,51 @@ struct PinBuf {  // page-locked host staging
     }
 };
 
+// The match table: every SfmDMatch record of every pair matched so far, in page-locked host memory so that a chunk's
+// records are copied device -> host straight into their final place (no staging buffer, no second copy on the host), on
+// the copy stream, while the next chunk's kernels run.  Falls back to pageable memory when the pinned allocation fails
+// (very large tables): the copies then go through the driver's own staging and are synchronous, nothing else changes.
+struct HostTable {
+    SfmDMatch* p = nullptr;
+    size_t n = 0, cap = 0;
+    bool pinned = false;
+    SfmDMatch* data() const { return p; }
+    size_t size() const { return n; }
+    size_t capacity() const { return cap; }
+    void clear() { n = 0; }
+    void resize_down(size_t m) { if (m < n) n = m; }
+    void release() {
+        if (p) {
+            if (pinned) cudaFreeHost(p);
+            else std::free(p);
+        }
+        p = nullptr;
+        n = cap = 0;
+    }
+    // Capacity for `want` records.  `drain` is synchronised before the old block is given up: copies into it may be in flight.
+    int reserve(size_t want, cudaStream_t drain) {
+        if (want <= cap) return SFMM_OK;
+        const size_t ncap = std::max<size_t>(want, 1 << 12);
+        void* q = nullptr;
+        bool pin = true;
+        if (cudaMallocHost(&q, ncap * sizeof(SfmDMatch)) != cudaSuccess) {
+            (void)cudaGetLastError();
+            pin = false;
+            q = std::malloc(ncap * sizeof(SfmDMatch));
+            if (!q) return SFMM_ENOMEM;
+        }
+        if (drain) cudaStreamSynchronize(drain);
+        if (n) std::memcpy(q, p, n * sizeof(SfmDMatch));
+        const size_t keep = n;
+        release();
+        p = static_cast<SfmDMatch*>(q);
+        n = keep;
+        cap = ncap;
+        pinned = pin;
+        return SFMM_OK;
+    }
+};
+
 struct PairSlot {  // where a computed pair lives in the host table
     int64_t offset;
     int32_t count;
@@ -120,11 +165,11 @@ struct ChunkPlan {
 // One chunk in flight: its stream, device scratch, pinned staging and events.
 struct Slot {
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_knn0 = nullptr, ev_knn1 = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_knn0 = nullptr, ev_knn1 = nullptr, ev_done = nullptr, ev_copied = nullptr;
+    bool copy_pending = false;  // records of this slot's last chunk are still being copied to the host table (ev_copied)
     DevBuf d_pairs, d_tiles, d_ftiles, d_knn, d_colmin, d_tile_count, d_tile_off, d_pair_count, d_pair_off, d_matches, d_left, d_right;
     DevBuf d_cand_count, d_cand_idx, d_pair_of_row;  // TF32 rank + refine path
     PinBuf meta;     // [total u64][pair_off u64 x n][pair_count i32 x n]
-    PinBuf records;  // SfmDMatch staging
     PinBuf points;   // aligned-point staging (left then right)
     ChunkPlan plan;
     int64_t first = 0, n = 0;  // pair range [first, first+n) of the caller's list
@@ -134,14 +179,14 @@ struct Slot {
                           &d_cand_count, &d_cand_idx, &d_pair_of_row})
             b->release();
         meta.release();
-        records.release();
         points.release();
         if (ev_knn0) cudaEventDestroy(ev_knn0);
         if (ev_knn1) cudaEventDestroy(ev_knn1);
         if (ev_done) cudaEventDestroy(ev_done);
+        if (ev_copied) cudaEventDestroy(ev_copied);
         if (stream) cudaStreamDestroy(stream);
         stream = nullptr;
-        ev_knn0 = ev_knn1 = ev_done = nullptr;
+        ev_knn0 = ev_knn1 = ev_done = ev_copied = nullptr;
     }
 };
 
@@ -188,7 +233,12 @@ struct SfmmCtx {
     uint64_t total_rows = 0;  // blob rows, including the zero rows that align every image to 4 rows
     DevBuf blob;
     size_t blob_bytes = 0;
-    PinBuf pack[2];  // double-buffered re-pitch staging for set_descriptors
+    PinBuf pack[2];  // double-buffered pinned staging for set_descriptors
+    std::vector<uint64_t> raw_row0;  // first row of every image counted without alignment rows (n_images + 1)
+    std::vector<uint32_t> raw_row0_32;
+    DevBuf d_raw, d_raw_row0;        // the caller's rows as uploaded (tightly packed), before ingest_rows_kernel
+    cudaEvent_t ev_blob = nullptr;   // the blob is complete on the device (recorded on slot[0]'s stream)
+    bool blob_async = false;
 
     DevBuf d_idx, d_dist;  // sfmm_knn_pair
     DevBuf d_points;       // imagesPts2D (double2 per blob row), optional
@@ -199,7 +249,7 @@ struct SfmmCtx {
     std::vector<int32_t> res_counts;
     std::vector<int64_t> res_offsets;  // offsets into the consolidated view
     std::vector<PairSlot> res_slots;
-    std::vector<SfmDMatch> table;  // every record, in the order the pairs were given
+    HostTable table;  // every record, in the order the pairs were given
     std::vector<double2> pts_left, pts_right;  // aligned points of every record (when points are set)
     std::unordered_map<uint64_t, int64_t> index;
     int64_t n_matches = 0;
@@ -680,6 +730,11 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
     sl.first = first;
     sl.n = n;
     sl.busy = true;
+    if (ctx->blob_async) CU_TRY(ctx, cudaStreamWaitEvent(sl.stream, ctx->ev_blob, 0));  // sfmm_set_descriptors does not wait for its upload
+    if (sl.copy_pending) {  // the previous chunk's records are still leaving this slot's buffers on the copy stream
+        CU_TRY(ctx, cudaStreamWaitEvent(sl.stream, sl.ev_copied, 0));
+        sl.copy_pending = false;
+    }
     const bool cross = ctx->cfg.cross_check != 0;
     const size_t np = plan.pairs.size(), nft = plan.ftiles.size();
     CU_TRY(ctx, sl.d_pairs.ensure(std::max<size_t>(1, np) * sizeof(PairDesc)));
@@ -802,22 +857,14 @@ int collect_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt) {
         if (ctx->table.capacity() < old_size + total) {
             const double seen = static_cast<double>(sl.first + sl.n), all = static_cast<double>(std::max<int64_t>(ctx->call_pairs, sl.first + sl.n));
             const size_t guess = static_cast<size_t>((static_cast<double>(old_size - ctx->call_base + total) * all / seen) * 1.05) + 1024;
-            try {
-                ctx->table.reserve(std::max(old_size + static_cast<size_t>(total), ctx->call_base + guess));
-            } catch (const std::bad_alloc&) {
+            if (ctx->table.reserve(std::max(old_size + static_cast<size_t>(total), ctx->call_base + guess), ctx->copy_stream))
                 return fail(ctx, SFMM_ENOMEM, "match_pairs: out of host memory for the match table");
-            }
         }
-        CU_TRY(ctx, sl.records.ensure(static_cast<size_t>(total) * sizeof(SfmDMatch)));
-        CU_TRY(ctx, cudaMemcpyAsync(sl.records.p, sl.d_matches.p, static_cast<size_t>(total) * sizeof(SfmDMatch), cudaMemcpyDeviceToHost,
+        // device -> host straight into the table, asynchronously: the next chunk's kernels (other slot) run meanwhile; this slot's
+        // next launch waits for ev_copied, the call ends with a synchronisation of the copy stream
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->table.p + old_size, sl.d_matches.p, static_cast<size_t>(total) * sizeof(SfmDMatch), cudaMemcpyDeviceToHost,
                                     ctx->copy_stream));
-        CU_TRY(ctx, cudaStreamSynchronize(ctx->copy_stream));
-        const SfmDMatch* rec = static_cast<const SfmDMatch*>(sl.records.p);
-        try {
-            ctx->table.insert(ctx->table.end(), rec, rec + total);
-        } catch (const std::bad_alloc&) {
-            return fail(ctx, SFMM_ENOMEM, "match_pairs: out of host memory for the match table");
-        }
+        ctx->table.n = old_size + static_cast<size_t>(total);
         ctx->stats.d2h_bytes += static_cast<int64_t>(total * sizeof(SfmDMatch));
         if (ctx->have_points) {
             const size_t pb = static_cast<size_t>(total) * sizeof(double2);
@@ -834,6 +881,8 @@ int collect_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt) {
             }
             ctx->stats.d2h_bytes += static_cast<int64_t>(2 * pb);
         }
+        CU_TRY(ctx, cudaEventRecord(sl.ev_copied, ctx->copy_stream));
+        sl.copy_pending = true;
     }
     int64_t running = 0;
     for (size_t i = 0; i < np; ++i) {
@@ -890,32 +939,69 @@ void begin_stats(SfmmCtx* ctx) {
     ctx->stats.last_knn_launches = 0;
 }
 
-// Re-pitch blob rows [r0, r1) of the caller's images into `dst` (pitch bytes per row, zeroed padding).
-void pack_rows(const SfmmCtx* ctx, const void* const* data, const size_t* step_bytes, size_t row_bytes, uint64_t r0, uint64_t r1,
-               unsigned char* dst) {
-    const size_t pitch = ctx->pitch;
-    const bool widen = ctx->src_elem_type == SFMM_U8 && ctx->elem_type_pending == SFMM_F32;  // NORM_L2 on CV_8U rows
-    // image holding blob row r0
-    int32_t img = static_cast<int32_t>(std::upper_bound(ctx->row0.begin(), ctx->row0.end(), static_cast<uint32_t>(r0)) - ctx->row0.begin()) - 1;
-    for (uint64_t r = r0; r < r1; ++r, dst += pitch) {
-        while (img + 1 < ctx->n_images && ctx->row0[img + 1] <= r) ++img;
-        const uint64_t local = r - ctx->row0[img];
-        if (local < static_cast<uint64_t>(ctx->rows[img])) {
-            const size_t step = step_bytes ? step_bytes[img] : row_bytes;
-            const unsigned char* src = static_cast<const unsigned char*>(data[img]) + local * step;
-            if (widen) {  // bytes -> the same integers as fp32 (exact), zero padding up to the pitch
-                float* f = reinterpret_cast<float*>(dst);
-                const size_t n = pitch / sizeof(float);
-                for (size_t c = 0; c < row_bytes; ++c) f[c] = static_cast<float>(src[c]);
-                for (size_t c = row_bytes; c < n; ++c) f[c] = 0.f;
-            } else {
-                std::memcpy(dst, src, row_bytes);
-                if (pitch > row_bytes) std::memset(dst + row_bytes, 0, pitch - row_bytes);
-            }
+// Copies the caller's rows [r0, r1) -- counted over all images back to back, WITHOUT the blob's alignment rows -- into `dst`,
+// tightly packed (row_bytes per row).  A cv::Mat is normally continuous (step == row_bytes): its share is one memcpy.  The
+// re-pitch to 16-byte-multiple rows, the zero padding and the u8 -> fp32 widening happen on the GPU (ingest_rows_kernel).
+void pack_raw(const SfmmCtx* ctx, const void* const* data, const size_t* step_bytes, size_t row_bytes, uint64_t r0, uint64_t r1,
+              unsigned char* dst) {
+    int32_t img = static_cast<int32_t>(std::upper_bound(ctx->raw_row0.begin(), ctx->raw_row0.end(), r0) - ctx->raw_row0.begin()) - 1;
+    uint64_t r = r0;
+    while (r < r1) {
+        while (img + 1 < ctx->n_images && ctx->raw_row0[img + 1] <= r) ++img;
+        const uint64_t local = r - ctx->raw_row0[img];
+        const uint64_t n = std::min<uint64_t>(r1 - r, static_cast<uint64_t>(ctx->rows[img]) - local);
+        const size_t step = step_bytes ? step_bytes[img] : row_bytes;
+        const unsigned char* src = static_cast<const unsigned char*>(data[img]) + local * step;
+        if (step == row_bytes || n == 1) {
+            std::memcpy(dst, src, n * row_bytes);
         } else {
-            std::memset(dst, 0, pitch);  // alignment rows between images
+            for (uint64_t k = 0; k < n; ++k) std::memcpy(dst + k * row_bytes, src + k * step, row_bytes);
+        }
+        dst += n * row_bytes;
+        r += n;
+    }
+}
+
+// raw (tightly packed caller rows) -> blob rows: 16-byte-multiple pitch, zeroed padding, zero rows that align every image to a
+// multiple of four rows; CV_8U rows under NORM_L2 are widened to fp32 here (exact).  One thread per 16 output bytes.
+template <bool WIDEN>
+__global__ void ingest_rows_kernel(const unsigned char* __restrict__ raw, const uint32_t* __restrict__ raw_row0 /* n_images + 1 */,
+                                   const uint32_t* __restrict__ row0 /* n_images */, int n_images, uint32_t total_rows, uint32_t chunks_per_row,
+                                   uint32_t row_bytes, uint4* __restrict__ blob) {
+    const uint64_t idx = static_cast<uint64_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const uint32_t r = static_cast<uint32_t>(idx / chunks_per_row), c = static_cast<uint32_t>(idx % chunks_per_row);
+    if (r >= total_rows) return;
+    int lo = 0, hi = n_images;  // last image whose first blob row is <= r (empty images share their successor's first row)
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (row0[mid] <= r) lo = mid; else hi = mid;
+    }
+    const uint32_t local = r - row0[lo];
+    const bool valid = local < raw_row0[lo + 1] - raw_row0[lo];
+    const unsigned char* src = raw + static_cast<size_t>(raw_row0[lo] + (valid ? local : 0)) * row_bytes;
+    uint4 out = make_uint4(0, 0, 0, 0);
+    if (valid) {
+        if constexpr (WIDEN) {
+            float f[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) f[k] = 4 * c + k < row_bytes ? static_cast<float>(src[4 * c + k]) : 0.f;
+            out = make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3]));
+        } else {
+            uint32_t w[4] = {0, 0, 0, 0};
+            if ((row_bytes & 15u) == 0) {  // float rows, 32- and 64-byte binary rows: aligned 16-byte loads
+                if (16 * c < row_bytes) blob[idx] = *reinterpret_cast<const uint4*>(src + 16 * c);
+                else blob[idx] = out;
+                return;
+            }
+#pragma unroll
+            for (int k = 0; k < 16; ++k) {
+                const uint32_t b = 16 * c + k;
+                if (b < row_bytes) w[k >> 2] |= static_cast<uint32_t>(src[b]) << (8 * (k & 3));
+            }
+            out = make_uint4(w[0], w[1], w[2], w[3]);
         }
     }
+    blob[idx] = out;
 }
 
 }  // namespace
@@ -977,11 +1063,12 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     for (Slot& sl : ctx->slot) {
         ok = ok && (e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) == cudaSuccess;
         ok = ok && (e = cudaEventCreate(&sl.ev_knn0)) == cudaSuccess && (e = cudaEventCreate(&sl.ev_knn1)) == cudaSuccess &&
-             (e = cudaEventCreate(&sl.ev_done)) == cudaSuccess;
+             (e = cudaEventCreate(&sl.ev_done)) == cudaSuccess && (e = cudaEventCreateWithFlags(&sl.ev_copied, cudaEventDisableTiming)) == cudaSuccess;
     }
     ok = ok && (e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking)) == cudaSuccess;
     ok = ok && (e = cudaEventCreate(&ctx->ev_begin)) == cudaSuccess && (e = cudaEventCreate(&ctx->ev_end)) == cudaSuccess;
     for (auto& ev : ctx->ev_pack) ok = ok && (e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming)) == cudaSuccess;
+    ok = ok && (e = cudaEventCreateWithFlags(&ctx->ev_blob, cudaEventDisableTiming)) == cudaSuccess;
     if (!ok) {
         sfmm_destroy(ctx);
         return fail(nullptr, SFMM_ECUDA, std::string("stream/event setup: ") + cudaGetErrorString(e));
@@ -1001,9 +1088,10 @@ SFMM_API void sfmm_destroy(SfmmCtx* ctx) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
-    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked, &ctx->d_nbkey, &ctx->d_row0, &ctx->d_half}) b->release();
+    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked, &ctx->d_nbkey, &ctx->d_row0, &ctx->d_half, &ctx->d_raw, &ctx->d_raw_row0}) b->release();
     for (PinBuf& p : ctx->pack) p.release();
-    for (cudaEvent_t ev : {ctx->ev_begin, ctx->ev_end, ctx->ev_pack[0], ctx->ev_pack[1]})
+    ctx->table.release();
+    for (cudaEvent_t ev : {ctx->ev_begin, ctx->ev_end, ctx->ev_pack[0], ctx->ev_pack[1], ctx->ev_blob})
         if (ev) cudaEventDestroy(ev);
     delete ctx;
 }
@@ -1072,40 +1160,65 @@ static int impl_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* cons
     ctx->pitch = pitch;
     ctx->total_rows = total;
     ctx->blob_bytes = bytes;
+    ctx->raw_row0.assign(static_cast<size_t>(n_images) + 1, 0);
+    for (int32_t i = 0; i < n_images; ++i) ctx->raw_row0[i + 1] = ctx->raw_row0[i] + static_cast<uint64_t>(rows[i]);
+    ctx->blob_async = false;
     if (data && bytes) {
-        // Re-pitch on the host into two pinned slabs (a few threads), each followed by its own
-        // async H2D: packing slab k+1 overlaps the copy of slab k.
+        // The caller's rows travel tightly packed: a few host threads copy them into two pinned slabs (one memcpy per image when the
+        // Mat is continuous), each slab followed by its own async H2D so that filling slab k+1 overlaps the copy of slab k; one
+        // kernel then re-pitches / pads / widens them into the blob.  Nothing here waits for the device: the blob's completion is an
+        // event the matching streams wait for (ev_blob), so the tail of the upload overlaps the caller's next steps.
         cudaStream_t st = ctx->slot[0].stream;
         const size_t row_bytes = static_cast<size_t>(cols) * elem;
-        const uint64_t slab_rows = std::max<uint64_t>(4, (16u << 20) / pitch);
-        const size_t slab_bytes = static_cast<size_t>(std::min<uint64_t>(slab_rows, total)) * pitch;
+        const uint64_t raw_rows = ctx->raw_row0[n_images];
+        CU_TRY(ctx, ctx->d_raw.ensure(std::max<size_t>(16, static_cast<size_t>(raw_rows) * row_bytes + 16)));
+        CU_TRY(ctx, ctx->d_raw_row0.ensure((static_cast<size_t>(n_images) + 1) * sizeof(uint32_t)));
+        CU_TRY(ctx, ctx->d_row0.ensure((static_cast<size_t>(n_images) + 1) * sizeof(uint32_t)));
+        ctx->raw_row0_32.assign(ctx->raw_row0.begin(), ctx->raw_row0.end());
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->d_raw_row0.p, ctx->raw_row0_32.data(), ctx->raw_row0_32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        CU_TRY(ctx, cudaMemcpyAsync(ctx->d_row0.p, ctx->row0.data(), static_cast<size_t>(n_images) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+        const uint64_t slab_rows = std::max<uint64_t>(1, (32u << 20) / row_bytes);
+        const size_t slab_bytes = static_cast<size_t>(std::min<uint64_t>(slab_rows, raw_rows)) * row_bytes;
         for (PinBuf& p : ctx->pack) CU_TRY(ctx, p.ensure(slab_bytes));
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
         int k = 0;
-        for (uint64_t b = 0; b < total; b += slab_rows, ++k) {
-            const uint64_t e = std::min(total, b + slab_rows);
+        for (uint64_t b = 0; b < raw_rows; b += slab_rows, ++k) {
+            const uint64_t e = std::min(raw_rows, b + slab_rows);
             PinBuf& pin = ctx->pack[k & 1];
             if (k >= 2) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_pack[k & 1]));  // its previous copy has left the slab
             unsigned char* dst = static_cast<unsigned char*>(pin.p);
             const uint64_t n_rows = e - b;
-            const unsigned workers = static_cast<unsigned>(std::min<uint64_t>(std::min(8u, hw), std::max<uint64_t>(1, (n_rows * pitch) >> 20)));
+            const unsigned workers = static_cast<unsigned>(std::min<uint64_t>(std::min(8u, hw), std::max<uint64_t>(1, (n_rows * row_bytes) >> 21)));
             if (workers <= 1) {
-                pack_rows(ctx, data, step_bytes, row_bytes, b, e, dst);
+                pack_raw(ctx, data, step_bytes, row_bytes, b, e, dst);
             } else {
                 std::vector<std::thread> pool;
                 const uint64_t per = (n_rows + workers - 1) / workers;
-                for (unsigned w = 0; w < workers; ++w) {
+                for (unsigned w = 1; w < workers; ++w) {
                     const uint64_t wb = b + w * per, we = std::min(e, wb + per);
                     if (wb >= we) break;
-                    pool.emplace_back(pack_rows, ctx, data, step_bytes, row_bytes, wb, we, dst + (wb - b) * pitch);
+                    pool.emplace_back(pack_raw, ctx, data, step_bytes, row_bytes, wb, we, dst + (wb - b) * row_bytes);
                 }
+                pack_raw(ctx, data, step_bytes, row_bytes, b, std::min(e, b + per), dst);  // this thread takes the first share
                 for (auto& t : pool) t.join();
             }
-            CU_TRY(ctx, cudaMemcpyAsync(static_cast<unsigned char*>(ctx->blob.p) + b * pitch, dst, n_rows * pitch, cudaMemcpyHostToDevice, st));
+            CU_TRY(ctx, cudaMemcpyAsync(static_cast<unsigned char*>(ctx->d_raw.p) + b * row_bytes, dst, n_rows * row_bytes, cudaMemcpyHostToDevice, st));
             CU_TRY(ctx, cudaEventRecord(ctx->ev_pack[k & 1], st));
-            ctx->stats.h2d_bytes += static_cast<int64_t>(n_rows * pitch);
+            ctx->stats.h2d_bytes += static_cast<int64_t>(n_rows * row_bytes);
         }
-        CU_TRY(ctx, cudaStreamSynchronize(st));
+        const uint32_t chunks = static_cast<uint32_t>(pitch / 16);
+        const uint64_t n_thr = total * chunks;
+        const unsigned grid = static_cast<unsigned>((n_thr + 255) / 256);
+        if (widen)
+            ingest_rows_kernel<true><<<grid, 256, 0, st>>>(ctx->d_raw.as<unsigned char>(), ctx->d_raw_row0.as<uint32_t>(), ctx->d_row0.as<uint32_t>(), n_images,
+                                                           static_cast<uint32_t>(total), chunks, static_cast<uint32_t>(row_bytes), ctx->blob.as<uint4>());
+        else
+            ingest_rows_kernel<false><<<grid, 256, 0, st>>>(ctx->d_raw.as<unsigned char>(), ctx->d_raw_row0.as<uint32_t>(), ctx->d_row0.as<uint32_t>(), n_images,
+                                                            static_cast<uint32_t>(total), chunks, static_cast<uint32_t>(row_bytes), ctx->blob.as<uint4>());
+        CU_TRY(ctx, cudaGetLastError());
+        ctx->stats.kernel_launches += 1;
+        CU_TRY(ctx, cudaEventRecord(ctx->ev_blob, st));
+        ctx->blob_async = true;
     }
     ctx->elem_type = blob_type;
     return SFMM_OK;
@@ -1123,6 +1236,10 @@ SFMM_API int sfmm_descriptor_blob(SfmmCtx* ctx, void** device_ptr, size_t* bytes
     int rc = require_descriptors(ctx);
     if (rc) return rc;
     if (!device_ptr || !bytes) return fail(ctx, SFMM_EINVAL, "descriptor_blob: NULL argument");
+    if (ctx->blob_async) {  // the caller will touch the blob from its own streams
+        CU_TRY(ctx, cudaEventSynchronize(ctx->ev_blob));
+        ctx->blob_async = false;
+    }
     *device_ptr = ctx->blob.p;
     *bytes = ctx->blob_bytes;
     ctx->float_prepared = false;  // the caller may overwrite the blob (broadcast): re-derive norms/eligibility
@@ -1248,7 +1365,9 @@ SFMM_API int sfmm_load_table(SfmmCtx* ctx, const char* path) {
         ctx->res_qt = std::move(qt);
         ctx->res_counts = std::move(counts);
         ctx->res_offsets = std::move(offsets);
-        ctx->table = std::move(table);
+        if (ctx->table.reserve(table.size(), ctx->copy_stream)) return fail(ctx, SFMM_ENOMEM, "load_table: out of host memory");
+        if (!table.empty()) std::memcpy(ctx->table.p, table.data(), table.size() * sizeof(SfmDMatch));
+        ctx->table.n = table.size();
         ctx->n_matches = h.n_matches;
         ctx->res_slots.reserve(static_cast<size_t>(h.n_pairs));
         for (int64_t i = 0; i < h.n_pairs; ++i) {
@@ -1340,7 +1459,7 @@ static int impl_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) {
         ctx->res_counts.resize(base_pairs);
         ctx->res_offsets.resize(base_pairs);
         ctx->res_slots.resize(base_pairs);
-        ctx->table.resize(ctx->call_base);
+        ctx->table.resize_down(ctx->call_base);
         ctx->pts_left.resize(base_pts);
         ctx->pts_right.resize(base_pts);
         ctx->n_matches = base_matches;

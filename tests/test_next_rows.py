@@ -123,8 +123,9 @@ def test_group_matcher_single_process_all_gpus():
                 g.set_descriptors(descs)
                 g.match_all_pairs()
             ts = g.transfer_stats()
-            blob = sum((r + 3) // 4 * 4 for r in rows) * 64
-            assert ts["h2d_bytes"] == blob and ts["nccl_bytes"] == blob * (n_dev - 1)  # uploaded once, broadcast to the rest
+            blob = sum((r + 3) // 4 * 4 for r in rows) * 64  # device layout: 64-byte rows, images aligned to four rows
+            assert ts["h2d_bytes"] == sum(rows) * 61          # uploaded once, as the caller's tightly packed 61-byte rows
+            assert ts["nccl_bytes"] == blob * (n_dev - 1)      # broadcast to every other device
             for (q, t) in synth.all_pairs(len(rows)):
                 assert g.getMatching(q, t).tobytes() == oracle.match_pair(descs[q], descs[t], 0, 0.8, cross).tobytes(), (q, t, cross)
             with pytest.raises(SfmmError) as e:
