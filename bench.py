@@ -17,8 +17,9 @@ shape (cfg4s) ride along in the N=1 line as `configs1_cfg2` and `float` blocks.
 
   value  : pair-matches/s with the descriptors already resident in HBM on every rank when the timed region
            starts; the region covers matching on all ranks AND the gather of every match list to rank 0's host
-           memory (N=1: the library's pipelined device->host path; N>1: per-chunk NCCL gather to rank 0 +
-           device->host there).  Timed on the device (CUDA events around each step), max over ranks.
+           memory (the library's pipelined device->host path on every rank; at N>1 into shared page-locked tables
+           rank 0 maps, --gather shared, with the NCCL forms of the gather measured beside it as gather_alt).
+           Timed on the device (CUDA events around each step), max over ranks.
   e2e    : the same metric through the public API with HOST buffers in: H2D of the descriptors, (NCCL
            broadcast), matching, (NCCL gather to rank 0), D2H of the match table.  Wall clock, max over ranks.
   resident_device_only: the round-1 definition of `value` (match lists left in HBM), for continuity.
@@ -373,8 +374,19 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
         acc["matches"] += k
         return c, mm
 
-    def resident_step():
+    def resident_step(gather=None):
         """Descriptors resident -> every match list in rank 0's host memory."""
+        gather = gather or args.gather
+        if world > 1 and gather == "shared":
+            t = D.match_and_share(m, pairs, shards, 0)
+            note_stats()
+            acc["matches"] += m.shared_table_info()[1]
+            return t
+        if world > 1 and gather == "nccl-once":
+            c, mm, k = D.match_shard(m, mine, rows)
+            note_stats()
+            acc["matches"] += k
+            return D.gather_results(pairs, shards, c, mm, 0)
         if world > 1:
             return D.match_and_gather(match_fn, pairs, shards, rows, 0)
         m.match_all_pairs()
@@ -414,6 +426,17 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
         sampler.__exit__()
     launches = m.stats()["kernel_launches"] - launches0
     res_acc = dict(acc)
+    gather_alt = None
+    if world > 1 and alt:  # the other forms of the gather step on the same resident descriptors, for the record
+        gather_alt = {}
+        for mode in ("shared", "nccl", "nccl-once"):
+            if mode == args.gather:
+                continue
+            resident_step(mode)
+            t_alt = timed_steps(2, lambda: resident_step(mode)) / 2
+            tt = torch.tensor([t_alt], dtype=torch.float64, device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            gather_alt[mode] = {"value": len(pairs) / (tt.item() * 1e-3), "ms_per_step": tt.item()}
 
     # ---- round-1 definition (match lists left in HBM): continuity + the kernel's share of a pure device step
     dev_ms = []
@@ -448,7 +471,7 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
     def e2e_step():
         s0 = m.stats()
         if world > 1:
-            table, _ = D.match_all_pairs_distributed(m, descs, 0)
+            table, _ = D.match_all_pairs_distributed(m, descs, 0, gather=args.gather)
         else:
             ta = time.perf_counter()
             m.set_descriptors(descs)
@@ -483,7 +506,7 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         e2e_ms = tmax.item()
         if rank == 0:
-            d2h = int(table.matches.nbytes + table.counts.nbytes)
+            d2h = int((table.nbytes if hasattr(table, "parts") else table.matches.nbytes) + table.counts.nbytes)
 
     out = None
     if rank == 0:
@@ -514,7 +537,7 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
                "resident_device_only": {"value": len(pairs) / (dev_only_max * 1e-3) if dev_only_max else None, "ms_per_step": dev_only_max,
                                         "note": "round-1 definition of `value`: match lists left in HBM (sfmm_match_pairs_device), library CUDA events"},
                "gpu_launches": launches_sum, "roofline": roof, "clocks": sampler.summary() if sampler else None,
-               "gather_chunks": D.gather_chunks(pairs, shards, rows) if world > 1 else None}
+               "gather_chunks": D.gather_chunks(pairs, shards, rows) if world > 1 else None, "gather_alt": gather_alt}
         if verify:
             get = table.getMatching if world > 1 else (lambda q, t: m.getMatching(q, t))
             out["verified"] = verify_pairs(get, pairs, descs, norm, verify, cross)
@@ -581,6 +604,10 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0)
     ap.add_argument("--e2e-warmup", type=int, default=2,
                     help="untimed end-to-end steps: the pipeline slots size their device/pinned buffers over the first two")
+    ap.add_argument("--gather", default="shared", choices=["shared", "nccl", "nccl-once"],
+                    help="N>1: how the match lists reach rank 0's host memory -- shared: every GPU copies its records over its own PCIe link "
+                         "into a shared page-locked table rank 0 maps; nccl: chunk-wise NCCL gather to rank 0's GPU + D2H there, overlapped "
+                         "with matching; nccl-once: one NCCL gather at the end (round 1).  The other two are reported as gather_alt")
     ap.add_argument("--verify", type=int, default=2, help="check this many random pairs of the e2e table against the CPU oracle (0 = off)")
     args = ap.parse_args()
 
@@ -625,12 +652,12 @@ def main():
                                        "(matching + gather + device->host), CUDA events per step, max over ranks",
                        "l2": "flushed between steps (256 MiB memset outside the timed events); the operand set is also larger than L2",
                        "parallelism": f"pairs sharded over {env.world} rank(s) by cost-sorted snake deal"
-                                      + (f"; NCCL broadcast (e2e only) + pipelined NCCL gather to rank 0 in {res['gather_chunks']} chunks" if env.world > 1 else "")},
+                                      + (f"; NCCL broadcast of the descriptors (e2e only); gather={args.gather}" if env.world > 1 else "")},
             "wall_ms_per_step": res["wall_ms_per_step"],
             "e2e": res["e2e"], "resident_device_only": res["resident_device_only"],
             "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "clocks": res["clocks"],
         }
-        for k in ("alt_engine", "verified"):
+        for k in ("alt_engine", "verified", "gather_alt"):
             if k in res:
                 line[k] = res[k]
         if env.world == 1 and not args.no_cpu_baseline:

@@ -252,6 +252,17 @@ SFMM_API int sfmm_group_get_pair(const SfmmGroup* g, int32_t q, int32_t t, const
 /* Bytes moved by the last sfmm_group_set_descriptors: host->device (once) and device->device (NCCL). */
 SFMM_API int sfmm_group_transfer_stats(const SfmmGroup* g, int64_t* h2d_bytes, int64_t* nccl_bytes);
 
+/* Multi-PROCESS hosts (one rank per GPU): put this context's match table into a POSIX shared-memory segment
+ * ("<shm_prefix>.<generation>", page-locked with cudaHostRegister) instead of private pinned memory, so that the
+ * rank that assembles the all-pairs result maps the records this GPU copied over its OWN PCIe link -- no inter-GPU
+ * transfer and no second host copy ("gathered to rank 0" without a rank-0 funnel; the NCCL gather of
+ * sfm_danpipeline_b200/distributed.py remains the alternative).  shm_prefix = "/name" (no further slashes); NULL or ""
+ * returns to private memory.  Drops all results.  sfmm_shared_table_info reports the segment currently holding the
+ * table (it changes when the table grows) and the number of records in it; the segment is unlinked by
+ * sfmm_destroy / the next growth, a reader's existing mapping stays valid until it unmaps. */
+SFMM_API int sfmm_share_table(SfmmCtx* ctx, const char* shm_prefix);
+SFMM_API int sfmm_shared_table_info(const SfmmCtx* ctx, char* name, size_t name_capacity, int64_t* n_records);
+
 SFMM_API int sfmm_clear_results(SfmmCtx* ctx);
 SFMM_API int sfmm_get_stats(const SfmmCtx* ctx, SfmmStats* out);
 /* "major.minor.patch (sm_100a)" */

@@ -27,7 +27,7 @@ EXPORTS = (
     "sfmm_set_points", "sfmm_get_pair_points", "sfmm_save_table", "sfmm_load_table", "sfmm_image_rows",
     "sfmm_group_create", "sfmm_group_destroy", "sfmm_group_last_error", "sfmm_group_size", "sfmm_group_context",
     "sfmm_group_set_descriptors", "sfmm_group_match_all_pairs", "sfmm_group_match_pairs", "sfmm_group_get_pair",
-    "sfmm_group_transfer_stats",
+    "sfmm_group_transfer_stats", "sfmm_share_table", "sfmm_shared_table_info",
 )
 
 
@@ -91,6 +91,8 @@ def load() -> C.CDLL:
     L.sfmm_load_table.argtypes = [vp, C.c_char_p]
     L.sfmm_get_stats.argtypes = [vp, P(SfmmStats)]
     L.sfmm_image_rows.argtypes = [vp, i32, P(i32)]
+    L.sfmm_share_table.argtypes = [vp, C.c_char_p]
+    L.sfmm_shared_table_info.argtypes = [vp, C.c_char_p, sz, P(i64)]
     L.sfmm_group_create.argtypes = [P(SfmmConfig), i32, P(i32), P(vp)]
     L.sfmm_group_destroy.restype = None
     L.sfmm_group_destroy.argtypes = [vp]

@@ -24,6 +24,10 @@
 
 #include <cuda_runtime.h>
 #include <dlfcn.h>
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <nccl.h>  // types and prototypes only: the library is dlopen'ed by sfmm_group_create, never linked
 
 #include "../../include/sfm_match.h"
@@ -97,6 +101,12 @@ struct HostTable {
     SfmDMatch* p = nullptr;
     size_t n = 0, cap = 0;
     bool pinned = false;
+    // Shared mode (sfmm_share_table): the block is a POSIX shared-memory segment "<prefix>.<generation>", page-locked with
+    // cudaHostRegister, so that another process of the same host (rank 0 of a multi-process job) can map the records this GPU
+    // wrote over its own PCIe link -- the multi-process form of "every device copies into one host table".
+    std::string shm_prefix, shm_name;
+    int shm_generation = 0;
+    size_t map_bytes = 0;
     SfmDMatch* data() const { return p; }
     size_t size() const { return n; }
     size_t capacity() const { return cap; }
@@ -104,11 +114,21 @@ struct HostTable {
     void resize_down(size_t m) { if (m < n) n = m; }
     void release() {
         if (p) {
-            if (pinned) cudaFreeHost(p);
-            else std::free(p);
+            if (!shm_name.empty()) {
+                if (pinned) cudaHostUnregister(p);
+                munmap(p, map_bytes);
+                shm_unlink(shm_name.c_str());
+                shm_name.clear();
+            } else if (pinned) {
+                cudaFreeHost(p);
+            } else {
+                std::free(p);
+            }
         }
+        (void)cudaGetLastError();
         p = nullptr;
         n = cap = 0;
+        map_bytes = 0;
     }
     // Capacity for `want` records.  `drain` is synchronised before the old block is given up: copies into it may be in flight.
     int reserve(size_t want, cudaStream_t drain) {
@@ -116,20 +136,48 @@ struct HostTable {
         const size_t ncap = std::max<size_t>(want, 1 << 12);
         void* q = nullptr;
         bool pin = true;
-        if (cudaMallocHost(&q, ncap * sizeof(SfmDMatch)) != cudaSuccess) {
+        std::string name;
+        size_t bytes = ncap * sizeof(SfmDMatch);
+        if (!shm_prefix.empty()) {
+            name = shm_prefix + "." + std::to_string(shm_generation++);
+            bytes = (bytes + 4095) & ~size_t(4095);
+            const int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
+            if (fd < 0) return SFMM_ENOMEM;
+            if (ftruncate(fd, static_cast<off_t>(bytes)) != 0) {
+                close(fd);
+                shm_unlink(name.c_str());
+                return SFMM_ENOMEM;
+            }
+            q = mmap(nullptr, bytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_POPULATE, fd, 0);
+            close(fd);
+            if (q == MAP_FAILED) {
+                shm_unlink(name.c_str());
+                return SFMM_ENOMEM;
+            }
+            if (cudaHostRegister(q, bytes, cudaHostRegisterPortable) != cudaSuccess) {
+                (void)cudaGetLastError();
+                pin = false;  // still correct: copies into it are staged by the driver
+            }
+        } else if (cudaMallocHost(&q, bytes) != cudaSuccess) {
             (void)cudaGetLastError();
             pin = false;
-            q = std::malloc(ncap * sizeof(SfmDMatch));
+            q = std::malloc(bytes);
             if (!q) return SFMM_ENOMEM;
         }
         if (drain) cudaStreamSynchronize(drain);
         if (n) std::memcpy(q, p, n * sizeof(SfmDMatch));
         const size_t keep = n;
+        const std::string prefix = shm_prefix;
+        const int gen = shm_generation;
         release();
+        shm_prefix = prefix;
+        shm_generation = gen;
         p = static_cast<SfmDMatch*>(q);
         n = keep;
         cap = ncap;
         pinned = pin;
+        shm_name = name;
+        map_bytes = bytes;
         return SFMM_OK;
     }
 };
@@ -1376,6 +1424,30 @@ SFMM_API int sfmm_load_table(SfmmCtx* ctx, const char* path) {
         }
         return SFMM_OK;
     });
+}
+
+SFMM_API int sfmm_share_table(SfmmCtx* ctx, const char* shm_prefix) {
+    if (!ctx) return SFMM_EINVAL;
+    if (shm_prefix && shm_prefix[0] && (shm_prefix[0] != '/' || std::strchr(shm_prefix + 1, '/') || std::strlen(shm_prefix) > 200))
+        return fail(ctx, SFMM_EINVAL, "share_table: the prefix must be a POSIX shared-memory name: '/' + a name without further slashes");
+    int rc = bind_device(ctx);
+    if (rc) return rc;
+    if ((rc = sync_all(ctx))) return rc;
+    return guarded(ctx, [&]() -> int {
+        clear_results(ctx);
+        ctx->table.release();  // the next match call allocates the table in the new mode
+        ctx->table.shm_prefix = shm_prefix ? shm_prefix : "";
+        return SFMM_OK;
+    });
+}
+
+SFMM_API int sfmm_shared_table_info(const SfmmCtx* ctx, char* name, size_t name_capacity, int64_t* n_records) {
+    if (!ctx || !name || !n_records || name_capacity == 0) return SFMM_EINVAL;
+    if (ctx->table.shm_prefix.empty()) return SFMM_ESTATE;
+    if (ctx->table.shm_name.size() + 1 > name_capacity) return SFMM_ERANGE;
+    std::memcpy(name, ctx->table.shm_name.c_str(), ctx->table.shm_name.size() + 1);  // empty while nothing has been matched yet
+    *n_records = static_cast<int64_t>(ctx->table.size());
+    return SFMM_OK;
 }
 
 SFMM_API int sfmm_clear_results(SfmmCtx* ctx) {

@@ -65,14 +65,20 @@ def device_bytes_as_tensor(ptr: int, nbytes: int, device: int) -> torch.Tensor:
 def broadcast_descriptors(matcher, descriptors, src: int = 0, group=None):
     """Step 1.  `descriptors` is only read on rank `src`.  Returns (rows, cols)."""
     rank = dist.get_rank(group)
-    meta = [None]
+    dev = torch.device("cuda", matcher.device)
+    # the layout (image count, width, element type, rows per image) travels as two small tensors: no pickling on the path
+    head = torch.zeros(3, dtype=torch.int64, device=dev)
     if rank == src:
         matcher.set_descriptors(descriptors)
-        meta[0] = (list(matcher.rows), int(matcher.cols), bool(matcher.elem_u8))
-    dist.broadcast_object_list(meta, src=src, group=group)
-    rows, cols, elem_u8 = meta[0]
+        head = torch.tensor([len(matcher.rows), int(matcher.cols), int(bool(matcher.elem_u8))], dtype=torch.int64, device=dev)
+    dist.broadcast(head, src=src, group=group)
+    n_images, cols, elem_u8 = (int(x) for x in head.cpu().tolist())
+    rows_t = torch.tensor(matcher.rows, dtype=torch.int32, device=dev) if rank == src else torch.empty(n_images, dtype=torch.int32, device=dev)
+    if n_images:
+        dist.broadcast(rows_t, src=src, group=group)
+    rows = rows_t.cpu().tolist() if rank != src else list(matcher.rows)
     if rank != src:
-        matcher.reserve_descriptors(rows, cols, elem_u8)
+        matcher.reserve_descriptors(rows, cols, bool(elem_u8))
     ptr, nbytes = matcher.descriptor_blob()
     if nbytes:
         blob = device_bytes_as_tensor(ptr, nbytes, matcher.device)
@@ -206,12 +212,15 @@ def chunk_bounds(shard_rows_q: np.ndarray, n_chunks: int) -> list[tuple[int, int
 
 
 def gather_chunks(pairs: np.ndarray, shards: list[np.ndarray], rows) -> int:
-    """How many chunks the pipelined gather uses: one per ~4 Mi query rows of the busiest rank (a few ms of
-    matching each on a B200 -- long enough to hide a chunk's transfer, short enough that the last, unhidden
-    chunk is a small fraction), between 1 and 16.  The same on every rank."""
+    """How many chunks the pipelined NCCL gather uses: one per ~16 Mi query rows of the busiest rank, between 2 (so that
+    something overlaps) and 8; 1 for small jobs.  Measured at cfg-3 on 2 GPUs: a chunk boundary costs ~0.75 ms (the GPU idles
+    while the host notices the end of the chunk, posts the sends and plans the next launch), the last chunk's device -> host
+    copy is exposed -- 16 chunks cost 12 ms per step, the optimum is near sqrt(total copy time / boundary cost).  The same on every rank."""
     rows = np.asarray(rows, np.int64)
     busiest = max((int(rows[pairs[sh, 0]].sum()) for sh in shards if len(sh)), default=0)
-    return int(min(16, max(1, -(-busiest // (4 << 20)))))
+    if busiest <= (4 << 20):
+        return 1
+    return int(min(8, max(2, -(-busiest // (16 << 20)))))
 
 
 def match_and_gather(match_fn, pairs: np.ndarray, shards: list[np.ndarray], rows, dst: int = 0, group=None,
@@ -353,6 +362,107 @@ def match_and_gather(match_fn, pairs: np.ndarray, shards: list[np.ndarray], rows
     return _own(PairTable(pairs, counts, offsets, host[:used].numpy().view(DMATCH_DTYPE).reshape(-1)), buf)
 
 
+# --------------------------------------------------------------------------- gather through a shared pinned host table
+@dataclass
+class ShardedPairTable:
+    """All-pairs result on the destination rank when every rank wrote its records into its own shared-memory table
+    (``match_and_share``): pair i lives in ``parts[owner[i]][offsets[i] : offsets[i] + counts[i]]``.  Same look-up interface
+    as PairTable.  The parts are read-only maps of the other ranks' tables: valid until one of them matches again
+    (``detach()`` copies everything into one private PairTable)."""
+    pairs: np.ndarray    # (n,2) int32
+    counts: np.ndarray   # (n,) int32
+    offsets: np.ndarray  # (n,) int64, inside the owner's part
+    owner: np.ndarray    # (n,) int16
+    parts: list          # one DMATCH_DTYPE array per rank
+
+    def getMatching(self, idx_query: int, idx_train: int) -> np.ndarray:
+        if not hasattr(self, "_index"):
+            self._index = {(int(q), int(t)): i for i, (q, t) in enumerate(self.pairs)}
+        i = self._index[(idx_query, idx_train)]
+        return self.parts[self.owner[i]][self.offsets[i]: self.offsets[i] + self.counts[i]]
+
+    @property
+    def n_matches(self) -> int:
+        return int(sum(len(p) for p in self.parts))
+
+    @property
+    def nbytes(self) -> int:
+        return int(sum(p.nbytes for p in self.parts))
+
+    @property
+    def matches(self) -> np.ndarray:
+        return np.concatenate(self.parts) if self.parts else np.zeros(0, DMATCH_DTYPE)
+
+    def detach(self) -> PairTable:
+        base = np.concatenate([[0], np.cumsum([len(p) for p in self.parts])]).astype(np.int64)
+        return PairTable(self.pairs, self.counts.copy(), self.offsets + base[self.owner], self.matches)
+
+
+def assemble_shared(pairs: np.ndarray, shards: list[np.ndarray], metas: list[np.ndarray], prefix_base: str,
+                    shm_dir: str = "/dev/shm") -> ShardedPairTable:
+    """Destination side of match_and_share.  metas[r] = int32 [generation, n_lo, n_hi, counts of rank r's shard...]."""
+    counts = np.zeros(len(pairs), np.int32)
+    offsets = np.zeros(len(pairs), np.int64)
+    owner = np.zeros(len(pairs), np.int16)
+    parts = []
+    for r, meta in enumerate(metas):
+        gen, n = int(meta[0]), (int(meta[1]) & 0xFFFFFFFF) | (int(meta[2]) << 32)
+        c = np.asarray(meta[3: 3 + len(shards[r])], np.int32)
+        counts[shards[r]] = c
+        offsets[shards[r]] = np.concatenate([[0], np.cumsum(c[:-1], dtype=np.int64)]) if len(c) else 0  # records lie in pair order
+        owner[shards[r]] = r
+        assert int(c.sum()) == n, (r, int(c.sum()), n)
+        if n:
+            parts.append(np.memmap(f"{shm_dir}{prefix_base}{r}.{gen}", dtype=DMATCH_DTYPE, mode="r", shape=(n,)))
+        else:
+            parts.append(np.zeros(0, DMATCH_DTYPE))
+    return ShardedPairTable(pairs, counts, offsets, owner, parts)
+
+
+def enable_shared_tables(matcher, group=None) -> str:
+    """Once per matcher: every rank moves its match table into a shared-memory segment named after a job nonce that
+    rank 0 draws and broadcasts.  Returns the common prefix ("/sfmm_<nonce>_"; rank r's table is "<prefix>r.<generation>")."""
+    base = getattr(matcher, "_shm_prefix_base", None)
+    if base:
+        return base
+    import os
+    dev = torch.device("cuda", matcher.device)
+    nonce = torch.tensor([int.from_bytes(os.urandom(7), "little")], dtype=torch.int64, device=dev)
+    dist.broadcast(nonce, src=0, group=group)
+    base = f"/sfmm_{int(nonce.item()):x}_"
+    matcher.share_table(f"{base}{dist.get_rank(group)}")
+    matcher._shm_prefix_base = base
+    return base
+
+
+def match_and_share(matcher, pairs: np.ndarray, shards: list[np.ndarray], dst: int = 0, group=None):
+    """Steps 3 + 4 without a funnel: every rank matches its shard through the library's own pipelined host path -- chunk k's
+    records go device -> host over THIS GPU's PCIe link, straight into its (shared, page-locked) match table, while chunk k+1
+    is being matched -- and `dst` maps the other ranks' tables.  The only traffic between ranks is one small NCCL gather of
+    per-pair counts.  Returns a ShardedPairTable on `dst`, None elsewhere."""
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    base = enable_shared_tables(matcher, group)
+    mine = pairs[shards[rank]]
+    matcher.clear_results()
+    matcher.match_pairs(mine)
+    _p, counts, _o, _m = matcher.result_table(copy=False)
+    name, n = matcher.shared_table_info()
+    gen = int(name.rsplit(".", 1)[1]) if name else 0
+    width = 3 + max(len(sh) for sh in shards)
+    meta = np.zeros(width, np.int32)
+    meta[0], meta[2] = gen, n >> 32
+    meta[1:2] = np.array([n & 0xFFFFFFFF], np.uint32).view(np.int32)
+    meta[3: 3 + len(counts)] = counts
+    dev = torch.device("cuda", matcher.device)
+    t = torch.from_numpy(meta).to(dev)
+    out = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
+    dist.gather(t, out, dst=dst, group=group)
+    if rank != dst:
+        return None
+    metas = [o.cpu().numpy() for o in out]
+    return assemble_shared(pairs, shards, metas, base)
+
+
 # --------------------------------------------------------------------------- one rank's shard
 _SHARD_BUF: dict = {}
 
@@ -388,10 +498,15 @@ def match_shard(matcher, mine: np.ndarray, rows, fraction: float = 0.25, slot: i
 
 
 # --------------------------------------------------------------------------- the whole job
-def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, resident: bool = False, pipelined: bool = True):
+def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, resident: bool = False, gather: str = "shared"):
     """Steps 1-4 on every rank of the default (NCCL) group.  `descriptors` is read on rank `dst`
-    only; `resident=True` skips step 1 (descriptors already broadcast); `pipelined=False` matches the whole
-    shard first and gathers once at the end (gather_results).  Returns (PairTable on dst | None, info dict)."""
+    only; `resident=True` skips step 1 (descriptors already broadcast).  `gather` picks step 4:
+      "shared"  every rank's records go device -> host over its own PCIe link into a shared page-locked table that `dst` maps
+                (match_and_share; the default: no funnel, no GPU time spent on transfers),
+      "nccl"    chunk-wise NCCL gather to `dst`'s device, copied to host there while the next chunk is matched (match_and_gather),
+      "nccl-once" the whole shard first, one NCCL gather at the end (gather_results).
+    Returns (PairTable / ShardedPairTable on dst | None, info dict)."""
+    pipelined = gather == "nccl"
     import os
     import time
     trace = os.environ.get("SFMM_TRACE") == "1"
@@ -406,7 +521,11 @@ def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, 
     mine = pairs[shards[rank]]
     t2 = time.perf_counter()
     n = 0
-    if pipelined:
+    if gather == "shared":
+        table = match_and_share(matcher, pairs, shards, dst, group)
+        n = matcher.shared_table_info()[1]
+        t3 = t4 = time.perf_counter()
+    elif pipelined:
         def match_fn(chunk, slot):
             nonlocal n
             c, m, k = match_shard(matcher, chunk, rows, slot=slot)

@@ -192,6 +192,16 @@ class Matcher:
     def clear_results(self):
         self._check(self._L.sfmm_clear_results(self._ctx))
 
+    def share_table(self, shm_prefix: str | None):
+        """Keep the match table in a POSIX shared-memory segment other processes of this host can map (see sfm_match.h)."""
+        self._check(self._L.sfmm_share_table(self._ctx, shm_prefix.encode() if shm_prefix else None))
+
+    def shared_table_info(self) -> tuple[str, int]:
+        """(segment name, records in it) of the shared table; the name is '' until something has been matched."""
+        buf, n = C.create_string_buffer(256), C.c_int64()
+        self._check(self._L.sfmm_shared_table_info(self._ctx, buf, 256, C.byref(n)))
+        return buf.value.decode(), int(n.value)
+
     def stats(self) -> dict:
         s = _lib.SfmmStats()
         self._check(self._L.sfmm_get_stats(self._ctx, C.byref(s)))

@@ -122,3 +122,32 @@ def test_returned_tables_do_not_alias_each_other():
     import gc
     gc.collect()
     assert any(x.data_ptr() == a.data_ptr() for x in D._POOL.free)  # handed back only once the table is gone
+
+
+def test_assemble_shared_tables_from_segments(tmp_path):
+    """Destination side of the shared-table gather (match_and_share): directory + read-only maps of every rank's segment."""
+    rows = [120, 0, 300, 64, 1, 200]
+    descs = synth.binary_images(len(rows), rows, seed=4)
+    pairs = D.all_pairs(len(rows))
+    world = 3
+    shards = D.shard_pairs(pairs, rows, world)
+    base = "/sfmm_test_"
+    metas = []
+    width = 3 + max(len(sh) for sh in shards)
+    for r in range(world):
+        res = [oracle.match_pair(descs[q], descs[t], 0) for q, t in pairs[shards[r]]]
+        cat = np.concatenate(res) if res else np.zeros(0, oracle.DMATCH_DTYPE)
+        gen = 5 + r
+        if len(cat):
+            cat.tofile(str(tmp_path) + f"{base}{r}.{gen}")
+        meta = np.zeros(width, np.int32)
+        meta[0], meta[1], meta[2] = gen, len(cat), 0
+        meta[3: 3 + len(res)] = [len(x) for x in res]
+        metas.append(meta)
+    table = D.assemble_shared(pairs, shards, metas, base, shm_dir=str(tmp_path))
+    for q, t in pairs:
+        assert np.asarray(table.getMatching(int(q), int(t))).tobytes() == oracle.match_pair(descs[q], descs[t], 0).tobytes()
+    flat = table.detach()
+    assert int(flat.counts.sum()) == len(flat.matches) == table.n_matches
+    for q, t in pairs:
+        assert flat.getMatching(int(q), int(t)).tobytes() == oracle.match_pair(descs[q], descs[t], 0).tobytes()

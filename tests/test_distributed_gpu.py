@@ -36,13 +36,17 @@ def _worker(rank, world, port, out_path):
         descs = synth.binary_images(len(rows), rows, seed=41)
         descs[1] = np.zeros((0, 61), np.uint8)
         with Matcher(NORM_HAMMING, device=rank) as m:
-            for _ in range(2):  # twice: cached buffers, re-broadcast
-                table, info = D.match_all_pairs_distributed(m, descs if rank == 0 else None, 0)
+            ok = True
+            for gather in ("shared", "nccl", "nccl-once"):  # every form of step 4 gives the same table
+                for _ in range(2):  # twice: cached buffers, re-broadcast
+                    table, info = D.match_all_pairs_distributed(m, descs if rank == 0 else None, 0, gather=gather)
+                if rank == 0:
+                    for (q, t) in synth.all_pairs(len(rows)):
+                        ok &= np.asarray(table.getMatching(q, t)).tobytes() == oracle.match_pair(descs[q], descs[t], 0).tobytes()
+                    ok &= int(table.counts.sum()) == len(table.matches)
+                table = None
+                dist.barrier()
             if rank == 0:
-                ok = True
-                for (q, t) in synth.all_pairs(len(rows)):
-                    ok &= np.asarray(table.getMatching(q, t)).tobytes() == oracle.match_pair(descs[q], descs[t], 0).tobytes()
-                ok &= int(table.counts.sum()) == len(table.matches)
                 open(out_path, "w").write("ok" if ok else "mismatch")
     finally:
         dist.destroy_process_group()
