@@ -33,8 +33,11 @@ struct KnnTile {
     uint32_t q0;     // first query row (image-relative) of the tile
     uint32_t t0;     // train range [t0, t1), image-relative
     uint32_t t1;
-    uint32_t split;  // which partial list this tile writes
+    uint32_t split;  // which partial list this tile writes; bit 31 = "reverse" tile (roles of the two images swapped: its rows'
+                     // 1-NN are the forward problem's column minima), bit 30 = the reverse tile's rows are GATHERED through the pair's
+                     // candidate list (q0 counts list entries), see filter.cuh: cross_mark / cross_compact
 };
+static constexpr uint32_t TILE_REVERSE = 0x80000000u, TILE_GATHER = 0x40000000u, TILE_SPLIT_MASK = 0x3FFFFFFFu;
 
 // One thread block of the ratio/cross-check/compaction kernels.
 struct FilterTile {

@@ -176,6 +176,77 @@ filter_write_kernel(const FilterTile* __restrict__ ftiles, const PairDesc* __res
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------------
+// Symmetric cross-check without a second full pass (tensor kernels).  Only the train rows that some query row of the pair
+// selected as its nearest neighbour AND that passed the ratio test can end up in the match list, so only THEIR column minima
+// are needed: typically an eighth of the train image instead of all of it.
+//   cross_mark    : every query row that passes the ratio test flags its nearest train row        (flags: one byte per train row)
+//   cross_compact : per pair, the flagged rows in ascending order -> candidate list; the pair's "reverse" work items (128
+//                   candidate rows each, bit 30/31 of KnnTile::split) are appended to the launch's reverse item list
+// The 2-NN kernel then runs the reverse items only (rows gathered through the list, the whole query image streamed past
+// them) and the filter looks the minima up as before.  Cost: matches/Nt of a forward pass instead of a whole one.
+template <bool IS_FLOAT>
+__global__ void __launch_bounds__(FILTER_THREADS)
+cross_mark_kernel(const FilterTile* __restrict__ ftiles, const PairDesc* __restrict__ pairs, const KnnEntry* __restrict__ knn, float ratio,
+                  unsigned char* __restrict__ flags) {
+    const FilterTile ft = ftiles[blockIdx.x];
+    const PairDesc pd = pairs[ft.pair];
+#pragma unroll
+    for (int k = 0; k < FILTER_PER_THREAD; ++k) {
+        const uint32_t q = ft.q0 + threadIdx.x * FILTER_PER_THREAD + k;
+        if (q >= pd.nq) continue;
+        unsigned long long k1, k2;
+        merged_top2(knn, pd, q, k1, k2);
+        if (k2 == KEY_NONE) continue;
+        if (!(key_distance<IS_FLOAT>(k1) <= __fmul_rn(ratio, key_distance<IS_FLOAT>(k2)))) continue;
+        flags[pd.col_off + static_cast<uint32_t>(k1)] = 1;  // (several rows may write the same byte: same value)
+    }
+}
+
+// One CTA per pair.  cand[col_off ..] receives the flagged train rows in ascending order, n_cand[pair] their number.
+static constexpr int COMPACT_THREADS = 256;
+__global__ void __launch_bounds__(COMPACT_THREADS)
+cross_compact_kernel(const PairDesc* __restrict__ pairs, const unsigned char* __restrict__ flags, uint32_t* __restrict__ cand,
+                     uint32_t* __restrict__ n_cand, KnnTile* __restrict__ rtiles, uint32_t* __restrict__ n_rtiles, uint32_t rows_per_item) {
+    PairDesc pd = pairs[blockIdx.x];
+    if (pd.n_splits == 0) pd.nt = 0;  // a pair without work (no query rows / fewer than two train rows) owns no flags
+    __shared__ uint32_t warp_tot[COMPACT_THREADS / 32];
+    __shared__ uint32_t carry_sh, first_item;
+    if (threadIdx.x == 0) carry_sh = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < pd.nt; base += COMPACT_THREADS) {
+        const uint32_t t = base + threadIdx.x;
+        const uint32_t f = (t < pd.nt && flags[pd.col_off + t]) ? 1u : 0u;
+        const uint32_t ballot = __ballot_sync(0xFFFFFFFFu, f);
+        const uint32_t lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+        if (lane == 0) warp_tot[w] = __popc(ballot);
+        __syncthreads();
+        uint32_t wbase = 0;
+        for (uint32_t i = 0; i < w; ++i) wbase += warp_tot[i];
+        const uint32_t carry = carry_sh;
+        if (f) cand[pd.col_off + carry + wbase + __popc(ballot & ((1u << lane) - 1u))] = t;
+        __syncthreads();
+        if (threadIdx.x == COMPACT_THREADS - 1) carry_sh = carry + wbase + __popc(ballot);
+        __syncthreads();
+    }
+    const uint32_t nc = carry_sh;
+    const uint32_t items = (nc + rows_per_item - 1) / rows_per_item;
+    if (threadIdx.x == 0) {
+        n_cand[blockIdx.x] = nc;
+        first_item = items ? atomicAdd(n_rtiles, items) : 0u;
+    }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < items; i += COMPACT_THREADS) {
+        KnnTile kt;
+        kt.pair = blockIdx.x;
+        kt.q0 = i * rows_per_item;  // first candidate-list entry of the item
+        kt.t0 = 0;                  // the whole query image is streamed past the candidates
+        kt.t1 = pd.nq;
+        kt.split = TILE_REVERSE | TILE_GATHER;
+        rtiles[first_item + i] = kt;
+    }
+}
+
 // Raw merged 2-NN list of ONE pair as (train index, float distance) arrays -- what
 // cv::BFMatcher::knnMatch(k=2) returns (src/Sfm.cpp:599); for parity tests (sfmm_knn_pair).
 template <bool IS_FLOAT>

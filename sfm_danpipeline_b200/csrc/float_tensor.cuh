@@ -579,7 +579,7 @@ __device__ __forceinline__ float collect_threshold(bool valid, float nq2, const 
 template <int MODE, int GROUPS = 2>
 __device__ __forceinline__ void finish_rows(uint4* merge /* [GROUPS-1][FT_M] */, const Top2& best, uint32_t grp, uint32_t row, uint32_t qrow, uint32_t nq,
                                             bool reverse, uint32_t split, unsigned long long knn_off, unsigned long long col_off,
-                                            KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin) {
+                                            KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, uint32_t out_row) {
     if (grp != 0) merge[(grp - 1) * FT_M + row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
     if constexpr (GROUPS == 2) asm volatile("bar.sync 1, 256;" ::: "memory");  // the epilogue warps only
     else asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -597,7 +597,7 @@ __device__ __forceinline__ void finish_rows(uint4* merge /* [GROUPS-1][FT_M] */,
             k2 = min(min(k2, hi), o2);
         }
         if (reverse) {  // column minimum of the forward problem: (d^2, lowest query index); splits merge by atomicMin
-            if (k1 != KEY_NONE) atomicMin(colmin + col_off + qrow, k1);
+            if (k1 != KEY_NONE) atomicMin(colmin + col_off + out_row, k1);  // (out_row == qrow unless the rows were gathered)
         } else {
             KnnEntry e;
             if constexpr (MODE == TM_I8 || MODE == TM_I8P || tm_is_rank(MODE)) {
@@ -759,8 +759,8 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             // Symmetric cross-check = the same problem with the roles swapped: a "reverse" tile (bit 31 of
             // split) takes its rows from the train image and streams the query image; its row-wise 1-NN is
             // the column minimum the filter needs (lowest query index on ties, by the same insertion rule).
-            const bool reverse = (tile.split >> 31) != 0;
-            tile.split &= 0x7FFFFFFFu;
+            const bool reverse = (tile.split & TILE_REVERSE) != 0;  // (gathered reverse tiles are a TMEM-A kernel feature)
+            tile.split &= TILE_SPLIT_MASK;
             if (reverse) {
                 const uint32_t r0 = pd.q_row0, n = pd.nq;
                 pd.q_row0 = pd.t_row0; pd.nq = pd.nt;
@@ -891,7 +891,7 @@ tensor_knn2_kernel(const __grid_constant__ CUtensorMap tmap, const float* __rest
             if constexpr (tm_is_collect(MODE)) {
                 if (n_splits == 1 && qrow < nq) *cand_count_row = fill;
             } else {
-                finish_rows<MODE, 2>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin);
+                finish_rows<MODE, 2>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin, qrow);
             }
         }
     }

@@ -64,6 +64,8 @@ struct FtsSmem {  // after the 1024-byte aligned operand area
     FtItem item[2];
     alignas(16) float nb[FTS_NB_STAGES][FT_N];
     float rowval[2][FT_M];
+    uint32_t arow[2][FT_M];  // blob row behind every row of the item's query tile (0xFFFFFFFF: none -> zeros); gathered for TILE_GATHER items
+    uint32_t orow[2][FT_M];  // image-relative row the result of that tile row belongs to
     uint4 merge[2][(FTS_MAX_GROUPS - 1) * FT_M];
 };
 
@@ -124,12 +126,15 @@ __global__ void __launch_bounds__(fts_threads(GROUPS), 1)
 tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ a_src /* the matrix the tensor map describes: rows of KB*128 bytes */,
                       const uint32_t total_rows, const float* __restrict__ norms /* int32 popcounts when INT8 */,
                    const float* __restrict__ nb_src /* per train row: |t|^2, or binary_nbkey_kernel's key part when INT8 */,
-                      const KnnTile* __restrict__ tiles, const uint32_t n_items, const PairDesc* __restrict__ pairs,
+                      const KnnTile* __restrict__ tiles, const uint32_t n_items_arg, const PairDesc* __restrict__ pairs,
                       KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, const uint32_t key_mul /* = 512 */, const uint32_t i8_bias /* TM_I8P: the descriptors' bit length; rank / collect modes: float bits of the key-table offset C */,
-                      uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */) {
+                      uint32_t* __restrict__ cand_count, uint32_t* __restrict__ cand_idx /* TM_TF32_COLLECT */,
+                      const uint32_t* __restrict__ n_items_dev /* non-NULL: the item count lives on the device (cross-check reverse pass) */,
+                      const uint32_t* __restrict__ xcand /* per pair at col_off: candidate train rows */, const uint32_t* __restrict__ n_xcand) {
     constexpr int KIND = OperandOf<MODE>::kind;
     constexpr int KB_ELEMS = OperandOf<MODE>::kb_elems;
     constexpr int ACC_STAGES = fts_acc_stages(KB);
+    const uint32_t n_items = n_items_dev ? __ldg(n_items_dev) : n_items_arg;
     constexpr int FULL_RING = GROUPS > ACC_STAGES ? GROUPS : ACC_STAGES;  // "accumulator ready" barriers, see their initialisation
     constexpr uint32_t A_COLS = KB * 32;            // TMEM columns of one query-tile buffer
     constexpr uint32_t ACC_COL0 = 2 * A_COLS;       // first accumulator column
@@ -255,14 +260,16 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             mbar_wait_relaxed(&sm.item_empty[slot], ((it >> 1) & 1) ^ 1);
             KnnTile tile = tiles[item];
             PairDesc pd = pairs[tile.pair];
-            // "reverse" tile (bit 31 of split): the symmetric cross-check's column minima, roles swapped
-            const bool reverse = (tile.split >> 31) != 0;
-            tile.split &= 0x7FFFFFFFu;
+            // "reverse" tile: the symmetric cross-check's column minima, roles of the two images swapped; with TILE_GATHER its
+            // rows are the pair's candidate train rows (filter.cuh), addressed through the candidate list
+            const bool reverse = (tile.split & TILE_REVERSE) != 0, gather = (tile.split & TILE_GATHER) != 0;
+            tile.split &= TILE_SPLIT_MASK;
             if (reverse) {
                 const uint32_t r0 = pd.q_row0, n = pd.nq;
                 pd.q_row0 = pd.t_row0; pd.nq = pd.nt;
                 pd.t_row0 = r0; pd.nt = n;
             }
+            if (gather) pd.nq = __ldg(n_xcand + tile.pair);  // rows of this side = entries of the candidate list
             if (lane == 0) {
                 FtItem& o = sm.item[slot];
                 o.a_row = pd.q_row0 + tile.q0;
@@ -276,7 +283,13 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             for (int rr = 0; rr < FT_M / 32; ++rr) {
                 const uint32_t row = rr * 32 + lane, qrow = tile.q0 + row;
                 const bool valid = qrow < pd.nq;
-                const float nq2 = valid ? __ldg(norms + pd.q_row0 + qrow) : 0.f;
+                // image-relative row behind this tile row; rows past the image (but inside the blob) are another image's:
+                // computed on, never read -- as with TMA's box
+                const uint32_t irow = gather ? (valid ? __ldg(xcand + pd.col_off + qrow) : 0xFFFFFFFFu) : qrow;
+                const uint32_t grow = (gather && !valid) ? 0xFFFFFFFFu : pd.q_row0 + irow;
+                sm.arow[slot][row] = grow;
+                sm.orow[slot][row] = irow;
+                const float nq2 = valid ? __ldg(norms + grow) : 0.f;
                 float v;
                 if constexpr (tm_is_collect(MODE)) {
                     v = collect_threshold<MODE == TM_F16_COLLECT>(valid, nq2, pd, knn, qrow, __uint_as_float(i8_bias));
@@ -295,7 +308,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t slot = it & 1;
             mbar_wait_relaxed(&sm.item_full[slot], (it >> 1) & 1);
-            const uint32_t grow = sm.item[slot].a_row + row;
+            const uint32_t grow = sm.arow[slot][row];
             mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
             mbar_wait_relaxed(&sm.a_empty[slot], ((it >> 1) & 1) ^ 1);  // the MMAs of the item before last are done with this buffer
             tc_fence_after();
@@ -337,6 +350,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             const bool reverse = im.reverse != 0;
             const unsigned long long knn_off = im.knn_off, col_off = im.col_off;
             const float cq = sm.rowval[slot][row];  // TM_TF32_COLLECT: the threshold tau
+            const uint32_t out_row = sm.orow[slot][row];  // == qrow unless the item's rows are gathered
             mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
 
             Top2 best;
@@ -421,7 +435,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             if constexpr (tm_is_collect(MODE)) {
                 if (n_splits == 1 && qrow < nq) *cand_count_row = fill;
             } else {
-                finish_rows<MODE, GROUPS>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin);
+                finish_rows<MODE, GROUPS>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin, out_row);
             }
         }
     }

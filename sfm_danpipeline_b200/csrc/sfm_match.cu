@@ -202,10 +202,11 @@ struct ChunkPlan {
     uint64_t knn_entries = 0;
     uint64_t col_entries = 0;
     uint64_t max_matches = 0;
+    uint64_t max_rtiles = 0;  // upper bound of the cross-check's gathered reverse items (cross_compact_kernel)
     double work = 0;  // algorithmic POPC32 ops / FLOPs of the knn launch
     void clear() {
         pairs.clear(); tiles.clear(); ftiles.clear(); pair_of_row.clear();
-        knn_entries = col_entries = max_matches = 0;
+        knn_entries = col_entries = max_matches = max_rtiles = 0;
         work = 0;
     }
 };
@@ -217,6 +218,7 @@ struct Slot {
     bool copy_pending = false;  // records of this slot's last chunk are still being copied to the host table (ev_copied)
     DevBuf d_pairs, d_tiles, d_ftiles, d_knn, d_colmin, d_tile_count, d_tile_off, d_pair_count, d_pair_off, d_matches, d_left, d_right;
     DevBuf d_cand_count, d_cand_idx, d_pair_of_row;  // TF32 rank + refine path
+    DevBuf d_xflags, d_xcand, d_n_xcand, d_rtiles, d_n_rtiles;  // cross-check through candidate columns (filter.cuh)
     PinBuf meta;     // [total u64][pair_off u64 x n][pair_count i32 x n]
     PinBuf points;   // aligned-point staging (left then right)
     ChunkPlan plan;
@@ -224,7 +226,7 @@ struct Slot {
     bool busy = false;
     void release() {
         for (DevBuf* b : {&d_pairs, &d_tiles, &d_ftiles, &d_knn, &d_colmin, &d_tile_count, &d_tile_off, &d_pair_count, &d_pair_off, &d_matches, &d_left, &d_right,
-                          &d_cand_count, &d_cand_idx, &d_pair_of_row})
+                          &d_cand_count, &d_cand_idx, &d_pair_of_row, &d_xflags, &d_xcand, &d_n_xcand, &d_rtiles, &d_n_rtiles})
             b->release();
         meta.release();
         points.release();
@@ -248,6 +250,7 @@ struct SfmmCtx {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_pack[2] = {nullptr, nullptr};
     mutable std::string err;
     int csa_level = 2;
+    bool cross_full_reverse = false;  // SFMM_CROSS_FULL=1: the round-1 cross-check (a full reverse pass), for A/B measurements
     int epi_groups = 2;  // epilogue groups of the TMEM-A float kernels (SFMM_EPI_GROUPS=4: measured slower, see float_tensor_ts.cuh)
     size_t fx_attr_smem = 0;
 
@@ -367,6 +370,16 @@ uint32_t query_tile_rows(const SfmmCtx* ctx) {
     return BK_THREADS * (binary_words(ctx->cols) >= 16 ? 2 : 4);
 }
 
+// Does the tensor path of the current descriptor set run the TMEM-A kernel (float_tensor_ts.cuh)?  Mirrors launch_tensor_t.
+bool tensor_uses_ts(const SfmmCtx* ctx) {
+    if (!ctx->use_tensor) return false;
+    if (ctx->tensor_ts >= 0) return ctx->tensor_ts != 0;
+    if (ctx->elem_type == SFMM_F32) return ctx->tensor_f16;
+    return ctx->i8_bias != 0 || ctx->tensor_kblocks <= 2;
+}
+// Cross-check through candidate columns + gathered reverse items: the TMEM-A kernel's query loaders can gather rows.
+bool cross_by_candidates(const SfmmCtx* ctx) { return ctx->cfg.cross_check && tensor_uses_ts(ctx) && !ctx->tensor_refine && !ctx->cross_full_reverse; }
+
 // ---------------------------------------------------------------------------- planning
 // Turn n pairs of qt into device work descriptors.
 int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
@@ -421,7 +434,9 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
                 kt.split = s;
                 plan.tiles.push_back(kt);
             }
-        if (ctx->use_tensor && ctx->cfg.cross_check) {
+        if (cross_by_candidates(ctx)) {
+            plan.max_rtiles += (pd.nt + q_tile - 1) / q_tile;  // reverse items are made on the device, from the candidate columns
+        } else if (ctx->use_tensor && ctx->cfg.cross_check) {
             // tensor kernels: the cross-check's column minima come from "reverse" tiles (roles swapped,
             // bit 31 of split), see float_tensor.cuh; rows = train rows, streamed = query rows
             uint32_t rsplits = std::min<uint32_t>(splits_wanted, std::max<uint32_t>(1, pd.nq / (2 * t_gran)));
@@ -429,7 +444,7 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
             rsplits = (pd.nq + rper - 1) / rper;
             for (uint32_t r0 = 0; r0 < pd.nt; r0 += q_tile)
                 for (uint32_t s2 = 0; s2 < rsplits; ++s2)
-                    plan.tiles.push_back(KnnTile{static_cast<uint32_t>(i), r0, s2 * rper, std::min(pd.nq, (s2 + 1) * rper), s2 | 0x80000000u});
+                    plan.tiles.push_back(KnnTile{static_cast<uint32_t>(i), r0, s2 * rper, std::min(pd.nq, (s2 + 1) * rper), s2 | TILE_REVERSE});
         }
         pd.n_ftiles = (pd.nq + FILTER_TILE - 1) / FILTER_TILE;
         for (uint32_t f = 0; f < pd.n_ftiles; ++f) plan.ftiles.push_back(FilterTile{static_cast<uint32_t>(i), f * FILTER_TILE});
@@ -488,10 +503,13 @@ cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     return cudaGetLastError();
 }
 
+// `tiles` / `n_items_dev`: NULL = the slot's planned tile list (n_tiles of them); otherwise a device-made list whose length
+// lives on the device (at most n_tiles) -- the cross-check's gathered reverse items.
 template <int KB, int MODE>
-cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
+cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnTile* tiles_dev = nullptr, const uint32_t* n_items_dev = nullptr) {
     // persistent: one CTA per SM (shared memory allows no more) walks the tile list with stride gridDim.x
     const uint32_t grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(ctx->sm_count));
+    const KnnTile* tiles = tiles_dev ? tiles_dev : (const KnnTile*)sl.d_tiles.as<KnnTile>();
     const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_TF32_EXACT || MODE == TM_F16_EXACT || tm_is_rank(MODE)) ? (const float*)ctx->d_nbkey.as<float>()
                                                                                                               : (const float*)ctx->d_norms.as<float>();
     // measured (profiles/tensor_variants_r01.txt): TMEM-A wins for the binary engine and the fp16 float path, shared-memory-A for TF32
@@ -503,7 +521,8 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
         auto kern = tensor_knn2_kernel<KB, MODE>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        kern<<<grid, FT_THREADS, smem, sl.stream>>>(ctx->tmap, (const float*)ctx->d_norms.as<float>(), nb_src, (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles,
+        if (tiles_dev) return cudaErrorInvalidValue;  // gathered reverse items need the TMEM-A kernel (cross_by_candidates)
+        kern<<<grid, FT_THREADS, smem, sl.stream>>>(ctx->tmap, (const float*)ctx->d_norms.as<float>(), nb_src, tiles, n_tiles,
                                                     (const PairDesc*)sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
                                                     sl.d_colmin.as<unsigned long long>(), 512u, aux, sl.d_cand_count.as<uint32_t>(),
                                                     sl.d_cand_idx.as<uint32_t>());
@@ -516,9 +535,10 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         kern<<<grid, threads, smem, sl.stream>>>(ctx->tmap, a_src, static_cast<uint32_t>(ctx->total_rows), (const float*)ctx->d_norms.as<float>(), nb_src,
-                                                 (const KnnTile*)sl.d_tiles.as<KnnTile>(), n_tiles, (const PairDesc*)sl.d_pairs.as<PairDesc>(),
+                                                 tiles, n_tiles, (const PairDesc*)sl.d_pairs.as<PairDesc>(),
                                                  sl.d_knn.as<KnnEntry>(), sl.d_colmin.as<unsigned long long>(), 512u, aux,
-                                                 sl.d_cand_count.as<uint32_t>(), sl.d_cand_idx.as<uint32_t>());
+                                                 sl.d_cand_count.as<uint32_t>(), sl.d_cand_idx.as<uint32_t>(), n_items_dev,
+                                                 (const uint32_t*)sl.d_xcand.as<uint32_t>(), (const uint32_t*)sl.d_n_xcand.as<uint32_t>());
         return cudaGetLastError();
     };
     // SFMM_EPI_GROUPS=4: four epilogue groups for the 32-bit-key float modes (an experiment that measured 5 % slower than two,
@@ -530,14 +550,24 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
 }
 
 template <int MODE>
-cudaError_t launch_tensor(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks) {
+cudaError_t launch_tensor(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks, const KnnTile* tiles_dev = nullptr, const uint32_t* n_items_dev = nullptr) {
     switch (kblocks) {
-        case 1: return launch_tensor_t<1, MODE>(ctx, sl, n_tiles);
-        case 2: return launch_tensor_t<2, MODE>(ctx, sl, n_tiles);
-        case 3: return launch_tensor_t<3, MODE>(ctx, sl, n_tiles);
-        case 4: return launch_tensor_t<4, MODE>(ctx, sl, n_tiles);
+        case 1: return launch_tensor_t<1, MODE>(ctx, sl, n_tiles, tiles_dev, n_items_dev);
+        case 2: return launch_tensor_t<2, MODE>(ctx, sl, n_tiles, tiles_dev, n_items_dev);
+        case 3: return launch_tensor_t<3, MODE>(ctx, sl, n_tiles, tiles_dev, n_items_dev);
+        case 4: return launch_tensor_t<4, MODE>(ctx, sl, n_tiles, tiles_dev, n_items_dev);
     }
     return cudaErrorInvalidValue;
+}
+
+// The exact tensor modes (results final after one pass) dispatched on the descriptor type; used for the forward pass and for the
+// cross-check's gathered reverse pass.
+cudaError_t launch_tensor_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnTile* tiles_dev = nullptr, const uint32_t* n_items_dev = nullptr) {
+    if (ctx->elem_type == SFMM_F32)
+        return ctx->tensor_f16 ? launch_tensor<TM_F16_EXACT>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev)
+                               : launch_tensor<TM_TF32_EXACT>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev);
+    return ctx->i8_bias ? launch_tensor<TM_I8P>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev)
+                        : launch_tensor<TM_I8>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev);
 }
 
 // Arbitrary float data: TF32 ranking pass -> candidate collection (same tiles) -> exact refinement.
@@ -812,12 +842,36 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
         const uint32_t nt = static_cast<uint32_t>(plan.tiles.size());
         cudaError_t e;
         if (ctx->elem_type == SFMM_F32 && ctx->use_tensor && ctx->tensor_refine) e = launch_tensor_refine(ctx, sl, nt, ctx->tensor_kblocks);
-        else if (ctx->elem_type == SFMM_F32 && ctx->use_tensor && ctx->tensor_f16) e = launch_tensor<TM_F16_EXACT>(ctx, sl, nt, ctx->tensor_kblocks);
-        else if (ctx->elem_type == SFMM_F32) e = ctx->use_tensor ? launch_tensor<TM_TF32_EXACT>(ctx, sl, nt, ctx->tensor_kblocks) : launch_float_exact(ctx, sl, nt);
-        else if (ctx->use_tensor) e = ctx->i8_bias ? launch_tensor<TM_I8P>(ctx, sl, nt, ctx->tensor_kblocks) : launch_tensor<TM_I8>(ctx, sl, nt, ctx->tensor_kblocks);
+        else if (ctx->use_tensor) e = launch_tensor_exact(ctx, sl, nt);
+        else if (ctx->elem_type == SFMM_F32) e = launch_float_exact(ctx, sl, nt);
         else e = cross ? launch_binary<true>(ctx, sl, nt) : launch_binary<false>(ctx, sl, nt);
         CU_TRY(ctx, e);
         ctx->stats.kernel_launches += 1;
+        if (cross_by_candidates(ctx) && !knn_only && nft && plan.max_rtiles) {
+            // Symmetric cross-check through candidate columns (filter.cuh): flag the train rows that ratio-passing query rows chose,
+            // compact them per pair, and run the 2-NN kernel again on "reverse" items whose rows are gathered through those lists.
+            CU_TRY(ctx, sl.d_xflags.ensure(plan.col_entries));
+            CU_TRY(ctx, sl.d_xcand.ensure(plan.col_entries * sizeof(uint32_t)));
+            CU_TRY(ctx, sl.d_n_xcand.ensure(np * sizeof(uint32_t)));
+            CU_TRY(ctx, sl.d_rtiles.ensure(plan.max_rtiles * sizeof(KnnTile)));
+            CU_TRY(ctx, sl.d_n_rtiles.ensure(sizeof(uint32_t)));
+            CU_TRY(ctx, cudaMemsetAsync(sl.d_xflags.p, 0, plan.col_entries, sl.stream));
+            CU_TRY(ctx, cudaMemsetAsync(sl.d_n_rtiles.p, 0, sizeof(uint32_t), sl.stream));
+            const float ratio = ctx->cfg.ratio;
+            if (ctx->elem_type == SFMM_F32)
+                cross_mark_kernel<true><<<static_cast<unsigned>(nft), FILTER_THREADS, 0, sl.stream>>>(sl.d_ftiles.as<FilterTile>(), sl.d_pairs.as<PairDesc>(),
+                                                                                                     sl.d_knn.as<KnnEntry>(), ratio, sl.d_xflags.as<unsigned char>());
+            else
+                cross_mark_kernel<false><<<static_cast<unsigned>(nft), FILTER_THREADS, 0, sl.stream>>>(sl.d_ftiles.as<FilterTile>(), sl.d_pairs.as<PairDesc>(),
+                                                                                                      sl.d_knn.as<KnnEntry>(), ratio, sl.d_xflags.as<unsigned char>());
+            cross_compact_kernel<<<static_cast<unsigned>(np), COMPACT_THREADS, 0, sl.stream>>>(sl.d_pairs.as<PairDesc>(), sl.d_xflags.as<unsigned char>(),
+                                                                                               sl.d_xcand.as<uint32_t>(), sl.d_n_xcand.as<uint32_t>(),
+                                                                                               sl.d_rtiles.as<KnnTile>(), sl.d_n_rtiles.as<uint32_t>(), FT_M);
+            CU_TRY(ctx, cudaGetLastError());
+            CU_TRY(ctx, launch_tensor_exact(ctx, sl, static_cast<uint32_t>(std::min<uint64_t>(plan.max_rtiles, 0xFFFFFFFFull)), sl.d_rtiles.as<KnnTile>(),
+                                            sl.d_n_rtiles.as<uint32_t>()));
+            ctx->stats.kernel_launches += 3;
+        }
     }
     CU_TRY(ctx, cudaEventRecord(sl.ev_knn1, sl.stream));
     if (knn_only) {
@@ -1106,6 +1160,7 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* s = std::getenv("SFMM_TENSOR_TS")) ctx->tensor_ts = std::atoi(s) != 0 ? 1 : 0;
     if (const char* s = std::getenv("SFMM_CSA_LEVEL")) ctx->csa_level = std::max(0, std::min(3, std::atoi(s)));
+    if (const char* s = std::getenv("SFMM_CROSS_FULL")) ctx->cross_full_reverse = std::atoi(s) != 0;
     if (const char* s = std::getenv("SFMM_EPI_GROUPS")) ctx->epi_groups = std::atoi(s) == 4 ? 4 : 2;
     bool ok = (e = cudaSetDevice(cfg->device)) == cudaSuccess;
     for (Slot& sl : ctx->slot) {

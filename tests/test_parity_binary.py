@@ -298,3 +298,38 @@ def test_randomised_differential_vs_oracle(cols, rows, seed, cross, levels):
         m.match_all_pairs()
         for q, t in synth.all_pairs(len(descs)):
             _expect_equal(m.getMatching(q, t), oracle.match_pair(descs[q], descs[t], 0, 0.8, cross))
+
+
+@pytest.mark.parametrize("full", ["0", "1"])
+def test_cross_check_candidate_columns_and_full_reverse_agree(full, monkeypatch):
+    """The tensor engines take the symmetric cross-check's column minima from "reverse" work items: by default only for the
+    candidate train rows (those a ratio-passing query row selected; rows gathered through per-pair lists), with
+    SFMM_CROSS_FULL=1 for every train row (round 1).  Both must equal cv2's crossCheck=True lists, ragged / empty / tiny images
+    and heavy ties included."""
+    monkeypatch.setenv("SFMM_CROSS_FULL", full)
+    for name in ("temple_akaze", "temple_orb"):
+        g = GoldenSet(name)
+        with Matcher(NORM_HAMMING, 0.8, True, binary_engine=BINARY_TENSOR) as m:
+            m.set_descriptors(g.descs)
+            m.match_all_pairs()
+            for p, (q, t, *_r) in enumerate(g.pairs):
+                got = m.getMatching(q, t)
+                eq, et, ed = g.expected(p, True)
+                assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all() and (got["distance"] == ed).all(), (name, q, t)
+    rng = np.random.default_rng(99)
+    descs = [rng.integers(0, 2, (n, 61), dtype=np.uint8) * 255 for n in (700, 0, 513, 1, 2, 1024, 129, 5000)]  # few values: many ties
+    descs[1] = np.zeros((0, 61), np.uint8)
+    with Matcher(NORM_HAMMING, 0.9, True, binary_engine=BINARY_TENSOR) as m:
+        m.set_descriptors(descs)
+        m.match_all_pairs()
+        for (q, t) in synth.all_pairs(len(descs)):
+            _expect_equal(m.getMatching(q, t), oracle.match_pair(descs[q], descs[t], 0, 0.9, True, threads=4))
+        _expect_equal(m.match_pair(7, 5), oracle.match_pair(descs[7], descs[5], 0, 0.9, True, threads=4))  # on demand, q > t
+    sift = GoldenSet("temple_sift")
+    with Matcher(1, 0.8, True) as m:  # float path (fp16 tensor kernel)
+        m.set_descriptors(sift.descs)
+        m.match_all_pairs()
+        for p, (q, t, *_r) in enumerate(sift.pairs):
+            got = m.getMatching(q, t)
+            eq, et, ed = sift.expected(p, True)
+            assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all() and (got["distance"] == ed).all(), (q, t)
