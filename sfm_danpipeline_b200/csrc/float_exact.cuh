@@ -49,14 +49,30 @@ static inline size_t float_exact_smem_bytes(int kq /* quad-words per row */) {
 __global__ void __launch_bounds__(FX_THREADS, 2)
 float_exact_knn2_kernel(const float* __restrict__ blob, int kq /* row pitch in float4 */,
                         const KnnTile* __restrict__ tiles, const PairDesc* __restrict__ pairs,
-                        KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, int cross) {
+                        KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, int cross,
+                        const uint32_t* __restrict__ n_items_dev /* non-NULL: the tile count lives on the device */,
+                        const uint32_t* __restrict__ xcand, const uint32_t* __restrict__ n_xcand /* candidate train rows per pair (filter.cuh) */) {
     extern __shared__ __align__(16) float fx_smem[];
     const int KP = kq * 4 + 4;  // padded pitch in floats
     float* sq = fx_smem;
     float* st = fx_smem + FX_BQ * KP;
 
-    const KnnTile tile = tiles[blockIdx.x];
-    const PairDesc pd = pairs[tile.pair];
+    if (n_items_dev && blockIdx.x >= __ldg(n_items_dev)) return;
+    KnnTile tile = tiles[blockIdx.x];
+    PairDesc pd = pairs[tile.pair];
+    // "reverse + gather" tile (cross-check through candidate columns, filter.cuh): the tile's rows are candidate train rows
+    // addressed through the pair's list, the whole query image is streamed past them, and each row's nearest neighbour is the
+    // forward problem's column minimum (lowest query index on ties) -> colmin instead of a 2-NN entry.
+    const bool rgather = (tile.split & (TILE_REVERSE | TILE_GATHER)) == (TILE_REVERSE | TILE_GATHER);
+    tile.split &= TILE_SPLIT_MASK;
+    const uint32_t* list = nullptr;
+    if (rgather) {
+        const uint32_t r0 = pd.q_row0;
+        pd.q_row0 = pd.t_row0; pd.t_row0 = r0;
+        pd.nt = pd.nq;
+        pd.nq = __ldg(n_xcand + tile.pair);
+        list = xcand + pd.col_off;
+    }
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
 
     const float4* gq = reinterpret_cast<const float4*>(blob) + (size_t)pd.q_row0 * kq;
@@ -65,7 +81,8 @@ float_exact_knn2_kernel(const float* __restrict__ blob, int kq /* row pitch in f
     // query tile (clamped rows) -> smem
     for (int i = tid; i < FX_BQ * kq; i += FX_THREADS) {
         const int r = i / kq, c = i - r * kq;
-        const uint32_t row = min(tile.q0 + r, pd.nq - 1);
+        uint32_t row = min(tile.q0 + r, pd.nq - 1);
+        if (rgather) row = __ldg(list + row);
         cp_async16(sq + r * KP + c * 4, gq + (size_t)row * kq + c);
     }
     const uint32_t n_rows = tile.t1 - tile.t0;
@@ -152,10 +169,14 @@ float_exact_knn2_kernel(const float* __restrict__ blob, int kq /* row pitch in f
         }
         const uint32_t qr = tile.q0 + ty * 4 + i;
         if (tx == 0 && qr < pd.nq) {
-            KnnEntry e;
-            e.x = k1[i];
-            e.y = k2[i];
-            knn[pd.knn_off + (size_t)tile.split * pd.nq + qr] = e;
+            if (rgather) {
+                if (k1[i] != KEY_NONE) atomicMin(colmin + pd.col_off + __ldg(list + qr), k1[i]);
+            } else {
+                KnnEntry e;
+                e.x = k1[i];
+                e.y = k2[i];
+                knn[pd.knn_off + (size_t)tile.split * pd.nq + qr] = e;
+            }
         }
     }
 }

@@ -379,6 +379,9 @@ bool tensor_uses_ts(const SfmmCtx* ctx) {
 }
 // Cross-check through candidate columns + gathered reverse items: the TMEM-A kernel's query loaders can gather rows.
 bool cross_by_candidates(const SfmmCtx* ctx) { return ctx->cfg.cross_check && tensor_uses_ts(ctx) && !ctx->tensor_refine && !ctx->cross_full_reverse; }
+// Arbitrary floats (tensor ranking + exact refinement): the candidate columns' minima come from the exact fp32 kernel, which
+// gathers its rows the same way -- candidates/Nt of an exact pass instead of running the whole pair on the exact kernel.
+bool cross_by_candidates_exact(const SfmmCtx* ctx) { return ctx->cfg.cross_check && ctx->use_tensor && ctx->tensor_refine; }
 
 // ---------------------------------------------------------------------------- planning
 // Turn n pairs of qt into device work descriptors.
@@ -434,7 +437,9 @@ int plan_chunk(SfmmCtx* ctx, const int32_t* qt, int64_t n, ChunkPlan& plan) {
                 kt.split = s;
                 plan.tiles.push_back(kt);
             }
-        if (cross_by_candidates(ctx)) {
+        if (cross_by_candidates_exact(ctx)) {
+            plan.max_rtiles += (pd.nt + FX_BQ - 1) / FX_BQ;
+        } else if (cross_by_candidates(ctx)) {
             plan.max_rtiles += (pd.nt + q_tile - 1) / q_tile;  // reverse items are made on the device, from the candidate columns
         } else if (ctx->use_tensor && ctx->cfg.cross_check) {
             // tensor kernels: the cross-check's column minima come from "reverse" tiles (roles swapped,
@@ -489,7 +494,7 @@ cudaError_t launch_binary(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
     return cudaErrorInvalidValue;
 }
 
-cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
+cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnTile* tiles_dev = nullptr, const uint32_t* n_items_dev = nullptr) {
     const int kq = static_cast<int>(ctx->pitch / 16);
     const size_t smem = float_exact_smem_bytes(kq);
     if (smem > ctx->fx_attr_smem) {  // per context == per device
@@ -498,8 +503,9 @@ cudaError_t launch_float_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles) {
         ctx->fx_attr_smem = smem;
     }
     float_exact_knn2_kernel<<<n_tiles, FX_THREADS, smem, sl.stream>>>(
-        ctx->blob.as<float>(), kq, sl.d_tiles.as<KnnTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
-        sl.d_colmin.as<unsigned long long>(), ctx->cfg.cross_check ? 1 : 0);
+        ctx->blob.as<float>(), kq, tiles_dev ? tiles_dev : (const KnnTile*)sl.d_tiles.as<KnnTile>(), sl.d_pairs.as<PairDesc>(), sl.d_knn.as<KnnEntry>(),
+        sl.d_colmin.as<unsigned long long>(), (ctx->cfg.cross_check && !tiles_dev) ? 1 : 0, n_items_dev, (const uint32_t*)sl.d_xcand.as<uint32_t>(),
+        (const uint32_t*)sl.d_n_xcand.as<uint32_t>());
     return cudaGetLastError();
 }
 
@@ -716,7 +722,7 @@ int prepare_float(SfmmCtx* ctx) {
             ctx->tensor_kblocks = ctx->cols * 2 / 128;
             ctx->use_tensor = true;
             ctx->tensor_f16 = true;
-        } else if (ctx->tensor_eligible || (finite && !ctx->cfg.cross_check)) {
+        } else if (ctx->tensor_eligible || finite) {
             // arbitrary floats whose magnitudes fit fp16 (|v| <= sqrt(max |x|^2) < 65504): the ranking and collection passes
             // contract an fp16 round-to-nearest copy (same 10-bit significand as TF32, half the MMA time, no power cap);
             // the refinement reads the fp32 blob either way
@@ -762,8 +768,7 @@ int prepare_float(SfmmCtx* ctx) {
     }
     if (ctx->cfg.float_mode == SFMM_FLOAT_TENSOR && !ctx->use_tensor)
         return fail(ctx, SFMM_EINVAL,
-                    "SFMM_FLOAT_TENSOR needs a descriptor width that is a multiple of 32 up to 128, finite values, and -- with cross_check -- "
-                    "TF32-exact descriptors (integer values |v|<=2047, row norm^2 <= 2^20); use SFMM_FLOAT_AUTO or SFMM_FLOAT_EXACT");
+                    "SFMM_FLOAT_TENSOR needs a descriptor width that is a multiple of 32 up to 128 and finite values; use SFMM_FLOAT_AUTO or SFMM_FLOAT_EXACT");
     ctx->float_prepared = true;
     ctx->stats.float_path = ctx->use_tensor ? (ctx->tensor_refine ? 3 : SFMM_FLOAT_TENSOR) : SFMM_FLOAT_EXACT;
     return SFMM_OK;
@@ -847,7 +852,8 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
         else e = cross ? launch_binary<true>(ctx, sl, nt) : launch_binary<false>(ctx, sl, nt);
         CU_TRY(ctx, e);
         ctx->stats.kernel_launches += 1;
-        if (cross_by_candidates(ctx) && !knn_only && nft && plan.max_rtiles) {
+        const bool by_exact = cross_by_candidates_exact(ctx);
+        if ((cross_by_candidates(ctx) || by_exact) && !knn_only && nft && plan.max_rtiles) {
             // Symmetric cross-check through candidate columns (filter.cuh): flag the train rows that ratio-passing query rows chose,
             // compact them per pair, and run the 2-NN kernel again on "reverse" items whose rows are gathered through those lists.
             CU_TRY(ctx, sl.d_xflags.ensure(plan.col_entries));
@@ -866,10 +872,11 @@ int launch_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt, int64_t first, int64
                                                                                                       sl.d_knn.as<KnnEntry>(), ratio, sl.d_xflags.as<unsigned char>());
             cross_compact_kernel<<<static_cast<unsigned>(np), COMPACT_THREADS, 0, sl.stream>>>(sl.d_pairs.as<PairDesc>(), sl.d_xflags.as<unsigned char>(),
                                                                                                sl.d_xcand.as<uint32_t>(), sl.d_n_xcand.as<uint32_t>(),
-                                                                                               sl.d_rtiles.as<KnnTile>(), sl.d_n_rtiles.as<uint32_t>(), FT_M);
+                                                                                               sl.d_rtiles.as<KnnTile>(), sl.d_n_rtiles.as<uint32_t>(), by_exact ? FX_BQ : FT_M);
             CU_TRY(ctx, cudaGetLastError());
-            CU_TRY(ctx, launch_tensor_exact(ctx, sl, static_cast<uint32_t>(std::min<uint64_t>(plan.max_rtiles, 0xFFFFFFFFull)), sl.d_rtiles.as<KnnTile>(),
-                                            sl.d_n_rtiles.as<uint32_t>()));
+            const uint32_t max_items = static_cast<uint32_t>(std::min<uint64_t>(plan.max_rtiles, 0xFFFFFFFFull));
+            CU_TRY(ctx, by_exact ? launch_float_exact(ctx, sl, max_items, sl.d_rtiles.as<KnnTile>(), sl.d_n_rtiles.as<uint32_t>())
+                                 : launch_tensor_exact(ctx, sl, max_items, sl.d_rtiles.as<KnnTile>(), sl.d_n_rtiles.as<uint32_t>()));
             ctx->stats.kernel_launches += 3;
         }
     }

@@ -170,10 +170,36 @@ def test_arbitrary_floats_use_rank_and_refine_and_equal_the_exact_kernel():
             for p, (q, t, kd, ki, *_r) in enumerate(g.pairs):
                 idx, dist = m.knn_pair(q, t)
                 _check_knn_within_tolerance(idx, dist, ki, kd)  # and within 1e-4 of OpenCV
-    with Matcher(NORM_L2, 0.8, True, float_mode=FLOAT_AUTO) as m:  # cross-check on arbitrary floats: exact kernel
+    # cross-check on arbitrary floats: ranking + refinement forward, the candidate columns' minima from the exact kernel (rows
+    # gathered through the candidate lists) -- bit-identical to running everything on the exact kernel
+    with Matcher(NORM_L2, 0.8, True, float_mode=FLOAT_AUTO) as m, Matcher(NORM_L2, 0.8, True, float_mode=FLOAT_EXACT) as mx:
         m.set_descriptors(g.descs)
+        mx.set_descriptors(g.descs)
         m.match_all_pairs()
-        assert m.stats()["float_path"] == FLOAT_EXACT
+        mx.match_all_pairs()
+        assert m.stats()["float_path"] == 3 and mx.stats()["float_path"] == FLOAT_EXACT
+        _tables_equal(m, mx)
+        assert sum(len(m.getMatching(q, t)) for q, t in synth.all_pairs(len(g.descs))) > 50
+
+
+def test_arbitrary_floats_cross_check_at_cfg4_size_equals_the_exact_kernel():
+    rng = np.random.default_rng(8)
+    a = synth.float_images(3, [8000, 4100, 129], seed=16, integer=False)
+    a[1][:5] = a[1][7]                       # identical train rows: lowest index in both directions
+    a[0][11] = a[1][7]
+    a.append(np.zeros((0, 128), np.float32))  # an image without descriptors
+    a.append((rng.random((2, 128)) * 100).astype(np.float32))
+    with Matcher(NORM_L2, 0.8, True) as m, Matcher(NORM_L2, 0.8, True, float_mode=FLOAT_EXACT) as mx:
+        m.set_descriptors(a)
+        mx.set_descriptors(a)
+        m.match_all_pairs()
+        mx.match_all_pairs()
+        assert m.stats()["float_path"] == 3
+        _tables_equal(m, mx)
+        got, exp = m.getMatching(0, 1), oracle.match_pair(a[0], a[1], 1, 0.8, True, threads=8)
+        assert abs(len(got) - len(exp)) <= 2  # vs OpenCV: decisions may flip only inside the 1e-4 tolerance
+        both = np.intersect1d(got["queryIdx"], exp["queryIdx"])
+        assert len(both) >= len(exp) - 2
 
 
 def test_rank_and_refine_at_cfg4_size_near_duplicates_and_ties():
