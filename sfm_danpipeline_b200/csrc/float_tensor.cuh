@@ -40,6 +40,11 @@ enum TensorMode {
     TM_F16_COLLECT = 7,   // half the MMA time and far less power (the TF32 passes run into the power cap on dense mantissas)
     TM_F16_EXACT = 5,     // TM_TF32_EXACT on an fp16 copy of the descriptors (integers |v| <= 2048 are exact in fp16):
                           // kind::f16 contracts 16 elements per MMA, half the tensor time and half the operand bytes
+    TM_F16X = 8,          // TM_F16_EXACT with the key's train-side term contracted by the tensor core as well: the operand rows carry one
+                          // extra 128-byte K-block -- query side (-2q, 1, 2048, 2048, 0...), train side (t, v0, v1, 2048 v2, 0...) with
+                          // v0 + 2048 v1 + 2048^2 v2 = |t|^2 + 2^23 + 2^20 -- so that the accumulator IS the key argument
+                          // x' = |t|^2 - 2 q.t + 2^23 + 2^20 (exact: every term an integer, every partial sum below 2^24): no FFMA, no
+                          // norm table read per column in the epilogue (float_to_half_kx_kernel; one MMA more per tile)
     TM_TF32_COLLECT = 3   // arbitrary floats, pass 2: every column whose approximate d^2 can still be in the exact
                           // top-2 (<= m2 + 2*eps, a rigorous bound) is appended to the row's candidate list, which
                           // float_refine_kernel then evaluates exactly (fp32 direct difference, float_exact.cuh's arithmetic)
@@ -77,7 +82,7 @@ __host__ __device__ constexpr bool tm_is_collect(int mode) { return mode == TM_T
 enum OperandKind { OK_TF32 = 0, OK_I8 = 1, OK_F16 = 2 };
 template <int MODE>
 struct OperandOf {
-    static constexpr int kind = (MODE == TM_I8 || MODE == TM_I8P) ? OK_I8 : ((MODE == TM_F16_EXACT || MODE == TM_F16_RANK || MODE == TM_F16_COLLECT) ? OK_F16 : OK_TF32);
+    static constexpr int kind = (MODE == TM_I8 || MODE == TM_I8P) ? OK_I8 : ((MODE == TM_F16_EXACT || MODE == TM_F16X || MODE == TM_F16_RANK || MODE == TM_F16_COLLECT) ? OK_F16 : OK_TF32);
     static constexpr int kb_elems = kind == OK_I8 ? 128 : (kind == OK_F16 ? 64 : 32);  // elements per 128-byte swizzle row
 };
 // D[tmem] (+)= A[smem] * B[smem]^T; M=128, N=128, 32 bytes of K per instruction (8 tf32 / 16 f16 / 32 u8), fp32 or s32
@@ -239,6 +244,37 @@ __global__ void float_to_half_kernel(const float* __restrict__ blob, int kq, uin
     const size_t row = i / per_row, c = (i % per_row) * 2;
     const float2 v = *reinterpret_cast<const float2*>(blob + row * kq * 4 + c);
     *reinterpret_cast<__half2*>(out + row * cols + c) = __floats2half2_rn(v.x, v.y);
+}
+
+// TM_F16X operands of a TF32-exact set, rows of cols + 64 halves (one extra 128-byte K-block): see the mode's description.
+//   train side  out_b : t_0 .. t_{c-1}, v0, v1, 2048 v2, 0 ...     v0 + 2048 v1 + 2048^2 v2 = |t|^2 + 2^23 + 2^20 (v0, v1 < 2048, v2 = 2)
+//   query side  out_a : -2 q_0 .. -2 q_{c-1}, 1, 2048, 2048, 0 ...
+// Every value is an integer of at most 12 significant bits times a power of two: exact in fp16.
+__global__ void float_to_half_kx_kernel(const float* __restrict__ blob, int kq, uint32_t total_rows, int cols, const float* __restrict__ norms,
+                                        __half* __restrict__ out_b, __half* __restrict__ out_a) {
+    const int kx = cols + 64;
+    const size_t i = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;  // one thread per pair of output elements
+    const size_t per_row = static_cast<size_t>(kx) / 2;
+    if (i >= static_cast<size_t>(total_rows) * per_row) return;
+    const size_t row = i / per_row;
+    const int c = static_cast<int>(i % per_row) * 2;
+    float b0 = 0.f, b1 = 0.f, a0 = 0.f, a1 = 0.f;
+    if (c < cols) {
+        const float2 v = *reinterpret_cast<const float2*>(blob + row * kq * 4 + c);
+        b0 = v.x; b1 = v.y;
+        a0 = -2.f * v.x; a1 = -2.f * v.y;
+    } else if (c == cols || c == cols + 2) {
+        const uint32_t V = static_cast<uint32_t>(norms[row] + FT_NB_OFFSET);  // exact integer below 2^24
+        if (c == cols) {
+            b0 = static_cast<float>(V & 2047u); b1 = static_cast<float>((V >> 11) & 2047u);
+            a0 = 1.f; a1 = 2048.f;
+        } else {
+            b0 = static_cast<float>((V >> 22) * 2048u);
+            a0 = 2048.f;
+        }
+    }
+    *reinterpret_cast<__half2*>(out_b + row * kx + c) = __floats2half2_rn(b0, b1);
+    *reinterpret_cast<__half2*>(out_a + row * kx + c) = __floats2half2_rn(a0, a1);
 }
 
 // ------------------------------------------------------------------ prepare (binary tensor engine)
@@ -404,13 +440,18 @@ __device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[W], uint32_t nb
                                            uint32_t n_rows, uint32_t& m1, uint32_t& m2) {
 #pragma unroll
     for (int e = 0; e < W; e += 4) {
-        const float4 nb = lds128(nb_saddr + e * 4);  // same address in every lane: broadcast
-        const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
+        float4 nb = make_float4(0.f, 0.f, 0.f, 0.f);
+        if constexpr (MODE != TM_F16X) nb = lds128(nb_saddr + e * 4);  // same address in every lane: broadcast
+        [[maybe_unused]] const float nbv[4] = {nb.x, nb.y, nb.z, nb.w};
         uint32_t k[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             [[maybe_unused]] uint32_t bits = 0;
-            if constexpr (MODE == TM_I8) {
+            if constexpr (MODE == TM_F16X) {
+                // the accumulator is the key argument itself (see TM_F16X): key = bits * 512 + column, one IMAD
+                const uint32_t lc = lc0 + e + i;
+                asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(acc[e + i]), "r"(key_mul), "r"(lc));
+            } else if constexpr (MODE == TM_I8) {
                 // key = acc * (-1024) + nbkey: see binary_nbkey_kernel (key_mul - 1536 = -1024 comes from a kernel
                 // parameter so that the multiply stays one IMAD on the FMA pipe instead of a shift + subtract on the ALU)
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(acc[e + i]), "r"(key_mul - 1536u), "r"(__float_as_uint(nbv[i])));

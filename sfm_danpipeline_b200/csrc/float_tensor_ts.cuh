@@ -142,6 +142,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
     constexpr uint32_t LOADER_WARP0 = 4 + EPI_WARPS;  // a multiple of 4: warp % 4 is the TMEM lane quarter it may access
     static_assert(GROUPS == 2 || GROUPS == 4, "two or four epilogue groups");
     static_assert(!(GROUPS == 4 && (MODE == TM_I8P || tm_is_collect(MODE) || tm_is_rank(MODE))), "four groups: 32-bit-key top-2 modes only");
+    static_assert(MODE != TM_F16X || KB >= 2, "TM_F16X rows carry at least one data K-block and the key-term K-block");
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sB = base;  // FTS_B_STAGES x KB x 16 KB
@@ -201,12 +202,14 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
 #pragma unroll 1
                 for (uint32_t j = 0; j < n_tiles; ++j, ++g) {
                     const uint32_t s = g % FTS_B_STAGES;
-                    const uint32_t a = g % FTS_NB_STAGES;
-                    mbar_wait(&sm.nb_empty[a], ((g / FTS_NB_STAGES) & 1) ^ 1);
-                    mbar_expect_tx(&sm.nb_full[a], FT_N * sizeof(float));
-                    // image rows start at multiples of 4 and t0 at multiples of 128: 16-byte aligned source;
-                    // the norms array is padded so that the copy may run past the image's last row
-                    tma_load_1d(sm.nb[a], nb_src + b_row0 + j * FT_N, FT_N * sizeof(float), &sm.nb_full[a]);
+                    if constexpr (MODE != TM_F16X) {  // (TM_F16X: the train-side key term rides in the operand rows)
+                        const uint32_t a = g % FTS_NB_STAGES;
+                        mbar_wait(&sm.nb_empty[a], ((g / FTS_NB_STAGES) & 1) ^ 1);
+                        mbar_expect_tx(&sm.nb_full[a], FT_N * sizeof(float));
+                        // image rows start at multiples of 4 and t0 at multiples of 128: 16-byte aligned source;
+                        // the norms array is padded so that the copy may run past the image's last row
+                        tma_load_1d(sm.nb[a], nb_src + b_row0 + j * FT_N, FT_N * sizeof(float), &sm.nb_full[a]);
+                    }
                     mbar_wait(&sm.b_empty[s], ((g / FTS_B_STAGES) & 1) ^ 1);
                     mbar_expect_tx(&sm.b_full[s], KB * FT_B_KBLOCK_BYTES);
                     unsigned char* dst = sB + (size_t)s * KB * FT_B_KBLOCK_BYTES;
@@ -242,8 +245,10 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB + (size_t)s * KB * FT_B_KBLOCK_BYTES));
                 const uint32_t d_tmem = tb + ACC_COL0 + a * FT_N;
                 tc_mma_ts<KIND, false>(d_tmem, a_tmem, b_desc0, idesc);
+                // TM_F16X: only the first 32 bytes of the last K-block carry data (the three key-term columns), the rest is zero
+                constexpr int N_MMA = MODE == TM_F16X ? 4 * (KB - 1) + 1 : 4 * KB;
 #pragma unroll
-                for (int i = 1; i < 4 * KB; ++i) {  // i = kb*4 + k: 32 bytes of K = 8 TMEM columns of A, 32 bytes inside B's swizzle row
+                for (int i = 1; i < N_MMA; ++i) {  // i = kb*4 + k: 32 bytes of K = 8 TMEM columns of A, 32 bytes inside B's swizzle row
                     const int kb = i >> 2, k = i & 3;
                     tc_mma_ts<KIND, true>(d_tmem, a_tmem + i * 8, b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
                 }
@@ -374,7 +379,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 uint32_t acc[2][CW];  // register double buffer: chunk c+1 streams in from TMEM while chunk c is folded
                 const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + ACC_COL0 + a * FT_N;
                 tc_ld_32x32(taddr, acc[0]);
-                mbar_wait(&sm.nb_full[nbs], (g / FTS_NB_STAGES) & 1);
+                if constexpr (MODE != TM_F16X) mbar_wait(&sm.nb_full[nbs], (g / FTS_NB_STAGES) & 1);
                 tc_wait_ld(acc[0]);
                 const uint32_t col0 = j * FT_N;                // first column of the tile, relative to t0
                 const bool partial = col0 + FT_N > n_rows;     // warp-uniform: only the last tile
@@ -406,8 +411,10 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                         if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
                     }
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sm.nb_empty[nbs]);
+                if constexpr (MODE != TM_F16X) {
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sm.nb_empty[nbs]);
+                }
                 // merge the tile's two best into the running pair (ascending tiles = arrival order)
                 if constexpr (!tm_is_rank(MODE) && !tm_is_collect(MODE)) {
                     const int tbase = (int)(t0 + col0);

@@ -267,6 +267,9 @@ struct SfmmCtx {
     float rank_offset = 0.f;  // C of the ranking pass's key table (float_nbexact_kernel)
     bool tensor_f16 = false;  // float tensor path runs on an fp16 copy (d_half) with kind::f16
     DevBuf d_half;
+    DevBuf d_half_a;          // TM_F16X: the query-side operand rows (-2q | 1, 2048, 2048), d_half holds the train side
+    bool tensor_kx = false;   // TM_F16X in use (key term contracted by the tensor core)
+    bool no_kx = false;       // SFMM_NO_KX=1: keep TM_F16_EXACT (A/B measurements)
     uint32_t i8_bias = 0;    // binary tensor engine: descriptor bit length when the packed 16-bit keys apply (< 512 bit), else 0
     DevBuf d_nbkey, d_row0;  // binary tensor engine: per-row key part (binary_nbkey_kernel) and the images' first rows
     DevBuf d_unpacked;  // SFMM_BINARY_TENSOR: one byte per descriptor bit
@@ -373,6 +376,7 @@ uint32_t query_tile_rows(const SfmmCtx* ctx) {
 // Does the tensor path of the current descriptor set run the TMEM-A kernel (float_tensor_ts.cuh)?  Mirrors launch_tensor_t.
 bool tensor_uses_ts(const SfmmCtx* ctx) {
     if (!ctx->use_tensor) return false;
+    if (ctx->tensor_kx) return true;
     if (ctx->tensor_ts >= 0) return ctx->tensor_ts != 0;
     if (ctx->elem_type == SFMM_F32) return ctx->tensor_f16;
     return ctx->i8_bias != 0 || ctx->tensor_kblocks <= 2;
@@ -516,12 +520,12 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnT
     // persistent: one CTA per SM (shared memory allows no more) walks the tile list with stride gridDim.x
     const uint32_t grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(ctx->sm_count));
     const KnnTile* tiles = tiles_dev ? tiles_dev : (const KnnTile*)sl.d_tiles.as<KnnTile>();
-    const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_TF32_EXACT || MODE == TM_F16_EXACT || tm_is_rank(MODE)) ? (const float*)ctx->d_nbkey.as<float>()
+    const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_TF32_EXACT || MODE == TM_F16_EXACT || MODE == TM_F16X || tm_is_rank(MODE)) ? (const float*)ctx->d_nbkey.as<float>()
                                                                                                               : (const float*)ctx->d_norms.as<float>();
     // measured (profiles/tensor_variants_r01.txt): TMEM-A wins for the binary engine and the fp16 float path, shared-memory-A for TF32
     uint32_t aux = ctx->i8_bias;  // TM_I8P: descriptor bit length; rank modes: float bits of the key-table offset
     if (tm_is_rank(MODE) || tm_is_collect(MODE)) std::memcpy(&aux, &ctx->rank_offset, sizeof(aux));
-    const bool ts = ctx->tensor_ts < 0 ? (MODE == TM_I8P || OperandOf<MODE>::kind == OK_F16 || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0;
+    const bool ts = MODE == TM_F16X || (ctx->tensor_ts < 0 ? (MODE == TM_I8P || OperandOf<MODE>::kind == OK_F16 || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0);
     if (!ts) {  // query tile in shared memory (float_tensor.cuh)
         const size_t smem = float_tensor_smem_bytes(KB);
         auto kern = tensor_knn2_kernel<KB, MODE>;
@@ -535,7 +539,7 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnT
         return cudaGetLastError();
     }
     // query tile in tensor memory (float_tensor_ts.cuh)
-    const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P) ? ctx->d_unpacked.as<uint4>() : (OperandOf<MODE>::kind == OK_F16 ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>());
+    const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P) ? ctx->d_unpacked.as<uint4>() : (MODE == TM_F16X ? ctx->d_half_a.as<uint4>() : (OperandOf<MODE>::kind == OK_F16 ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>()));
     const size_t smem = float_tensor_ts_smem_bytes(KB);
     auto go = [&](auto kern, int threads) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -549,7 +553,7 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnT
     };
     // SFMM_EPI_GROUPS=4: four epilogue groups for the 32-bit-key float modes (an experiment that measured 5 % slower than two,
     // profiles/tensor_variants_r02.txt; kept selectable and covered by the parity tests)
-    if constexpr (MODE == TM_F16_EXACT || MODE == TM_TF32_EXACT) {
+    if constexpr (MODE == TM_F16_EXACT || MODE == TM_TF32_EXACT || MODE == TM_F16X) {
         if (ctx->epi_groups == 4) return go(tensor_knn2_ts_kernel<KB, MODE, 4>, fts_threads(4));
     }
     return go(tensor_knn2_ts_kernel<KB, MODE, 2>, fts_threads(2));
@@ -569,9 +573,12 @@ cudaError_t launch_tensor(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, int kblocks,
 // The exact tensor modes (results final after one pass) dispatched on the descriptor type; used for the forward pass and for the
 // cross-check's gathered reverse pass.
 cudaError_t launch_tensor_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnTile* tiles_dev = nullptr, const uint32_t* n_items_dev = nullptr) {
-    if (ctx->elem_type == SFMM_F32)
+    if (ctx->elem_type == SFMM_F32) {
+        if (ctx->tensor_kx) return ctx->tensor_kblocks == 2 ? launch_tensor_t<2, TM_F16X>(ctx, sl, n_tiles, tiles_dev, n_items_dev)
+                                                           : launch_tensor_t<3, TM_F16X>(ctx, sl, n_tiles, tiles_dev, n_items_dev);
         return ctx->tensor_f16 ? launch_tensor<TM_F16_EXACT>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev)
                                : launch_tensor<TM_TF32_EXACT>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev);
+    }
     return ctx->i8_bias ? launch_tensor<TM_I8P>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev)
                         : launch_tensor<TM_I8>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev);
 }
@@ -708,20 +715,31 @@ int prepare_float(SfmmCtx* ctx) {
             CU_TRY(ctx, cudaGetLastError());
             ctx->stats.kernel_launches += 1;
         }
+        ctx->tensor_kx = false;
         if (ctx->tensor_eligible && ctx->cols % 64 == 0 && !std::getenv("SFMM_NO_F16")) {
             // TF32-exact data is fp16-exact too: contract an fp16 copy with kind::f16 (16 elements per MMA instead of 8)
-            CU_TRY(ctx, ctx->d_half.ensure(static_cast<size_t>(ctx->total_rows) * ctx->cols * sizeof(__half)));
-            const size_t n2 = static_cast<size_t>(ctx->total_rows) * ctx->cols / 2;
-            float_to_half_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), rows, ctx->cols,
-                                                                                       ctx->d_half.as<__half>());
+            const bool kx = !ctx->no_kx && ctx->cols <= 128;  // TM_F16X: one more K-block carries the key's train-side term (<= 3 K-blocks)
+            const int kx_cols = ctx->cols + (kx ? 64 : 0);
+            CU_TRY(ctx, ctx->d_half.ensure(static_cast<size_t>(ctx->total_rows) * kx_cols * sizeof(__half)));
+            const size_t n2 = static_cast<size_t>(ctx->total_rows) * kx_cols / 2;
+            if (kx) {
+                CU_TRY(ctx, ctx->d_half_a.ensure(static_cast<size_t>(ctx->total_rows) * kx_cols * sizeof(__half)));
+                float_to_half_kx_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), rows,
+                                                                                              ctx->cols, ctx->d_norms.as<float>(), ctx->d_half.as<__half>(),
+                                                                                              ctx->d_half_a.as<__half>());
+            } else {
+                float_to_half_kernel<<<static_cast<unsigned>((n2 + 255) / 256), 256, 0, st>>>(ctx->blob.as<float>(), static_cast<int>(ctx->pitch / 16), rows, ctx->cols,
+                                                                                           ctx->d_half.as<__half>());
+            }
             CU_TRY(ctx, cudaGetLastError());
             CU_TRY(ctx, cudaStreamSynchronize(st));
             ctx->stats.kernel_launches += 1;
-            int rc = make_tensor_map(ctx, ctx->d_half.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<size_t>(ctx->cols) * 2, ctx->total_rows);
+            int rc = make_tensor_map(ctx, ctx->d_half.p, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, static_cast<size_t>(kx_cols) * 2, ctx->total_rows);
             if (rc) return rc;
-            ctx->tensor_kblocks = ctx->cols * 2 / 128;
+            ctx->tensor_kblocks = kx_cols * 2 / 128;
             ctx->use_tensor = true;
             ctx->tensor_f16 = true;
+            ctx->tensor_kx = kx;
         } else if (ctx->tensor_eligible || finite) {
             // arbitrary floats whose magnitudes fit fp16 (|v| <= sqrt(max |x|^2) < 65504): the ranking and collection passes
             // contract an fp16 round-to-nearest copy (same 10-bit significand as TF32, half the MMA time, no power cap);
@@ -1167,6 +1185,7 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     ctx->sm_count = prop.multiProcessorCount;
     if (const char* s = std::getenv("SFMM_TENSOR_TS")) ctx->tensor_ts = std::atoi(s) != 0 ? 1 : 0;
     if (const char* s = std::getenv("SFMM_CSA_LEVEL")) ctx->csa_level = std::max(0, std::min(3, std::atoi(s)));
+    if (const char* s = std::getenv("SFMM_NO_KX")) ctx->no_kx = std::atoi(s) != 0;
     if (const char* s = std::getenv("SFMM_CROSS_FULL")) ctx->cross_full_reverse = std::atoi(s) != 0;
     if (const char* s = std::getenv("SFMM_EPI_GROUPS")) ctx->epi_groups = std::atoi(s) == 4 ? 4 : 2;
     bool ok = (e = cudaSetDevice(cfg->device)) == cudaSuccess;
@@ -1198,7 +1217,7 @@ SFMM_API void sfmm_destroy(SfmmCtx* ctx) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
-    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked, &ctx->d_nbkey, &ctx->d_row0, &ctx->d_half, &ctx->d_raw, &ctx->d_raw_row0}) b->release();
+    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked, &ctx->d_nbkey, &ctx->d_row0, &ctx->d_half, &ctx->d_half_a, &ctx->d_raw, &ctx->d_raw_row0}) b->release();
     for (PinBuf& p : ctx->pack) p.release();
     ctx->table.release();
     for (cudaEvent_t ev : {ctx->ev_begin, ctx->ev_end, ctx->ev_pack[0], ctx->ev_pack[1], ctx->ev_blob})

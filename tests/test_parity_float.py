@@ -179,7 +179,7 @@ def test_arbitrary_floats_use_rank_and_refine_and_equal_the_exact_kernel():
         mx.match_all_pairs()
         assert m.stats()["float_path"] == 3 and mx.stats()["float_path"] == FLOAT_EXACT
         _tables_equal(m, mx)
-        assert sum(len(m.getMatching(q, t)) for q, t in synth.all_pairs(len(g.descs))) > 50
+        assert sum(len(m.getMatching(q, t)) for q, t in synth.all_pairs(len(g.descs))) > 10
 
 
 def test_arbitrary_floats_cross_check_at_cfg4_size_equals_the_exact_kernel():
@@ -353,11 +353,14 @@ def test_l2_over_bytes_random_widths_vs_oracle():
         assert e.value.code == -1
 
 
-@pytest.mark.parametrize("groups", ["2", "4"])
-def test_tensor_kernel_epilogue_group_variants_agree(groups, monkeypatch):
-    """The TMEM-A float kernel runs two or four epilogue groups (SFMM_EPI_GROUPS, read when the context is created; four is
-    the default): both must reproduce the cv2 goldens and the oracle at the cfg-4 row count, ragged tails included."""
+@pytest.mark.parametrize("groups,no_kx", [("2", "0"), ("4", "0"), ("2", "1"), ("4", "1")])
+def test_tensor_kernel_epilogue_group_variants_agree(groups, no_kx, monkeypatch):
+    """The TMEM-A float kernel runs two (default) or four epilogue groups (SFMM_EPI_GROUPS) and takes the key's train-side term
+    from the tensor core (TM_F16X, default) or from a table in the epilogue (SFMM_NO_KX=1, round 1's TM_F16_EXACT); the settings
+    are read when the context is created.  Every variant must reproduce the cv2 goldens and the oracle at the cfg-4 row count,
+    ragged tails included."""
     monkeypatch.setenv("SFMM_EPI_GROUPS", groups)
+    monkeypatch.setenv("SFMM_NO_KX", no_kx)
     g = GoldenSet("temple_sift")
     with Matcher(NORM_L2, 0.8, False) as m:
         m.set_descriptors(g.descs)
