@@ -91,11 +91,33 @@ def main_l2_on_bytes(imgs):
     print("akaze/L2 (4 images) matches", int(rec["match_count"].sum()), "cross", int(rec["match_cross"].sum()))
 
 
+def main_orb_features(imgs):
+    """Golden for the next row of the path, descriptor extraction (getFeature, src/Sfm.cpp:303-392), ORB branch (:358-384):
+    the gray images themselves (the GPU box has no /root/reference) and what cv::ORB::detectAndCompute returns for them."""
+    orb = cv2.ORB_create(500, 1.2, 8, 31, 0, 2, cv2.ORB_HARRIS_SCORE, 31, 20)
+    rec = {"images": np.stack(imgs)}
+    counts, kp_all, d_all = [], [], []
+    for g in imgs:
+        kps, desc = orb.detectAndCompute(g, None)
+        counts.append(len(kps))
+        kp_all.append(np.array([[k.pt[0], k.pt[1], k.size, k.angle, k.response, k.octave] for k in kps], np.float32))
+        d_all.append(desc)
+    rec.update(counts=np.array(counts, np.int32), keypoints=np.concatenate(kp_all), descriptors=np.concatenate(d_all))
+    # colour -> gray the way imread + cvtColor(BGR2GRAY) does it, for the optional device-side conversion: first image only
+    files = sorted(glob.glob(os.path.join(TEMPLE, "*.png")))
+    rec["bgr0"] = cv2.imread(files[0])
+    np.savez_compressed(os.path.join(HERE, "temple_orb_features.npz"), **rec)
+    print("orb features", counts)
+
+
 def main():
     imgs = temple_gray()
     if "--only-l2-on-bytes" in sys.argv:
         return main_l2_on_bytes(imgs)
+    if "--only-orb-features" in sys.argv:
+        return main_orb_features(imgs)
     main_l2_on_bytes(imgs)
+    main_orb_features(imgs)
 
     akaze = cv2.AKAZE_create(cv2.AKAZE_DESCRIPTOR_MLDB, 0, 3, 0.001, 4, 4, cv2.KAZE_DIFF_PM_G2)
     d = [akaze.detectAndCompute(g, None)[1] for g in imgs]
