@@ -6,7 +6,8 @@ across ranks + NCCL broadcast/gather) and ``synth`` (seeded descriptor sets for 
 """
 from ._lib import (BINARY_AUTO, BINARY_POPC, BINARY_TENSOR, DMATCH_DTYPE, FLOAT_AUTO, FLOAT_EXACT, FLOAT_TENSOR, NORM_HAMMING,  # noqa: F401
                    NORM_L2, SfmmError)
+from .features import KEYPOINT_DTYPE, OrbExtractor, extract_features  # noqa: F401
 from .matcher import GroupMatcher, Matcher  # noqa: F401
 
-__all__ = ["Matcher", "GroupMatcher", "SfmmError", "DMATCH_DTYPE", "NORM_HAMMING", "NORM_L2", "FLOAT_AUTO", "FLOAT_EXACT",
+__all__ = ["Matcher", "GroupMatcher", "OrbExtractor", "extract_features", "KEYPOINT_DTYPE", "SfmmError", "DMATCH_DTYPE", "NORM_HAMMING", "NORM_L2", "FLOAT_AUTO", "FLOAT_EXACT",
            "FLOAT_TENSOR", "BINARY_AUTO", "BINARY_POPC", "BINARY_TENSOR"]

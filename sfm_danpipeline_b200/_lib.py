@@ -29,6 +29,8 @@ EXPORTS = (
     "sfmm_group_set_descriptors", "sfmm_group_match_all_pairs", "sfmm_group_match_pairs", "sfmm_group_get_pair",
     "sfmm_group_transfer_stats", "sfmm_share_table", "sfmm_shared_table_info",
 )
+#: every symbol include/sfm_features.h declares
+FEATURE_EXPORTS = ("sfmm_orb_create", "sfmm_orb_destroy", "sfmm_orb_last_error", "sfmm_orb_detect_and_compute", "sfmm_orb_stats")
 
 
 class SfmmConfig(C.Structure):
@@ -91,6 +93,13 @@ def load() -> C.CDLL:
     L.sfmm_load_table.argtypes = [vp, C.c_char_p]
     L.sfmm_get_stats.argtypes = [vp, P(SfmmStats)]
     L.sfmm_image_rows.argtypes = [vp, i32, P(i32)]
+    L.sfmm_orb_create.argtypes = [i32, P(vp)]
+    L.sfmm_orb_destroy.restype = None
+    L.sfmm_orb_destroy.argtypes = [vp]
+    L.sfmm_orb_last_error.restype = C.c_char_p
+    L.sfmm_orb_last_error.argtypes = [vp]
+    L.sfmm_orb_detect_and_compute.argtypes = [vp, vp, i32, i32, sz, i32, vp, vp, i32, P(i32)]
+    L.sfmm_orb_stats.argtypes = [vp, P(i64), P(C.c_double)]
     L.sfmm_share_table.argtypes = [vp, C.c_char_p]
     L.sfmm_shared_table_info.argtypes = [vp, C.c_char_p, sz, P(i64)]
     L.sfmm_group_create.argtypes = [P(SfmmConfig), i32, P(i32), P(vp)]

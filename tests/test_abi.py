@@ -31,6 +31,19 @@ def test_exports_match_header():
         assert getattr(L, name) is not None
 
 
+def test_feature_exports_match_header():
+    hdr = open(os.path.join(ROOT, "include", "sfm_features.h")).read()
+    declared = set(re.findall(r"SFMM_API\s+[\w\s\*]+?\b(sfmm_\w+)\s*\(", hdr))
+    assert declared == set(_lib.FEATURE_EXPORTS), declared ^ set(_lib.FEATURE_EXPORTS)
+    L = _lib.load()
+    for name in declared:
+        assert getattr(L, name) is not None
+    for cite in ("src/Sfm.cpp:303-392", "src/Sfm.cpp:360-371", "src/Sfm.cpp:373", "include/Utilities.h:26"):
+        assert cite in hdr
+    from sfm_danpipeline_b200 import KEYPOINT_DTYPE
+    assert KEYPOINT_DTYPE.itemsize == 28  # cv::KeyPoint
+
+
 def test_header_cites_the_reference_interface():
     hdr = open(os.path.join(ROOT, "include", "sfm_match.h")).read()
     for cite in ("src/Sfm.cpp:590-608", "src/Sfm.cpp:511-515", "include/Sfm.h:60", "include/Utilities.h:27"):
