@@ -581,6 +581,51 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
     return out, descs, norm
 
 
+def orb_block(local):
+    """The next row of the path (SURVEY.md 8f-4): ORB extraction on the GPU vs cv::ORB on the host cores, on the reference's
+    own fixture (the ten 640 x 480 data/temple images, committed as a golden), with the parity check in the same run."""
+    from sfm_danpipeline_b200 import OrbExtractor
+    z = np.load(os.path.join(ROOT, "tests", "golden", "temple_orb_features.npz"))
+    imgs = [np.ascontiguousarray(x) for x in z["images"]]
+    offs = np.concatenate([[0], np.cumsum(z["counts"])])
+    out = {"workload": "ORB(500, 1.2, 8, 31, 0, 2, HARRIS, 31, 20) on the 10 data/temple images (640 x 480), src/Sfm.cpp:358-384"}
+    with OrbExtractor(local) as orb:
+        for im in imgs:
+            orb.detectAndCompute(im)  # warm-up: buffers, taps
+        ok = True
+        dev_ms = 0.0
+        t0 = time.perf_counter()
+        reps = 5
+        for _ in range(reps):
+            for i, im in enumerate(imgs):
+                kp, d = orb.detectAndCompute(im)
+                dev_ms += orb.stats()["last_ms"]
+        wall = time.perf_counter() - t0
+        for i, im in enumerate(imgs):  # parity: keypoint set + bit-exact descriptors vs the cv2 golden
+            kp, d = orb.detectAndCompute(im)
+            ref = {(int(k[5]), float(k[0]), float(k[1])): (float(k[3]), float(k[4]), bytes(dd)) for k, dd in zip(z["keypoints"][offs[i]:offs[i + 1]], z["descriptors"][offs[i]:offs[i + 1]])}
+            got = {(int(k["octave"]), float(k["x"]), float(k["y"])): (float(k["angle"]), float(k["response"]), bytes(dd)) for k, dd in zip(kp, d)}
+            ok &= got == ref
+        out.update(images_per_s=reps * len(imgs) / wall, ms_per_image_e2e=1e3 * wall / (reps * len(imgs)), ms_per_image_device=dev_ms / (reps * len(imgs)),
+                   kernel_launches_per_image=orb.stats()["kernel_launches"] // ((reps + 2) * len(imgs)),
+                   verified="keypoint sets equal, angles / responses / descriptors bit-identical to the cv2 golden" if ok else "MISMATCH")
+    try:
+        import cv2
+        cv2.setNumThreads(os.cpu_count() or 1)
+        ref = cv2.ORB_create(500, 1.2, 8, 31, 0, 2, cv2.ORB_HARRIS_SCORE, 31, 20)
+        ref.detectAndCompute(imgs[0], None)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            for im in imgs:
+                ref.detectAndCompute(im, None)
+        dt = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": 3 * len(imgs) / dt, "unit": "images/s", "cores": cv2.getNumThreads(), "kind": "reference",
+                               "sample": f"cv2 {cv2.__version__} ORB.detectAndCompute, 30 images, {dt:.2f} s"}
+    except Exception:
+        pass
+    return out
+
+
 # ------------------------------------------------------------------------------ GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -672,6 +717,7 @@ def main():
         k4, n4, d4, _w = WORKLOADS["cfg4s"]
         r4, _d, _n = measure(env, args, "cfg4s", k4, n4, d4, steps=3, warmup=3, e2e_steps=2, e2e_warmup=2, verify=1)
         line["float"] = {k: r4[k] for k in ("workload", "engine", "value", "ms_per_step", "e2e", "resident_device_only", "roofline", "verified")}
+        line["orb_extraction"] = orb_block(env.local)
     if env.rank == 0:
         print(json.dumps(line), flush=True)
     if env.world > 1:

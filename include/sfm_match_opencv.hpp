@@ -21,6 +21,7 @@
 
 #include <opencv2/core.hpp>
 
+#include "sfm_features.h"
 #include "sfm_match.h"
 
 namespace sfmm {
@@ -244,6 +245,49 @@ class MultiGpuMatcher {
         if (rc != SFMM_OK) throw Error(rc, sfmm_group_last_error(g_));
     }
     SfmmGroup* g_;
+};
+
+// Drop-in for the ORB branch of StructFromMotion::getFeature (src/Sfm.cpp:358-384): replaces
+//     cv::Ptr<cv::ORB> detector = cv::ORB::create(500, 1.2f, 8, 31, 0, 2, cv::ORB::HARRIS_SCORE, 31, 20);
+//     detector->detectAndCompute(image, cv::noArray(), kps, descriptors, false);
+// with the GPU extractor of sfm_features.h (the reference's parameters are built in).  Same keypoints on every pyramid level,
+// bit-identical angle / response / size / descriptor; the order inside a level is row-major instead of std::nth_element's.
+static_assert(sizeof(cv::KeyPoint) == sizeof(SfmKeyPoint), "cv::KeyPoint and SfmKeyPoint must have the same layout");
+class OrbExtractor {
+  public:
+    explicit OrbExtractor(int device = 0) : orb_(nullptr) {
+        const int rc = sfmm_orb_create(device, &orb_);
+        if (rc != SFMM_OK) throw Error(rc, sfmm_orb_last_error(nullptr));
+    }
+    ~OrbExtractor() { sfmm_orb_destroy(orb_); }
+    OrbExtractor(const OrbExtractor&) = delete;
+    OrbExtractor& operator=(const OrbExtractor&) = delete;
+
+    void detectAndCompute(const cv::Mat& image, std::vector<cv::KeyPoint>& kps, cv::Mat& descriptors) {
+        if (image.empty() || image.depth() != CV_8U || (image.channels() != 1 && image.channels() != 3))
+            throw Error(SFMM_EINVAL, "OrbExtractor: 8-bit gray or BGR image expected");
+        std::vector<SfmKeyPoint> k(1024);
+        std::vector<uint8_t> d(1024 * 32);
+        int32_t n = 0;
+        int rc = sfmm_orb_detect_and_compute(orb_, image.data, image.rows, image.cols, image.step, image.channels(), k.data(), d.data(), 1024, &n);
+        if (rc == SFMM_ERANGE && n > 1024) {  // more than 1024 keypoints: only through ties
+            k.resize(n);
+            d.resize(static_cast<size_t>(n) * 32);
+            rc = sfmm_orb_detect_and_compute(orb_, image.data, image.rows, image.cols, image.step, image.channels(), k.data(), d.data(), n, &n);
+        }
+        if (rc != SFMM_OK) throw Error(rc, sfmm_orb_last_error(orb_));
+        kps.resize(static_cast<size_t>(n));
+        if (n > 0) std::memcpy(static_cast<void*>(kps.data()), k.data(), static_cast<size_t>(n) * sizeof(SfmKeyPoint));
+        if (n > 0) {
+            descriptors.create(n, 32, CV_8U);
+            for (int i = 0; i < n; ++i) std::memcpy(descriptors.data + static_cast<size_t>(i) * descriptors.step, d.data() + static_cast<size_t>(i) * 32, 32);
+        } else {
+            descriptors.release();
+        }
+    }
+
+  private:
+    SfmmOrb* orb_;
 };
 
 }  // namespace sfmm

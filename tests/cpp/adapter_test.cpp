@@ -94,6 +94,23 @@ int main(int argc, char** argv) {
             if (!refused) { printf("mixed descriptor widths were accepted\n"); return 1; }
             matcher.compute(imagesDescriptors);
         }
+        if (argc > 3) {  // ORB extraction through the adapter: argv[3] = raw 8-bit gray image file "rows cols" header + pixels, expected count
+            FILE* g = fopen(argv[3], "rb");
+            int32_t dims[3];
+            if (!g || !rd(g, dims, sizeof dims)) return 2;
+            std::vector<unsigned char> pix(static_cast<size_t>(dims[0]) * dims[1]);
+            if (!rd(g, pix.data(), pix.size())) return 2;
+            fclose(g);
+            cv::Mat image(dims[0], dims[1], CV_8U, pix.data());
+            sfmm::OrbExtractor orb(0);
+            std::vector<cv::KeyPoint> kps;
+            cv::Mat desc;
+            orb.detectAndCompute(image, kps, desc);
+            if (static_cast<int>(kps.size()) != dims[2] || desc.rows != dims[2] || desc.cols != 32) { printf("orb count mismatch %zu\n", kps.size()); return 1; }
+            for (size_t i = 0; i < kps.size(); ++i)
+                if (kps[i].class_id != -1 || kps[i].octave < 0 || kps[i].octave > 7 || kps[i].angle < 0.f || kps[i].angle >= 360.f) { printf("orb keypoint fields\n"); return 1; }
+            printf("orb ok: %zu keypoints\n", kps.size());
+        }
         std::vector<cv::DMatch> rev;  // q>t is never asked by the reference; the adapter computes it on demand
         matcher.getMatching(1, 0, &rev);
         printf("adapter ok: %d images, reverse pair gave %zu matches\n", n, rev.size());

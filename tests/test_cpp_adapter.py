@@ -55,6 +55,11 @@ def test_patched_getmatching_equals_oracle(tmp_path, kind, cross):
     _write_case(case, descs, norm, cross)
     import torch
     n_dev = torch.cuda.device_count()  # every visible GPU: the group broadcasts with NCCL when there is more than one
-    r = subprocess.run([exe, case, str(n_dev)], capture_output=True, text=True)
+    z = np.load(os.path.join(ROOT, "tests", "golden", "temple_orb_features.npz"))
+    img_file = str(tmp_path / "image.bin")
+    with open(img_file, "wb") as f:  # sfmm::OrbExtractor on the reference's first temple image: cv::ORB finds 500 keypoints there
+        f.write(np.array([480, 640, int(z["counts"][0])], np.int32).tobytes())
+        f.write(np.ascontiguousarray(z["images"][0]).tobytes())
+    r = subprocess.run([exe, case, str(n_dev), img_file], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout + r.stderr
-    assert "adapter ok" in r.stdout and f"multi-gpu ok on {n_dev} device(s)" in r.stdout
+    assert "adapter ok" in r.stdout and f"multi-gpu ok on {n_dev} device(s)" in r.stdout and "orb ok: 500 keypoints" in r.stdout
