@@ -378,9 +378,10 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
         """Descriptors resident -> every match list in rank 0's host memory."""
         gather = gather or args.gather
         if world > 1 and gather == "shared":
-            t = D.match_and_share(m, pairs, shards, 0)
+            t = D.match_and_share(m, pairs, shards, 0, rows=rows)
             note_stats()
-            acc["matches"] += m.shared_table_info()[1]
+            if not getattr(m, "_shm_unavailable", False):
+                acc["matches"] += m.shared_table_info()[1]
             return t
         if world > 1 and gather == "nccl-once":
             c, mm, k = D.match_shard(m, mine, rows)
@@ -537,7 +538,8 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
                "resident_device_only": {"value": len(pairs) / (dev_only_max * 1e-3) if dev_only_max else None, "ms_per_step": dev_only_max,
                                         "note": "round-1 definition of `value`: match lists left in HBM (sfmm_match_pairs_device), library CUDA events"},
                "gpu_launches": launches_sum, "roofline": roof, "clocks": sampler.summary() if sampler else None,
-               "gather_chunks": D.gather_chunks(pairs, shards, rows) if world > 1 else None, "gather_alt": gather_alt}
+               "gather_chunks": D.gather_chunks(pairs, shards, rows) if world > 1 else None, "gather_alt": gather_alt,
+               "gather_used": ("nccl (shared-memory tables did not fit in /dev/shm)" if getattr(m, "_shm_unavailable", False) else args.gather)}
         if verify:
             get = table.getMatching if world > 1 else (lambda q, t: m.getMatching(q, t))
             out["verified"] = verify_pairs(get, pairs, descs, norm, verify, cross)
@@ -653,6 +655,7 @@ def main():
                     help="N>1: how the match lists reach rank 0's host memory -- shared: every GPU copies its records over its own PCIe link "
                          "into a shared page-locked table rank 0 maps; nccl: chunk-wise NCCL gather to rank 0's GPU + D2H there, overlapped "
                          "with matching; nccl-once: one NCCL gather at the end (round 1).  The other two are reported as gather_alt")
+    ap.add_argument("--device-only-iters", type=int, default=3, help="iterations of the device-only (round-1 definition) measurement behind the roofline")
     ap.add_argument("--verify", type=int, default=2, help="check this many random pairs of the e2e table against the CPU oracle (0 = off)")
     args = ap.parse_args()
 
@@ -684,7 +687,7 @@ def main():
     e2e_steps = args.e2e_steps or max(2, min(args.steps, 3))
     res, descs, norm = measure(env, args, args.workload, kind, n_images, n_desc, steps=args.steps, warmup=args.warmup, e2e_steps=e2e_steps,
                                e2e_warmup=args.e2e_warmup, cross=args.cross_check, float_mode=fm, binary_engine=be,
-                               alt=not args.no_alt_engine, verify=args.verify, clocks=True)
+                               alt=not args.no_alt_engine, verify=args.verify, clocks=True, device_only_iters=max(1, args.device_only_iters))
     if env.rank == 0:
         line = {
             "metric": "image-pair matches/sec (all-pairs 2-NN + ratio test)", "value": res["value"], "unit": "pairs/s",
@@ -697,7 +700,7 @@ def main():
                                        "(matching + gather + device->host), CUDA events per step, max over ranks",
                        "l2": "flushed between steps (256 MiB memset outside the timed events); the operand set is also larger than L2",
                        "parallelism": f"pairs sharded over {env.world} rank(s) by cost-sorted snake deal"
-                                      + (f"; NCCL broadcast of the descriptors (e2e only); gather={args.gather}" if env.world > 1 else "")},
+                                      + (f"; NCCL broadcast of the descriptors (e2e only); gather={res['gather_used']}" if env.world > 1 else "")},
             "wall_ms_per_step": res["wall_ms_per_step"],
             "e2e": res["e2e"], "resident_device_only": res["resident_device_only"],
             "gpu_launches": res["gpu_launches"], "roofline": res["roofline"], "clocks": res["clocks"],

@@ -143,7 +143,9 @@ struct HostTable {
             bytes = (bytes + 4095) & ~size_t(4095);
             const int fd = shm_open(name.c_str(), O_CREAT | O_EXCL | O_RDWR, 0600);
             if (fd < 0) return SFMM_ENOMEM;
-            if (ftruncate(fd, static_cast<off_t>(bytes)) != 0) {
+            // posix_fallocate (not ftruncate): the blocks are reserved now, so a /dev/shm that is too small is an error code here and
+            // not a SIGBUS at the first copy into the mapping
+            if (posix_fallocate(fd, 0, static_cast<off_t>(bytes)) != 0) {
                 close(fd);
                 shm_unlink(name.c_str());
                 return SFMM_ENOMEM;
@@ -985,7 +987,8 @@ int collect_chunk(SfmmCtx* ctx, Slot& sl, const int32_t* qt) {
             const double seen = static_cast<double>(sl.first + sl.n), all = static_cast<double>(std::max<int64_t>(ctx->call_pairs, sl.first + sl.n));
             const size_t guess = static_cast<size_t>((static_cast<double>(old_size - ctx->call_base + total) * all / seen) * 1.05) + 1024;
             if (ctx->table.reserve(std::max(old_size + static_cast<size_t>(total), ctx->call_base + guess), ctx->copy_stream))
-                return fail(ctx, SFMM_ENOMEM, "match_pairs: out of host memory for the match table");
+                return fail(ctx, SFMM_ENOMEM, ctx->table.shm_prefix.empty() ? "match_pairs: out of host memory for the match table"
+                                                                            : "match_pairs: the shared-memory match table does not fit (/dev/shm too small?)");
         }
         // device -> host straight into the table, asynchronously: the next chunk's kernels (other slot) run meanwhile; this slot's
         // next launch waits for ev_copied, the call ends with a synchronisation of the copy stream

@@ -435,32 +435,60 @@ def enable_shared_tables(matcher, group=None) -> str:
     return base
 
 
-def match_and_share(matcher, pairs: np.ndarray, shards: list[np.ndarray], dst: int = 0, group=None):
+def match_and_share(matcher, pairs: np.ndarray, shards: list[np.ndarray], dst: int = 0, group=None, rows=None):
     """Steps 3 + 4 without a funnel: every rank matches its shard through the library's own pipelined host path -- chunk k's
     records go device -> host over THIS GPU's PCIe link, straight into its (shared, page-locked) match table, while chunk k+1
     is being matched -- and `dst` maps the other ranks' tables.  The only traffic between ranks is one small NCCL gather of
-    per-pair counts.  Returns a ShardedPairTable on `dst`, None elsewhere."""
+    per-pair counts.  Returns a ShardedPairTable on `dst`, None elsewhere.
+
+    If a rank cannot place its table in shared memory (a container with a small /dev/shm), every rank learns it through the
+    same gather and the whole group falls back, for this call and the following ones, to the chunk-wise NCCL gather
+    (match_and_gather; needs `rows`)."""
+    from ._lib import SFMM_ENOMEM, SfmmError
     rank, world = dist.get_rank(group), dist.get_world_size(group)
+    if getattr(matcher, "_shm_unavailable", False):
+        return _gather_over_nccl(matcher, pairs, shards, rows, dst, group)
     base = enable_shared_tables(matcher, group)
     mine = pairs[shards[rank]]
     matcher.clear_results()
-    matcher.match_pairs(mine)
-    _p, counts, _o, _m = matcher.result_table(copy=False)
-    name, n = matcher.shared_table_info()
-    gen = int(name.rsplit(".", 1)[1]) if name else 0
-    width = 3 + max(len(sh) for sh in shards)
+    failed = 0
+    try:
+        matcher.match_pairs(mine)
+    except SfmmError as e:
+        if e.code != SFMM_ENOMEM:
+            raise
+        failed = 1
+    width = 4 + max(len(sh) for sh in shards)
     meta = np.zeros(width, np.int32)
-    meta[0], meta[2] = gen, n >> 32
-    meta[1:2] = np.array([n & 0xFFFFFFFF], np.uint32).view(np.int32)
-    meta[3: 3 + len(counts)] = counts
+    counts = np.zeros(0, np.int32)
+    if not failed:
+        _p, counts, _o, _m = matcher.result_table(copy=False)
+        name, n = matcher.shared_table_info()
+        meta[0], meta[2] = (int(name.rsplit(".", 1)[1]) if name else 0), n >> 32
+        meta[1:2] = np.array([n & 0xFFFFFFFF], np.uint32).view(np.int32)
+        meta[4: 4 + len(counts)] = counts
+    meta[3] = failed
     dev = torch.device("cuda", matcher.device)
     t = torch.from_numpy(meta).to(dev)
-    out = [torch.empty_like(t) for _ in range(world)] if rank == dst else None
-    dist.gather(t, out, dst=dst, group=group)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t, group=group)  # (everyone needs the failure flags; the payload is a few KB per rank)
+    metas = [o.cpu().numpy() for o in out]
+    if any(int(m[3]) for m in metas):
+        matcher._shm_unavailable = True
+        matcher.share_table(None)
+        if rows is None:
+            raise SfmmError(SFMM_ENOMEM, "shared-memory match tables do not fit on this host and no row counts were given for the NCCL fallback")
+        return _gather_over_nccl(matcher, pairs, shards, rows, dst, group)
     if rank != dst:
         return None
-    metas = [o.cpu().numpy() for o in out]
-    return assemble_shared(pairs, shards, metas, base)
+    return assemble_shared(pairs, shards, [np.concatenate([m[:3], m[4:]]) for m in metas], base)
+
+
+def _gather_over_nccl(matcher, pairs, shards, rows, dst, group):
+    def match_fn(chunk, slot):
+        c, m, _k = match_shard(matcher, chunk, rows, slot=slot)
+        return c, m
+    return match_and_gather(match_fn, pairs, shards, rows, dst, group)
 
 
 # --------------------------------------------------------------------------- one rank's shard
@@ -522,8 +550,8 @@ def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, 
     t2 = time.perf_counter()
     n = 0
     if gather == "shared":
-        table = match_and_share(matcher, pairs, shards, dst, group)
-        n = matcher.shared_table_info()[1]
+        table = match_and_share(matcher, pairs, shards, dst, group, rows=rows)
+        n = 0 if getattr(matcher, "_shm_unavailable", False) else matcher.shared_table_info()[1]
         t3 = t4 = time.perf_counter()
     elif pipelined:
         def match_fn(chunk, slot):
