@@ -521,7 +521,8 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
         roof["kernel_share_of_device_only_step"] = kacc["knn_ms"] / max(kacc["step_ms"], 1e-9)
         key = f"{name}/{engine}/{'cross' if cross else 'plain'}"
         if key in env.traffic and n_images == WORKLOADS[name][1]:
-            roof["traffic"] = env.traffic[key]["bytes_per_launch"]
+            # measured by ncu per pair (one launch of the same kernel on the same workload), scaled to this run's pairs per launch
+            roof["traffic"] = env.traffic[key]["bytes_per_pair"] * len(mine) * device_only_iters / max(kacc["knn_launches"], 1)
             roof["traffic_source"] = env.traffic[key]["source"]
         else:
             roof["traffic_source"] = "no ncu --set full capture of this exact workload is committed: null"

@@ -1320,7 +1320,7 @@ static int impl_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* cons
             if (k >= 2) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_pack[k & 1]));  // its previous copy has left the slab
             unsigned char* dst = static_cast<unsigned char*>(pin.p);
             const uint64_t n_rows = e - b;
-            const unsigned workers = static_cast<unsigned>(std::min<uint64_t>(std::min(8u, hw), std::max<uint64_t>(1, (n_rows * row_bytes) >> 21)));
+            const unsigned workers = static_cast<unsigned>(std::min<uint64_t>(std::min(16u, hw), std::max<uint64_t>(1, (n_rows * row_bytes) >> 21)));
             if (workers <= 1) {
                 pack_raw(ctx, data, step_bytes, row_bytes, b, e, dst);
             } else {

@@ -35,6 +35,22 @@ def all_pairs(n_images: int) -> np.ndarray:
     return np.stack([q, t], 1).astype(np.int32)
 
 
+_SHARD_CACHE: dict = {}
+
+
+def shard_pairs_cached(n_images: int, rows, world_size: int):
+    """(all_pairs, shard_pairs) for a layout, computed once per (row counts, world size): the enumeration and the cost sort
+    depend on nothing else, and on a job of ~20 000 pairs they cost ~1 ms -- not nothing next to a 70 ms step on 8 GPUs."""
+    key = (int(n_images), tuple(int(r) for r in rows), int(world_size))
+    hit = _SHARD_CACHE.get(key)
+    if hit is None:
+        if len(_SHARD_CACHE) > 8:
+            _SHARD_CACHE.clear()
+        pairs = all_pairs(n_images)
+        hit = _SHARD_CACHE[key] = (pairs, shard_pairs(pairs, rows, world_size))
+    return hit
+
+
 def shard_pairs(pairs: np.ndarray, rows, world_size: int) -> list[np.ndarray]:
     """Indices (into `pairs`) owned by each rank.
 
@@ -544,8 +560,7 @@ def match_all_pairs_distributed(matcher, descriptors, dst: int = 0, group=None, 
         broadcast_descriptors(matcher, descriptors, dst, group)
     t1 = time.perf_counter()
     rows = matcher.rows
-    pairs = all_pairs(len(rows))
-    shards = shard_pairs(pairs, rows, world)
+    pairs, shards = shard_pairs_cached(len(rows), rows, world)
     mine = pairs[shards[rank]]
     t2 = time.perf_counter()
     n = 0

@@ -1,12 +1,7 @@
-mkdir -p gpurun_out/r2k; (timeout 300 python -m pytest tests -m gpu -x -q --timeout 100 > gpurun_out/r2k/pytest.log 2>&1; echo "pytest rc=$?" >> gpurun_out/r2k/pytest.log); tail -6 gpurun_out/r2k/pytest.log
-timeout 400 python bench.py > gpurun_out/r2k/bench_default.json 2> gpurun_out/r2k/bench_default.err; tail -3 gpurun_out/r2k/bench_default.err
-python - <<'PY'
-import json
-l=json.load(open('gpurun_out/r2k/bench_default.json'))
-print('value',l['value'],'e2e',l['e2e']['value'],'dev-only',l['resident_device_only']['value'],'frac',l['roofline']['frac'],l['roofline']['peak'],'verified',l.get('verified'))
-print('cfg2',l['configs1_cfg2']['value'],l['configs1_cfg2']['e2e']['value'],l['configs1_cfg2']['roofline']['frac'])
-print('float',l['float']['value'],l['float']['e2e']['value'],l['float']['roofline']['frac'])
-print('orb',l['orb_extraction'])
-print('alt',l['alt_engine']['pairs_per_s_per_gpu'],l['alt_engine']['roofline']['frac'],l['alt_engine']['roofline'].get('executed_popc_frac'))
-print('cpu',l['cpu_baseline'])
-PY
+mkdir -p gpurun_out/r2n
+ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2n/launches_default.csv python bench.py --steps 2 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 0 --device-only-iters 1 --e2e-steps 1 --e2e-warmup 1 > gpurun_out/r2n/launches_bench.log 2>&1
+tail -2 gpurun_out/r2n/launches_bench.log | cut -c1-200
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:tensor_knn2_ts -s 2 -c 1 -o gpurun_out/r2n/ts_i8p_cfg3 python bench.py --steps 1 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 0 --device-only-iters 1 --e2e-steps 1 --e2e-warmup 0 > gpurun_out/r2n/ncu1.log 2>&1; tail -2 gpurun_out/r2n/ncu1.log | cut -c1-200
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:tensor_knn2_ts -s 2 -c 1 -o gpurun_out/r2n/ts_f16x_cfg4s python bench.py --workload cfg4s --steps 1 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 0 --device-only-iters 1 --e2e-steps 1 --e2e-warmup 0 > gpurun_out/r2n/ncu2.log 2>&1; tail -2 gpurun_out/r2n/ncu2.log | cut -c1-200
+SFMM_BENCH_TRACE=1 timeout 100 python bench.py --steps 3 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 0 --device-only-iters 1 2>&1 | grep "e2e\]" | tail -2
+ls -la gpurun_out/r2n

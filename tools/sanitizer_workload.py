@@ -57,4 +57,29 @@ with Matcher(1, 0.8, False, float_mode=FLOAT_TENSOR) as m:
     m.set_descriptors(g)
     m.match_all_pairs()
     assert m.getMatching(0, 1).tobytes() == oracle.match_pair(g[0], g[1], 1, 0.8, False).tobytes()
+# round 2: L2 over CV_8U rows (widened on the device by ingest_rows_kernel), cross-check through candidate columns on the float /
+# arbitrary-float paths (exact kernel in reverse + gather mode), the key-term-in-the-MMA float kernel, ORB extraction
+u = [rng.integers(0, 256, (n, 61), dtype=np.uint8) for n in (140, 129, 3)]
+for cross in (False, True):
+    with Matcher(1, 0.9, cross) as m:
+        m.set_descriptors(u)
+        m.match_all_pairs()
+        for (q, t) in synth.all_pairs(3):
+            assert m.getMatching(q, t).tobytes() == oracle.match_pair(u[q], u[t], 1, 0.9, cross).tobytes()
+with Matcher(1, 0.8, True, float_mode=FLOAT_AUTO) as m, Matcher(1, 0.8, True, float_mode=FLOAT_EXACT) as mx:
+    for mm in (m, mx):
+        mm.set_descriptors(x)
+        mm.match_all_pairs()
+    assert m.stats()["float_path"] == 3
+    for (q, t) in synth.all_pairs(3):
+        assert m.getMatching(q, t).tobytes() == mx.getMatching(q, t).tobytes()
+from oracle import orb_oracle  # noqa: E402
+from sfm_danpipeline_b200 import OrbExtractor  # noqa: E402
+z = np.load(os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests", "golden", "temple_orb_features.npz"))
+img = np.ascontiguousarray(z["images"][1][100:330, 150:470])
+with OrbExtractor(0) as orb:
+    kp, desc = orb.detectAndCompute(img)
+okp, od = orb_oracle.detect_and_compute(img)
+assert {(int(k["octave"]), float(k["x"]), float(k["y"])): bytes(dd) for k, dd in zip(kp, desc)} == \
+       {(int(k["octave"]), float(k["x"]), float(k["y"])): bytes(dd) for k, dd in zip(okp, od)}
 print("sanitizer workload ok")
