@@ -45,6 +45,10 @@ enum TensorMode {
                           // v0 + 2048 v1 + 2048^2 v2 = |t|^2 + 2^23 + 2^20 -- so that the accumulator IS the key argument
                           // x' = |t|^2 - 2 q.t + 2^23 + 2^20 (exact: every term an integer, every partial sum below 2^24): no FFMA, no
                           // norm table read per column in the epilogue (float_to_half_kx_kernel; one MMA more per tile)
+    TM_F4P = 9,           // TM_I8P on the FP4 pipe: a bit is the E2M1 value 1.0 or 0.0 (one nibble), every block scale is 2^0, and
+                          // tcgen05.mma kind::mxf4.block_scale contracts 64 bits per instruction in the 64 cycles kind::i8 needs for 32 --
+                          // twice the rate on HALF the operand bytes (256 B per 512-bit row); products are 0 or 1 and the fp32 accumulator
+                          // holds integers <= 512, so q.t is exact (tools/mxf4_bench.cu checks it against popc(q & t)); TMEM-A kernel only
     TM_TF32_COLLECT = 3   // arbitrary floats, pass 2: every column whose approximate d^2 can still be in the exact
                           // top-2 (<= m2 + 2*eps, a rigorous bound) is appended to the row's candidate list, which
                           // float_refine_kernel then evaluates exactly (fp32 direct difference, float_exact.cuh's arithmetic)
@@ -79,11 +83,11 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __host__ __device__ constexpr bool tm_is_rank(int mode) { return mode == TM_TF32_RANK || mode == TM_F16_RANK; }
 __host__ __device__ constexpr bool tm_is_collect(int mode) { return mode == TM_TF32_COLLECT || mode == TM_F16_COLLECT; }
 // Operand type of a mode: what the tensor map describes and which tcgen05.mma kind contracts it.
-enum OperandKind { OK_TF32 = 0, OK_I8 = 1, OK_F16 = 2 };
+enum OperandKind { OK_TF32 = 0, OK_I8 = 1, OK_F16 = 2, OK_F4 = 3 };
 template <int MODE>
 struct OperandOf {
-    static constexpr int kind = (MODE == TM_I8 || MODE == TM_I8P) ? OK_I8 : ((MODE == TM_F16_EXACT || MODE == TM_F16X || MODE == TM_F16_RANK || MODE == TM_F16_COLLECT) ? OK_F16 : OK_TF32);
-    static constexpr int kb_elems = kind == OK_I8 ? 128 : (kind == OK_F16 ? 64 : 32);  // elements per 128-byte swizzle row
+    static constexpr int kind = MODE == TM_F4P ? OK_F4 : (MODE == TM_I8 || MODE == TM_I8P) ? OK_I8 : ((MODE == TM_F16_EXACT || MODE == TM_F16X || MODE == TM_F16_RANK || MODE == TM_F16_COLLECT) ? OK_F16 : OK_TF32);
+    static constexpr int kb_elems = (kind == OK_I8 || kind == OK_F4) ? 128 : (kind == OK_F16 ? 64 : 32);  // tensor-map elements per 128-byte swizzle row (nibble pairs travel as bytes)
 };
 // D[tmem] (+)= A[smem] * B[smem]^T; M=128, N=128, 32 bytes of K per instruction (8 tf32 / 16 f16 / 32 u8), fp32 or s32
 // accumulate.  Called by the WHOLE warp with warp-uniform operands; one elected lane issues.  (Issuing from inside
@@ -189,6 +193,9 @@ static constexpr uint32_t FT_IDESC = (1u << 4) | (2u << 7) | (2u << 10) | ((FT_N
 // kind::i8: D=S32 (bits 4-5 = 2), A=B=UINT8 (format 0), both K-major.
 static constexpr uint32_t FT_IDESC_I8 = (2u << 4) | (0u << 7) | (0u << 10) | ((FT_N >> 3) << 17) | ((FT_M >> 4) << 24);
 // kind::f16: D=F32 (1), A=B=F16 (format 0), both K-major.
+// kind::mxf4.block_scale (CUTLASS mma_sm100_desc.hpp, InstrDescriptorBlockScaled): a/b format E2M1 = 1 at bits 7 / 10, both K-major,
+// N >> 3 at 17, scale format UE8M0 = 1 at 23, M >> 4 at 24, scale-factor ids 0, K = 64 per instruction
+static constexpr uint32_t FT_IDESC_MXF4 = (1u << 7) | (1u << 10) | ((FT_N >> 3) << 17) | (1u << 23) | ((FT_M >> 4) << 24);
 static constexpr uint32_t FT_IDESC_F16 = (1u << 4) | (0u << 7) | (0u << 10) | ((FT_N >> 3) << 17) | ((FT_M >> 4) << 24);
 
 __device__ __forceinline__ float fmin3(float a, float b, float c) {
@@ -306,6 +313,30 @@ __global__ void binary_unpack_kernel(const uint32_t* __restrict__ blob, int word
     if (lane == 0) norms[row] = pc;
 }
 
+// TM_F4P operands: bits -> E2M1 nibbles (1.0 = 0x2, 0.0 = 0x0), element 2j in the low nibble of byte j; kbytes per row (a multiple of
+// 128), plus the popcount per row.  One warp per row; lane l expands the 8 bits [8l, 8l+8) of every 256-bit group into one 32-bit word.
+__global__ void binary_unpack4_kernel(const uint32_t* __restrict__ blob, int words, uint32_t total_rows, int kbytes,
+                                      uint8_t* __restrict__ out, int32_t* __restrict__ norms) {
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t* src = blob + (size_t)row * words;
+    int pc = 0;
+    for (int base = 0; base < kbytes; base += 128) {  // 128 output bytes = 256 bits = 8 words per step
+        const int w = base / 16 + lane / 4;
+        const uint32_t word = w < words ? src[w] : 0u;
+        const uint32_t byte = (word >> (8 * (lane & 3))) & 0xFFu;
+        pc += __popc(byte);
+        uint32_t o = 0;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) o |= ((byte >> j) & 1u) << (4 * j + 1);
+        *reinterpret_cast<uint32_t*>(out + (size_t)row * kbytes + base + lane * 4) = o;
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) pc += __shfl_xor_sync(0xFFFFFFFFu, pc, d);
+    if (lane == 0) norms[row] = pc;
+}
+
 // Per train row of the binary tensor engine: the part of the top-2 key that does not depend on the query,
 //     nbkey = (popc(t) + I8_BIAS) * 512 + (row inside its image mod 128),
 // so that the epilogue forms its key with ONE IMAD per accumulator element:
@@ -326,7 +357,8 @@ static constexpr uint32_t I8_BIAS = 512;  // popc(t) - 2 q.t >= -popc(q) >= -512
 // VIMNMX.U16x2 then keeps the two smallest keys of each half: 1.25 ALU ops per column instead of 2.5 --
 // the ALU pipe (64 lanes/clk/SM) was the epilogue's floor at 640 cycles per 128x128 tile.
 __global__ void binary_nbkey_kernel(const int32_t* __restrict__ popc, const uint32_t* __restrict__ row0 /* n_images, ascending */,
-                                    int n_images, uint32_t total_rows, uint32_t* __restrict__ nbkey, uint32_t packed_bias /* 0 = 32-bit keys */) {
+                                    int n_images, uint32_t total_rows, uint32_t* __restrict__ nbkey, uint32_t packed_bias /* 0 = 32-bit keys */,
+                                    uint32_t f4_offset = 0 /* TM_F4P: 2^31, cancels the magic number's contribution (chunk_top2_packed) */) {
     const uint32_t row = blockIdx.x * blockDim.x + threadIdx.x;
     if (row >= total_rows) return;
     int lo = 0, hi = n_images;  // last image whose first row is <= row
@@ -344,7 +376,7 @@ __global__ void binary_nbkey_kernel(const int32_t* __restrict__ popc, const uint
         // kernel (partial tile), it only has to stay inside its 16 bits
         const uint32_t pc16 = row + 16 < total_rows ? static_cast<uint32_t>(popc[row + 16]) : 0u;
         const uint32_t partner = (pc16 + packed_bias) << 6 | col6;
-        nbkey[row] = (lc & 16u) ? own : (own | partner << 16);  // (entries with bit 4 set are not read)
+        nbkey[row] = ((lc & 16u) ? own : (own | partner << 16)) + f4_offset;  // (entries with bit 4 set are not read)
     }
 }
 
@@ -467,6 +499,54 @@ __device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[W], uint32_t nb
     }
 }
 
+// TM_F16X with threshold skipping (round 2).  The exact fold above costs 2.5 VIMNMX per column at 64 lanes/clk/SM = 640 ALU
+// cycles per 128x128 tile against 576 cycles of MMAs: the ALU pipe, not the tensor pipe, set the pace (ncu r02: alu 71 %,
+// tensor 53 %).  But once a row has seen a few hundred train rows almost no column can still enter its top-2 -- a column matters
+// only if its distance is below the row's current second-smallest, which happens ~2 ln(Nt) times per row -- and in TM_F16X the
+// accumulator itself orders like the key (float bits of an integer in [2^23, 2^24): monotone as unsigned).  So the chunk is
+// reduced to one minimum per 8 columns with VIMNMX3 on the RAW accumulators (0.56 ALU ops per column, no IMAD), one warp vote
+// decides whether any of the warp's 32 rows has a column below its threshold `thrv`, and only then the 8-column blocks that hold
+// such a column get their keys formed and folded exactly.  The four block votes are issued together (no dependent vote -> branch
+// chain); `thrv` only ever decreases: from the tile's own second key after a chunk, from the merged list at the end of a tile and
+// from the other epilogue group's threshold (+1, see the kernel).  A column whose value EQUALS the threshold is skipped: columns
+// arrive in ascending index order, so an equal distance further on never replaces (cv::batchDistance's strict '<').
+// Cost is data dependent (train rows arriving by descending distance take the slow path every time), the result is not.
+template <int W = 32>
+__device__ __forceinline__ void chunk_top2_skipx(const uint32_t (&acc)[W], uint32_t key_mul, uint32_t lc0 /* first column of the chunk inside the tile */,
+                                                 uint32_t& thrv /* accumulator bits: only columns below can matter */, uint32_t& m1, uint32_t& m2) {
+    static_assert(W % 8 == 0, "8-column blocks");
+    constexpr int NB = W / 8;
+    uint32_t s[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const uint32_t* a = &acc[8 * b];
+        s[b] = min(__vimin3_u32(__vimin3_u32(a[0], a[1], a[2]), __vimin3_u32(a[3], a[4], a[5]), a[6]), a[7]);
+    }
+    uint32_t mn = NB == 4 ? min(__vimin3_u32(s[0], s[1], s[2]), s[NB - 1]) : min(s[0], s[NB - 1]);
+    if (__any_sync(0xFFFFFFFFu, mn < thrv)) {
+        bool hit[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) hit[b] = __any_sync(0xFFFFFFFFu, s[b] < thrv);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (hit[b]) {
+                uint32_t k[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const uint32_t lc = lc0 + 8 * b + i;
+                    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(acc[8 * b + i]), "r"(key_mul), "r"(lc));
+                }
+                top2_pair(m1, m2, k[0], k[1]);
+                top2_pair(m1, m2, k[2], k[3]);
+                top2_pair(m1, m2, k[4], k[5]);
+                top2_pair(m1, m2, k[6], k[7]);
+            }
+        }
+        // two keys of this tile are <= m2, so the row's second-smallest is; back to accumulator bits (m2 = none: 0x4B7FFFFF, above every accumulator)
+        thrv = min(thrv, 0x4B000000u | (m2 >> 9));
+    }
+}
+
 // TM_I8P: see binary_nbkey_kernel.  16 packed key pairs per 32-column chunk.
 __device__ __forceinline__ void top2_pair_u16x2(uint32_t& m1, uint32_t& m2, uint32_t a, uint32_t b) {
     const uint32_t lo = __vminu2(a, b), hi = __vmaxu2(a, b);
@@ -475,7 +555,10 @@ __device__ __forceinline__ void top2_pair_u16x2(uint32_t& m1, uint32_t& m2, uint
     m2 = __vimin3_u16x2(m2, loser, hi);
 }
 
-template <bool PARTIAL>
+// F4 (TM_F4P): the accumulators are fp32 integers; adding 2^23 leaves the integer in the low mantissa bits, and the exponent bits
+// 0x4B000000 drop out of the products -- times (-128 << 16) entirely, times -128 up to the constant 2^31 that binary_nbkey_kernel
+// folds into the table -- so the same two IMADs form the same key pair: one FADD per column more, on the FMA pipe.
+template <bool PARTIAL, bool F4 = false>
 __device__ __forceinline__ void chunk_top2_packed(const uint32_t (&acc)[32], uint32_t nb_saddr, uint32_t mul_lo /* -128 */, uint32_t mul_hi /* -128 << 16 */,
                                                   uint32_t col0 /* first column of the chunk, relative to t0 */, uint32_t n_rows,
                                                   uint32_t& m1, uint32_t& m2) {
@@ -486,9 +569,13 @@ __device__ __forceinline__ void chunk_top2_packed(const uint32_t (&acc)[32], uin
         uint32_t k[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            uint32_t hi;
-            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(acc[e + i + 16]), "r"(mul_hi), "r"(nbv[i]));
-            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(acc[e + i]), "r"(mul_lo), "r"(hi));
+            uint32_t hi, a_hi = acc[e + i + 16], a_lo = acc[e + i];
+            if constexpr (F4) {
+                a_hi = __float_as_uint(__uint_as_float(a_hi) + 8388608.f);
+                a_lo = __float_as_uint(__uint_as_float(a_lo) + 8388608.f);
+            }
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(hi) : "r"(a_hi), "r"(mul_hi), "r"(nbv[i]));
+            asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(a_lo), "r"(mul_lo), "r"(hi));
             if (PARTIAL) k[i] |= (col0 + e + i < n_rows ? 0u : 0xFFFFu) | (col0 + e + i + 16 < n_rows ? 0u : 0xFFFF0000u);
         }
         top2_pair_u16x2(m1, m2, k[0], k[1]);
@@ -622,9 +709,7 @@ __device__ __forceinline__ void finish_rows(uint4* merge /* [GROUPS-1][FT_M] */,
                                             bool reverse, uint32_t split, unsigned long long knn_off, unsigned long long col_off,
                                             KnnEntry* __restrict__ knn, unsigned long long* __restrict__ colmin, uint32_t out_row) {
     if (grp != 0) merge[(grp - 1) * FT_M + row] = make_uint4(best.d1, (uint32_t)best.i1, best.d2, (uint32_t)best.i2);
-    if constexpr (GROUPS == 2) asm volatile("bar.sync 1, 256;" ::: "memory");  // the epilogue warps only
-    else asm volatile("bar.sync 1, 512;" ::: "memory");
-    static_assert(GROUPS == 2 || GROUPS == 4, "named-barrier thread counts above");
+    asm volatile("bar.sync 1, %0;" ::"n"(128 * GROUPS) : "memory");  // the epilogue warps only
     if (grp == 0 && qrow < nq) {
         unsigned long long k1 = best.i1 < 0 ? KEY_NONE : make_key(best.d1, (uint32_t)best.i1);
         unsigned long long k2 = best.i2 < 0 ? KEY_NONE : make_key(best.d2, (uint32_t)best.i2);
@@ -641,7 +726,7 @@ __device__ __forceinline__ void finish_rows(uint4* merge /* [GROUPS-1][FT_M] */,
             if (k1 != KEY_NONE) atomicMin(colmin + col_off + out_row, k1);  // (out_row == qrow unless the rows were gathered)
         } else {
             KnnEntry e;
-            if constexpr (MODE == TM_I8 || MODE == TM_I8P || tm_is_rank(MODE)) {
+            if constexpr (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_F4P || tm_is_rank(MODE)) {
                 // i8: the Hamming distance stays an integer in the key (binary_knn.cuh's convention);
                 // rank pass: float bits of the approximate d^2 (only pass 2 reads it)
                 e.x = k1;

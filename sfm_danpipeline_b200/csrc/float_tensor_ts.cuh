@@ -41,7 +41,7 @@ static constexpr int FTS_MAX_GROUPS = 4;
 // TMEM budget (512 columns): two query-tile buffers of KB*32 columns + as many 128-column accumulators as fit, at most three.
 // KB = 4 (486-bit binary): 256 + 2 x 128; KB <= 2 (fp16 128-d float, 256-bit ORB): 128 + 3 x 128 -- the third stage lets the
 // MMA warp run two tiles ahead of the slowest epilogue group.
-__host__ __device__ constexpr int fts_acc_stages(int kb) { return (512 - 2 * kb * 32) / 128 >= 3 ? 3 : 2; }
+__host__ __device__ constexpr int fts_acc_stages(int kb, int a_bufs = 2) { return (512 - a_bufs * kb * 32) / 128 >= 3 ? 3 : 2; }
 // Epilogue groups (four warps each, one per TMEM lane quarter) take tiles round robin.  Two groups are the default everywhere.
 // Four groups (GROUPS = 4: 768 threads x 80 registers, 16-column chunks) were tried for the float path, whose 32-bit keys cost
 // 2.5 VIMNMX per column, on the theory that its epilogue warps were latency bound (ncu r01: alu 64 %, issue 65 %, tensor 42 %).
@@ -67,6 +67,7 @@ struct FtsSmem {  // after the 1024-byte aligned operand area
     uint32_t arow[2][FT_M];  // blob row behind every row of the item's query tile (0xFFFFFFFF: none -> zeros); gathered for TILE_GATHER items
     uint32_t orow[2][FT_M];  // image-relative row the result of that tile row belongs to
     uint4 merge[2][(FTS_MAX_GROUPS - 1) * FT_M];
+    uint32_t thr[2][FT_M];  // SKIP: the epilogue groups' common skip threshold per row of the item (a hint: stale values are only looser)
 };
 
 static inline size_t float_tensor_ts_smem_bytes(int kblocks) {
@@ -75,8 +76,18 @@ static inline size_t float_tensor_ts_smem_bytes(int kblocks) {
 
 // D[tmem] (+)= A[tmem] * B[smem]^T; whole warp calls, one elected lane issues (see tc_mma).
 template <int KIND, bool ACCUMULATE>
-__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc) {
-    if constexpr (KIND == OK_F16)
+__device__ __forceinline__ void tc_mma_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t tmem_sf = 0) {
+    if constexpr (KIND == OK_F4)  // e2m1 x e2m1 -> f32, K = 64 per instruction, one UE8M0 scale per 32 elements (all 2^0: tmem_sf.. hold 0x7F bytes)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred pe, p;\n\t"
+            "elect.sync _|pe, 0xffffffff;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "@pe tcgen05.mma.cta_group::1.kind::mxf4.block_scale.block32 [%0], [%1], %2, %3, [%5], [%6], p;\n\t"
+            "}" ::"r"(tmem_d),
+            "r"(tmem_a), "l"(desc_b), "r"(idesc), "n"(ACCUMULATE ? 1 : 0), "r"(tmem_sf), "r"(tmem_sf + 8)
+            : "memory");
+    else if constexpr (KIND == OK_F16)
         asm volatile(
             "{\n\t"
             ".reg .pred pe, p;\n\t"
@@ -119,9 +130,15 @@ __device__ __forceinline__ void tc_st_32x32(uint32_t taddr, const uint32_t (&r)[
         "r"(r[31])
         : "memory");
 }
+__device__ __forceinline__ void tc_st_32x8(uint32_t taddr, const uint32_t (&r)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
-template <int KB /* 128-byte K-blocks per row */, int MODE, int GROUPS = 2 /* epilogue groups of four warps: 2 or 4 */>
+template <int KB /* 128-byte K-blocks per row */, int MODE, int GROUPS = 2 /* epilogue groups of four warps: 2 or 4 */,
+          bool SKIP = false /* TM_F16X: threshold skipping in the epilogue (chunk_top2_skipx) */>
 __global__ void __launch_bounds__(fts_threads(GROUPS), 1)
 tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __restrict__ a_src /* the matrix the tensor map describes: rows of KB*128 bytes */,
                       const uint32_t total_rows, const float* __restrict__ norms /* int32 popcounts when INT8 */,
@@ -133,16 +150,27 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                       const uint32_t* __restrict__ xcand /* per pair at col_off: candidate train rows */, const uint32_t* __restrict__ n_xcand) {
     constexpr int KIND = OperandOf<MODE>::kind;
     constexpr int KB_ELEMS = OperandOf<MODE>::kb_elems;
-    constexpr int ACC_STAGES = fts_acc_stages(KB);
+    // SKIP with three K-blocks (128-d TM_F16X): ONE query-tile buffer, so that a third accumulator stage fits (96 + 3 x 128
+    // columns).  With two stages and two groups the MMA warp cannot start tile g + 2 before group g % 2 has read the last column of
+    // tile g, and that group then waits a whole MMA time for its next tile: ncu (r02, two stages) had the epilogue warps 26 % of
+    // their time in that wait while ALU and tensor pipes were both half idle.  The price is the item boundary: the next query tile
+    // is stored only after the last MMA of the item has read the old one (the loaders hold it in registers by then).
+    // TM_F4P: one buffer as well -- 64 + 3 x 128 columns leave room for the scale-factor words of kind::mxf4 (32 columns of 0x7F
+    // bytes = 2^0 in UE8M0 whatever the exact scale layout is), and its 512-cycle tiles need the third stage even more.
+    constexpr int A_BUFS = ((SKIP && KB == 3) || KIND == OK_F4) ? 1 : 2;
+    constexpr int ACC_STAGES = KIND == OK_F4 ? 3 : fts_acc_stages(KB, A_BUFS);
+    static_assert(KIND != OK_F4 || KB <= 2, "TM_F4P: query tile + three accumulators + scale factors must fit 512 TMEM columns");
     const uint32_t n_items = n_items_dev ? __ldg(n_items_dev) : n_items_arg;
     constexpr int FULL_RING = GROUPS > ACC_STAGES ? GROUPS : ACC_STAGES;  // "accumulator ready" barriers, see their initialisation
     constexpr uint32_t A_COLS = KB * 32;            // TMEM columns of one query-tile buffer
-    constexpr uint32_t ACC_COL0 = 2 * A_COLS;       // first accumulator column
+    constexpr uint32_t ACC_COL0 = A_BUFS * A_COLS;  // first accumulator column
+    [[maybe_unused]] constexpr uint32_t SF_COL0 = ACC_COL0 + ACC_STAGES * FT_N;  // TM_F4P: 32 columns of unit scale factors
     constexpr int EPI_WARPS = 4 * GROUPS;
     constexpr uint32_t LOADER_WARP0 = 4 + EPI_WARPS;  // a multiple of 4: warp % 4 is the TMEM lane quarter it may access
-    static_assert(GROUPS == 2 || GROUPS == 4, "two or four epilogue groups");
-    static_assert(!(GROUPS == 4 && (MODE == TM_I8P || tm_is_collect(MODE) || tm_is_rank(MODE))), "four groups: 32-bit-key top-2 modes only");
+    static_assert(GROUPS >= 2 && GROUPS <= 4, "two to four epilogue groups");
+    static_assert(!(GROUPS > 2 && (MODE == TM_I8P || MODE == TM_F4P || tm_is_collect(MODE) || tm_is_rank(MODE))), "four groups: 32-bit-key top-2 modes only");
     static_assert(MODE != TM_F16X || KB >= 2, "TM_F16X rows carry at least one data K-block and the key-term K-block");
+    static_assert(!SKIP || MODE == TM_F16X, "threshold skipping needs accumulators that order like the keys");
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sB = base;  // FTS_B_STAGES x KB x 16 KB
@@ -188,6 +216,18 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = sm.tmem_base;
+    if constexpr (KIND == OK_F4) {  // unit scale factors, written once by the four loader warps (one per TMEM lane quarter)
+        if (warp >= 4 + 4 * GROUPS) {
+            uint32_t ones[32];
+#pragma unroll
+            for (int i = 0; i < 32; ++i) ones[i] = 0x7F7F7F7Fu;
+            tc_st_32x32(tmem_base + ((((warp - 4 - 4 * GROUPS) * 32) << 16)) + SF_COL0, ones);
+            tc_wait_st();
+        }
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+    }
 
     if (warp == 0) {
         // ===================== TMA producer: train tiles only =====================
@@ -226,16 +266,18 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
     } else if (warp == 1) {
         // ===================== MMA issuer (whole warp, uniform; one elected lane issues) =====================
         const uint32_t tb = __shfl_sync(0xFFFFFFFFu, tmem_base, 0);
-        const uint32_t idesc = KIND == OK_I8 ? FT_IDESC_I8 : (KIND == OK_F16 ? FT_IDESC_F16 : FT_IDESC);
+        const uint32_t idesc = KIND == OK_F4 ? FT_IDESC_MXF4 : (KIND == OK_I8 ? FT_IDESC_I8 : (KIND == OK_F16 ? FT_IDESC_F16 : FT_IDESC));
+        [[maybe_unused]] const uint32_t sf_tmem = tb + SF_COL0;
         uint32_t g = 0, it = 0;
         for (uint32_t item = blockIdx.x; item < n_items; item += gridDim.x, ++it) {
             const uint32_t slot = it & 1;
             mbar_wait(&sm.item_full[slot], (it >> 1) & 1);
             const uint32_t n_tiles = __shfl_sync(0xFFFFFFFFu, sm.item[slot].n_tiles, 0);
             mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
-            mbar_wait(&sm.a_full[slot], (it >> 1) & 1);  // the loaders have stored this item's query tile
+            const uint32_t a_idx = A_BUFS == 2 ? slot : 0u, a_phase = A_BUFS == 2 ? (it >> 1) & 1 : it & 1;
+            mbar_wait(&sm.a_full[a_idx], a_phase);  // the loaders have stored this item's query tile
             tc_fence_after();
-            const uint32_t a_tmem = tb + slot * A_COLS;
+            const uint32_t a_tmem = tb + a_idx * A_COLS;
 #pragma unroll 1
             for (uint32_t j = 0; j < n_tiles; ++j, ++g) {
                 const uint32_t s = g % FTS_B_STAGES, a = g % ACC_STAGES;
@@ -244,18 +286,18 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 tc_fence_after();
                 const uint64_t b_desc0 = umma_desc_sw128(smem_u32(sB + (size_t)s * KB * FT_B_KBLOCK_BYTES));
                 const uint32_t d_tmem = tb + ACC_COL0 + a * FT_N;
-                tc_mma_ts<KIND, false>(d_tmem, a_tmem, b_desc0, idesc);
+                tc_mma_ts<KIND, false>(d_tmem, a_tmem, b_desc0, idesc, sf_tmem);
                 // TM_F16X: only the first 32 bytes of the last K-block carry data (the three key-term columns), the rest is zero
                 constexpr int N_MMA = MODE == TM_F16X ? 4 * (KB - 1) + 1 : 4 * KB;
 #pragma unroll
                 for (int i = 1; i < N_MMA; ++i) {  // i = kb*4 + k: 32 bytes of K = 8 TMEM columns of A, 32 bytes inside B's swizzle row
                     const int kb = i >> 2, k = i & 3;
-                    tc_mma_ts<KIND, true>(d_tmem, a_tmem + i * 8, b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc);
+                    tc_mma_ts<KIND, true>(d_tmem, a_tmem + i * 8, b_desc0 + ((kb * FT_B_KBLOCK_BYTES + k * 32) >> 4), idesc, sf_tmem);
                 }
                 tc_commit_elect(&sm.b_empty[s]);   // smem stage reusable once these MMAs have read it
                 tc_commit_elect(&sm.acc_full[g % FULL_RING]);  // accumulator ready for the group that takes this tile
             }
-            tc_commit_elect(&sm.a_empty[slot]);  // every MMA of this item has read the query tile: its TMEM buffer may be refilled
+            tc_commit_elect(&sm.a_empty[a_idx]);  // every MMA of this item has read the query tile: its TMEM buffer may be refilled
         }
     } else if (warp == 3) {
         // ===================== item prefetch =====================
@@ -315,26 +357,54 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             mbar_wait_relaxed(&sm.item_full[slot], (it >> 1) & 1);
             const uint32_t grow = sm.arow[slot][row];
             mbar_arrive(&sm.item_empty[slot]);  // every thread, after its own reads of the slot
-            mbar_wait_relaxed(&sm.a_empty[slot], ((it >> 1) & 1) ^ 1);  // the MMAs of the item before last are done with this buffer
-            tc_fence_after();
+            const uint32_t a_idx = A_BUFS == 2 ? slot : 0u, a_phase = A_BUFS == 2 ? (it >> 1) & 1 : it & 1;
             const bool ok = grow < total_rows;  // rows past the blob: zeros (rows past the image but inside the blob are
                                                 // another image's: computed on, never read -- as with TMA's box)
             const uint4* src = a_src + (size_t)(ok ? grow : 0) * (KB * 8);
-            const uint32_t taddr = tmem_base + ((lw * 32) << 16) + slot * A_COLS;
+            const uint32_t taddr = tmem_base + ((lw * 32) << 16) + a_idx * A_COLS;
+            if constexpr (A_BUFS == 2) {
+                mbar_wait_relaxed(&sm.a_empty[a_idx], a_phase ^ 1);  // the MMAs of the item before last are done with this buffer
+                tc_fence_after();
 #pragma unroll
-            for (int kb = 0; kb < KB; ++kb) {
-                uint32_t r[32];
+                for (int kb = 0; kb < KB; ++kb) {
+                    uint32_t r[32];
 #pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    const uint4 x = ok ? __ldg(src + kb * 8 + v) : make_uint4(0, 0, 0, 0);
-                    r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                    for (int v = 0; v < 8; ++v) {
+                        const uint4 x = ok ? __ldg(src + kb * 8 + v) : make_uint4(0, 0, 0, 0);
+                        r[4 * v + 0] = x.x; r[4 * v + 1] = x.y; r[4 * v + 2] = x.z; r[4 * v + 3] = x.w;
+                    }
+                    tc_st_32x32(taddr + kb * 32, r);
                 }
-                tc_st_32x32(taddr + kb * 32, r);
+            } else {
+                // one buffer: the row waits in registers until the previous item's last MMA has read the old tile
+                // (TM_F16X: only the first 32 bytes of the last K-block carry data, the rest of it is never read)
+                constexpr int FULL_KB = MODE == TM_F16X ? KB - 1 : KB;
+                uint32_t r[FULL_KB][32];
+                [[maybe_unused]] uint32_t rx[8];
+#pragma unroll
+                for (int kb = 0; kb < FULL_KB; ++kb)
+#pragma unroll
+                    for (int v = 0; v < 8; ++v) {
+                        const uint4 x = ok ? __ldg(src + kb * 8 + v) : make_uint4(0, 0, 0, 0);
+                        r[kb][4 * v + 0] = x.x; r[kb][4 * v + 1] = x.y; r[kb][4 * v + 2] = x.z; r[kb][4 * v + 3] = x.w;
+                    }
+                if constexpr (MODE == TM_F16X) {
+#pragma unroll
+                    for (int v = 0; v < 2; ++v) {
+                        const uint4 x = ok ? __ldg(src + (KB - 1) * 8 + v) : make_uint4(0, 0, 0, 0);
+                        rx[4 * v + 0] = x.x; rx[4 * v + 1] = x.y; rx[4 * v + 2] = x.z; rx[4 * v + 3] = x.w;
+                    }
+                }
+                mbar_wait_relaxed(&sm.a_empty[a_idx], a_phase ^ 1);
+                tc_fence_after();
+#pragma unroll
+                for (int kb = 0; kb < FULL_KB; ++kb) tc_st_32x32(taddr + kb * 32, r[kb]);
+                if constexpr (MODE == TM_F16X) tc_st_32x8(taddr + (KB - 1) * 32, rx);
             }
             tc_wait_st();
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&sm.a_full[slot]);
+            if (lane == 0) mbar_arrive(&sm.a_full[a_idx]);
         }
     } else if (warp >= 4) {
         // ===================== epilogue: fused top-2 =====================
@@ -369,8 +439,18 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 cand_count_row = cand_count + 2 * (size_t)(q_off + min(qrow, nq - 1)) + half;
                 cand_idx_row = cand_idx + (size_t)(q_off + min(qrow, nq - 1)) * FT_CAND_CAP + half * (FT_CAND_CAP / 2);
             }
+            // SKIP: only accumulators below thrv can still enter the row's top-2 (chunk_top2_skipx); rows whose result is never
+            // written never ask for the slow path.  The groups of a row share their thresholds through sm.thr: every group sees
+            // 1/GROUPS of the columns, together they see all of them, and the number of slow-path visits follows the columns
+            // seen.  The other groups' tiles may lie AFTER this group's next tile, where an equal distance must not win, hence
+            // their threshold + 1.  The word is a hint: written and read without ordering, a stale value is only looser; both
+            // writers of a row reset it before their first read of the item, and the named barrier at the end of every item
+            // (finish_rows) keeps the groups within the same item, so a slot never carries a previous item's value.
+            [[maybe_unused]] uint32_t thrv = qrow < nq ? 0xFFFFFFF0u : 0u;
+            [[maybe_unused]] volatile uint32_t* thr_shared = &sm.thr[it & 1][row];
+            if constexpr (SKIP) *thr_shared = thrv;
 #pragma unroll 1
-            for (uint32_t j = (half - g0) & (GROUPS - 1); j < n_tiles; j += GROUPS) {
+            for (uint32_t j = (half + GROUPS - g0 % GROUPS) % GROUPS; j < n_tiles; j += GROUPS) {
                 const uint32_t g = g0 + j;               // g % GROUPS == half
                 const uint32_t a = g % ACC_STAGES;
                 const uint32_t nbs = g % FTS_NB_STAGES;
@@ -396,10 +476,13 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                     } else if constexpr (tm_is_rank(MODE)) {
                         if (!partial) chunk_rank<false>(acc[c & 1], nb_saddr, col0 + c * 32, n_rows, r1, r2);
                         else chunk_rank<true>(acc[c & 1], nb_saddr, col0 + c * 32, n_rows, r1, r2);
-                    } else if constexpr (MODE == TM_I8P) {
+                    } else if constexpr (MODE == TM_I8P || MODE == TM_F4P) {
                         // (key_mul - 640 = -128 from the kernel parameter: stays an IMAD on the FMA pipe)
-                        if (!partial) chunk_top2_packed<false>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
-                        else chunk_top2_packed<true>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
+                        if (!partial) chunk_top2_packed<false, MODE == TM_F4P>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
+                        else chunk_top2_packed<true, MODE == TM_F4P>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
+                    } else if constexpr (SKIP) {
+                        if (!partial) chunk_top2_skipx<CW>(acc[c & 1], key_mul, c * CW, thrv, m1, m2);
+                        else chunk_top2<true, MODE, CW>(acc[c & 1], nb_saddr, cq, key_mul, c * CW, col0 + c * CW, n_rows, m1, m2);
                     } else {
                         if (!partial) chunk_top2<false, MODE, CW>(acc[c & 1], nb_saddr, cq, key_mul, c * CW, col0 + c * CW, n_rows, m1, m2);
                         else chunk_top2<true, MODE, CW>(acc[c & 1], nb_saddr, cq, key_mul, c * CW, col0 + c * CW, n_rows, m1, m2);
@@ -418,7 +501,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 // merge the tile's two best into the running pair (ascending tiles = arrival order)
                 if constexpr (!tm_is_rank(MODE) && !tm_is_collect(MODE)) {
                     const int tbase = (int)(t0 + col0);
-                    if constexpr (MODE == TM_I8P) {  // four 16-bit lane winners -> the tile's two smallest (hamming, column)
+                    if constexpr (MODE == TM_I8P || MODE == TM_F4P) {  // four 16-bit lane winners -> the tile's two smallest (hamming, column)
                         uint32_t q1, q2;
                         unpack_top2_u16x2(m1, m2, __float_as_uint(cq) - i8_bias, q1, q2);
                         if (q1 != 0xFFFFFFFFu) best.offer(q1 >> 9, tbase + (int)(q1 & 511u));
@@ -429,6 +512,12 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                         const uint32_t dadd = MODE == TM_I8 ? __float_as_uint(cq) - I8_BIAS : static_cast<uint32_t>(cq) - 1048576u;
                         if (m1 != 0xFFFFFFFFu) best.offer((m1 >> 9) + dadd, tbase + (int)(m1 & 511u));
                         if (m2 != 0xFFFFFFFFu) best.offer((m2 >> 9) + dadd, tbase + (int)(m2 & 511u));
+                        if constexpr (SKIP) {  // thresholds of the next tiles: own merged list, the other groups' + 1
+                            if (best.i2 >= 0) thrv = min(thrv, 0x4B000000u + (best.d2 - dadd));
+                            const uint32_t other = *thr_shared;
+                            *thr_shared = min(thrv, other);
+                            thrv = min(thrv, other + 1u);
+                        }
                     }
                 }
             }

@@ -272,6 +272,9 @@ struct SfmmCtx {
     DevBuf d_half_a;          // TM_F16X: the query-side operand rows (-2q | 1, 2048, 2048), d_half holds the train side
     bool tensor_kx = false;   // TM_F16X in use (key term contracted by the tensor core)
     bool no_kx = false;       // SFMM_NO_KX=1: keep TM_F16_EXACT (A/B measurements)
+    bool tensor_f4 = false;   // binary tensor engine on the FP4 pipe (TM_F4P: descriptors below 512 bit; SFMM_NO_F4=1 keeps kind::i8)
+    bool no_f4 = false;
+    bool no_skip = false;     // SFMM_NO_SKIP=1: TM_F16X folds every column (no threshold skipping; A/B measurements)
     uint32_t i8_bias = 0;    // binary tensor engine: descriptor bit length when the packed 16-bit keys apply (< 512 bit), else 0
     DevBuf d_nbkey, d_row0;  // binary tensor engine: per-row key part (binary_nbkey_kernel) and the images' first rows
     DevBuf d_unpacked;  // SFMM_BINARY_TENSOR: one byte per descriptor bit
@@ -522,13 +525,13 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnT
     // persistent: one CTA per SM (shared memory allows no more) walks the tile list with stride gridDim.x
     const uint32_t grid = std::min<uint32_t>(n_tiles, static_cast<uint32_t>(ctx->sm_count));
     const KnnTile* tiles = tiles_dev ? tiles_dev : (const KnnTile*)sl.d_tiles.as<KnnTile>();
-    const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_TF32_EXACT || MODE == TM_F16_EXACT || MODE == TM_F16X || tm_is_rank(MODE)) ? (const float*)ctx->d_nbkey.as<float>()
+    const float* nb_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_F4P || MODE == TM_TF32_EXACT || MODE == TM_F16_EXACT || MODE == TM_F16X || tm_is_rank(MODE)) ? (const float*)ctx->d_nbkey.as<float>()
                                                                                                               : (const float*)ctx->d_norms.as<float>();
     // measured (profiles/tensor_variants_r01.txt): TMEM-A wins for the binary engine and the fp16 float path, shared-memory-A for TF32
     uint32_t aux = ctx->i8_bias;  // TM_I8P: descriptor bit length; rank modes: float bits of the key-table offset
     if (tm_is_rank(MODE) || tm_is_collect(MODE)) std::memcpy(&aux, &ctx->rank_offset, sizeof(aux));
-    const bool ts = MODE == TM_F16X || (ctx->tensor_ts < 0 ? (MODE == TM_I8P || OperandOf<MODE>::kind == OK_F16 || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0);
-    if (!ts) {  // query tile in shared memory (float_tensor.cuh)
+    const bool ts = MODE == TM_F16X || MODE == TM_F4P || (ctx->tensor_ts < 0 ? (MODE == TM_I8P || OperandOf<MODE>::kind == OK_F16 || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0);
+    if constexpr (MODE != TM_F4P && MODE != TM_F16X) if (!ts) {  // query tile in shared memory (float_tensor.cuh)
         const size_t smem = float_tensor_smem_bytes(KB);
         auto kern = tensor_knn2_kernel<KB, MODE>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -541,7 +544,7 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnT
         return cudaGetLastError();
     }
     // query tile in tensor memory (float_tensor_ts.cuh)
-    const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P) ? ctx->d_unpacked.as<uint4>() : (MODE == TM_F16X ? ctx->d_half_a.as<uint4>() : (OperandOf<MODE>::kind == OK_F16 ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>()));
+    const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_F4P) ? ctx->d_unpacked.as<uint4>() : (MODE == TM_F16X ? ctx->d_half_a.as<uint4>() : (OperandOf<MODE>::kind == OK_F16 ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>()));
     const size_t smem = float_tensor_ts_smem_bytes(KB);
     auto go = [&](auto kern, int threads) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -555,6 +558,13 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnT
     };
     // SFMM_EPI_GROUPS=4: four epilogue groups for the 32-bit-key float modes (an experiment that measured 5 % slower than two,
     // profiles/tensor_variants_r02.txt; kept selectable and covered by the parity tests)
+    if constexpr (MODE == TM_F16X) {  // threshold skipping in the epilogue (float_tensor.cuh, chunk_top2_skipx) unless SFMM_NO_SKIP=1
+        if (!ctx->no_skip) {
+            if (ctx->epi_groups == 4) return go(tensor_knn2_ts_kernel<KB, MODE, 4, true>, fts_threads(4));
+            if (ctx->epi_groups == 3) return go(tensor_knn2_ts_kernel<KB, MODE, 3, true>, fts_threads(3));
+            return go(tensor_knn2_ts_kernel<KB, MODE, 2, true>, fts_threads(2));
+        }
+    }
     if constexpr (MODE == TM_F16_EXACT || MODE == TM_TF32_EXACT || MODE == TM_F16X) {
         if (ctx->epi_groups == 4) return go(tensor_knn2_ts_kernel<KB, MODE, 4>, fts_threads(4));
     }
@@ -581,6 +591,8 @@ cudaError_t launch_tensor_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const 
         return ctx->tensor_f16 ? launch_tensor<TM_F16_EXACT>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev)
                                : launch_tensor<TM_TF32_EXACT>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev);
     }
+    if (ctx->tensor_f4) return ctx->tensor_kblocks == 1 ? launch_tensor_t<1, TM_F4P>(ctx, sl, n_tiles, tiles_dev, n_items_dev)
+                                                        : launch_tensor_t<2, TM_F4P>(ctx, sl, n_tiles, tiles_dev, n_items_dev);
     return ctx->i8_bias ? launch_tensor<TM_I8P>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev)
                         : launch_tensor<TM_I8>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev);
 }
@@ -645,10 +657,13 @@ int prepare_binary_tensor(SfmmCtx* ctx) {
     if (ctx->elem_type != SFMM_U8 || ctx->float_prepared) return SFMM_OK;
     ctx->use_tensor = false;
     const int words = binary_words(ctx->cols);
-    const int kbytes = (words * 32 + 127) / 128 * 128;  // unpacked row: one byte per bit, whole 128-byte K-blocks
+    const int kbytes8 = (words * 32 + 127) / 128 * 128;  // unpacked row: one byte per bit, whole 128-byte K-blocks
+    // descriptors below 512 bit (packed 16-bit keys apply): one NIBBLE per bit and the FP4 pipe (TM_F4P) -- half the bytes, twice the rate
+    const bool f4 = ctx->cols * 8 < 512 && !ctx->no_f4 && !std::getenv("SFMM_I8_KEYS32");
+    const int kbytes = f4 ? (words * 16 + 127) / 128 * 128 : kbytes8;
     bool want = ctx->cfg.binary_engine == SFMM_BINARY_TENSOR;
-    if (want && kbytes > 512) return fail(ctx, SFMM_EINVAL, "SFMM_BINARY_TENSOR supports descriptors of at most 512 bits");
-    if (ctx->cfg.binary_engine == SFMM_BINARY_AUTO && kbytes <= 512 && ctx->total_rows > 0) {
+    if (want && kbytes8 > 512) return fail(ctx, SFMM_EINVAL, "SFMM_BINARY_TENSOR supports descriptors of at most 512 bits");
+    if (ctx->cfg.binary_engine == SFMM_BINARY_AUTO && kbytes8 <= 512 && ctx->total_rows > 0) {
         size_t free_b = 0, total_b = 0;
         CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
         want = static_cast<size_t>(ctx->total_rows) * kbytes <= free_b / 2 + ctx->d_unpacked.cap;  // (a buffer we already own counts as free)
@@ -659,8 +674,12 @@ int prepare_binary_tensor(SfmmCtx* ctx) {
             CU_TRY(ctx, ctx->d_unpacked.ensure(static_cast<size_t>(ctx->total_rows) * kbytes));
             CU_TRY(ctx, ctx->d_norms.ensure((static_cast<size_t>(ctx->total_rows) + 2 * FT_N) * sizeof(int32_t)));
             const uint32_t rows = static_cast<uint32_t>(ctx->total_rows);
-            binary_unpack_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ctx->blob.as<uint32_t>(), words, rows, kbytes, ctx->d_unpacked.as<uint8_t>(),
-                                                                 ctx->d_norms.as<int32_t>());
+            if (f4)
+                binary_unpack4_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ctx->blob.as<uint32_t>(), words, rows, kbytes, ctx->d_unpacked.as<uint8_t>(),
+                                                                      ctx->d_norms.as<int32_t>());
+            else
+                binary_unpack_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ctx->blob.as<uint32_t>(), words, rows, kbytes, ctx->d_unpacked.as<uint8_t>(),
+                                                                     ctx->d_norms.as<int32_t>());
             CU_TRY(ctx, cudaGetLastError());
             // query-independent part of the top-2 key per train row (popcount, bias, column inside its 128-row tile)
             CU_TRY(ctx, ctx->d_nbkey.ensure((static_cast<size_t>(ctx->total_rows) + 2 * FT_N) * sizeof(uint32_t)));
@@ -668,7 +687,8 @@ int prepare_binary_tensor(SfmmCtx* ctx) {
             CU_TRY(ctx, cudaMemcpyAsync(ctx->d_row0.p, ctx->row0.data(), static_cast<size_t>(ctx->n_images) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
             ctx->i8_bias = ctx->cols * 8 < 512 && !std::getenv("SFMM_I8_KEYS32") ? static_cast<uint32_t>(ctx->cols) * 8u : 0u;
             binary_nbkey_kernel<<<(rows + 255) / 256, 256, 0, st>>>(ctx->d_norms.as<int32_t>(), ctx->d_row0.as<uint32_t>(), ctx->n_images, rows,
-                                                                     ctx->d_nbkey.as<uint32_t>(), ctx->i8_bias);
+                                                                     ctx->d_nbkey.as<uint32_t>(), ctx->i8_bias, f4 ? 0x80000000u : 0u);
+            ctx->tensor_f4 = f4;
             CU_TRY(ctx, cudaGetLastError());
             CU_TRY(ctx, cudaStreamSynchronize(st));
             ctx->stats.kernel_launches += 2;
@@ -1189,8 +1209,10 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     if (const char* s = std::getenv("SFMM_TENSOR_TS")) ctx->tensor_ts = std::atoi(s) != 0 ? 1 : 0;
     if (const char* s = std::getenv("SFMM_CSA_LEVEL")) ctx->csa_level = std::max(0, std::min(3, std::atoi(s)));
     if (const char* s = std::getenv("SFMM_NO_KX")) ctx->no_kx = std::atoi(s) != 0;
+    if (const char* s = std::getenv("SFMM_NO_SKIP")) ctx->no_skip = std::atoi(s) != 0;
+    if (const char* s = std::getenv("SFMM_NO_F4")) ctx->no_f4 = std::atoi(s) != 0;
     if (const char* s = std::getenv("SFMM_CROSS_FULL")) ctx->cross_full_reverse = std::atoi(s) != 0;
-    if (const char* s = std::getenv("SFMM_EPI_GROUPS")) ctx->epi_groups = std::atoi(s) == 4 ? 4 : 2;
+    if (const char* s = std::getenv("SFMM_EPI_GROUPS")) ctx->epi_groups = std::max(2, std::min(4, std::atoi(s)));
     bool ok = (e = cudaSetDevice(cfg->device)) == cudaSuccess;
     for (Slot& sl : ctx->slot) {
         ok = ok && (e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) == cudaSuccess;

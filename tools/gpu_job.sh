@@ -1,7 +1,16 @@
-mkdir -p gpurun_out/r2n
-ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r2n/launches_default.csv python bench.py --steps 2 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 0 --device-only-iters 1 --e2e-steps 1 --e2e-warmup 1 > gpurun_out/r2n/launches_bench.log 2>&1
-tail -2 gpurun_out/r2n/launches_bench.log | cut -c1-200
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:tensor_knn2_ts -s 2 -c 1 -o gpurun_out/r2n/ts_i8p_cfg3 python bench.py --steps 1 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 0 --device-only-iters 1 --e2e-steps 1 --e2e-warmup 0 > gpurun_out/r2n/ncu1.log 2>&1; tail -2 gpurun_out/r2n/ncu1.log | cut -c1-200
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:tensor_knn2_ts -s 2 -c 1 -o gpurun_out/r2n/ts_f16x_cfg4s python bench.py --workload cfg4s --steps 1 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 0 --device-only-iters 1 --e2e-steps 1 --e2e-warmup 0 > gpurun_out/r2n/ncu2.log 2>&1; tail -2 gpurun_out/r2n/ncu2.log | cut -c1-200
-SFMM_BENCH_TRACE=1 timeout 100 python bench.py --steps 3 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 0 --device-only-iters 1 2>&1 | grep "e2e\]" | tail -2
-ls -la gpurun_out/r2n
+mkdir -p gpurun_out/r2v
+timeout 900 python -m pytest tests/test_parity_binary.py -m gpu -x -q 2>&1 | tail -5
+B="--steps 5 --warmup 3 --no-extra --no-alt-engine --no-cpu-baseline --verify 2 --device-only-iters 3"
+for w in cfg2 cfg3; do
+SFMM_NO_F4=1 timeout 300 python bench.py --workload $w $B > gpurun_out/r2v/${w}_i8.json 2> gpurun_out/r2v/${w}_i8.err
+timeout 300 python bench.py --workload $w $B > gpurun_out/r2v/${w}_f4.json 2> gpurun_out/r2v/${w}_f4.err
+done
+python - <<'PY'
+import json,glob
+for f in sorted(glob.glob('gpurun_out/r2v/*.json')):
+    try:
+        d=json.loads(open(f).read().strip().splitlines()[-1])
+        print(f.split('/')[-1], d['value'], d.get('resident_device_only',{}).get('value'), d['roofline'].get('frac'), d.get('verified'))
+    except Exception as e: print(f, 'ERR', e)
+PY
+tail -3 gpurun_out/r2v/cfg2_f4.err
