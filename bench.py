@@ -283,7 +283,7 @@ def load_peaks():
     return peaks, tc, traffic
 
 
-def roofline_block(stats_path, norm, engine, knn_ms, knn_work, knn_launches, step_ms_sum, n_sm, peaks, tc):
+def roofline_block(stats_path, norm, engine, knn_ms, knn_work, knn_launches, step_ms_sum, n_sm, peaks, tc, tensor_kind=0):
     """The dominant kernel against the pipe that bounds it.  knn_work = algorithmic POPC32 ops (Hamming) / FLOPs (L2)."""
     sm_max_mhz = float(peaks.get("sm_max_mhz", 1965.0))
     bf16 = float(peaks.get("bf16_tflops", 1590.0))
@@ -292,13 +292,23 @@ def roofline_block(stats_path, norm, engine, knn_ms, knn_work, knn_launches, ste
     if engine == "tensor":
         macs = knn_work / 16.0 * 512.0  # 512 u8 MACs per 16 algorithmic POPC32 (one 486-bit distance)
         ach = 2.0 * macs / knn_s / 1e12
-        if "i8_tops" in tc:
-            peak, src = float(tc["i8_tops"]), "of measured: tcgen05.mma kind::i8 issue-only microbenchmark on this pool (profiles/tcgen05_peaks_r02.json)"
+        i8_peak = float(tc["i8_tops"]) if "i8_tops" in tc else 2.0 * bf16
+        if tensor_kind == 2:  # TM_F4P: bits as E2M1 nibbles on the FP4 pipe
+            peak = float(tc.get("mxf4_tops", 2.0 * i8_peak))
+            src = ("of measured: tcgen05.mma kind::mxf4.block_scale issue-only microbenchmark on this pool (tools/mxf4_bench.cu, profiles/tcgen05_peaks_r02.json)"
+                   if "mxf4_tops" in tc else "of 2 x the kind::i8 peak (kind::mxf4 contracts 64 elements in the 64 cycles kind::i8 needs for 32)")
+            how = "tcgen05 kind::mxf4 on bits unpacked to E2M1 nibbles, unit block scales"
+        elif "i8_tops" in tc:
+            peak, src = i8_peak, "of measured: tcgen05.mma kind::i8 issue-only microbenchmark on this pool (profiles/tcgen05_peaks_r02.json)"
+            how = "tcgen05 kind::i8 on bits unpacked to bytes"
         else:
-            peak, src = 2.0 * bf16, f"of measured (inferred): 2 x {bf16_src}; int8 dense is nominally twice bf16"
-        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TOP/s",
-                "peak_source": src + "; ops = 2*Nq*Nt*512 per pair, tcgen05 kind::i8 on bits unpacked to bytes",
-                "nominal": {"peak": 4500.0, "frac": ach / 4500.0, "note": "B200 dense int8/fp8 nominal 4.5 POP/s"},
+            peak, src = i8_peak, f"of measured (inferred): 2 x {bf16_src}; int8 dense is nominally twice bf16"
+            how = "tcgen05 kind::i8 on bits unpacked to bytes"
+        roof = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TOP/s", "tensor_kind": {1: "i8", 2: "mxf4"}.get(tensor_kind, "i8"),
+                "peak_source": src + "; ops = 2*Nq*Nt*512 per pair, " + how,
+                "vs_i8_pipe": {"peak": i8_peak, "frac": ach / i8_peak, "note": "the same work against the kind::i8 rate round 1 and the first half of round 2 ran at"},
+                "nominal": {"peak": 9000.0 if tensor_kind == 2 else 4500.0, "frac": ach / (9000.0 if tensor_kind == 2 else 4500.0),
+                            "note": "B200 dense nominal: fp4 9 POP/s, int8/fp8 4.5 POP/s"},
                 "popc_equivalent": {"achieved_GPOPC32": knn_work / knn_s / 1e9,
                                     "x_nominal_popc_roofline": knn_work / knn_s / 1e9 / (n_sm * 16 * sm_max_mhz * 1e6 / 1e9)}}
     elif norm == 0:
@@ -516,7 +526,7 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
         # kernel time: CUDA events around the 2-NN launches of the device-only iterations (one stream, launches back to back; in the
         # host-table pipeline two chunk slots are in flight and an event pair would also cover the wait for the other slot's kernel)
         roof = roofline_block(m.stats()["float_path"], norm, engine, kacc["knn_ms"], kacc["knn_work"], kacc["knn_launches"],
-                              kacc["step_ms"], n_sm, env.peaks, env.tc)
+                              kacc["step_ms"], n_sm, env.peaks, env.tc, tensor_kind=int(m.stats().get("tensor_kind", 0)))
         roof["kernel_share_of_step"] = min(1.0, kacc["knn_ms"] / device_only_iters / max(ms_per_step, 1e-9))
         roof["kernel_share_of_device_only_step"] = kacc["knn_ms"] / max(kacc["step_ms"], 1e-9)
         key = f"{name}/{engine}/{'cross' if cross else 'plain'}"
@@ -569,8 +579,8 @@ def measure(env, args, name, kind, n_images, n_desc, *, steps, warmup, e2e_steps
                         nl += st["last_knn_launches"]
                 per = float(np.mean(ms))
                 n_sm = torch.cuda.get_device_properties(local).multi_processor_count
-                r2 = roofline_block(m2.stats()["float_path"], 0, other, knn, work, nl, per * len(ms), n_sm, env.peaks, env.tc)
-                out["alt_engine"] = {"binary_engine": "tensor (tcgen05 kind::i8 on unpacked bits)" if other == "tensor" else "popc (XOR + carry-save + POPC, packed bits)",
+                r2 = roofline_block(m2.stats()["float_path"], 0, other, knn, work, nl, per * len(ms), n_sm, env.peaks, env.tc, tensor_kind=int(m2.stats().get("tensor_kind", 0)))
+                out["alt_engine"] = {"binary_engine": "tensor (tcgen05 on unpacked bits)" if other == "tensor" else "popc (XOR + carry-save + POPC, packed bits)",
                                      "pairs_per_s_per_gpu": len(mine) / (per * 1e-3), "ms_per_step": per, "matches_per_step_this_rank": int(n),
                                      "definition": "resident_device_only (match lists left in HBM)", "roofline": r2,
                                      "note": "same workload, same run, identical match tables; selectable with SfmmConfig.binary_engine"}

@@ -120,6 +120,8 @@ typedef struct SfmmStats {
     int64_t float_path;        /* L2: 0 = not decided yet, SFMM_FLOAT_EXACT or SFMM_FLOAT_TENSOR = the kernel in use,
                                   3 = tensor-core fp16/TF32 ranking + exact refinement (arbitrary floats);
                                   Hamming: SFMM_FLOAT_TENSOR when the tensor engine is in use, else 0 */
+    int64_t tensor_kind;       /* tcgen05.mma kind of the 2-NN kernel in use: 0 = none (CUDA-core kernels), 1 = kind::i8 (bits as bytes),
+                                  2 = kind::mxf4 (bits as E2M1 nibbles, unit block scales), 3 = kind::f16, 4 = kind::tf32 */
 } SfmmStats;
 
 typedef struct SfmmCtx SfmmCtx;

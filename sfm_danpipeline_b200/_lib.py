@@ -42,7 +42,8 @@ class SfmmConfig(C.Structure):
 class SfmmStats(C.Structure):
     _fields_ = [("kernel_launches", C.c_int64), ("pairs_matched", C.c_int64), ("h2d_bytes", C.c_int64),
                 ("d2h_bytes", C.c_int64), ("last_match_ms", C.c_double), ("last_knn_ms", C.c_double),
-                ("last_knn_work", C.c_double), ("last_knn_launches", C.c_int64), ("float_path", C.c_int64)]
+                ("last_knn_work", C.c_double), ("last_knn_launches", C.c_int64), ("float_path", C.c_int64),
+                ("tensor_kind", C.c_int64)]
 
 
 class SfmmError(RuntimeError):

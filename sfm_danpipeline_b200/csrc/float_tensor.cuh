@@ -49,6 +49,12 @@ enum TensorMode {
                           // tcgen05.mma kind::mxf4.block_scale contracts 64 bits per instruction in the 64 cycles kind::i8 needs for 32 --
                           // twice the rate on HALF the operand bytes (256 B per 512-bit row); products are 0 or 1 and the fp32 accumulator
                           // holds integers <= 512, so q.t is exact (tools/mxf4_bench.cu checks it against popc(q & t)); TMEM-A kernel only
+    TM_F4X = 10,          // TM_F4P with the key's train-side term contracted by the tensor core as well (what TM_F16X is to TM_F16_EXACT), for
+                          // descriptors that leave 17 spare elements in their last K-block (AKAZE: 488 of 512).  Query bits are 1.0, train
+                          // bits 2.0, and the spare elements carry 6,...,6,1 on the query side and a digit expansion of 512 - popc(t) on the
+                          // train side (binary_unpack4x_kernel), so the accumulator is  x = 2 q.t - popc(t) + 512  -- an exact positive
+                          // integer that orders the columns of a row like the Hamming distance, descending.  The epilogue compares raw
+                          // accumulators (no table, no IMAD per column) and forms keys only where a column can still enter the row's top-2
     TM_TF32_COLLECT = 3   // arbitrary floats, pass 2: every column whose approximate d^2 can still be in the exact
                           // top-2 (<= m2 + 2*eps, a rigorous bound) is appended to the row's candidate list, which
                           // float_refine_kernel then evaluates exactly (fp32 direct difference, float_exact.cuh's arithmetic)
@@ -86,7 +92,7 @@ __host__ __device__ constexpr bool tm_is_collect(int mode) { return mode == TM_T
 enum OperandKind { OK_TF32 = 0, OK_I8 = 1, OK_F16 = 2, OK_F4 = 3 };
 template <int MODE>
 struct OperandOf {
-    static constexpr int kind = MODE == TM_F4P ? OK_F4 : (MODE == TM_I8 || MODE == TM_I8P) ? OK_I8 : ((MODE == TM_F16_EXACT || MODE == TM_F16X || MODE == TM_F16_RANK || MODE == TM_F16_COLLECT) ? OK_F16 : OK_TF32);
+    static constexpr int kind = (MODE == TM_F4P || MODE == TM_F4X) ? OK_F4 : (MODE == TM_I8 || MODE == TM_I8P) ? OK_I8 : ((MODE == TM_F16_EXACT || MODE == TM_F16X || MODE == TM_F16_RANK || MODE == TM_F16_COLLECT) ? OK_F16 : OK_TF32);
     static constexpr int kb_elems = (kind == OK_I8 || kind == OK_F4) ? 128 : (kind == OK_F16 ? 64 : 32);  // tensor-map elements per 128-byte swizzle row (nibble pairs travel as bytes)
 };
 // D[tmem] (+)= A[smem] * B[smem]^T; M=128, N=128, 32 bytes of K per instruction (8 tf32 / 16 f16 / 32 u8), fp32 or s32
@@ -337,6 +343,46 @@ __global__ void binary_unpack4_kernel(const uint32_t* __restrict__ blob, int wor
     if (lane == 0) norms[row] = pc;
 }
 
+// TM_F4X operands (see the mode): out_a = query side, bits as 1.0 (nibble 0x2), spare elements 6 x16, 1; out_b = train side, bits as 2.0
+// (nibble 0x4), spare elements = digits of E = 512 - popc(t): floor(E / 36) elements of 6.0 (x 6 = 36), then the rest r = 3 b + c as
+// two elements u/2 + v/2 (x 6) with u + v = b and one element c (x 1).  Every value is an E2M1 number, every product and every partial
+// sum a small integer: exact.  One warp per row; the caller guarantees bits + 17 <= 2 * kbytes.
+__global__ void binary_unpack4x_kernel(const uint32_t* __restrict__ blob, int words, uint32_t total_rows, int kbytes, int bits,
+                                       uint8_t* __restrict__ out_b, uint8_t* __restrict__ out_a, int32_t* __restrict__ norms) {
+    const uint32_t row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= total_rows) return;
+    const int lane = threadIdx.x & 31;
+    const uint32_t* src = blob + (size_t)row * words;
+    int pc = lane < words ? __popc(src[lane]) : 0;  // words <= 32
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) pc += __shfl_xor_sync(0xFFFFFFFFu, pc, d);
+    const int E = 512 - pc, a = E / 36, r = E - 36 * a, b = r / 3, c = r - 3 * b;
+    // b = u + v in units of 3 (element values u/2, v/2 from {0, .5, 1, 1.5, 2, 3, 4}); nibble codes of the E2M1 values
+    const int u = b <= 4 ? b : (b <= 7 ? (b == 5 ? 4 : 6) : 8), v = b - u;
+    auto code = [](int units) -> uint32_t { return units <= 4 ? (uint32_t)units : (units == 6 ? 5u : 6u); };  // value units/2 -> nibble
+    for (int base = 0; base < kbytes; base += 128) {
+        const int w = base / 16 + lane / 4;
+        const uint32_t word = w < words ? src[w] : 0u;
+        const uint32_t byte = (word >> (8 * (lane & 3))) & 0xFFu;
+        uint32_t oa = 0, ob = 0;
+        const int e0 = (base + lane * 4) * 2;  // first of this lane's 8 elements
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int s = e0 + j - bits;  // spare element index
+            uint32_t na = ((byte >> j) & 1u) << 1, nb = ((byte >> j) & 1u) << 2;
+            if (s >= 0 && s < 17) {
+                na = s < 16 ? 7u : 2u;
+                nb = s < 14 ? (s < a ? 7u : 0u) : (s == 14 ? code(u) : (s == 15 ? code(v) : (uint32_t)(2 * c)));
+            }
+            oa |= na << (4 * j);
+            ob |= nb << (4 * j);
+        }
+        *reinterpret_cast<uint32_t*>(out_a + (size_t)row * kbytes + base + lane * 4) = oa;
+        *reinterpret_cast<uint32_t*>(out_b + (size_t)row * kbytes + base + lane * 4) = ob;
+    }
+    if (lane == 0) norms[row] = pc;
+}
+
 // Per train row of the binary tensor engine: the part of the top-2 key that does not depend on the query,
 //     nbkey = (popc(t) + I8_BIAS) * 512 + (row inside its image mod 128),
 // so that the epilogue forms its key with ONE IMAD per accumulator element:
@@ -446,6 +492,16 @@ struct Top2 {
     }
 };
 
+// TM_F4X: accumulator x = 2 q.t - popc(t) + 512 (fp32, an integer in [24, 1000]) -> key (popc(t) - 2 q.t + 512) << 9 | column, the
+// TM_I8 key.  (2^23 + 1024) - x is exact and leaves 1024 - x in the low mantissa bits; the exponent bits vanish in the product by 512.
+static constexpr float F4X_KMAGIC = 8388608.f + 1024.f;
+__device__ __forceinline__ uint32_t f4x_key(uint32_t acc_bits, uint32_t key_mul, uint32_t lc) {
+    const uint32_t b = __float_as_uint(F4X_KMAGIC - __uint_as_float(acc_bits));
+    uint32_t k;
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k) : "r"(b), "r"(key_mul), "r"(lc));
+    return k;
+}
+
 // (m1 <= m2) <- two smallest of {m1, m2, a, b}
 __device__ __forceinline__ void top2_pair(uint32_t& m1, uint32_t& m2, uint32_t a, uint32_t b) {
     const uint32_t lo = min(a, b), hi = max(a, b);
@@ -483,6 +539,8 @@ __device__ __forceinline__ void chunk_top2(const uint32_t (&acc)[W], uint32_t nb
                 // the accumulator is the key argument itself (see TM_F16X): key = bits * 512 + column, one IMAD
                 const uint32_t lc = lc0 + e + i;
                 asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(k[i]) : "r"(acc[e + i]), "r"(key_mul), "r"(lc));
+            } else if constexpr (MODE == TM_F4X) {
+                k[i] = f4x_key(acc[e + i], key_mul, lc0 + e + i);
             } else if constexpr (MODE == TM_I8) {
                 // key = acc * (-1024) + nbkey: see binary_nbkey_kernel (key_mul - 1536 = -1024 comes from a kernel
                 // parameter so that the multiply stays one IMAD on the FMA pipe instead of a shift + subtract on the ALU)
@@ -544,6 +602,40 @@ __device__ __forceinline__ void chunk_top2_skipx(const uint32_t (&acc)[W], uint3
         }
         // two keys of this tile are <= m2, so the row's second-smallest is; back to accumulator bits (m2 = none: 0x4B7FFFFF, above every accumulator)
         thrv = min(thrv, 0x4B000000u | (m2 >> 9));
+    }
+}
+
+// The same for TM_F4X, where LARGER accumulators are nearer: block maxima of the raw (positive) floats against the float threshold
+// `thrf` = the accumulator value of the row's current second-nearest column (-1: none yet, +inf: row never written).
+template <int W = 32>
+__device__ __forceinline__ void chunk_top2_skipx_f4(const uint32_t (&acc)[W], uint32_t key_mul, uint32_t lc0, float& thrf, uint32_t& m1, uint32_t& m2) {
+    static_assert(W % 8 == 0, "8-column blocks");
+    constexpr int NB = W / 8;
+    uint32_t s[NB];
+#pragma unroll
+    for (int b = 0; b < NB; ++b) {
+        const uint32_t* a = &acc[8 * b];
+        s[b] = max(__vimax3_u32(__vimax3_u32(a[0], a[1], a[2]), __vimax3_u32(a[3], a[4], a[5]), a[6]), a[7]);
+    }
+    const uint32_t mx = NB == 4 ? max(__vimax3_u32(s[0], s[1], s[2]), s[NB - 1]) : max(s[0], s[NB - 1]);
+    if (__any_sync(0xFFFFFFFFu, __uint_as_float(mx) > thrf)) {
+        bool hit[NB];
+#pragma unroll
+        for (int b = 0; b < NB; ++b) hit[b] = __any_sync(0xFFFFFFFFu, __uint_as_float(s[b]) > thrf);
+#pragma unroll
+        for (int b = 0; b < NB; ++b) {
+            if (hit[b]) {
+                uint32_t k[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) k[i] = f4x_key(acc[8 * b + i], key_mul, lc0 + 8 * b + i);
+                top2_pair(m1, m2, k[0], k[1]);
+                top2_pair(m1, m2, k[2], k[3]);
+                top2_pair(m1, m2, k[4], k[5]);
+                top2_pair(m1, m2, k[6], k[7]);
+            }
+        }
+        // accumulator value of the tile's second key: (2^23 + 1024) - (2^23 + v) = 1024 - v, exact (m2 = none: far below zero)
+        thrf = fmaxf(thrf, F4X_KMAGIC - __uint_as_float(0x4B000000u | (m2 >> 9)));
     }
 }
 
@@ -726,7 +818,7 @@ __device__ __forceinline__ void finish_rows(uint4* merge /* [GROUPS-1][FT_M] */,
             if (k1 != KEY_NONE) atomicMin(colmin + col_off + out_row, k1);  // (out_row == qrow unless the rows were gathered)
         } else {
             KnnEntry e;
-            if constexpr (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_F4P || tm_is_rank(MODE)) {
+            if constexpr (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_F4P || MODE == TM_F4X || tm_is_rank(MODE)) {
                 // i8: the Hamming distance stays an integer in the key (binary_knn.cuh's convention);
                 // rank pass: float bits of the approximate d^2 (only pass 2 reads it)
                 e.x = k1;

@@ -168,9 +168,12 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
     constexpr int EPI_WARPS = 4 * GROUPS;
     constexpr uint32_t LOADER_WARP0 = 4 + EPI_WARPS;  // a multiple of 4: warp % 4 is the TMEM lane quarter it may access
     static_assert(GROUPS >= 2 && GROUPS <= 4, "two to four epilogue groups");
-    static_assert(!(GROUPS > 2 && (MODE == TM_I8P || MODE == TM_F4P || tm_is_collect(MODE) || tm_is_rank(MODE))), "four groups: 32-bit-key top-2 modes only");
+    static_assert(!(GROUPS > 2 && (MODE == TM_I8P || tm_is_collect(MODE) || tm_is_rank(MODE))), "more than two groups: exact top-2 modes only");
+    static_assert(!(GROUPS == 4 && MODE == TM_F4P), "the packed fold works on 32-column chunks");
     static_assert(MODE != TM_F16X || KB >= 2, "TM_F16X rows carry at least one data K-block and the key-term K-block");
-    static_assert(!SKIP || MODE == TM_F16X, "threshold skipping needs accumulators that order like the keys");
+    static_assert(!SKIP || MODE == TM_F16X || MODE == TM_F4X, "threshold skipping needs accumulators that order like the keys");
+    static_assert(MODE != TM_F4X || SKIP, "TM_F4X exists with the skipping epilogue only (TM_F4P is the plain fold)");
+    constexpr bool NO_NB = MODE == TM_F16X || MODE == TM_F4X;  // no per-column table: the train-side key term rides in the operand rows
     extern __shared__ unsigned char ft_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(ft_smem_raw) + 1023) & ~uintptr_t(1023));
     unsigned char* sB = base;  // FTS_B_STAGES x KB x 16 KB
@@ -242,7 +245,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
 #pragma unroll 1
                 for (uint32_t j = 0; j < n_tiles; ++j, ++g) {
                     const uint32_t s = g % FTS_B_STAGES;
-                    if constexpr (MODE != TM_F16X) {  // (TM_F16X: the train-side key term rides in the operand rows)
+                    if constexpr (!NO_NB) {
                         const uint32_t a = g % FTS_NB_STAGES;
                         mbar_wait(&sm.nb_empty[a], ((g / FTS_NB_STAGES) & 1) ^ 1);
                         mbar_expect_tx(&sm.nb_full[a], FT_N * sizeof(float));
@@ -448,7 +451,10 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             // (finish_rows) keeps the groups within the same item, so a slot never carries a previous item's value.
             [[maybe_unused]] uint32_t thrv = qrow < nq ? 0xFFFFFFF0u : 0u;
             [[maybe_unused]] volatile uint32_t* thr_shared = &sm.thr[it & 1][row];
-            if constexpr (SKIP) *thr_shared = thrv;
+            // TM_F4X: larger accumulators are nearer, the threshold is the accumulator VALUE of the second-nearest column so far
+            // (-1: none yet; +inf: row never written); the shared word holds float bits, the other groups' threshold counts - 1
+            [[maybe_unused]] float thrf = qrow < nq ? -1.f : __int_as_float(0x7f800000);
+            if constexpr (SKIP) *thr_shared = MODE == TM_F4X ? __float_as_uint(thrf) : thrv;
 #pragma unroll 1
             for (uint32_t j = (half + GROUPS - g0 % GROUPS) % GROUPS; j < n_tiles; j += GROUPS) {
                 const uint32_t g = g0 + j;               // g % GROUPS == half
@@ -459,7 +465,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                 uint32_t acc[2][CW];  // register double buffer: chunk c+1 streams in from TMEM while chunk c is folded
                 const uint32_t taddr = tmem_base + ((quarter * 32) << 16) + ACC_COL0 + a * FT_N;
                 tc_ld_32x32(taddr, acc[0]);
-                if constexpr (MODE != TM_F16X) mbar_wait(&sm.nb_full[nbs], (g / FTS_NB_STAGES) & 1);
+                if constexpr (!NO_NB) mbar_wait(&sm.nb_full[nbs], (g / FTS_NB_STAGES) & 1);
                 tc_wait_ld(acc[0]);
                 const uint32_t col0 = j * FT_N;                // first column of the tile, relative to t0
                 const bool partial = col0 + FT_N > n_rows;     // warp-uniform: only the last tile
@@ -480,6 +486,9 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                         // (key_mul - 640 = -128 from the kernel parameter: stays an IMAD on the FMA pipe)
                         if (!partial) chunk_top2_packed<false, MODE == TM_F4P>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
                         else chunk_top2_packed<true, MODE == TM_F4P>(acc[c & 1], nb_saddr, key_mul - 640u, (key_mul - 640u) << 16, col0 + c * 32, n_rows, m1, m2);
+                    } else if constexpr (SKIP && MODE == TM_F4X) {
+                        if (!partial) chunk_top2_skipx_f4<CW>(acc[c & 1], key_mul, c * CW, thrf, m1, m2);
+                        else chunk_top2<true, MODE, CW>(acc[c & 1], nb_saddr, cq, key_mul, c * CW, col0 + c * CW, n_rows, m1, m2);
                     } else if constexpr (SKIP) {
                         if (!partial) chunk_top2_skipx<CW>(acc[c & 1], key_mul, c * CW, thrv, m1, m2);
                         else chunk_top2<true, MODE, CW>(acc[c & 1], nb_saddr, cq, key_mul, c * CW, col0 + c * CW, n_rows, m1, m2);
@@ -494,7 +503,7 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                         if (lane == 0) mbar_arrive(&sm.acc_empty[a]);
                     }
                 }
-                if constexpr (MODE != TM_F16X) {
+                if constexpr (!NO_NB) {
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&sm.nb_empty[nbs]);
                 }
@@ -509,10 +518,15 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                     } else {
                         // i8: the key carries popc(t) - 2 q.t + I8_BIAS; popc(q) (the bits of cq) completes the Hamming distance.
                         // exact float modes: the key carries d^2 - |q|^2 + 2^20 (float_nbexact_kernel); |q|^2 is an integer <= 2^20
-                        const uint32_t dadd = MODE == TM_I8 ? __float_as_uint(cq) - I8_BIAS : static_cast<uint32_t>(cq) - 1048576u;
+                        const uint32_t dadd = (MODE == TM_I8 || MODE == TM_F4X) ? __float_as_uint(cq) - I8_BIAS : static_cast<uint32_t>(cq) - 1048576u;
                         if (m1 != 0xFFFFFFFFu) best.offer((m1 >> 9) + dadd, tbase + (int)(m1 & 511u));
                         if (m2 != 0xFFFFFFFFu) best.offer((m2 >> 9) + dadd, tbase + (int)(m2 & 511u));
-                        if constexpr (SKIP) {  // thresholds of the next tiles: own merged list, the other groups' + 1
+                        if constexpr (SKIP && MODE == TM_F4X) {  // the same in accumulator values: 1024 - key value
+                            if (best.i2 >= 0) thrf = fmaxf(thrf, F4X_KMAGIC - __uint_as_float(0x4B000000u | (best.d2 - dadd)));
+                            const float other = __uint_as_float(*thr_shared);
+                            *thr_shared = __float_as_uint(fmaxf(thrf, other));
+                            thrf = fmaxf(thrf, other - 1.f);
+                        } else if constexpr (SKIP) {  // thresholds of the next tiles: own merged list, the other groups' + 1
                             if (best.i2 >= 0) thrv = min(thrv, 0x4B000000u + (best.d2 - dadd));
                             const uint32_t other = *thr_shared;
                             *thr_shared = min(thrv, other);

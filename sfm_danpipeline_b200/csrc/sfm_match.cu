@@ -253,6 +253,7 @@ struct SfmmCtx {
     mutable std::string err;
     int csa_level = 2;
     bool cross_full_reverse = false;  // SFMM_CROSS_FULL=1: the round-1 cross-check (a full reverse pass), for A/B measurements
+    bool epi_groups_set = false;
     int epi_groups = 2;  // epilogue groups of the TMEM-A float kernels (SFMM_EPI_GROUPS=4: measured slower, see float_tensor_ts.cuh)
     size_t fx_attr_smem = 0;
 
@@ -269,10 +270,12 @@ struct SfmmCtx {
     float rank_offset = 0.f;  // C of the ranking pass's key table (float_nbexact_kernel)
     bool tensor_f16 = false;  // float tensor path runs on an fp16 copy (d_half) with kind::f16
     DevBuf d_half;
+    DevBuf d_f4_a;            // TM_F4X: the query-side operand rows (bits as 1.0 | 6 x16, 1), d_unpacked holds the train side
     DevBuf d_half_a;          // TM_F16X: the query-side operand rows (-2q | 1, 2048, 2048), d_half holds the train side
     bool tensor_kx = false;   // TM_F16X in use (key term contracted by the tensor core)
     bool no_kx = false;       // SFMM_NO_KX=1: keep TM_F16_EXACT (A/B measurements)
     bool tensor_f4 = false;   // binary tensor engine on the FP4 pipe (TM_F4P: descriptors below 512 bit; SFMM_NO_F4=1 keeps kind::i8)
+    bool tensor_f4x = false;  // TM_F4X: key term in the MMA + threshold-skipping epilogue (needs 17 spare elements per row; SFMM_NO_F4X=1 / SFMM_NO_SKIP=1: TM_F4P)
     bool no_f4 = false;
     bool no_skip = false;     // SFMM_NO_SKIP=1: TM_F16X folds every column (no threshold skipping; A/B measurements)
     uint32_t i8_bias = 0;    // binary tensor engine: descriptor bit length when the packed 16-bit keys apply (< 512 bit), else 0
@@ -530,8 +533,8 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnT
     // measured (profiles/tensor_variants_r01.txt): TMEM-A wins for the binary engine and the fp16 float path, shared-memory-A for TF32
     uint32_t aux = ctx->i8_bias;  // TM_I8P: descriptor bit length; rank modes: float bits of the key-table offset
     if (tm_is_rank(MODE) || tm_is_collect(MODE)) std::memcpy(&aux, &ctx->rank_offset, sizeof(aux));
-    const bool ts = MODE == TM_F16X || MODE == TM_F4P || (ctx->tensor_ts < 0 ? (MODE == TM_I8P || OperandOf<MODE>::kind == OK_F16 || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0);
-    if constexpr (MODE != TM_F4P && MODE != TM_F16X) if (!ts) {  // query tile in shared memory (float_tensor.cuh)
+    const bool ts = MODE == TM_F16X || MODE == TM_F4P || MODE == TM_F4X || (ctx->tensor_ts < 0 ? (MODE == TM_I8P || OperandOf<MODE>::kind == OK_F16 || (MODE == TM_I8 && KB <= 2)) : ctx->tensor_ts != 0);
+    if constexpr (MODE != TM_F4P && MODE != TM_F4X && MODE != TM_F16X) if (!ts) {  // query tile in shared memory (float_tensor.cuh)
         const size_t smem = float_tensor_smem_bytes(KB);
         auto kern = tensor_knn2_kernel<KB, MODE>;
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -544,7 +547,7 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnT
         return cudaGetLastError();
     }
     // query tile in tensor memory (float_tensor_ts.cuh)
-    const uint4* a_src = (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_F4P) ? ctx->d_unpacked.as<uint4>() : (MODE == TM_F16X ? ctx->d_half_a.as<uint4>() : (OperandOf<MODE>::kind == OK_F16 ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>()));
+    const uint4* a_src = MODE == TM_F4X ? ctx->d_f4_a.as<uint4>() : (MODE == TM_I8 || MODE == TM_I8P || MODE == TM_F4P) ? ctx->d_unpacked.as<uint4>() : (MODE == TM_F16X ? ctx->d_half_a.as<uint4>() : (OperandOf<MODE>::kind == OK_F16 ? ctx->d_half.as<uint4>() : ctx->blob.as<uint4>()));
     const size_t smem = float_tensor_ts_smem_bytes(KB);
     auto go = [&](auto kern, int threads) -> cudaError_t {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -565,10 +568,18 @@ cudaError_t launch_tensor_t(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const KnnT
             return go(tensor_knn2_ts_kernel<KB, MODE, 2, true>, fts_threads(2));
         }
     }
-    if constexpr (MODE == TM_F16_EXACT || MODE == TM_TF32_EXACT || MODE == TM_F16X) {
-        if (ctx->epi_groups == 4) return go(tensor_knn2_ts_kernel<KB, MODE, 4>, fts_threads(4));
+    if constexpr (MODE == TM_F4P) {
+        if (ctx->epi_groups == 3) return go(tensor_knn2_ts_kernel<KB, MODE, 3>, fts_threads(3));
     }
-    return go(tensor_knn2_ts_kernel<KB, MODE, 2>, fts_threads(2));
+    if constexpr (MODE == TM_F4X) {  // three epilogue groups by default (+2-3 %, same variants file); SFMM_EPI_GROUPS=2 for two
+        if (ctx->epi_groups_set && ctx->epi_groups == 2) return go(tensor_knn2_ts_kernel<KB, MODE, 2, true>, fts_threads(2));
+        return go(tensor_knn2_ts_kernel<KB, MODE, 3, true>, fts_threads(3));
+    } else {
+        if constexpr (MODE == TM_F16_EXACT || MODE == TM_TF32_EXACT || MODE == TM_F16X) {
+            if (ctx->epi_groups == 4) return go(tensor_knn2_ts_kernel<KB, MODE, 4>, fts_threads(4));
+        }
+        return go(tensor_knn2_ts_kernel<KB, MODE, 2>, fts_threads(2));
+    }
 }
 
 template <int MODE>
@@ -591,6 +602,8 @@ cudaError_t launch_tensor_exact(SfmmCtx* ctx, Slot& sl, uint32_t n_tiles, const 
         return ctx->tensor_f16 ? launch_tensor<TM_F16_EXACT>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev)
                                : launch_tensor<TM_TF32_EXACT>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev);
     }
+    if (ctx->tensor_f4x) return ctx->tensor_kblocks == 1 ? launch_tensor_t<1, TM_F4X>(ctx, sl, n_tiles, tiles_dev, n_items_dev)
+                                                         : launch_tensor_t<2, TM_F4X>(ctx, sl, n_tiles, tiles_dev, n_items_dev);
     if (ctx->tensor_f4) return ctx->tensor_kblocks == 1 ? launch_tensor_t<1, TM_F4P>(ctx, sl, n_tiles, tiles_dev, n_items_dev)
                                                         : launch_tensor_t<2, TM_F4P>(ctx, sl, n_tiles, tiles_dev, n_items_dev);
     return ctx->i8_bias ? launch_tensor<TM_I8P>(ctx, sl, n_tiles, ctx->tensor_kblocks, tiles_dev, n_items_dev)
@@ -656,6 +669,8 @@ int make_tensor_map(SfmmCtx* ctx, void* base, CUtensorMapDataType dtype, size_t 
 int prepare_binary_tensor(SfmmCtx* ctx) {
     if (ctx->elem_type != SFMM_U8 || ctx->float_prepared) return SFMM_OK;
     ctx->use_tensor = false;
+    ctx->tensor_f4 = false;
+    ctx->tensor_f4x = false;
     const int words = binary_words(ctx->cols);
     const int kbytes8 = (words * 32 + 127) / 128 * 128;  // unpacked row: one byte per bit, whole 128-byte K-blocks
     // descriptors below 512 bit (packed 16-bit keys apply): one NIBBLE per bit and the FP4 pipe (TM_F4P) -- half the bytes, twice the rate
@@ -674,7 +689,17 @@ int prepare_binary_tensor(SfmmCtx* ctx) {
             CU_TRY(ctx, ctx->d_unpacked.ensure(static_cast<size_t>(ctx->total_rows) * kbytes));
             CU_TRY(ctx, ctx->d_norms.ensure((static_cast<size_t>(ctx->total_rows) + 2 * FT_N) * sizeof(int32_t)));
             const uint32_t rows = static_cast<uint32_t>(ctx->total_rows);
-            if (f4)
+            // TM_F4X pays once a row's threshold has settled, i.e. on long train images: measured (one B200, 486 bit) -4 % at 5 000 rows per
+            // image, +13 % at 10 000 (profiles/tensor_variants_r02.txt); SFMM_F4X=1 / SFMM_NO_F4X=1 force either
+            const int64_t max_rows = ctx->rows.empty() ? 0 : *std::max_element(ctx->rows.begin(), ctx->rows.end());
+            const char* f4x_env = std::getenv("SFMM_F4X");
+            const bool f4x = f4 && ctx->cols * 8 + 17 <= kbytes * 2 && !ctx->no_skip && !std::getenv("SFMM_NO_F4X") &&
+                             ((f4x_env && std::atoi(f4x_env) != 0) || max_rows >= 7000);
+            if (f4x) {
+                CU_TRY(ctx, ctx->d_f4_a.ensure(static_cast<size_t>(ctx->total_rows) * kbytes));
+                binary_unpack4x_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ctx->blob.as<uint32_t>(), words, rows, kbytes, ctx->cols * 8, ctx->d_unpacked.as<uint8_t>(),
+                                                                       ctx->d_f4_a.as<uint8_t>(), ctx->d_norms.as<int32_t>());
+            } else if (f4)
                 binary_unpack4_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ctx->blob.as<uint32_t>(), words, rows, kbytes, ctx->d_unpacked.as<uint8_t>(),
                                                                       ctx->d_norms.as<int32_t>());
             else
@@ -689,6 +714,7 @@ int prepare_binary_tensor(SfmmCtx* ctx) {
             binary_nbkey_kernel<<<(rows + 255) / 256, 256, 0, st>>>(ctx->d_norms.as<int32_t>(), ctx->d_row0.as<uint32_t>(), ctx->n_images, rows,
                                                                      ctx->d_nbkey.as<uint32_t>(), ctx->i8_bias, f4 ? 0x80000000u : 0u);
             ctx->tensor_f4 = f4;
+            ctx->tensor_f4x = f4x;
             CU_TRY(ctx, cudaGetLastError());
             CU_TRY(ctx, cudaStreamSynchronize(st));
             ctx->stats.kernel_launches += 2;
@@ -700,6 +726,7 @@ int prepare_binary_tensor(SfmmCtx* ctx) {
     }
     ctx->float_prepared = true;
     ctx->stats.float_path = ctx->use_tensor ? SFMM_FLOAT_TENSOR : 0;
+    ctx->stats.tensor_kind = ctx->use_tensor ? (ctx->tensor_f4 ? 2 : 1) : 0;
     return SFMM_OK;
 }
 
@@ -811,6 +838,7 @@ int prepare_float(SfmmCtx* ctx) {
                     "SFMM_FLOAT_TENSOR needs a descriptor width that is a multiple of 32 up to 128 and finite values; use SFMM_FLOAT_AUTO or SFMM_FLOAT_EXACT");
     ctx->float_prepared = true;
     ctx->stats.float_path = ctx->use_tensor ? (ctx->tensor_refine ? 3 : SFMM_FLOAT_TENSOR) : SFMM_FLOAT_EXACT;
+    ctx->stats.tensor_kind = ctx->use_tensor ? (ctx->tensor_f16 ? 3 : 4) : 0;
     return SFMM_OK;
 }
 
@@ -1212,7 +1240,7 @@ SFMM_API int sfmm_create(const SfmmConfig* cfg, SfmmCtx** out) {
     if (const char* s = std::getenv("SFMM_NO_SKIP")) ctx->no_skip = std::atoi(s) != 0;
     if (const char* s = std::getenv("SFMM_NO_F4")) ctx->no_f4 = std::atoi(s) != 0;
     if (const char* s = std::getenv("SFMM_CROSS_FULL")) ctx->cross_full_reverse = std::atoi(s) != 0;
-    if (const char* s = std::getenv("SFMM_EPI_GROUPS")) ctx->epi_groups = std::max(2, std::min(4, std::atoi(s)));
+    if (const char* s = std::getenv("SFMM_EPI_GROUPS")) { ctx->epi_groups = std::max(2, std::min(4, std::atoi(s))); ctx->epi_groups_set = true; }
     bool ok = (e = cudaSetDevice(cfg->device)) == cudaSuccess;
     for (Slot& sl : ctx->slot) {
         ok = ok && (e = cudaStreamCreateWithFlags(&sl.stream, cudaStreamNonBlocking)) == cudaSuccess;
@@ -1242,7 +1270,7 @@ SFMM_API void sfmm_destroy(SfmmCtx* ctx) {
         cudaStreamSynchronize(ctx->copy_stream);
         cudaStreamDestroy(ctx->copy_stream);
     }
-    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked, &ctx->d_nbkey, &ctx->d_row0, &ctx->d_half, &ctx->d_half_a, &ctx->d_raw, &ctx->d_raw_row0}) b->release();
+    for (DevBuf* b : {&ctx->blob, &ctx->d_idx, &ctx->d_dist, &ctx->d_norms, &ctx->d_flags, &ctx->d_points, &ctx->d_unpacked, &ctx->d_nbkey, &ctx->d_row0, &ctx->d_half, &ctx->d_half_a, &ctx->d_f4_a, &ctx->d_raw, &ctx->d_raw_row0}) b->release();
     for (PinBuf& p : ctx->pack) p.release();
     ctx->table.release();
     for (cudaEvent_t ev : {ctx->ev_begin, ctx->ev_end, ctx->ev_pack[0], ctx->ev_pack[1], ctx->ev_blob})
@@ -1299,6 +1327,7 @@ static int impl_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* cons
     ctx->tensor_refine = false;
     ctx->have_points = false;
     ctx->stats.float_path = 0;
+    ctx->stats.tensor_kind = 0;
     const size_t bytes = static_cast<size_t>(total) * pitch;
     CU_TRY(ctx, ctx->blob.ensure(std::max<size_t>(bytes, 16)));
     ctx->rows.assign(rows, rows + n_images);

@@ -333,3 +333,62 @@ def test_cross_check_candidate_columns_and_full_reverse_agree(full, monkeypatch)
             got = m.getMatching(q, t)
             eq, et, ed = sift.expected(p, True)
             assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all() and (got["distance"] == ed).all(), (q, t)
+
+
+# ----------------------------------------------------------------- round 2: the FP4 pipe (kind::mxf4) behind the tensor engine
+@pytest.mark.parametrize("env,kind", [({}, 2), ({"SFMM_F4X": "1"}, 2), ({"SFMM_F4X": "1", "SFMM_EPI_GROUPS": "2"}, 2), ({"SFMM_NO_F4": "1"}, 1),
+                                      ({"SFMM_EPI_GROUPS": "3"}, 2), ({"SFMM_F4X": "1", "SFMM_NO_SKIP": "1"}, 2)])
+def test_tensor_engine_kinds_agree_with_cv2_and_oracle(env, kind, monkeypatch):
+    """Descriptors below 512 bit run on the FP4 pipe: TM_F4P (packed keys, every column folded), or -- by default once an image has 7 000
+    rows, forced here with SFMM_F4X=1 -- TM_F4X (key term in the MMA + threshold-skipping epilogue; AKAZE has the 17 spare elements it
+    needs, ORB has none and stays on TM_F4P); or on kind::i8 (SFMM_NO_F4=1); two or three epilogue groups.  The settings are read when the context is created; every variant must reproduce the cv2 goldens, cross-check
+    included, and the oracle on ragged / tied / duplicated rows."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    for name in ("temple_akaze", "temple_orb"):
+        g = GoldenSet(name)
+        for cross in (False, True):
+            with Matcher(NORM_HAMMING, 0.8, cross) as m:
+                m.set_descriptors(g.descs)
+                m.match_all_pairs()
+                assert m.stats()["float_path"] == 2 and m.stats()["tensor_kind"] == kind
+                for p, (q, t, *_r) in enumerate(g.pairs):
+                    got = m.getMatching(q, t)
+                    eq, et, ed = g.expected(p, cross)
+                    assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all() and (got["distance"] == ed).all(), (name, q, t, cross)
+    rng = np.random.default_rng(7)
+    base = rng.integers(0, 256, (3000, 61), dtype=np.uint8)
+    base[:, 60] &= 0x3F  # AKAZE's two pad bits
+    dup = np.concatenate([base[:50]] * 3 + [base[50:1500]])  # triplicated rows: ties in both slots
+    extremes = np.concatenate([np.zeros((2, 61), np.uint8), np.full((2, 61), 255, np.uint8), base[:200]])
+    extremes[2:4, 60] = 0x3F
+    descs = [base, dup, base[::-1].copy(), extremes, base[:1], np.zeros((0, 61), np.uint8), base[:129]]
+    for cross in (False, True):
+        with Matcher(NORM_HAMMING, 0.8, cross) as m:
+            m.set_descriptors(descs)
+            m.match_all_pairs()
+            for (q, t) in synth.all_pairs(len(descs)):
+                _expect_equal(m.getMatching(q, t), oracle.match_pair(descs[q], descs[t], 0, 0.8, cross, threads=8))
+
+
+@pytest.mark.parametrize("order", ["descending", "ascending"])
+def test_threshold_skipping_is_order_independent(order, monkeypatch):
+    """The skipping epilogue's cost depends on the order the train rows arrive in, its result must not: train rows sorted by their
+    distance to one query row -- nearest last (every block takes the slow path) or nearest first (none does after the first tile) --
+    and many exact ties."""
+    monkeypatch.setenv("SFMM_F4X", "1")
+    rng = np.random.default_rng(11)
+    q = rng.integers(0, 256, (300, 61), dtype=np.uint8)
+    t = rng.integers(0, 256, (6000, 61), dtype=np.uint8)
+    t[::7] = t[3]  # ties
+    q[:, 60] &= 0x3F
+    t[:, 60] &= 0x3F
+    d = np.unpackbits(t ^ q[0], axis=1).sum(1)
+    idx = np.argsort(d, kind="stable")
+    t = t[idx[::-1] if order == "descending" else idx].copy()
+    for cross in (False, True):
+        with Matcher(NORM_HAMMING, 0.8, cross) as m:
+            m.set_descriptors([q, t])
+            m.match_all_pairs()
+            assert m.stats()["tensor_kind"] == 2
+            _expect_equal(m.getMatching(0, 1), oracle.match_pair(q, t, 0, 0.8, cross, threads=8))

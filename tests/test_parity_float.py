@@ -377,3 +377,34 @@ def test_tensor_kernel_epilogue_group_variants_agree(groups, no_kx, monkeypatch)
             m.match_all_pairs()
             for (q, t) in synth.all_pairs(3):
                 assert m.getMatching(q, t).tobytes() == oracle.match_pair(descs[q], descs[t], 1, 0.8, cross, threads=8).tobytes(), (q, t, cross)
+
+
+@pytest.mark.parametrize("env", [{}, {"SFMM_NO_SKIP": "1"}, {"SFMM_EPI_GROUPS": "3"}, {"SFMM_EPI_GROUPS": "4"}])
+def test_threshold_skipping_epilogue_variants_agree(env, monkeypatch):
+    """TM_F16X's epilogue skips the blocks of columns that cannot enter a row's top-2 any more (default; two, three or four epilogue
+    groups sharing their thresholds) or folds every column (SFMM_NO_SKIP=1).  Cost depends on the arrival order of the train rows,
+    results must not: random order, nearest-last and nearest-first orders, exact ties and duplicated rows."""
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    g = GoldenSet("temple_sift")
+    for cross in (False, True):
+        with Matcher(NORM_L2, 0.8, cross) as m:
+            m.set_descriptors(g.descs)
+            m.match_all_pairs()
+            assert m.stats()["float_path"] == FLOAT_TENSOR
+            for p, (q, t, *_r) in enumerate(g.pairs):
+                got = m.getMatching(q, t)
+                eq, et, ed = g.expected(p, cross)
+                assert (got["queryIdx"] == eq).all() and (got["trainIdx"] == et).all() and (got["distance"] == ed).all(), (q, t, cross)
+    a, b = synth.float_images(2, [700, 6000], seed=9)
+    b[::5] = b[2]  # ties
+    d = ((b - a[0]) ** 2).sum(1)
+    idx = np.argsort(d, kind="stable")
+    sets = [b, b[idx].copy(), b[idx[::-1]].copy()]
+    for cross in (False, True):
+        with Matcher(NORM_L2, 0.8, cross) as m:
+            m.set_descriptors([a] + sets)
+            m.match_pairs([(0, 1), (0, 2), (0, 3), (3, 0)])
+            for (q, t) in [(0, 1), (0, 2), (0, 3), (3, 0)]:
+                descs = [a] + sets
+                assert m.getMatching(q, t).tobytes() == oracle.match_pair(descs[q], descs[t], 1, 0.8, cross, threads=8).tobytes(), (q, t, cross)
