@@ -181,6 +181,10 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+    [[maybe_unused]] constexpr uint32_t FTS_THR_NEUTRAL = MODE == TM_F4X ? 0xBF800000u /* -1.f */ : 0xFFFFFFF0u;  // "no threshold yet" in sm.thr
+    if constexpr (SKIP) {
+        for (uint32_t i = threadIdx.x; i < 2 * FT_M; i += blockDim.x) (&sm.thr[0][0])[i] = FTS_THR_NEUTRAL;
+    }
     if (threadIdx.x == 0) {
         for (int s = 0; s < 2; ++s) {
             mbar_init(&sm.a_full[s], 4);   // the four loader warps
@@ -446,15 +450,15 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             // written never ask for the slow path.  The groups of a row share their thresholds through sm.thr: every group sees
             // 1/GROUPS of the columns, together they see all of them, and the number of slow-path visits follows the columns
             // seen.  The other groups' tiles may lie AFTER this group's next tile, where an equal distance must not win, hence
-            // their threshold + 1.  The word is a hint: written and read without ordering, a stale value is only looser; both
-            // writers of a row reset it before their first read of the item, and the named barrier at the end of every item
-            // (finish_rows) keeps the groups within the same item, so a slot never carries a previous item's value.
+            // their threshold + 1.  The word is a hint (a stale value is only looser), exchanged with ONE shared-memory atomic per
+            // tile (min / max returns what the others had).  Items alternate between two slots; group 0 resets the next item's slot
+            // before the named barrier that ends every item (finish_rows), which nobody passes before all groups have finished the
+            // item -- so a slot never carries a previous item's value and plain stores never meet the atomics (racecheck clean).
             [[maybe_unused]] uint32_t thrv = qrow < nq ? 0xFFFFFFF0u : 0u;
-            [[maybe_unused]] volatile uint32_t* thr_shared = &sm.thr[it & 1][row];
+            [[maybe_unused]] uint32_t* thr_shared = &sm.thr[it & 1][row];
             // TM_F4X: larger accumulators are nearer, the threshold is the accumulator VALUE of the second-nearest column so far
             // (-1: none yet; +inf: row never written); the shared word holds float bits, the other groups' threshold counts - 1
             [[maybe_unused]] float thrf = qrow < nq ? -1.f : __int_as_float(0x7f800000);
-            if constexpr (SKIP) *thr_shared = MODE == TM_F4X ? __float_as_uint(thrf) : thrv;
 #pragma unroll 1
             for (uint32_t j = (half + GROUPS - g0 % GROUPS) % GROUPS; j < n_tiles; j += GROUPS) {
                 const uint32_t g = g0 + j;               // g % GROUPS == half
@@ -523,13 +527,12 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
                         if (m2 != 0xFFFFFFFFu) best.offer((m2 >> 9) + dadd, tbase + (int)(m2 & 511u));
                         if constexpr (SKIP && MODE == TM_F4X) {  // the same in accumulator values: 1024 - key value
                             if (best.i2 >= 0) thrf = fmaxf(thrf, F4X_KMAGIC - __uint_as_float(0x4B000000u | (best.d2 - dadd)));
-                            const float other = __uint_as_float(*thr_shared);
-                            *thr_shared = __float_as_uint(fmaxf(thrf, other));
+                            // (-1, +inf and the positive accumulator values order as signed integers like as floats)
+                            const float other = __int_as_float(atomicMax(reinterpret_cast<int*>(thr_shared), __float_as_int(thrf)));
                             thrf = fmaxf(thrf, other - 1.f);
                         } else if constexpr (SKIP) {  // thresholds of the next tiles: own merged list, the other groups' + 1
                             if (best.i2 >= 0) thrv = min(thrv, 0x4B000000u + (best.d2 - dadd));
-                            const uint32_t other = *thr_shared;
-                            *thr_shared = min(thrv, other);
+                            const uint32_t other = atomicMin(thr_shared, thrv);
                             thrv = min(thrv, other + 1u);
                         }
                     }
@@ -545,6 +548,9 @@ tensor_knn2_ts_kernel(const __grid_constant__ CUtensorMap tmap, const uint4* __r
             if constexpr (tm_is_collect(MODE)) {
                 if (n_splits == 1 && qrow < nq) *cand_count_row = fill;
             } else {
+                if constexpr (SKIP) {
+                    if (half == 0) sm.thr[(it + 1) & 1][row] = FTS_THR_NEUTRAL;  // next item's slot, see above
+                }
                 finish_rows<MODE, GROUPS>(sm.merge[it & 1], best, half, row, qrow, nq, reverse, split, knn_off, col_off, knn, colmin, out_row);
             }
         }

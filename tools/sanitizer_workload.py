@@ -3,8 +3,8 @@
     compute-sanitizer --tool memcheck  python tools/sanitizer_workload.py
     compute-sanitizer --tool racecheck python tools/sanitizer_workload.py
 
-Covers the POPC kernel, the tensor kernels (i8 packed / i8 / fp16 / TF32 exact / TF32 rank+collect+refine, TMEM-A and
-shared-memory-A forms), the exact fp32 kernel, cross-check on and off,
+Covers the POPC kernel, the tensor kernels (fp4 packed / fp4 with the key term in the MMA / i8 packed / i8 / fp16 / TF32 exact /
+TF32 rank+collect+refine, TMEM-A and shared-memory-A forms, plain and threshold-skipping epilogues), the exact fp32 kernel, cross-check on and off,
 empty / tiny / ragged images, single-pair and raw-knn calls; every result is compared with the oracle."""
 import os
 import sys
@@ -82,4 +82,21 @@ with OrbExtractor(0) as orb:
 okp, od = orb_oracle.detect_and_compute(img)
 assert {(int(k["octave"]), float(k["x"]), float(k["y"])): bytes(dd) for k, dd in zip(kp, desc)} == \
        {(int(k["octave"]), float(k["x"]), float(k["y"])): bytes(dd) for k, dd in zip(okp, od)}
+# second half of round 2: the FP4 pipe -- TM_F4P is what the binary sets above ran on; TM_F4X (key term in the MMA, threshold-skipping epilogue with
+# shared-memory atomics between the groups; forced, the sets are small) with two and three epilogue groups, kind::i8, and the plain fold of TM_F16X
+for env in ({"SFMM_F4X": "1"}, {"SFMM_F4X": "1", "SFMM_EPI_GROUPS": "2"}, {"SFMM_NO_F4": "1"}, {"SFMM_NO_SKIP": "1"}, {"SFMM_EPI_GROUPS": "3"}):
+    os.environ.update(env)
+    for cross in (False, True):
+        with Matcher(0, 0.8, cross) as m:
+            m.set_descriptors(d)
+            m.match_all_pairs()
+            for (q, t) in synth.all_pairs(4):
+                assert m.getMatching(q, t).tobytes() == oracle.match_pair(d[q], d[t], 0, 0.8, cross).tobytes()
+        with Matcher(1, 0.8, cross) as m:
+            m.set_descriptors(f)
+            m.match_all_pairs()
+            for (q, t) in synth.all_pairs(3):
+                assert m.getMatching(q, t).tobytes() == oracle.match_pair(f[q], f[t], 1, 0.8, cross).tobytes()
+    for k in env:
+        del os.environ[k]
 print("sanitizer workload ok")
