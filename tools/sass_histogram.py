@@ -12,7 +12,7 @@ import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "sfm_danpipeline_b200", "csrc", "libsfmmatch.so")
-KEY = ["UTCIMMA", "UTCHMMA", "UTCQMMA", "UTCMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "UTCBAR", "SYNCS", "ELECT", "POPC", "LOP3", "VIMNMX", "VIMNMX3",
+KEY = ["UTCIMMA", "UTCHMMA", "UTCOMMA", "UTCQMMA", "UTCMMA", "LDTM", "STTM", "UTMALDG", "UBLKCP", "UTCBAR", "SYNCS", "ELECT", "POPC", "LOP3", "VIMNMX", "VIMNMX3",
        "IMAD", "FFMA", "REDUX", "ATOMS", "ATOMG", "HMMA", "IMMA", "LDS", "LDG", "STG"]
 
 
