@@ -386,6 +386,15 @@ struct SfmmOrb {
     void* h_pin = nullptr;  // pinned staging for the image
     size_t h_pin_cap = 0;
     void* h_out = nullptr;  // pinned: count + keypoints + descriptors
+    // The per-image work is a fixed sequence of ~51 small launches (640 x 480: launch latency, not the GPU, set the 0.51 ms): it is
+    // captured ONCE per geometry into a CUDA graph.  Only the resize chain is serial; each level's FAST -> NMS -> pick chain and its
+    // blur chain fork off onto side streams as soon as the level's image exists and join before the final selection, so the graph
+    // has up to 17 concurrent branches.  SFMM_ORB_NO_GRAPH=1 issues the same fork/join sequence eagerly.
+    cudaStream_t side[2 * N_LEVELS] = {};
+    cudaEvent_t ev_ext[N_LEVELS] = {}, ev_side[2 * N_LEVELS] = {};
+    cudaGraphExec_t graph_exec = nullptr;
+    const void* graph_key[6] = {};  // what the captured graph has baked in: geometry, channels, buffers
+    bool use_graph = true;
     int64_t launches = 0;
     double last_ms = 0;
     mutable std::string err;
@@ -518,6 +527,10 @@ SFMM_API void sfmm_orb_destroy(SfmmOrb* o) {
     if (!o) return;
     cudaSetDevice(o->device);
     if (o->st) cudaStreamSynchronize(o->st);
+    if (o->graph_exec) cudaGraphExecDestroy(o->graph_exec);
+    for (cudaStream_t s : o->side) if (s) cudaStreamDestroy(s);
+    for (cudaEvent_t e : o->ev_ext) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : o->ev_side) if (e) cudaEventDestroy(e);
     for (Buf* b : {&o->pool, &o->d_src, &o->d_counts, &o->d_lv, &o->d_keys, &o->d_kps, &o->d_desc}) b->release();
     if (o->h_pin) cudaFreeHost(o->h_pin);
     if (o->h_out) cudaFreeHost(o->h_out);
@@ -545,6 +558,11 @@ SFMM_API int sfmm_orb_create(int32_t device, SfmmOrb** out) {
     o->device = device;
     bool ok = cudaSetDevice(device) == cudaSuccess && cudaStreamCreateWithFlags(&o->st, cudaStreamNonBlocking) == cudaSuccess &&
               cudaEventCreate(&o->ev0) == cudaSuccess && cudaEventCreate(&o->ev1) == cudaSuccess;
+    for (int i = 0; ok && i < 2 * N_LEVELS; ++i)
+        ok = cudaStreamCreateWithFlags(&o->side[i], cudaStreamNonBlocking) == cudaSuccess &&
+             cudaEventCreateWithFlags(&o->ev_side[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; ok && i < N_LEVELS; ++i) ok = cudaEventCreateWithFlags(&o->ev_ext[i], cudaEventDisableTiming) == cudaSuccess;
+    if (const char* e2 = std::getenv("SFMM_ORB_NO_GRAPH")) o->use_graph = std::atoi(e2) == 0;
     // constants: the learned pattern, the disc's half-widths (orb.cpp: umax), cv::getGaussianKernel(7, 2, CV_32F)
     int umax[HALF_PATCH + 2] = {0};
     {
@@ -618,65 +636,101 @@ SFMM_API int sfmm_orb_detect_and_compute(SfmmOrb* o, const uint8_t* image, int32
     }
     for (int y = 0; y < rows; ++y) std::memcpy(static_cast<unsigned char*>(o->h_pin) + y * row_bytes, image + static_cast<size_t>(y) * step_bytes, row_bytes);
     ORB_TRY(o, o->d_src.ensure(bytes));
-    ORB_TRY(o, cudaEventRecord(o->ev0, st));
-    ORB_TRY(o, cudaMemcpyAsync(o->d_src.p, o->h_pin, bytes, cudaMemcpyHostToDevice, st));
-    int* d_n_cand = static_cast<int*>(o->d_counts.p);
-    int* d_n_pick = d_n_cand + N_LEVELS;
-    int* d_n_out = d_n_pick + N_LEVELS;
-    int* d_hist = d_n_out + 1;
-    ORB_TRY(o, cudaMemsetAsync(o->d_counts.p, 0, (2 * N_LEVELS + 1 + N_LEVELS * 256) * sizeof(int), st));
-    const float harris_k = 0.04f;
-    const float hs = 1.f / ((1 << 2) * HARRIS_BLOCK * 255.f);
-    const float scale_sq_sq = hs * hs * hs * hs;
-    const dim3 blk(32, 8);
-    for (int l = 0; l < N_LEVELS; ++l) {
-        Level& L = o->lv[l];
-        const dim3 ge((L.pitch + 31) / 32, (L.h + 2 * BORDER + 7) / 8), gi((L.w + 31) / 32, (L.h + 7) / 8);
-        if (l == 0) {
-            orb_level0_kernel<<<ge, blk, 0, st>>>(static_cast<const unsigned char*>(o->d_src.p), row_bytes, channels, L.w, L.h, L.ext, L.pitch);
-        } else {
-            Level& P = o->lv[l - 1];
-            orb_resize_kernel<<<ge, blk, 0, st>>>(P.ext + static_cast<size_t>(BORDER) * P.pitch + BORDER, P.pitch, P.w, P.h, L.ofsx, L.cx1, L.ofsy, L.cy1, L.w, L.h,
-                                                  L.ext, L.pitch);
-        }
-        const unsigned char* interior = L.ext + static_cast<size_t>(BORDER) * L.pitch + BORDER;
-        orb_fast_score_kernel<<<gi, blk, 0, st>>>(interior, L.pitch, L.w, L.h, L.score);
-        orb_nms_kernel<<<gi, blk, 0, st>>>(L.score, L.w, L.h, L.cand, L.cand_score, L.cand_cap, d_n_cand + l, d_hist + l * 256);
-        orb_pick_fast_kernel<<<1, 256, 0, st>>>(interior, L.pitch, L.cand, L.cand_score, d_n_cand + l, L.cand_cap, d_hist + l * 256, 2 * L.quota, L.pick,
-                                                L.pick_resp, d_n_pick + l, harris_k, scale_sq_sq);
-        // the blurred copy: frame = the unblurred frame (ORB blurs the level in place inside its framed buffer), interior = blur
-        ORB_TRY(o, cudaMemcpyAsync(L.blur, L.ext, static_cast<size_t>(L.h + 2 * BORDER) * L.pitch, cudaMemcpyDeviceToDevice, st));
-        orb_blur_rows_kernel<<<dim3((L.w + 31) / 32, (L.h + 6 + 7) / 8), blk, 0, st>>>(L.ext, L.pitch, L.w, L.h, L.rows);
-        orb_blur_cols_kernel<<<gi, blk, 0, st>>>(L.rows, L.w, L.h, L.blur, L.pitch);
-        o->launches += 6;
-    }
-    orb_pick_harris_kernel<<<1, 1024, 0, st>>>(static_cast<const LevelDev*>(o->d_lv.p), d_n_pick, static_cast<KeyInfo*>(o->d_keys.p), d_n_out, MAX_OUT);
-    orb_angle_kernel<<<(MAX_OUT + 7) / 8, 256, 0, st>>>(static_cast<const LevelDev*>(o->d_lv.p), static_cast<const KeyInfo*>(o->d_keys.p), d_n_out, MAX_OUT,
-                                                       static_cast<SfmKeyPoint*>(o->d_kps.p));
-    orb_describe_kernel<<<(MAX_OUT + 7) / 8, 256, 0, st>>>(static_cast<const LevelDev*>(o->d_lv.p), static_cast<const KeyInfo*>(o->d_keys.p),
-                                                          static_cast<const SfmKeyPoint*>(o->d_kps.p), d_n_out, MAX_OUT,
-                                                          static_cast<unsigned char*>(o->d_desc.p));
-    o->launches += 3;
-    ORB_TRY(o, cudaGetLastError());
-    // results: the count first, then exactly that many records
     int* h_count = static_cast<int*>(o->h_out);
-    ORB_TRY(o, cudaMemcpyAsync(h_count, d_n_out, sizeof(int), cudaMemcpyDeviceToHost, st));
+    unsigned char* h = static_cast<unsigned char*>(o->h_out) + 64;
+    // the whole image: upload, pyramid, detection, description, results (count + MAX_OUT records: 245 KB, the first `count` are valid)
+    auto enqueue = [&]() -> cudaError_t {
+        cudaError_t e;
+#define ORB_Q(expr) do { if ((e = (expr)) != cudaSuccess) return e; } while (0)
+        ORB_Q(cudaMemcpyAsync(o->d_src.p, o->h_pin, bytes, cudaMemcpyHostToDevice, st));
+        int* d_n_cand = static_cast<int*>(o->d_counts.p);
+        int* d_n_pick = d_n_cand + N_LEVELS;
+        int* d_n_out = d_n_pick + N_LEVELS;
+        int* d_hist = d_n_out + 1;
+        ORB_Q(cudaMemsetAsync(o->d_counts.p, 0, (2 * N_LEVELS + 1 + N_LEVELS * 256) * sizeof(int), st));
+        const float harris_k = 0.04f;
+        const float hs = 1.f / ((1 << 2) * HARRIS_BLOCK * 255.f);
+        const float scale_sq_sq = hs * hs * hs * hs;
+        const dim3 blk(32, 8);
+        for (int l = 0; l < N_LEVELS; ++l) {
+            Level& L = o->lv[l];
+            const dim3 ge((L.pitch + 31) / 32, (L.h + 2 * BORDER + 7) / 8), gi((L.w + 31) / 32, (L.h + 7) / 8);
+            if (l == 0) {
+                orb_level0_kernel<<<ge, blk, 0, st>>>(static_cast<const unsigned char*>(o->d_src.p), row_bytes, channels, L.w, L.h, L.ext, L.pitch);
+            } else {
+                Level& P = o->lv[l - 1];
+                orb_resize_kernel<<<ge, blk, 0, st>>>(P.ext + static_cast<size_t>(BORDER) * P.pitch + BORDER, P.pitch, P.w, P.h, L.ofsx, L.cx1, L.ofsy, L.cy1, L.w, L.h,
+                                                      L.ext, L.pitch);
+            }
+            // fork: the level's image exists
+            cudaStream_t sa = o->side[2 * l], sb = o->side[2 * l + 1];
+            ORB_Q(cudaEventRecord(o->ev_ext[l], st));
+            ORB_Q(cudaStreamWaitEvent(sa, o->ev_ext[l], 0));
+            ORB_Q(cudaStreamWaitEvent(sb, o->ev_ext[l], 0));
+            const unsigned char* interior = L.ext + static_cast<size_t>(BORDER) * L.pitch + BORDER;
+            orb_fast_score_kernel<<<gi, blk, 0, sa>>>(interior, L.pitch, L.w, L.h, L.score);
+            orb_nms_kernel<<<gi, blk, 0, sa>>>(L.score, L.w, L.h, L.cand, L.cand_score, L.cand_cap, d_n_cand + l, d_hist + l * 256);
+            orb_pick_fast_kernel<<<1, 256, 0, sa>>>(interior, L.pitch, L.cand, L.cand_score, d_n_cand + l, L.cand_cap, d_hist + l * 256, 2 * L.quota, L.pick,
+                                                    L.pick_resp, d_n_pick + l, harris_k, scale_sq_sq);
+            // the blurred copy: frame = the unblurred frame (ORB blurs the level in place inside its framed buffer), interior = blur
+            ORB_Q(cudaMemcpyAsync(L.blur, L.ext, static_cast<size_t>(L.h + 2 * BORDER) * L.pitch, cudaMemcpyDeviceToDevice, sb));
+            orb_blur_rows_kernel<<<dim3((L.w + 31) / 32, (L.h + 6 + 7) / 8), blk, 0, sb>>>(L.ext, L.pitch, L.w, L.h, L.rows);
+            orb_blur_cols_kernel<<<gi, blk, 0, sb>>>(L.rows, L.w, L.h, L.blur, L.pitch);
+            ORB_Q(cudaEventRecord(o->ev_side[2 * l], sa));
+            ORB_Q(cudaEventRecord(o->ev_side[2 * l + 1], sb));
+        }
+        for (int i = 0; i < 2 * N_LEVELS; ++i) ORB_Q(cudaStreamWaitEvent(st, o->ev_side[i], 0));  // join
+        orb_pick_harris_kernel<<<1, 1024, 0, st>>>(static_cast<const LevelDev*>(o->d_lv.p), d_n_pick, static_cast<KeyInfo*>(o->d_keys.p), d_n_out, MAX_OUT);
+        orb_angle_kernel<<<(MAX_OUT + 7) / 8, 256, 0, st>>>(static_cast<const LevelDev*>(o->d_lv.p), static_cast<const KeyInfo*>(o->d_keys.p), d_n_out, MAX_OUT,
+                                                           static_cast<SfmKeyPoint*>(o->d_kps.p));
+        orb_describe_kernel<<<(MAX_OUT + 7) / 8, 256, 0, st>>>(static_cast<const LevelDev*>(o->d_lv.p), static_cast<const KeyInfo*>(o->d_keys.p),
+                                                              static_cast<const SfmKeyPoint*>(o->d_kps.p), d_n_out, MAX_OUT,
+                                                              static_cast<unsigned char*>(o->d_desc.p));
+        ORB_Q(cudaGetLastError());
+        ORB_Q(cudaMemcpyAsync(h_count, d_n_out, sizeof(int), cudaMemcpyDeviceToHost, st));
+        ORB_Q(cudaMemcpyAsync(h, o->d_kps.p, sizeof(SfmKeyPoint) * MAX_OUT, cudaMemcpyDeviceToHost, st));
+        ORB_Q(cudaMemcpyAsync(h + sizeof(SfmKeyPoint) * MAX_OUT, o->d_desc.p, static_cast<size_t>(32) * MAX_OUT, cudaMemcpyDeviceToHost, st));
+#undef ORB_Q
+        return cudaSuccess;
+    };
+    if (o->use_graph) {
+        const void* key[6] = {reinterpret_cast<const void*>(static_cast<uintptr_t>(rows)), reinterpret_cast<const void*>(static_cast<uintptr_t>(cols)),
+                              reinterpret_cast<const void*>(static_cast<uintptr_t>(channels)), o->pool.p, o->d_src.p, o->h_pin};
+        if (!o->graph_exec || std::memcmp(key, o->graph_key, sizeof(key)) != 0) {
+            if (o->graph_exec) {
+                cudaGraphExecDestroy(o->graph_exec);
+                o->graph_exec = nullptr;
+            }
+            cudaGraph_t graph = nullptr;
+            ORB_TRY(o, cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+            const cudaError_t qe = enqueue();
+            const cudaError_t ce = cudaStreamEndCapture(st, &graph);  // always: never leave the streams capturing
+            if (qe != cudaSuccess || ce != cudaSuccess) {
+                if (graph) cudaGraphDestroy(graph);
+                (void)cudaGetLastError();
+                return ofail(o, SFMM_ECUDA, std::string("orb_detect_and_compute: graph capture: ") + cudaGetErrorString(qe != cudaSuccess ? qe : ce));
+            }
+            const cudaError_t ie = cudaGraphInstantiate(&o->graph_exec, graph, 0);
+            cudaGraphDestroy(graph);
+            ORB_TRY(o, ie);
+            std::memcpy(o->graph_key, key, sizeof(key));
+        }
+        ORB_TRY(o, cudaEventRecord(o->ev0, st));
+        ORB_TRY(o, cudaGraphLaunch(o->graph_exec, st));
+    } else {
+        ORB_TRY(o, cudaEventRecord(o->ev0, st));
+        ORB_TRY(o, enqueue());
+    }
+    ORB_TRY(o, cudaEventRecord(o->ev1, st));
     ORB_TRY(o, cudaStreamSynchronize(st));
+    o->launches += 6 * N_LEVELS + 3;
     const int n = *h_count;
     if (n > MAX_OUT) return ofail(o, SFMM_ERANGE, "orb_detect_and_compute: more than 4096 keypoints (ties)");
     *count = n;
     if (n > capacity) return ofail(o, SFMM_ERANGE, "orb_detect_and_compute: output capacity too small (count holds the size needed)");
     if (n) {
-        unsigned char* h = static_cast<unsigned char*>(o->h_out) + 64;
-        ORB_TRY(o, cudaMemcpyAsync(h, o->d_kps.p, sizeof(SfmKeyPoint) * n, cudaMemcpyDeviceToHost, st));
-        ORB_TRY(o, cudaMemcpyAsync(h + sizeof(SfmKeyPoint) * MAX_OUT, o->d_desc.p, static_cast<size_t>(32) * n, cudaMemcpyDeviceToHost, st));
-        ORB_TRY(o, cudaEventRecord(o->ev1, st));
-        ORB_TRY(o, cudaStreamSynchronize(st));
         std::memcpy(keypoints, h, sizeof(SfmKeyPoint) * n);
         std::memcpy(descriptors, h + sizeof(SfmKeyPoint) * MAX_OUT, static_cast<size_t>(32) * n);
-    } else {
-        ORB_TRY(o, cudaEventRecord(o->ev1, st));
-        ORB_TRY(o, cudaStreamSynchronize(st));
     }
     float ms = 0.f;
     if (cudaEventElapsedTime(&ms, o->ev0, o->ev1) == cudaSuccess) o->last_ms = ms;
