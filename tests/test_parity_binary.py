@@ -392,3 +392,30 @@ def test_threshold_skipping_is_order_independent(order, monkeypatch):
             m.match_all_pairs()
             assert m.stats()["tensor_kind"] == 2
             _expect_equal(m.getMatching(0, 1), oracle.match_pair(q, t, 0, 0.8, cross, threads=8))
+
+
+def test_f4x_key_term_covers_every_popcount(monkeypatch):
+    """TM_F4X writes 512 - popc(t) into the spare elements of every train row as E2M1 digits (binary_unpack4x_kernel): every popcount
+    0..486 must come out right, with query rows of every popcount as well (popc(q) completes the distance in the epilogue)."""
+    monkeypatch.setenv("SFMM_F4X", "1")
+    rng = np.random.default_rng(3)
+    rows = []
+    for k in range(487):
+        bits = np.zeros(488, np.uint8)
+        bits[rng.choice(486, k, replace=False)] = 1
+        rows.append(np.packbits(bits, bitorder="little"))
+    t = np.stack(rows)
+    q = t[rng.permutation(487)].copy()
+    q[::3] ^= rng.integers(0, 256, q[::3].shape, dtype=np.uint8)
+    q[:, 60] &= 0x3F
+    for cross in (False, True):
+        with Matcher(NORM_HAMMING, 0.95, cross) as m:
+            m.set_descriptors([q, t, t[::-1].copy()])
+            m.match_all_pairs()
+            assert m.stats()["tensor_kind"] == 2
+            for (a, b) in synth.all_pairs(3):
+                d = [q, t, t[::-1].copy()]
+                _expect_equal(m.getMatching(a, b), oracle.match_pair(d[a], d[b], 0, 0.95, cross, threads=4))
+                idx, dist = m.knn_pair(a, b)
+                odist, oidx = oracle.knn2_c(d[a], d[b], 0)
+                assert (idx == oidx).all() and (dist == odist).all()
