@@ -226,8 +226,12 @@ def test_tensor_engine_equals_cv2_golden(name, cross):
             assert (idx == ki).all() and (dist == kd).all()
 
 
-@pytest.mark.parametrize("cols", [16, 32, 61, 64])
-def test_tensor_engine_widths_ties_ragged(cols):
+@pytest.mark.parametrize("f4x", ["0", "1"])
+@pytest.mark.parametrize("cols", [16, 29, 32, 61, 64])
+def test_tensor_engine_widths_ties_ragged(cols, f4x, monkeypatch):
+    # f4x = 1 forces TM_F4X where the rows have the 17 spare elements it needs (16 and 29 bytes: one K-block; 61: two), the others
+    # stay on TM_F4P (32 bytes: no spare) / kind::i8 (64 bytes)
+    monkeypatch.setenv("SFMM_F4X", f4x)
     rng = np.random.default_rng(cols)
     descs = [rng.integers(0, 2, (n, cols), dtype=np.uint8) * 255 for n in (700, 513, 1024, 3, 0, 129)]
     descs[4] = np.zeros((0, cols), np.uint8)

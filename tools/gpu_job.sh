@@ -1,9 +1,13 @@
-mkdir -p gpurun_out/r3e
+mkdir -p gpurun_out/r3f
 timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-B="--steps 5 --warmup 3 --no-extra --no-alt-engine --no-cpu-baseline --verify 2 --device-only-iters 3"
-for w in temple_akaze temple_sift; do
-SFMM_BENCH_TRACE=1 timeout 200 python bench.py --workload $w $B > gpurun_out/r3e/$w.json 2> gpurun_out/r3e/$w.err; grep "e2e\]" gpurun_out/r3e/$w.err | tail -2
-python -c "import json; d=json.loads(open('gpurun_out/r3e/$w.json').read().strip().splitlines()[-1]); print('$w', d['value'], d['e2e']['value'], d['resident_device_only']['value'], d['ms_per_step'])"
-done
-timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/r3e/launches_default.csv python bench.py --steps 2 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 0 --device-only-iters 1 --e2e-steps 1 --e2e-warmup 1 > gpurun_out/r3e/launches_bench.log 2>&1
-wc -l gpurun_out/r3e/launches_default.csv
+timeout 200 python __graft_entry__.py --smoke 2>&1 | tail -1
+(time timeout 900 python bench.py > gpurun_out/r3f/default_line.json 2> gpurun_out/r3f/default_line.err) 2>&1 | grep real
+(time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r3f/reference_line.json 2> gpurun_out/r3f/reference_line.err) 2>&1 | grep real
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r3f/default_line.json').read().strip().splitlines()[-1])
+print('default', d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline'].get('traffic'), d['verified'], d['clocks'])
+print('cfg2', d['configs1_cfg2']['value'], d['configs1_cfg2']['e2e']['value'], 'float', d['float']['value'], d['float']['e2e']['value'], 'orb', d['orb_extraction']['images_per_s'], d['orb_extraction']['verified'][:40])
+r=json.loads(open('gpurun_out/r3f/reference_line.json').read().strip().splitlines()[-1])
+print('reference', r.get('value'), r.get('unit'), r.get('cpu_baseline'))
+PY
