@@ -10,6 +10,7 @@
 // Two chunk slots (own stream, own scratch, own pinned staging) are kept in flight so that the
 // device->host copy and host-side bookkeeping of chunk k overlap the kernels of chunk k+1.
 #include <algorithm>
+#include <chrono>
 #include <cfloat>
 #include <cmath>
 #include <cstdio>
@@ -1630,7 +1631,10 @@ static int impl_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) {
     if (rc) return rc;
     if (n_pairs < 0 || (n_pairs > 0 && !qt)) return fail(ctx, SFMM_EINVAL, "match_pairs: bad argument");
     if ((rc = bind_device(ctx))) return rc;
+    const bool trace = std::getenv("SFMM_TRACE_HOST") != nullptr;  // development aid: where the host time of a call goes
+    const auto t_start = std::chrono::steady_clock::now();
     if ((rc = prepare_float(ctx))) return rc;
+    const auto t_prepared = std::chrono::steady_clock::now();
     begin_stats(ctx);
     ctx->call_pairs = n_pairs;
     ctx->call_base = ctx->table.size();
@@ -1695,10 +1699,17 @@ static int impl_match_pairs(SfmmCtx* ctx, const int32_t* qt, int64_t n_pairs) {
         throw;  // mapped to an error code by the entry point's guard
     }
     // device time of the whole call: from the first launch to the later of the two streams
+    const auto t_issued = std::chrono::steady_clock::now();
     CU_TRY(ctx, cudaEventRecord(ctx->ev_end, ctx->slot[0].stream));
     if ((rc = sync_all(ctx))) return rc;
     float ms = 0.f;
     CU_TRY(ctx, cudaEventElapsedTime(&ms, ctx->ev_begin, ctx->ev_end));
+    if (trace) {
+        const auto t_done = std::chrono::steady_clock::now();
+        auto us = [](auto a, auto b) { return std::chrono::duration<double, std::micro>(b - a).count(); };
+        std::fprintf(stderr, "[sfmm] match_pairs(%lld): prepare %.0f us, launch+collect loop %.0f us, final sync %.0f us; device %.0f us\n",
+                     static_cast<long long>(n_pairs), us(t_start, t_prepared), us(t_prepared, t_issued), us(t_issued, t_done), ms * 1e3);
+    }
     ctx->stats.last_match_ms = ms;
     ctx->stats.pairs_matched += n_pairs;
     return SFMM_OK;

@@ -1,13 +1,2 @@
-mkdir -p gpurun_out/r3f
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 200 python __graft_entry__.py --smoke 2>&1 | tail -1
-(time timeout 900 python bench.py > gpurun_out/r3f/default_line.json 2> gpurun_out/r3f/default_line.err) 2>&1 | grep real
-(time timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r3f/reference_line.json 2> gpurun_out/r3f/reference_line.err) 2>&1 | grep real
-python - <<'PY'
-import json
-d=json.loads(open('gpurun_out/r3f/default_line.json').read().strip().splitlines()[-1])
-print('default', d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline'].get('traffic'), d['verified'], d['clocks'])
-print('cfg2', d['configs1_cfg2']['value'], d['configs1_cfg2']['e2e']['value'], 'float', d['float']['value'], d['float']['e2e']['value'], 'orb', d['orb_extraction']['images_per_s'], d['orb_extraction']['verified'][:40])
-r=json.loads(open('gpurun_out/r3f/reference_line.json').read().strip().splitlines()[-1])
-print('reference', r.get('value'), r.get('unit'), r.get('cpu_baseline'))
-PY
+SFMM_TRACE_HOST=1 timeout 120 python tools/e2e_breakdown.py binary 50 5000 2>&1 | tail -4
+SFMM_TRACE_HOST=1 timeout 120 python tools/e2e_breakdown.py float 60 8000 2>&1 | tail -4
