@@ -654,7 +654,7 @@ def main():
     ap.add_argument("--float-mode", default="auto", choices=["auto", "exact", "tensor"])
     ap.add_argument("--binary-engine", default="auto", choices=["auto", "popc", "tensor"],
                     help="auto = the library default (tensor engine for <= 512-bit descriptors); popc = XOR+CSA+POPC kernel "
-                         "(the north-star design); tensor = tcgen05 kind::i8 engine.  The other engine is reported as alt_engine")
+                         "(the north-star design); tensor = tcgen05 engine (FP4 pipe below 512 bit, kind::i8 at 512).  The other engine is reported as alt_engine")
     ap.add_argument("--no-alt-engine", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs1_cfg2 and float blocks of the N=1 line")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)

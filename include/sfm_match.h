@@ -90,10 +90,11 @@ enum {
 /* Which pipe evaluates Hamming distances.  Results are bit-identical. */
 enum {
     SFMM_BINARY_AUTO = 0,   /* default: the tensor engine when the descriptors are <= 512 bit and their unpacked copy
-                               (8x the packed bytes) fits in half of the free device memory, else POPC */
+                               (4x the packed bytes, 8x at exactly 512 bit) fits in half of the free device memory, else POPC */
     SFMM_BINARY_POPC = 1,   /* the north-star design: XOR + carry-save + POPC on the integer pipes, packed descriptors */
-    SFMM_BINARY_TENSOR = 2  /* bits unpacked to {0,1} bytes, popc(a)+popc(b)-2a.b on tcgen05 kind::i8 (~6x the POPC rate);
-                               SFMM_EINVAL for descriptors > 512 bit */
+    SFMM_BINARY_TENSOR = 2  /* popc(a)+popc(b)-2a.b with a.b on the tensor cores: below 512 bit every bit an E2M1 nibble on the
+                               FP4 pipe (tcgen05 kind::mxf4, unit block scales), at 512 bit a {0,1} byte on kind::i8 (~8-10x the
+                               POPC rate); SFMM_EINVAL for descriptors > 512 bit */
 };
 
 typedef struct SfmmConfig {

@@ -1,7 +1,7 @@
 // Tensor-core 2-NN kernel, "TS" form: the QUERY tile lives in tensor memory, only train tiles go through
 // shared memory.  Same maths, same epilogue pieces and the same results as tensor_knn2_kernel (float_tensor.cuh).
-// Default for the binary engine (TM_I8P, and TM_I8 up to 256 bit) and the fp16 float path (TM_F16_EXACT), where it
-// measured faster; TF32 modes default to the shared-memory-A kernel (SFMM_TENSOR_TS=0/1 forces either;
+// Default for the binary engine (the FP4 modes TM_F4P / TM_F4X, which exist in this form only; TM_I8P, and TM_I8 up to 256 bit) and
+// the fp16 float path (TM_F16X / TM_F16_EXACT), where it measured faster; TF32 modes default to the shared-memory-A kernel (SFMM_TENSOR_TS=0/1 forces either;
 // profiles/tensor_variants_r01.txt has every A/B).
 //
 // Why: with both operands in shared memory every tcgen05.mma (M=128, N=128, 32 bytes of K) reads 4 KB of A
@@ -18,6 +18,8 @@
 // the first version with the MMA warp 30 % of its time in the acc_empty wait).
 //
 // TMEM map (512 columns): query tile A0 | A1 (KB*32 columns each) | 128-column accumulators, two (KB = 3, 4) or three (KB <= 2).
+// (Round 2: the FP4 modes and the skipping TM_F16X kernel keep ONE query-tile buffer and always three accumulators; the FP4 modes
+// add 32 columns of unit scale factors behind them -- see A_BUFS in the kernel.)
 // A row r of the tile is TMEM lane r; its K bytes are packed in order into 32-bit columns (32 bytes = 8
 // columns per MMA), which is exactly what a thread gets when it reads its row from global memory as
 // 32-bit words -- so four loader warps (one per TMEM lane quarter) copy rows global -> registers ->
