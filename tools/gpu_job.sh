@@ -1,3 +1,10 @@
-SFMM_CHUNKS=16 timeout 120 python tools/repro_tmp.py 30 10000 2>&1 | tail -1 | cut -c1-200
-timeout 120 python tools/repro_tmp.py 130 10000 2>&1 | tail -1 | cut -c1-200
-timeout 600 compute-sanitizer --tool memcheck python tools/repro_tmp.py 130 10000 2>&1 | grep -v "^$" | head -30 | cut -c1-300
+mkdir -p gpurun_out/r3h
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 200 python __graft_entry__.py --smoke 2>&1 | tail -1
+(time timeout 900 python bench.py > gpurun_out/r3h/default_line.json 2> gpurun_out/r3h/default_line.err) 2>&1 | grep real
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/r3h/default_line.json').read().strip().splitlines()[-1])
+print('default', d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline'].get('traffic'), d['verified'], d['clocks'], d['gpu_launches'])
+print('cfg2', d['configs1_cfg2']['value'], d['configs1_cfg2']['e2e']['value'], 'float', d['float']['value'], d['float']['e2e']['value'], 'orb', d['orb_extraction']['images_per_s'])
+PY
