@@ -1,10 +1,9 @@
-mkdir -p gpurun_out/r3h
-timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-timeout 200 python __graft_entry__.py --smoke 2>&1 | tail -1
-(time timeout 900 python bench.py > gpurun_out/r3h/default_line.json 2> gpurun_out/r3h/default_line.err) 2>&1 | grep real
-python - <<'PY'
+mkdir -p gpurun_out/r3i
+N=$(nvidia-smi -L | wc -l)
+T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29551"
+(time timeout 600 $T bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r3i/bench_n${N}_cfg3.json 2> gpurun_out/r3i/bench_n${N}_cfg3.err) 2>&1 | grep real
+python - <<PY
 import json
-d=json.loads(open('gpurun_out/r3h/default_line.json').read().strip().splitlines()[-1])
-print('default', d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline'].get('traffic'), d['verified'], d['clocks'], d['gpu_launches'])
-print('cfg2', d['configs1_cfg2']['value'], d['configs1_cfg2']['e2e']['value'], 'float', d['float']['value'], d['float']['e2e']['value'], 'orb', d['orb_extraction']['images_per_s'])
+d=json.loads(open('gpurun_out/r3i/bench_n${N}_cfg3.json').read().strip().splitlines()[-1])
+print('N=${N}', d['value'], d['ms_per_step'], d['e2e']['value'], d['resident_device_only']['value'], d['verified'], d['clocks'])
 PY
