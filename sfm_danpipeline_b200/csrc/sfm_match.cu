@@ -10,6 +10,7 @@
 // Two chunk slots (own stream, own scratch, own pinned staging) are kept in flight so that the
 // device->host copy and host-side bookkeeping of chunk k overlap the kernels of chunk k+1.
 #include <algorithm>
+#include <atomic>
 #include <chrono>
 #include <cfloat>
 #include <cmath>
@@ -1361,35 +1362,71 @@ static int impl_set_descriptors(SfmmCtx* ctx, int32_t n_images, const void* cons
         ctx->raw_row0_32.assign(ctx->raw_row0.begin(), ctx->raw_row0.end());
         CU_TRY(ctx, cudaMemcpyAsync(ctx->d_raw_row0.p, ctx->raw_row0_32.data(), ctx->raw_row0_32.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
         CU_TRY(ctx, cudaMemcpyAsync(ctx->d_row0.p, ctx->row0.data(), static_cast<size_t>(n_images) * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
-        const uint64_t slab_rows = std::max<uint64_t>(1, (32u << 20) / row_bytes);
+        // Slabs of 8 MB: the first slab's fill and the last slab's copy are the only parts of the pipeline that do not overlap.  The
+        // worker threads live for the whole call (one spawn per call, not per slab): slab k is announced through `gen`, every worker
+        // copies its share and counts `left` down; the calling thread takes the first share, waits for the others and issues the copy.
+        const uint64_t slab_rows = std::max<uint64_t>(1, (8u << 20) / row_bytes);
         const size_t slab_bytes = static_cast<size_t>(std::min<uint64_t>(slab_rows, raw_rows)) * row_bytes;
         for (PinBuf& p : ctx->pack) CU_TRY(ctx, p.ensure(slab_bytes));
         const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+        unsigned workers = static_cast<unsigned>(std::min<uint64_t>(std::min(16u, hw), std::max<uint64_t>(1, (raw_rows * row_bytes) >> 21)));
+        struct Slab { uint64_t b = 0, e = 0; unsigned char* dst = nullptr; };
+        Slab cur;
+        std::atomic<int64_t> gen{0};   // slab number + 1 that `cur` describes; -1: done
+        std::atomic<int> left{0};      // workers that have not finished the current slab yet
+        auto share = [&](const Slab& sl, unsigned w) {
+            const uint64_t n_rows = sl.e - sl.b, per = (n_rows + workers - 1) / workers;
+            const uint64_t wb = sl.b + w * per, we = std::min(sl.e, wb + per);
+            if (wb < we) pack_raw(ctx, data, step_bytes, row_bytes, wb, we, sl.dst + (wb - sl.b) * row_bytes);
+        };
+        std::vector<std::thread> pool;
+        try {
+            pool.reserve(workers);
+            for (unsigned w = 1; w < workers; ++w)
+                pool.emplace_back([&, w]() {
+                    int64_t seen = 0;
+                    for (;;) {
+                        int64_t g;
+                        while ((g = gen.load(std::memory_order_acquire)) == seen) std::this_thread::yield();
+                        if (g < 0) return;
+                        seen = g;
+                        share(cur, w);
+                        left.fetch_sub(1, std::memory_order_release);
+                    }
+                });
+        } catch (...) {  // out of threads: go on with the ones that started (nothing has been announced yet)
+        }
+        workers = static_cast<unsigned>(pool.size()) + 1;
+        auto stop_pool = [&]() {
+            gen.store(-1, std::memory_order_release);
+            for (auto& t : pool) t.join();
+        };
         int k = 0;
         for (uint64_t b = 0; b < raw_rows; b += slab_rows, ++k) {
             const uint64_t e = std::min(raw_rows, b + slab_rows);
             PinBuf& pin = ctx->pack[k & 1];
-            if (k >= 2) CU_TRY(ctx, cudaEventSynchronize(ctx->ev_pack[k & 1]));  // its previous copy has left the slab
-            unsigned char* dst = static_cast<unsigned char*>(pin.p);
-            const uint64_t n_rows = e - b;
-            const unsigned workers = static_cast<unsigned>(std::min<uint64_t>(std::min(16u, hw), std::max<uint64_t>(1, (n_rows * row_bytes) >> 21)));
-            if (workers <= 1) {
-                pack_raw(ctx, data, step_bytes, row_bytes, b, e, dst);
-            } else {
-                std::vector<std::thread> pool;
-                const uint64_t per = (n_rows + workers - 1) / workers;
-                for (unsigned w = 1; w < workers; ++w) {
-                    const uint64_t wb = b + w * per, we = std::min(e, wb + per);
-                    if (wb >= we) break;
-                    pool.emplace_back(pack_raw, ctx, data, step_bytes, row_bytes, wb, we, dst + (wb - b) * row_bytes);
+            if (k >= 2) {  // its previous copy has left the slab
+                const cudaError_t ce = cudaEventSynchronize(ctx->ev_pack[k & 1]);
+                if (ce != cudaSuccess) {
+                    stop_pool();
+                    CU_TRY(ctx, ce);
                 }
-                pack_raw(ctx, data, step_bytes, row_bytes, b, std::min(e, b + per), dst);  // this thread takes the first share
-                for (auto& t : pool) t.join();
             }
-            CU_TRY(ctx, cudaMemcpyAsync(static_cast<unsigned char*>(ctx->d_raw.p) + b * row_bytes, dst, n_rows * row_bytes, cudaMemcpyHostToDevice, st));
-            CU_TRY(ctx, cudaEventRecord(ctx->ev_pack[k & 1], st));
+            cur = Slab{b, e, static_cast<unsigned char*>(pin.p)};
+            left.store(static_cast<int>(pool.size()), std::memory_order_relaxed);
+            gen.store(k + 1, std::memory_order_release);
+            share(cur, 0);  // this thread takes the first share
+            while (left.load(std::memory_order_acquire) != 0) std::this_thread::yield();
+            const uint64_t n_rows = e - b;
+            cudaError_t ce = cudaMemcpyAsync(static_cast<unsigned char*>(ctx->d_raw.p) + b * row_bytes, cur.dst, n_rows * row_bytes, cudaMemcpyHostToDevice, st);
+            if (ce == cudaSuccess) ce = cudaEventRecord(ctx->ev_pack[k & 1], st);
+            if (ce != cudaSuccess) {
+                stop_pool();
+                CU_TRY(ctx, ce);
+            }
             ctx->stats.h2d_bytes += static_cast<int64_t>(n_rows * row_bytes);
         }
+        stop_pool();
         const uint32_t chunks = static_cast<uint32_t>(pitch / 16);
         const uint64_t n_thr = total * chunks;
         const unsigned grid = static_cast<unsigned>((n_thr + 255) / 256);

@@ -1,9 +1,5 @@
-mkdir -p gpurun_out/r3i
-N=$(nvidia-smi -L | wc -l)
-T="python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29551"
-(time timeout 600 $T bench.py --gpus $N --steps 5 --warmup 3 > gpurun_out/r3i/bench_n${N}_cfg3.json 2> gpurun_out/r3i/bench_n${N}_cfg3.err) 2>&1 | grep real
-python - <<PY
-import json
-d=json.loads(open('gpurun_out/r3i/bench_n${N}_cfg3.json').read().strip().splitlines()[-1])
-print('N=${N}', d['value'], d['ms_per_step'], d['e2e']['value'], d['resident_device_only']['value'], d['verified'], d['clocks'])
-PY
+B="--steps 1 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 2 --device-only-iters 1 --e2e-steps 3 --e2e-warmup 1"
+SFMM_BENCH_TRACE=1 SFMM_TRACE_HOST=1 timeout 200 python bench.py $B 2>&1 | grep "e2e\]\|sfmm\]\|verified" | tail -5 | cut -c1-250
+SFMM_BENCH_TRACE=1 timeout 200 python bench.py --workload cfg4s $B 2>&1 | grep "e2e\]" | tail -2
+SFMM_BENCH_TRACE=1 timeout 200 python bench.py --workload cfg2 $B 2>&1 | grep "e2e\]" | tail -2
+timeout 600 python -m pytest tests/test_parity_binary.py tests/test_next_rows.py tests/test_cpp_adapter.py -m gpu -x -q 2>&1 | tail -2
