@@ -678,12 +678,20 @@ int prepare_binary_tensor(SfmmCtx* ctx) {
     // descriptors below 512 bit (packed 16-bit keys apply): one NIBBLE per bit and the FP4 pipe (TM_F4P) -- half the bytes, twice the rate
     const bool f4 = ctx->cols * 8 < 512 && !ctx->no_f4 && !std::getenv("SFMM_I8_KEYS32");
     const int kbytes = f4 ? (words * 16 + 127) / 128 * 128 : kbytes8;
+    // TM_F4X pays once a row's threshold has settled, i.e. on long train images: measured (one B200, 486 bit) -4 % at 5 000 rows per
+    // image, +13 % at 10 000 (profiles/tensor_variants_r02.txt); SFMM_F4X=1 / SFMM_NO_F4X=1 force either.  It keeps TWO operand arrays.
+    const int64_t max_rows = ctx->rows.empty() ? 0 : *std::max_element(ctx->rows.begin(), ctx->rows.end());
+    const char* f4x_env = std::getenv("SFMM_F4X");
+    bool f4x = f4 && ctx->cols * 8 + 17 <= kbytes * 2 && !ctx->no_skip && !std::getenv("SFMM_NO_F4X") &&
+               ((f4x_env && std::atoi(f4x_env) != 0) || max_rows >= 7000);
     bool want = ctx->cfg.binary_engine == SFMM_BINARY_TENSOR;
     if (want && kbytes8 > 512) return fail(ctx, SFMM_EINVAL, "SFMM_BINARY_TENSOR supports descriptors of at most 512 bits");
     if (ctx->cfg.binary_engine == SFMM_BINARY_AUTO && kbytes8 <= 512 && ctx->total_rows > 0) {
         size_t free_b = 0, total_b = 0;
         CU_TRY(ctx, cudaMemGetInfo(&free_b, &total_b));
-        want = static_cast<size_t>(ctx->total_rows) * kbytes <= free_b / 2 + ctx->d_unpacked.cap;  // (a buffer we already own counts as free)
+        const size_t one = static_cast<size_t>(ctx->total_rows) * kbytes, have = free_b / 2 + ctx->d_unpacked.cap + ctx->d_f4_a.cap;  // (buffers we already own count as free)
+        if (f4x && 2 * one > have) f4x = false;  // the second array does not fit: TM_F4P needs one
+        want = one <= have;
     }
     if (want) {
         if (ctx->total_rows > 0) {
@@ -691,12 +699,6 @@ int prepare_binary_tensor(SfmmCtx* ctx) {
             CU_TRY(ctx, ctx->d_unpacked.ensure(static_cast<size_t>(ctx->total_rows) * kbytes));
             CU_TRY(ctx, ctx->d_norms.ensure((static_cast<size_t>(ctx->total_rows) + 2 * FT_N) * sizeof(int32_t)));
             const uint32_t rows = static_cast<uint32_t>(ctx->total_rows);
-            // TM_F4X pays once a row's threshold has settled, i.e. on long train images: measured (one B200, 486 bit) -4 % at 5 000 rows per
-            // image, +13 % at 10 000 (profiles/tensor_variants_r02.txt); SFMM_F4X=1 / SFMM_NO_F4X=1 force either
-            const int64_t max_rows = ctx->rows.empty() ? 0 : *std::max_element(ctx->rows.begin(), ctx->rows.end());
-            const char* f4x_env = std::getenv("SFMM_F4X");
-            const bool f4x = f4 && ctx->cols * 8 + 17 <= kbytes * 2 && !ctx->no_skip && !std::getenv("SFMM_NO_F4X") &&
-                             ((f4x_env && std::atoi(f4x_env) != 0) || max_rows >= 7000);
             if (f4x) {
                 CU_TRY(ctx, ctx->d_f4_a.ensure(static_cast<size_t>(ctx->total_rows) * kbytes));
                 binary_unpack4x_kernel<<<(rows + 7) / 8, 256, 0, st>>>(ctx->blob.as<uint32_t>(), words, rows, kbytes, ctx->cols * 8, ctx->d_unpacked.as<uint8_t>(),

@@ -1,5 +1,11 @@
-B="--steps 1 --warmup 1 --no-extra --no-alt-engine --no-cpu-baseline --verify 2 --device-only-iters 1 --e2e-steps 3 --e2e-warmup 1"
-SFMM_BENCH_TRACE=1 SFMM_TRACE_HOST=1 timeout 200 python bench.py $B 2>&1 | grep "e2e\]\|sfmm\]\|verified" | tail -5 | cut -c1-250
-SFMM_BENCH_TRACE=1 timeout 200 python bench.py --workload cfg4s $B 2>&1 | grep "e2e\]" | tail -2
-SFMM_BENCH_TRACE=1 timeout 200 python bench.py --workload cfg2 $B 2>&1 | grep "e2e\]" | tail -2
-timeout 600 python -m pytest tests/test_parity_binary.py tests/test_next_rows.py tests/test_cpp_adapter.py -m gpu -x -q 2>&1 | tail -2
+# the end-of-round verification: every GPU test, the smoke test and the default bench line
+mkdir -p gpurun_out/final
+timeout 1500 python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+timeout 200 python __graft_entry__.py --smoke 2>&1 | tail -1
+(time timeout 900 python bench.py > gpurun_out/final/default_line.json 2> gpurun_out/final/default_line.err) 2>&1 | grep real
+python - <<'PY'
+import json
+d=json.loads(open('gpurun_out/final/default_line.json').read().strip().splitlines()[-1])
+print('default', d['value'], d['e2e']['value'], d['roofline']['frac'], d['roofline'].get('traffic'), d['verified'], d['clocks'], d['gpu_launches'])
+print('cfg2', d['configs1_cfg2']['value'], d['configs1_cfg2']['e2e']['value'], 'float', d['float']['value'], d['float']['e2e']['value'], 'orb', d['orb_extraction']['images_per_s'])
+PY
