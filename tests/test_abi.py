@@ -134,3 +134,36 @@ def test_nccl_is_not_a_link_time_dependency():
     import subprocess
     out = subprocess.run(["ldd", _lib.LIB_PATH], capture_output=True, text=True).stdout
     assert "nccl" not in out.lower()
+
+
+def test_stats_mirror_matches_the_header():
+    """The ctypes mirror of SfmmStats lists exactly the header's fields, in order (all 8-byte fields: no padding questions)."""
+    import re
+    text = open(os.path.join(ROOT, "include", "sfm_match.h")).read()
+    body = re.search(r"typedef struct SfmmStats \{(.*?)\} SfmmStats;", text, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(int64_t|double)\s+(\w+)\s*;", body)
+    assert [n for _t, n in fields] == [n for n, _c in _lib.SfmmStats._fields_]
+    for (t, n), (_n, c) in zip(fields, _lib.SfmmStats._fields_):
+        assert c is (C.c_int64 if t == "int64_t" else C.c_double), n
+    assert C.sizeof(_lib.SfmmStats) == 8 * len(fields)
+    assert "tensor_kind" in dict(_lib.SfmmStats._fields_)
+
+
+def test_f4x_digit_expansion_is_exact():
+    """TM_F4X (csrc/float_tensor.cuh, binary_unpack4x_kernel) writes E = 512 - popc(t) into 17 spare elements as E2M1 digits against the
+    query-side constants 6 x16, 1.  Restated here: every E in 0..512 is reproduced exactly from representable digits (the kernel itself is
+    checked for every popcount by tests/test_parity_binary.py::test_f4x_key_term_covers_every_popcount on the GPU)."""
+    e2m1 = {0: 0.0, 1: 0.5, 2: 1.0, 3: 1.5, 4: 2.0, 5: 3.0, 6: 4.0, 7: 6.0}  # nibble -> value
+    def code(units):  # units of 0.5 -> nibble (the kernel's lambda)
+        return units if units <= 4 else (5 if units == 6 else 6)
+    for pc in range(0, 513):
+        E = 512 - pc
+        a, r = divmod(E, 36)
+        b, c = divmod(r, 3)
+        u = b if b <= 4 else ((4 if b == 5 else 6) if b <= 7 else 8)
+        v = b - u
+        assert a <= 14 and u in (0, 1, 2, 3, 4, 6, 8) and v in (0, 1, 2, 3) and c in (0, 1, 2)
+        train = [7 if s < a else 0 for s in range(14)] + [code(u), code(v), 2 * c]
+        query = [7] * 16 + [2]
+        assert sum(e2m1[q] * e2m1[t] for q, t in zip(query, train)) == E, pc
