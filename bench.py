@@ -23,9 +23,11 @@ shape (cfg4s) ride along in the N=1 line as `configs1_cfg2` and `float` blocks.
   e2e    : the same metric through the public API with HOST buffers in: H2D of the descriptors, (NCCL
            broadcast), matching, (NCCL gather to rank 0), D2H of the match table.  Wall clock, max over ranks.
   resident_device_only: the round-1 definition of `value` (match lists left in HBM), for continuity.
-  roofline: the 2-NN kernel that actually ran against its bound: the tensor pipe (default engines) or the POPC
-           pipe / FP32 lanes (--binary-engine popc, --float-mode exact).  Peaks: measured tcgen05 issue rates
-           (profiles/tcgen05_peaks_r02.json, tools/pipe_bench) when present, else MEASURED_PEAKS.json scaled.
+  roofline: the 2-NN kernel that actually ran against its bound: the tensor pipe (default engines: `tensor_kind` says which --
+           kind::mxf4 for binary descriptors below 512 bit, with `vs_i8_pipe` beside it for continuity with the kind::i8
+           kernel of round 1; kind::i8 at 512 bit; kind::f16 for floats) or the POPC pipe / FP32 lanes (--binary-engine
+           popc, --float-mode exact).  Peaks: measured tcgen05 issue rates (profiles/tcgen05_peaks_r02.json, from
+           tools/tc_bench.cu and tools/mxf4_bench.cu) when present, else MEASURED_PEAKS.json scaled.
   alt_engine: the other Hamming engine on the same shard in the same run.
   verified: `--verify` (default 2) random pairs of the end-to-end table, byte-compared with the CPU oracle.
   cpu_baseline: the reference's own CPU path (OpenCV BFMatcher via cv2, else the C oracle) on a bounded sample
